@@ -1,0 +1,75 @@
+"""ORACLE support (test infrastructure only): generate ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_goldens [case ...]
+
+Each fixture holds fingerprints (per-tensor norms and sums + a strided sample of the flat vector, see
+``fb_oracle.fingerprint``) of: the seed-0 initialisation, the accumulated regularised gradient after one full-batch
+step of ``fullbatch.training.train`` (training.py:121-185), the raw and regularised gradients of the first two
+microbatches (recorded around ``GradRegularizer.__call__``, modules.py:346-348), BN running statistics after the step,
+and the scalar ``stats`` of ``_record_stats`` (training.py:85-119).  Inputs are ``fb_oracle.synthetic_cifar`` (seed 1234).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import fb_oracle as O
+from . import reference_harness as H
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> (depth, microbatch, N, dtype)
+CASES = {
+    "r18_mb16_n32_f64": (18, 16, 32, "float64"),
+    "r18_mb16_n32_f32": (18, 16, 32, "float32"),
+    "r18_mb128_n256_f64": (18, 128, 256, "float64"),
+    "r18_mb128_n256_f32": (18, 128, 256, "float32"),
+    "r152_mb4_n8_f64": (152, 4, 8, "float64"),
+}
+STRIDE = 4999
+HYP = dict(lr=0.8, block_strength=0.5, eps=1e-2)
+
+
+def pack(prefix, fp, out):
+    for k, v in fp.items():
+        out[f"{prefix}.{k}"] = np.asarray(v)
+
+
+def make_case(name):
+    depth, mb, n, dts = CASES[name]
+    dt = getattr(torch, dts)
+    cfg = H.make_cfg(depth=depth, batch_size=mb, sub_batch=mb, grad_clip=None, warmup=0,
+                     accumulation_dtype="double" if dt == torch.float64 else "float", **HYP)
+    model = H.construct_reference_model(cfg, seed=0, dtype=dt)
+    X, Y = O.synthetic_cifar(n, dtype=dt)
+    out = {}
+    pack("init", O.fingerprint([p.detach() for p in model.parameters()], STRIDE), out)
+    rec = []
+    t0 = time.time()
+    stats, avg = H.run_reference_train(model, X, Y, cfg, dtype=dt, record=rec)
+    elapsed = time.time() - t0
+    pack("avg", O.fingerprint(avg, STRIDE), out)
+    for i, r in enumerate(rec[:2]):
+        pack(f"mb{i}.raw", O.fingerprint(r["raw"], STRIDE), out)
+        pack(f"mb{i}.reg", O.fingerprint(r["reg"], STRIDE), out)
+    bufs = [b.detach() for k, b in model.named_buffers() if not k.endswith("num_batches_tracked")]
+    pack("buffers", O.fingerprint(bufs, 97), out)
+    scalars = {k: float(v[0]) for k, v in stats.items() if len(v) and k in
+               ("train_loss", "train_acc", "param_norm", "grad_norm", "full_loss")}
+    scalars["grad_norm_train"] = [float(stats[f"grad_norm_train_{i}"][0]) for i in range(n // mb)]
+    meta = dict(case=name, depth=depth, mb=mb, n=n, dtype=dts, stride=STRIDE, hyp=HYP, scalars=scalars,
+                torch=torch.__version__, threads=torch.get_num_threads(), reference_seconds=elapsed,
+                num_params=int(sum(p.numel() for p in model.parameters())))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(f"[golden] {name}: {elapsed:.1f}s {scalars}", flush=True)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    for case in (sys.argv[1:] or list(CASES)):
+        make_case(case)
