@@ -1,0 +1,650 @@
+// Convolutions of the full-batch step as tcgen05 implicit GEMMs (sm_100a).
+//
+//   conv_gemm_kernel : out[128-pixel tile, N_TILE] = sum_steps A_step * B_step^T
+//                      A = NHWC activation boxes fetched by 4-D TMA with a per-tap spatial shift (halo / padding comes
+//                      from TMA out-of-bounds zero fill), B = weight rows, both K-major SWIZZLE_128B tiles, fp32
+//                      accumulation in TMEM.  Serves conv forward, dgrad (stride 1 and the 4 phases of stride 2),
+//                      1x1 convs and the im2col'ed stem.  bf16 hi/lo operand splitting is expressed as extra steps.
+//   wgrad_kernel     : partial[co, (tap,ci)] = sum_pixels dY[pixel, co] * X[pixel + tap, ci]; both operands are
+//                      MN-major (the channel dimension is contiguous in NHWC), split-K over 128-pixel blocks,
+//                      up to 8 (tap, ci-block) accumulators of 64 TMEM columns per CTA.
+//
+// Reference call sites replaced: torch.nn.Conv2d forward (fullbatch/models/resnets.py:69-73,206-210,285-291) and its
+// autograd backward (fullbatch/training/training.py:82, fullbatch/models/modules.py:230).
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fullbatch_b200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s failed: %s", what, cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(void* blob, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return FB_ERR_DRIVER;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  alignas(64) CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", int(r), rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return FB_ERR_DRIVER;
+  }
+  memcpy(blob, &m, sizeof(m));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv_gemm_kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct alignas(64) ConvGemmKParams {
+  CUtensorMap a_maps[FB_MAX_A_MAPS];
+  CUtensorMap b_maps[FB_MAX_B_MAPS];
+  fb_tap_step steps[FB_MAX_TAP_STEPS];
+  int n_steps, cblocks;
+  int tile_w, tile_h, tile_n;
+  int grid_h, grid_n;
+  int n_total;
+  float* out;
+  long long out_sn, out_sh, out_sw;
+  int accumulate;
+};
+
+constexpr int kTileM = 128;                   // pixels per CTA tile == UMMA M
+constexpr int kBlockK = 64;                   // bf16 elements per K block == one 128-byte swizzle row
+constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KiB
+
+__device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, int grid_h, int& n0, int& h0) {
+  if (tile_n == 1) {
+    const int per_img = grid_h / tile_h;
+    n0 = tile / per_img;
+    h0 = (tile % per_img) * tile_h;
+  } else {
+    n0 = tile * tile_n;
+    h0 = 0;
+  }
+}
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
+  constexpr int B_BYTES = N_TILE * kBlockK * 2;
+  constexpr int STAGE_BYTES = kATileBytes + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int n0, h0;
+  tile_origin(blockIdx.x, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+  const int n_tile0 = blockIdx.y * N_TILE;
+  const int total = p.n_steps * p.cblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        const fb_tap_step st = p.steps[it / p.cblocks];
+        const int cb = it % p.cblocks;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_4d(sa, &p.a_maps[st.a_map], &full_bar[s], cb * kBlockK, st.dw, h0 + st.dh, n0);
+        tma_load_2d(sa + kATileBytes, &p.b_maps[st.b_map], &full_bar[s], st.b_k0 + cb * kBlockK, n_tile0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, 2);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + kATileBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(accum_bar);
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global (fp32 NHWC) ----------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int w = r % p.tile_w;
+    const int h = (r / p.tile_w) % p.tile_h;
+    const int n = r / (p.tile_w * p.tile_h);
+    const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
+    float* dst = p.out + (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw +
+                 n_tile0;
+    mbar_wait(accum_bar, 0, 3);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < N_TILE / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          if (p.accumulate) {
+            const float4 e = d4[j];
+            o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+          }
+          d4[j] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, N_TILE);
+}
+
+template <int N_TILE, int STAGES>
+static int launch_conv_gemm(const ConvGemmKParams& kp, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kATileBytes + N_TILE * kBlockK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_gemm_kernel<N_TILE, STAGES><<<grid, 192, smem, stream>>>(kp);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad_kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct alignas(64) WgradKParams {
+  CUtensorMap dy_map;
+  CUtensorMap x_maps[FB_MAX_A_MAPS];
+  fb_wgrad_tap taps[FB_MAX_WGRAD_TAPS];
+  int n_taps, cblocks, planes, slots_per_cta;
+  int cout, cin;
+  int tile_w, tile_h, tile_n;
+  int grid_h, grid_n;
+  int splits, n_pixblocks;
+  float* partial;
+};
+
+constexpr int kWgAStages = 2;
+constexpr int kWgBStages = 6;
+constexpr int kWgABytes = 2 * kATileBytes;  // two 64-channel chunks of dY: [chunk][128 pixels][64 co]
+constexpr int kWgBBytes = kATileBytes;      // [128 pixels][64 ci]
+constexpr int kWgTmemCols = 512;
+
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kWgAStages * kWgABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kWgBBytes);
+  uint64_t* a_empty = a_full + kWgAStages;
+  uint64_t* b_full = a_empty + kWgAStages;
+  uint64_t* b_empty = b_full + kWgBStages;
+  uint64_t* accum_bar = b_empty + kWgBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kWgBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kWgTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int co0 = blockIdx.x * 128;
+  const int slot0 = blockIdx.y * p.slots_per_cta;
+  const int n_slots_total = p.n_taps * p.cblocks;
+  const int n_slots = min(p.slots_per_cta, n_slots_total - slot0);
+  const int split = blockIdx.z;
+  const int pb0 = int((long long)split * p.n_pixblocks / p.splits);
+  const int pb1 = int((long long)(split + 1) * p.n_pixblocks / p.splits);
+  const bool two_chunks = (co0 + 64) < p.cout;
+  const int k_total = p.n_taps * p.cin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        int n0, h0;
+        tile_origin(pb, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+        const int as = ia % kWgAStages;
+        mbar_wait(&a_empty[as], ((ia / kWgAStages) & 1) ^ 1, 11);
+        uint8_t* sa = smem_a + as * kWgABytes;
+        mbar_arrive_expect_tx(&a_full[as], two_chunks ? kWgABytes : kATileBytes);
+        tma_load_4d(sa, &p.dy_map, &a_full[as], co0, 0, h0, n0);
+        if (two_chunks) tma_load_4d(sa + kATileBytes, &p.dy_map, &a_full[as], co0 + 64, 0, h0, n0);
+        ++ia;
+        for (int j = 0; j < n_slots; ++j) {
+          const int s = slot0 + j;
+          const fb_wgrad_tap tap = p.taps[s % p.n_taps];
+          const int cb = s / p.n_taps;
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const int bs = ib % kWgBStages;
+            mbar_wait(&b_empty[bs], ((ib / kWgBStages) & 1) ^ 1, 12);
+            mbar_arrive_expect_tx(&b_full[bs], kWgBBytes);
+            tma_load_4d(smem_b + bs * kWgBBytes, &p.x_maps[tap.phase * p.planes + pl], &b_full[bs], cb * kBlockK,
+                        tap.dw, h0 + tap.dh, n0);
+            ++ib;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      int ia = 0, ib = 0;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        const int as = ia % kWgAStages;
+        mbar_wait(&a_full[as], (ia / kWgAStages) & 1, 13);
+        const uint32_t a_base = smem_u32(smem_a + as * kWgABytes);
+        for (int j = 0; j < n_slots; ++j) {
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const int bs = ib % kWgBStages;
+            mbar_wait(&b_full[bs], (ib / kWgBStages) & 1, 14);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(smem_b + bs * kWgBBytes);
+#pragma unroll
+            for (int k = 0; k < kTileM / 16; ++k) {
+              // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO),
+              // groups of 8 pixel rows are 1024 bytes apart (SBO)
+              const uint64_t da = make_smem_desc_sw128(a_base + k * 2048, kATileBytes, 1024);
+              const uint64_t db = make_smem_desc_sw128(b_base + k * 2048, kATileBytes, 1024);
+              tc_mma_bf16(tmem_base + j * 64, da, db, idesc, (pb != pb0 || pl != 0 || k != 0) ? 1u : 0u);
+            }
+            tc_commit(&b_empty[bs]);
+            ++ib;
+          }
+        }
+        tc_commit(&a_empty[as]);
+        ++ia;
+      }
+      tc_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    const bool valid = co < p.cout;
+    float* row = p.partial + ((long long)split * p.cout + co) * k_total;
+    mbar_wait(accum_bar, 0, 15);
+    tc_fence_after();
+    for (int j = 0; j < n_slots; ++j) {
+      const int s = slot0 + j;
+      const int tap = s % p.n_taps;
+      const int cb = s / p.n_taps;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(row + tap * p.cin + cb * kBlockK + c * 32);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            d4[t] = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
+                                __uint_as_float(v[4 * t + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kWgTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad finalize: deterministic split-K reduction + scatter to OIHW
+// ---------------------------------------------------------------------------------------------------------------
+// block = (co, 32-wide ci block); blockDim = 32 * taps
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int taps,
+                                      int cin_stored, int mode, float* __restrict__ g) {
+  __shared__ float tile[32 * 9];
+  const int co = blockIdx.y;
+  const int ci0 = blockIdx.x * 32;
+  const int t = threadIdx.x;
+  const int k_total = (mode == 0) ? taps * cin_stored : cin_stored;
+  const long long split_stride = (long long)cout * k_total;
+  if (mode == 0) {
+    const int tap = t / 32, cil = t % 32;
+    float acc = 0.f;
+    if (ci0 + cil < cin) {
+      const float* src = partial + (long long)co * k_total + tap * cin_stored + ci0 + cil;
+      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+    }
+    tile[cil * taps + tap] = acc;
+    __syncthreads();
+    const int ci = ci0 + t / taps;
+    if (ci < cin) g[((long long)co * cin + ci0) * taps + t] = tile[t];
+  } else {
+    // columns already in (ci, tap) order: plain reduction of the first cin*taps columns
+    const int col = ci0 * taps + t;
+    if (col < cin * taps) {
+      const float* src = partial + (long long)co * k_total + col;
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+      g[(long long)co * cin * taps + col] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight prep: OIHW fp32 -> bf16 hi/lo GEMM operands
+// ---------------------------------------------------------------------------------------------------------------
+// block = 32 co x 32 ci x taps, 256 threads
+__global__ void weight_prep_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                   __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo, long long ld_f,
+                                   __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo,
+                                   long long ld_d) {
+  extern __shared__ float wtile[];  // [32 co][32 ci * taps + 1]
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int row_len = 32 * taps;
+  const int pitch = row_len + 1;
+  for (int i = threadIdx.x; i < 32 * row_len; i += blockDim.x) {
+    const int co = i / row_len, r = i % row_len;
+    wtile[co * pitch + r] = w[((long long)(co0 + co) * cin + ci0) * taps + r];
+  }
+  __syncthreads();
+  // wf[co][tap][ci]
+  for (int i = threadIdx.x; i < 32 * row_len; i += blockDim.x) {
+    const int ci = i % 32, tap = (i / 32) % taps, co = i / (32 * taps);
+    const float v = wtile[co * pitch + ci * taps + tap];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const long long o = (long long)(co0 + co) * ld_f + (long long)tap * cin + ci0 + ci;
+    wf_hi[o] = hi;
+    if (wf_lo) wf_lo[o] = lo;
+  }
+  if (wd_hi) {
+    // wd[ci][tap][co]
+    for (int i = threadIdx.x; i < 32 * row_len; i += blockDim.x) {
+      const int co = i % 32, tap = (i / 32) % taps, ci = i / (32 * taps);
+      const float v = wtile[co * pitch + ci * taps + tap];
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const long long o = (long long)(ci0 + ci) * ld_d + (long long)tap * cout + co0 + co;
+      wd_hi[o] = hi;
+      if (wd_lo) wd_lo[o] = lo;
+    }
+  }
+}
+
+// small-cin (stem) variant: wf[co][k] = w[co][k], k = ci*taps + tap, row stride ld_f (padding columns stay untouched)
+__global__ void weight_prep_direct_kernel(const float* __restrict__ w, int cout, int k, __nv_bfloat16* __restrict__ wf_hi,
+                                          __nv_bfloat16* __restrict__ wf_lo, long long ld_f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * k) return;
+  const int co = i / k, kk = i % k;
+  __nv_bfloat16 hi, lo;
+  split_bf16(w[i], hi, lo);
+  wf_hi[co * ld_f + kk] = hi;
+  if (wf_lo) wf_lo[co * ld_f + kk] = lo;
+}
+
+}  // namespace fb
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace fb;
+
+extern "C" int fb_version(void) { return 100; }
+
+extern "C" int fb_last_error(char* buf, size_t n) {
+  if (buf && n) {
+    strncpy(buf, g_err, n - 1);
+    buf[n - 1] = 0;
+  }
+  return static_cast<int>(strlen(g_err));
+}
+
+extern "C" int fb_tmap_encode_act4d(void* host_blob, const void* base, int c, int w, int h, int n, int64_t stride_w,
+                                    int64_t stride_h, int64_t stride_n, int box_c, int box_w, int box_h, int box_n) {
+  FB_REQUIRE(host_blob && base, "fb_tmap_encode_act4d: null pointer");
+  FB_REQUIRE(box_c == 64, "fb_tmap_encode_act4d: box_c must be 64 (one 128-byte swizzle row), got %d", box_c);
+  FB_REQUIRE(box_w >= 1 && box_w <= 256 && box_h >= 1 && box_h <= 256 && box_n >= 1 && box_n <= 256,
+             "fb_tmap_encode_act4d: bad box %d %d %d", box_w, box_h, box_n);
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride_w * 2) % 16 == 0 && (stride_h * 2) % 16 == 0 &&
+                 (stride_n * 2) % 16 == 0,
+             "fb_tmap_encode_act4d: base and strides must be 16-byte aligned");
+  cuuint64_t dims[4] = {cuuint64_t(c), cuuint64_t(w), cuuint64_t(h), cuuint64_t(n)};
+  cuuint64_t strides[3] = {cuuint64_t(stride_w * 2), cuuint64_t(stride_h * 2), cuuint64_t(stride_n * 2)};
+  cuuint32_t box[4] = {cuuint32_t(box_c), cuuint32_t(box_w), cuuint32_t(box_h), cuuint32_t(box_n)};
+  return encode(host_blob, base, 4, dims, strides, box);
+}
+
+extern "C" int fb_tmap_encode_mat2d(void* host_blob, const void* base, int k, int rows, int64_t ld, int box_k,
+                                    int box_rows) {
+  FB_REQUIRE(host_blob && base, "fb_tmap_encode_mat2d: null pointer");
+  FB_REQUIRE(box_k == 64 && box_rows >= 1 && box_rows <= 256, "fb_tmap_encode_mat2d: bad box %d x %d", box_k, box_rows);
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+             "fb_tmap_encode_mat2d: base and row stride must be 16-byte aligned");
+  cuuint64_t dims[2] = {cuuint64_t(k), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld * 2)};
+  cuuint32_t box[2] = {cuuint32_t(box_k), cuuint32_t(box_rows)};
+  return encode(host_blob, base, 2, dims, strides, box);
+}
+
+extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
+  FB_REQUIRE(a && a->host_a_maps && a->host_b_maps && a->out, "fb_conv_gemm: null pointer");
+  FB_REQUIRE(a->n_a_maps >= 1 && a->n_a_maps <= FB_MAX_A_MAPS && a->n_b_maps >= 1 && a->n_b_maps <= FB_MAX_B_MAPS,
+             "fb_conv_gemm: map counts out of range (%d, %d)", a->n_a_maps, a->n_b_maps);
+  FB_REQUIRE(a->n_steps >= 1 && a->n_steps <= FB_MAX_TAP_STEPS && a->cblocks >= 1, "fb_conv_gemm: bad step count %d",
+             a->n_steps);
+  FB_REQUIRE(a->tile_w * a->tile_h * a->tile_n == 128, "fb_conv_gemm: tile %dx%dx%d is not 128 pixels", a->tile_w,
+             a->tile_h, a->tile_n);
+  FB_REQUIRE(a->tile_n == 1 ? (a->grid_h % a->tile_h == 0) : (a->tile_h == a->grid_h),
+             "fb_conv_gemm: tile does not divide the pixel grid (grid_h %d, tile_h %d, tile_n %d)", a->grid_h, a->tile_h,
+             a->tile_n);
+  for (int i = 0; i < a->n_steps; ++i)
+    FB_REQUIRE(a->steps[i].a_map >= 0 && a->steps[i].a_map < a->n_a_maps && a->steps[i].b_map >= 0 &&
+                   a->steps[i].b_map < a->n_b_maps,
+               "fb_conv_gemm: step %d references a missing map", i);
+  if (!(a->n_tile == 64 || a->n_tile == 128 || a->n_tile == 256) || a->n_total % a->n_tile != 0) {
+    set_error("fb_conv_gemm: unsupported n_tile %d for n_total %d", a->n_tile, a->n_total);
+    return FB_ERR_UNSUPPORTED;
+  }
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->out_sn % 4 == 0 && a->out_sh % 4 == 0 &&
+                 a->out_sw % 4 == 0,
+             "fb_conv_gemm: output must be 16-byte aligned with strides multiple of 4");
+  ConvGemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  memcpy(kp.a_maps, a->host_a_maps, size_t(a->n_a_maps) * FB_TMAP_BYTES);
+  memcpy(kp.b_maps, a->host_b_maps, size_t(a->n_b_maps) * FB_TMAP_BYTES);
+  memcpy(kp.steps, a->steps, sizeof(fb_tap_step) * a->n_steps);
+  kp.n_steps = a->n_steps;
+  kp.cblocks = a->cblocks;
+  kp.tile_w = a->tile_w;
+  kp.tile_h = a->tile_h;
+  kp.tile_n = a->tile_n;
+  kp.grid_h = a->grid_h;
+  kp.grid_n = a->grid_n;
+  kp.n_total = a->n_total;
+  kp.out = a->out;
+  kp.out_sn = a->out_sn;
+  kp.out_sh = a->out_sh;
+  kp.out_sw = a->out_sw;
+  kp.accumulate = a->accumulate;
+  const int m_tiles = (a->tile_n == 1) ? a->grid_n * (a->grid_h / a->tile_h) : (a->grid_n + a->tile_n - 1) / a->tile_n;
+  dim3 grid(m_tiles, a->n_total / a->n_tile, 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // FB_GEMM_DEEP=1: one CTA per SM with a deep TMA ring; default: two co-resident CTAs per SM with shallower rings,
+  // so that one CTA's TMEM->global epilogue overlaps the other CTA's MMA main loop.
+  static const bool deep = [] {
+    const char* e = getenv("FB_GEMM_DEEP");
+    return e && e[0] == '1';
+  }();
+  switch (a->n_tile) {
+    case 64: return deep ? launch_conv_gemm<64, 8>(kp, grid, st) : launch_conv_gemm<64, 4>(kp, grid, st);
+    case 128: return deep ? launch_conv_gemm<128, 6>(kp, grid, st) : launch_conv_gemm<128, 3>(kp, grid, st);
+    default: return launch_conv_gemm<256, 4>(kp, grid, st);
+  }
+}
+
+extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
+  FB_REQUIRE(a && a->host_dy_map && a->host_x_maps && a->partial, "fb_conv_wgrad: null pointer");
+  FB_REQUIRE(a->planes >= 1 && a->planes <= 2 && a->n_x_maps >= a->planes && a->n_x_maps <= FB_MAX_A_MAPS,
+             "fb_conv_wgrad: bad planes/maps (%d, %d)", a->planes, a->n_x_maps);
+  FB_REQUIRE(a->n_taps >= 1 && a->n_taps <= FB_MAX_WGRAD_TAPS && a->cblocks >= 1 && a->cin == 64 * a->cblocks,
+             "fb_conv_wgrad: bad taps/cblocks/cin (%d, %d, %d)", a->n_taps, a->cblocks, a->cin);
+  FB_REQUIRE(a->slots_per_cta >= 1 && a->slots_per_cta <= 8, "fb_conv_wgrad: slots_per_cta must be 1..8");
+  FB_REQUIRE(a->tile_w * a->tile_h * a->tile_n == 128, "fb_conv_wgrad: tile is not 128 pixels");
+  FB_REQUIRE(a->tile_n == 1 ? (a->grid_h % a->tile_h == 0) : (a->tile_h == a->grid_h),
+             "fb_conv_wgrad: tile does not divide the pixel grid");
+  for (int i = 0; i < a->n_taps; ++i)
+    FB_REQUIRE((a->taps[i].phase + 1) * a->planes <= a->n_x_maps, "fb_conv_wgrad: tap %d references a missing map", i);
+  const int n_pixblocks =
+      (a->tile_n == 1) ? a->grid_n * (a->grid_h / a->tile_h) : (a->grid_n + a->tile_n - 1) / a->tile_n;
+  FB_REQUIRE(a->splits >= 1 && a->splits <= n_pixblocks, "fb_conv_wgrad: splits %d must be in 1..%d", a->splits,
+             n_pixblocks);
+  FB_REQUIRE(a->cout % 64 == 0, "fb_conv_wgrad: cout must be a multiple of 64");
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  memcpy(&kp.dy_map, a->host_dy_map, FB_TMAP_BYTES);
+  memcpy(kp.x_maps, a->host_x_maps, size_t(a->n_x_maps) * FB_TMAP_BYTES);
+  memcpy(kp.taps, a->taps, sizeof(fb_wgrad_tap) * a->n_taps);
+  kp.n_taps = a->n_taps;
+  kp.cblocks = a->cblocks;
+  kp.planes = a->planes;
+  kp.slots_per_cta = a->slots_per_cta;
+  kp.cout = a->cout;
+  kp.cin = a->cin;
+  kp.tile_w = a->tile_w;
+  kp.tile_h = a->tile_h;
+  kp.tile_n = a->tile_n;
+  kp.grid_h = a->grid_h;
+  kp.grid_n = a->grid_n;
+  kp.splits = a->splits;
+  kp.n_pixblocks = n_pixblocks;
+  kp.partial = a->partial;
+  const int n_slots_total = a->n_taps * a->cblocks;
+  dim3 grid((a->cout + 127) / 128, (n_slots_total + a->slots_per_cta - 1) / a->slots_per_cta, a->splits);
+  constexpr int smem = kWgAStages * kWgABytes + kWgBStages * kWgBBytes + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(kp);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_wgrad_finalize(const float* partial, int splits, int cout, int cin, int taps, int cin_stored, int mode,
+                                 float* g_oihw, void* stream) {
+  FB_REQUIRE(partial && g_oihw && splits >= 1, "fb_wgrad_finalize: bad arguments");
+  FB_REQUIRE(taps == 1 || taps == 9, "fb_wgrad_finalize: taps must be 1 or 9");
+  FB_REQUIRE(mode == 1 || cin % 32 == 0, "fb_wgrad_finalize: cin must be a multiple of 32 in mode 0");
+  dim3 grid((cin + 31) / 32, cout);
+  wgrad_finalize_kernel<<<grid, 32 * taps, 0, static_cast<cudaStream_t>(stream)>>>(partial, splits, cout, cin, taps,
+                                                                                   cin_stored, mode, g_oihw);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_weight_prep(const float* w_oihw, int cout, int cin, int taps, void* wf_hi, void* wf_lo, int64_t ld_f,
+                              void* wd_hi, void* wd_lo, int64_t ld_d, void* stream) {
+  FB_REQUIRE(w_oihw && wf_hi, "fb_weight_prep: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cin % 32 != 0) {
+    FB_REQUIRE(wd_hi == nullptr, "fb_weight_prep: dgrad layout needs cin %% 32 == 0");
+    const int total = cout * cin * taps;
+    weight_prep_direct_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_oihw, cout, cin * taps,
+                                                                   static_cast<__nv_bfloat16*>(wf_hi),
+                                                                   static_cast<__nv_bfloat16*>(wf_lo), ld_f);
+  } else {
+    FB_REQUIRE(cout % 32 == 0 && (taps == 1 || taps == 9), "fb_weight_prep: unsupported shape %d %d %d", cout, cin, taps);
+    dim3 grid(cin / 32, cout / 32);
+    const size_t smem = size_t(32) * (32 * taps + 1) * sizeof(float);
+    weight_prep_kernel<<<grid, 256, smem, st>>>(w_oihw, cout, cin, taps, static_cast<__nv_bfloat16*>(wf_hi),
+                                                static_cast<__nv_bfloat16*>(wf_lo), ld_f,
+                                                static_cast<__nv_bfloat16*>(wd_hi), static_cast<__nv_bfloat16*>(wd_lo),
+                                                ld_d);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,580 @@
+// Bandwidth-bound layer kernels of the full-batch step (sm_100a): BatchNorm (train mode) statistics / apply / backward
+// fused with ReLU and the residual add, AvgPool2d(2), stem im2col, and the pooled-linear-cross-entropy head.
+// All of them are coalesced, 16-byte vectorised streaming kernels; reductions are two-stage and deterministic
+// (fixed partition, fixed summation order), so repeated runs are bit-identical
+// (cf. measure_floating_point_accuracy.py / fullbatch/training/training.py:429-600).
+//
+// Reference call sites replaced: torch.nn.BatchNorm2d / ReLU(inplace) / `out += identity`
+// (fullbatch/models/resnets.py:71,207-230,296-316), AvgPool2d (resnets.py:149), AdaptiveAvgPool2d + Linear
+// (resnets.py:106-107), LabelSmoothCrossEntropyLoss (fullbatch/models/modules.py:96-101), accuracy count
+// (fullbatch/training/training.py:80) and their autograd backward.
+#include "../../include/fullbatch_b200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+
+constexpr int kMaxChunks = 1000;
+typedef __nv_bfloat16 bf16;
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load8_bf16(const bf16* p, float (&v)[8]) {
+  const bf16x8 t = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(t.v[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+// split 8 fp32 values into hi/lo bf16 and store (lo optional)
+__device__ __forceinline__ void store8_split(bf16* hi, bf16* lo, long long off, const float (&v)[8]) {
+  bf16x8 h, l;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bf16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0);
+    split_bf16(v[2 * i + 1], h1, l1);
+    h.v[i] = __halves2bfloat162(h0, h1);
+    l.v[i] = __halves2bfloat162(l0, l1);
+  }
+  *reinterpret_cast<bf16x8*>(hi + off) = h;
+  if (lo) *reinterpret_cast<bf16x8*>(lo + off) = l;
+}
+__device__ __forceinline__ void store8_bf16(bf16* dst, long long off, const float (&v)[8]) {
+  bf16x8 h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h.v[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<bf16x8*>(dst + off) = h;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-channel column reductions over a [P][C] fp32 matrix: shared skeleton for BN statistics and BN backward.
+// Block = 256 threads = TX float4-columns x TY rows; grid = (chunks, column slabs).  partial[chunk][2][C].
+// ---------------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ y, const float* __restrict__ dA,
+                                                        const bf16* __restrict__ mask, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, long long P, int C, int TX,
+                                                        int rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float4 red[2][256];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
+  const int c = (blockIdx.y * TX + tx) * 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(P, r0 + rows_per_chunk);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  float4 mu = s1, rs = s1;
+  if (BWD) {
+    mu = *reinterpret_cast<const float4*>(mean + c);
+    rs = *reinterpret_cast<const float4*>(rstd + c);
+  }
+  for (long long r = r0 + ty; r < r1; r += TY) {
+    const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
+    if (!BWD) {
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
+    } else {
+      float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
+      if (mask) {
+        const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
+        const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
+        const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
+        d.x = m01.x > 0.f ? d.x : 0.f;
+        d.y = m01.y > 0.f ? d.y : 0.f;
+        d.z = m23.x > 0.f ? d.z : 0.f;
+        d.w = m23.y > 0.f ? d.w : 0.f;
+      }
+      s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+      s2.x += d.x * (v.x - mu.x) * rs.x;
+      s2.y += d.y * (v.y - mu.y) * rs.y;
+      s2.z += d.z * (v.z - mu.z) * rs.z;
+      s2.w += d.w * (v.w - mu.w) * rs.w;
+    }
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < TY; ++j) {
+      const float4 a = red[0][j * TX + tx], b = red[1][j * TX + tx];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    float* dst = partial + (long long)blockIdx.x * 2 * C;
+    *reinterpret_cast<float4*>(dst + c) = s1;
+    *reinterpret_cast<float4*>(dst + C + c) = s2;
+  }
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, long long P,
+                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s1 += partial[(long long)k * 2 * C + c];
+    s2 += partial[(long long)k * 2 * C + C + c];
+  }
+  const double m = s1 / double(P);
+  double var = s2 / double(P) - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mean[c] = float(m);
+  rstd[c] = float(1.0 / sqrt(var + double(eps)));
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(m);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  }
+}
+
+// coef[0][C] = sum dz / P, coef[1][C] = sum dz*xhat / P; dgamma = sum dz*xhat, dbeta = sum dz
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, long long P,
+                                       float* __restrict__ coef, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s1 += partial[(long long)k * 2 * C + c];
+    s2 += partial[(long long)k * 2 * C + C + c];
+  }
+  dbeta[c] = float(s1);
+  dgamma[c] = float(s2);
+  coef[c] = float(s1 / double(P));
+  coef[C + c] = float(s2 / double(P));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BN apply (+ second normalised branch, + residual, + ReLU) -> bf16 hi/lo
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
+  const long long total8 = a.P * a.C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = i * 8;
+    const int c = int(off % a.C);
+    float y[8], mu[8], rs[8], ga[8], be[8], o[8];
+    load8(a.y + off, y);
+    load8(a.mean + c, mu);
+    load8(a.rstd + c, rs);
+    load8(a.gamma + c, ga);
+    load8(a.beta + c, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (y[j] - mu[j]) * (rs[j] * ga[j]) + be[j];
+    if (a.y2) {
+      load8(a.y2 + off, y);
+      load8(a.mean2 + c, mu);
+      load8(a.rstd2 + c, rs);
+      load8(a.gamma2 + c, ga);
+      load8(a.beta2 + c, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += (y[j] - mu[j]) * (rs[j] * ga[j]) + be[j];
+    }
+    if (a.res_hi) {
+      float rh[8];
+      load8_bf16(static_cast<const bf16*>(a.res_hi) + off, rh);
+      if (a.res_lo) {
+        float rl[8];
+        load8_bf16(static_cast<const bf16*>(a.res_lo) + off, rl);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rh[j] += rl[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += rh[j];
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    store8_split(static_cast<bf16*>(a.out_hi), static_cast<bf16*>(a.out_lo), off, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BN backward apply: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) -> bf16; optional dz (fp32) output
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, const float* __restrict__ coef) {
+  const long long total8 = a.P * a.C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = i * 8;
+    const int c = int(off % a.C);
+    float d[8], y[8], mu[8], rs[8], ga[8], c1[8], c2[8], o[8];
+    load8(a.dA + off, d);
+    if (a.mask_hi) {
+      float m[8];
+      load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
+    }
+    load8(a.y + off, y);
+    load8(a.mean + c, mu);
+    load8(a.rstd + c, rs);
+    load8(a.gamma + c, ga);
+    load8(coef + c, c1);
+    load8(coef + a.C + c, c2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (y[j] - mu[j]) * rs[j];
+      o[j] = (ga[j] * rs[j]) * (d[j] - c1[j] - xhat * c2[j]);
+    }
+    store8_bf16(static_cast<bf16*>(a.dy_bf16), off, o);
+    if (a.dz_out) {
+      if (a.dz_accumulate) {
+        float e[8];
+        load8(a.dz_out + off, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += e[j];
+      }
+      store8(a.dz_out + off, d);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AvgPool2d(2)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void avgpool2_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int n, int h, int w,
+                                    int c, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total8 = (long long)n * ho * wo * c / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = i * 8;
+    const int cc = int(off % c);
+    long long pix = off / c;
+    const int x = int(pix % wo);
+    pix /= wo;
+    const int yy = int(pix % ho);
+    const int img = int(pix / ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long src = (((long long)img * h + (2 * yy + dy)) * w + (2 * x + dx)) * c + cc;
+        float v[8];
+        load8_bf16(in_hi + src, v);
+        if (in_lo) {
+          float l[8];
+          load8_bf16(in_lo + src, l);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += l[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+    store8_split(out_hi, out_lo, off, acc);
+  }
+}
+
+__global__ void avgpool2_bwd_kernel(const float* __restrict__ dP, int n, int h, int w, int c, float* __restrict__ dX,
+                                    int accumulate) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total4 = (long long)n * h * w * c / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = i * 4;
+    const int cc = int(off % c);
+    long long pix = off / c;
+    const int x = int(pix % w);
+    pix /= w;
+    const int yy = int(pix % h);
+    const int img = int(pix / h);
+    const float4 g = *reinterpret_cast<const float4*>(dP + (((long long)img * ho + yy / 2) * wo + x / 2) * c + cc);
+    float4 o = make_float4(0.25f * g.x, 0.25f * g.y, 0.25f * g.z, 0.25f * g.w);
+    if (accumulate) {
+      const float4 e = *reinterpret_cast<const float4*>(dX + off);
+      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+    }
+    *reinterpret_cast<float4*>(dX + off) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stem im2col: x NCHW fp32 -> 3x3/pad-1 patches [n*1024][64] bf16 hi/lo, column = ci*9 + kh*3 + kw
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void stem_im2col_kernel(const float* __restrict__ x, const long long* __restrict__ labels,
+                                   const long long* __restrict__ perm, const int* __restrict__ first_dev,
+                                   long long first, int n, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
+                                   long long* __restrict__ labels_out) {
+  if (first_dev) first += (long long)(*first_dev) * n;
+  const long long total = (long long)n * 1024 * 8;  // 8 groups of 8 columns per pixel
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int grp = int(i & 7);
+    const long long pix = i >> 3;
+    const int w = int(pix & 31), h = int((pix >> 5) & 31);
+    const int img = int(pix >> 10);
+    const long long src_img = perm ? perm[first + img] : first + img;
+    const float* xi = x + src_img * 3072;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = grp * 8 + j;
+      float val = 0.f;
+      if (k < 27) {
+        const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
+        const int hh = h + kh - 1, ww = w + kw - 1;
+        if (hh >= 0 && hh < 32 && ww >= 0 && ww < 32) val = xi[ci * 1024 + hh * 32 + ww];
+      }
+      v[j] = val;
+    }
+    store8_split(p_hi, p_lo, pix * 64 + grp * 8, v);
+    if (labels_out && grp == 0 && (pix & 1023) == 0) labels_out[img] = labels[src_img];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// head: global average pool -> linear -> label-smoothed cross entropy (+accuracy) and backward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 16;
+
+// grid = n, block = 128
+__global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo,
+                                                       int n, int hw, int c, const float* __restrict__ fc_w,
+                                                       const float* __restrict__ fc_b,
+                                                       const long long* __restrict__ labels, int classes,
+                                                       float smoothing, float* __restrict__ pooled,
+                                                       float* __restrict__ dlogits, float* __restrict__ loss_n,
+                                                       float* __restrict__ correct_n) {
+  extern __shared__ float sp[];  // c floats + classes logits
+  float* logits = sp + c;
+  const int img = blockIdx.x;
+  const float inv = 1.f / float(hw);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) {
+      const long long o = ((long long)img * hw + p) * c + ch;
+      s += __bfloat162float(a_hi[o]) + (a_lo ? __bfloat162float(a_lo[o]) : 0.f);
+    }
+    s *= inv;
+    sp[ch] = s;
+    pooled[(long long)img * c + ch] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cls = warp; cls < classes; cls += 4) {
+    float s = 0.f;
+    for (int ch = lane; ch < c; ch += 32) s += sp[ch] * fc_w[(long long)cls * c + ch];
+    s = warp_sum(s);
+    if (lane == 0) logits[cls] = s + fc_b[cls];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int label = int(labels[img]);
+    float mx = logits[0];
+    int arg = 0;
+    for (int k = 1; k < classes; ++k)
+      if (logits[k] > mx) {
+        mx = logits[k];
+        arg = k;
+      }
+    float se = 0.f;
+    for (int k = 0; k < classes; ++k) se += expf(logits[k] - mx);
+    const float lse = mx + logf(se);
+    const float w_off = smoothing / float(classes - 1), w_on = 1.f - smoothing;
+    float loss = 0.f;
+    for (int k = 0; k < classes; ++k) {
+      const float logp = logits[k] - lse;
+      const float wk = (k == label) ? w_on : w_off;
+      loss -= wk * logp;
+      // d/dz_k of -sum_j w_j logp_j = softmax_k * sum_j w_j - w_k; mean over the microbatch -> / n
+      const float wsum = w_on + w_off * float(classes - 1);
+      dlogits[img * kMaxClasses + k] = (expf(logp) * wsum - wk) / float(n);
+    }
+    loss_n[img] = loss;
+    correct_n[img] = (arg == label) ? 1.f : 0.f;
+  }
+}
+
+// grid = (c/128, n): dA[n][p][ch] = (sum_k dlogits[n][k] * W[k][ch]) / hw
+__global__ void __launch_bounds__(128) head_bwd_act_kernel(const float* __restrict__ dlogits,
+                                                           const float* __restrict__ fc_w, int hw, int c, int classes,
+                                                           float* __restrict__ dA) {
+  const int ch = blockIdx.x * 128 + threadIdx.x;
+  const int img = blockIdx.y;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int k = 0; k < classes; ++k) s += dlogits[img * kMaxClasses + k] * fc_w[(long long)k * c + ch];
+  s /= float(hw);
+  for (int p = 0; p < hw; ++p) dA[((long long)img * hw + p) * c + ch] = s;
+}
+
+// grid = c/128 (+ block 0 also reduces bias grad, loss, accuracy)
+__global__ void __launch_bounds__(128) head_bwd_param_kernel(const float* __restrict__ dlogits,
+                                                             const float* __restrict__ pooled,
+                                                             const float* __restrict__ loss_n,
+                                                             const float* __restrict__ correct_n, int n, int c,
+                                                             int classes, float* __restrict__ d_fcw,
+                                                             float* __restrict__ d_fcb, float* __restrict__ scal,
+                                                             int loss_slot, int correct_slot) {
+  const int ch = blockIdx.x * 128 + threadIdx.x;
+  if (ch < c) {
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float pv = pooled[(long long)i * c + ch];
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < classes) acc[k] += dlogits[i * kMaxClasses + k] * pv;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) d_fcw[(long long)k * c + ch] = acc[k];
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < classes) {
+      float s = 0.f;
+      for (int i = 0; i < n; ++i) s += dlogits[i * kMaxClasses + threadIdx.x];
+      d_fcb[threadIdx.x] = s;
+    } else if (threadIdx.x == 32) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s += loss_n[i];
+      scal[loss_slot] += float(s / double(n));
+    } else if (threadIdx.x == 64) {
+      float s = 0.f;
+      for (int i = 0; i < n; ++i) s += correct_n[i];
+      scal[correct_slot] += s;
+    }
+  }
+}
+
+static int reduce_geometry(long long P, int C, int& TX, int& slabs, int& chunks, int& rows_per_chunk) {
+  if (C % 4 != 0) return FB_ERR_UNSUPPORTED;
+  const int c4 = C / 4;
+  TX = c4 < 256 ? c4 : 256;
+  if (256 % TX != 0 || c4 % TX != 0) return FB_ERR_UNSUPPORTED;
+  slabs = c4 / TX;
+  const int TY = 256 / TX;
+  long long want = (P + TY * 4 - 1) / (TY * 4);  // >= 4 rows per thread
+  if (want < 1) want = 1;
+  chunks = int(want < kMaxChunks ? want : kMaxChunks);
+  rows_per_chunk = int((P + chunks - 1) / chunks);
+  chunks = int((P + rows_per_chunk - 1) / rows_per_chunk);
+  return 0;
+}
+
+static int stream_grid(long long work_items) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = (long long)kNumSMs * 16;
+  return int(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* mean, float* rstd, float* running_mean,
+                           float* running_var, float momentum, float eps, void* stream) {
+  FB_REQUIRE(y && ws && mean && rstd && P > 0, "fb_bn_stats: bad arguments");
+  int TX, slabs, chunks, rpc;
+  if (reduce_geometry(P, C, TX, slabs, chunks, rpc)) {
+    set_error("fb_bn_stats: unsupported channel count %d", C);
+    return FB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, P, C, TX, rpc, ws);
+  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, chunks, C, P, mean, rstd, running_mean, running_var,
+                                                            momentum, eps);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_bn_apply(const fb_bn_apply_args* a, void* stream) {
+  FB_REQUIRE(a && a->y && a->mean && a->rstd && a->gamma && a->beta && a->out_hi, "fb_bn_apply: null pointer");
+  FB_REQUIRE(a->C % 8 == 0 && a->P > 0, "fb_bn_apply: C must be a multiple of 8");
+  bn_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
+  FB_REQUIRE(a && a->dA && a->y && a->mean && a->rstd && a->gamma && a->ws && a->dgamma && a->dbeta && a->dy_bf16,
+             "fb_bn_bwd: null pointer");
+  FB_REQUIRE(a->C % 8 == 0 && a->P > 0, "fb_bn_bwd: C must be a multiple of 8");
+  int TX, slabs, chunks, rpc;
+  if (reduce_geometry(a->P, a->C, TX, slabs, chunks, rpc)) {
+    set_error("fb_bn_bwd: unsupported channel count %d", a->C);
+    return FB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* coef = a->ws + (long long)2 * a->C * kMaxChunks;
+  bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, static_cast<const bf16*>(a->mask_hi), a->mean,
+                                                              a->rstd, a->P, a->C, TX, rpc, a->ws);
+  bn_bwd_finalize_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->ws, chunks, a->C, a->P, coef, a->dgamma, a->dbeta);
+  bn_bwd_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, st>>>(*a, coef);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_avgpool2_fwd(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi,
+                               void* out_lo, void* stream) {
+  FB_REQUIRE(in_hi && out_hi && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "fb_avgpool2_fwd: bad arguments");
+  avgpool2_fwd_kernel<<<stream_grid((long long)n * h * w * c / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(in_hi), static_cast<const bf16*>(in_lo), n, h, w, c, static_cast<bf16*>(out_hi),
+      static_cast<bf16*>(out_lo));
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_avgpool2_bwd(const float* dP, int n, int h, int w, int c, float* dX, int accumulate, void* stream) {
+  FB_REQUIRE(dP && dX && h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "fb_avgpool2_bwd: bad arguments");
+  avgpool2_bwd_kernel<<<stream_grid((long long)n * h * w * c / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dP, n, h, w, c, dX, accumulate);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_stem_im2col(const float* x, const int64_t* labels, const int64_t* perm, const int32_t* first_dev,
+                              int64_t first, int n, void* patches_hi, void* patches_lo, int64_t* labels_out,
+                              void* stream) {
+  FB_REQUIRE(x && patches_hi && n > 0, "fb_stem_im2col: bad arguments");
+  FB_REQUIRE(!labels_out || labels, "fb_stem_im2col: labels_out needs labels");
+  stem_im2col_kernel<<<stream_grid((long long)n * 1024 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const long long*>(labels), reinterpret_cast<const long long*>(perm), first_dev, first, n,
+      static_cast<bf16*>(patches_hi), static_cast<bf16*>(patches_lo), reinterpret_cast<long long*>(labels_out));
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw, int c, const float* fc_w,
+                               const float* fc_b, const int64_t* labels, int classes, float smoothing, float* ws,
+                               float* scal, int loss_slot, int correct_slot, float* d_fcw, float* d_fcb, float* dA,
+                               void* stream) {
+  FB_REQUIRE(a_hi && fc_w && fc_b && labels && ws && scal && d_fcw && d_fcb && dA, "fb_head_fwd_bwd: null pointer");
+  if (classes > kMaxClasses || classes < 2) {
+    set_error("fb_head_fwd_bwd: classes %d not supported (max %d)", classes, kMaxClasses);
+    return FB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* pooled = ws;
+  float* dlogits = pooled + (long long)n * c;
+  float* loss_n = dlogits + (long long)n * kMaxClasses;
+  float* correct_n = loss_n + n;
+  head_fwd_kernel<<<n, 128, (c + kMaxClasses) * sizeof(float), st>>>(
+      static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
+      reinterpret_cast<const long long*>(labels), classes, smoothing, pooled, dlogits, loss_n, correct_n);
+  head_bwd_act_kernel<<<dim3((c + 127) / 128, n), 128, 0, st>>>(dlogits, fc_w, hw, c, classes, dA);
+  head_bwd_param_kernel<<<(c + 127) / 128, 128, 0, st>>>(dlogits, pooled, loss_n, correct_n, n, c, classes, d_fcw, d_fcb,
+                                                        scal, loss_slot, correct_slot);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}

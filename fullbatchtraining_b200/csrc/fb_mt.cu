@@ -1,0 +1,176 @@
+// Flat-buffer ("multi-tensor") kernels of the full-batch step (sm_100a).
+//
+// All parameters / gradients live in persistent flat fp32 buffers in model.parameters() order (the order of
+// fullbatch/training/utils.py:34), so every list-of-tensors `torch._foreach_*` sweep of the reference becomes one
+// vectorised, coalesced pass:
+//   fb_flat_sqnorm   : sum g^2                         (training.py:162, modules.py:223: 62 pow/sum kernels + stack)
+//   fb_fd_perturb    : eps_n, theta' = theta + eps_n*bs*g   (modules.py:215-226: clone + mul + add_)
+//   fb_fd_combine    : g += cf*(g2-g)/eps_n ; avg += (g-avg)/k   (modules.py:232-240 + training.py:45-47,165-168)
+// eps_n and the norms stay on the device (the reference syncs the host once per microbatch through alpha=eps_n).
+#include "../../include/fullbatch_b200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+
+constexpr int kSqBlocks = 1024;
+
+__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ x, long long n,
+                                                             double* __restrict__ partial) {
+  __shared__ double red[8];
+  float acc = 0.f;
+  const long long n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
+    const float v = x[n4 * 4 + threadIdx.x];
+    acc += v * v;
+  }
+  double d = warp_sum(double(acc));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restrict__ partial, int nblocks,
+                                                           float* __restrict__ scal, int slot) {
+  __shared__ double red[8];
+  double d = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) d += partial[i];
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    scal[slot] = float(s);
+  }
+}
+
+__global__ void __launch_bounds__(256) fd_perturb_kernel(const float* __restrict__ theta, const float* __restrict__ g,
+                                                         long long n, float bs, float eps, float* __restrict__ scal,
+                                                         int sq_slot, int eps_slot, float* __restrict__ norms_out,
+                                                         const int* __restrict__ cursor, float* __restrict__ theta_p) {
+  const float n2 = scal[sq_slot];
+  // modules.py:223: eps / sqrt(sum (bs*g)^2)
+  const float eps_n = eps / sqrtf(bs * bs * n2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[eps_slot] = eps_n;
+    if (norms_out) norms_out[cursor ? *cursor : 0] = n2;
+  }
+  const long long n4 = n / 4;
+  const float4* t4 = reinterpret_cast<const float4*>(theta);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* o4 = reinterpret_cast<float4*>(theta_p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 t = t4[i], v = g4[i];
+    o4[i] = make_float4(t.x + eps_n * (bs * v.x), t.y + eps_n * (bs * v.y), t.z + eps_n * (bs * v.z),
+                        t.w + eps_n * (bs * v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    theta_p[i] = theta[i] + eps_n * (bs * g[i]);
+  }
+}
+
+template <bool REG>
+__global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ g, const float* __restrict__ g2,
+                                                         float* __restrict__ avg, long long n,
+                                                         const float* __restrict__ scal, int eps_slot, float cf,
+                                                         int cf_slot, const int* __restrict__ cursor, int count0,
+                                                         int write_g) {
+  const float eps_n = REG ? scal[eps_slot] : 1.f;
+  if (REG && cf_slot >= 0) cf = scal[cf_slot];
+  const int count = count0 + (cursor ? *cursor : 0) + 1;
+  const float inv = float(1.0 / double(count));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gr = g[i];
+    if (REG) {
+      const float h = (g2[i] - gr) / eps_n;  // modules.py:232-234
+      gr = gr + cf * h;                       // modules.py:240
+      if (write_g) g[i] = gr;
+    }
+    if (avg) {
+      const float a = avg[i];
+      avg[i] = a + (gr - a) * inv;  // training.py:45-47
+    }
+  }
+}
+
+__global__ void cursor_add_kernel(int* cursor, int delta) { *cursor += delta; }
+
+__global__ void __launch_bounds__(256) flat_scale_kernel(float* __restrict__ x, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= alpha;
+}
+
+static int flat_grid(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)kNumSMs * 8;
+  return int(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, void* stream) {
+  FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm: bad arguments");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fb_flat_sqnorm: x must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sqnorm_partial_kernel<<<kSqBlocks, 256, 0, st>>>(x, n, ws);
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, kSqBlocks, scal, slot);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_fd_perturb(const float* theta, const float* g, int64_t n, float block_strength, float eps, float* scal,
+                             int sq_slot, int eps_slot, float* norms_out, const int32_t* cursor, float* theta_p,
+                             void* stream) {
+  FB_REQUIRE(theta && g && scal && theta_p && n > 0, "fb_fd_perturb: bad arguments");
+  FB_REQUIRE(((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) |
+               reinterpret_cast<uintptr_t>(theta_p)) & 15) == 0,
+             "fb_fd_perturb: buffers must be 16-byte aligned");
+  fd_perturb_kernel<<<flat_grid(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      theta, g, n, block_strength, eps, scal, sq_slot, eps_slot, norms_out, cursor, theta_p);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_fd_combine(float* g, const float* g2, float* avg, int64_t n, const float* scal, int eps_slot, float cf,
+                             int cf_slot, const int32_t* cursor, int32_t count0, int write_g, void* stream) {
+  FB_REQUIRE(g && g2 && scal && n > 0, "fb_fd_combine: bad arguments");
+  fd_combine_kernel<true><<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, g2, avg, n, scal, eps_slot, cf, cf_slot, cursor, count0, write_g);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_mean_accumulate(const float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0,
+                                  void* stream) {
+  FB_REQUIRE(g && avg && n > 0, "fb_mean_accumulate: bad arguments");
+  fd_combine_kernel<false><<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      const_cast<float*>(g), nullptr, avg, n, nullptr, 0, 0.f, -1, cursor, count0, 0);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream) {
+  FB_REQUIRE(cursor, "fb_cursor_add: null pointer");
+  cursor_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(cursor, delta);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_flat_scale(float* x, int64_t n, float alpha, void* stream) {
+  FB_REQUIRE(x && n > 0, "fb_flat_scale: bad arguments");
+  flat_scale_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, alpha);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,349 @@
+"""Host-side operator layer over the C ABI: builds TMA descriptors / tap tables for each convolution and wraps the
+layer kernels.  Everything here only prepares arguments; all arithmetic happens in the CUDA library (lib.py).
+
+Layouts: activations NHWC; a "split" activation is a pair of bf16 planes (hi, lo) with x ~= hi + lo (lo is None in
+plain-bf16 mode); conv outputs / activation gradients fp32 NHWC; dY bf16 NHWC; GEMM weights bf16 hi/lo as
+wf[cout][tap*cin + ci] and wd[cin][tap*cout + co].
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+NUM_SMS = 148
+
+
+def pixel_tile(h, w):
+    """128-pixel TMA box (tile_w, tile_h, tile_n) over an [n, h, w] pixel grid; the box always spans full rows."""
+    if w > 128 or 128 % w != 0:
+        raise RuntimeError(f"unsupported feature-map width {w} (no fallback path)")
+    tile_h = min(h, 128 // w)
+    if h % tile_h != 0 or 128 % (w * tile_h) != 0:
+        raise RuntimeError(f"unsupported feature-map size {h}x{w}")
+    return w, tile_h, 128 // (w * tile_h)
+
+
+class MapSet:
+    """A host array of CUtensorMap blobs plus references that keep the mapped tensors alive."""
+
+    def __init__(self, n):
+        self.n = n
+        self.buf = C.create_string_buffer(L.FB_TMAP_BYTES * n)
+        self.keep = []
+
+    def slot(self, i):
+        return C.addressof(self.buf) + i * L.FB_TMAP_BYTES
+
+    @property
+    def addr(self):
+        return C.addressof(self.buf)
+
+
+def encode_act(ms, i, plane, n, h, w, c, tile, phase=None):
+    """Map slot i <- 4-D view of an NHWC bf16 plane [n,h,w,c]; phase=(ph,pw) selects a stride-2 sub-grid."""
+    assert plane.dtype == torch.bfloat16 and plane.is_contiguous()
+    tw, th, tn = tile
+    base = plane.data_ptr()
+    if phase is None:
+        dims = (c, w, h, n)
+        strides = (c, w * c, h * w * c)
+    else:
+        ph, pw = phase
+        base += (ph * w + pw) * c * 2
+        dims = (c, w // 2, h // 2, n)
+        strides = (2 * c, 2 * w * c, h * w * c)
+    L.check(L.load().fb_tmap_encode_act4d(ms.slot(i), base, dims[0], dims[1], dims[2], dims[3], strides[0], strides[1],
+                                          strides[2], 64, tw, th, tn), "fb_tmap_encode_act4d")
+    ms.keep.append(plane)
+
+
+def encode_mat(ms, i, mat, k, rows, box_rows):
+    assert mat.dtype == torch.bfloat16 and mat.is_contiguous() and mat.dim() == 2
+    L.check(L.load().fb_tmap_encode_mat2d(ms.slot(i), mat.data_ptr(), k, rows, mat.stride(0), 64, box_rows),
+            "fb_tmap_encode_mat2d")
+    ms.keep.append(mat)
+
+
+def choose_n_tile(m_tiles, n_total):
+    for nt in (256, 128, 64):
+        if n_total % nt == 0 and m_tiles * (n_total // nt) >= NUM_SMS:
+            return nt
+    return 64
+
+
+def _s2_tap(k):
+    """3x3 / stride 2 / pad 1: input index 2*o + k - 1 -> (phase, shift in the phase grid)."""
+    return ((1, -1), (0, 0), (1, 0))[k]
+
+
+class ConvGemm:
+    """One launch of fb_conv_gemm with frozen arguments (descriptors are encoded once)."""
+
+    def __init__(self, a_maps, b_maps, steps, cblocks, tile, grid_h, grid_n, n_total, out, out_off, out_strides,
+                 accumulate, n_tile=None):
+        self.a_maps, self.b_maps = a_maps, b_maps
+        args = L.ConvGemmArgs()
+        args.host_a_maps, args.host_b_maps = a_maps.addr, b_maps.addr
+        args.n_a_maps, args.n_b_maps = a_maps.n, b_maps.n
+        if len(steps) > L.FB_MAX_TAP_STEPS:
+            raise RuntimeError("too many tap steps")
+        args.n_steps, args.cblocks = len(steps), cblocks
+        for i, (am, bm, dh, dw, k0) in enumerate(steps):
+            args.steps[i] = L.TapStep(am, bm, dh, dw, k0)
+        args.tile_w, args.tile_h, args.tile_n = tile
+        args.grid_h, args.grid_n = grid_h, grid_n
+        m_tiles = grid_n * (grid_h // tile[1]) if tile[2] == 1 else -(-grid_n // tile[2])
+        args.n_total = n_total
+        args.n_tile = n_tile or choose_n_tile(m_tiles, n_total)
+        self.out = out
+        args.out = out.data_ptr() + out_off * 4
+        args.out_sn, args.out_sh, args.out_sw = out_strides
+        args.accumulate = int(accumulate)
+        self.args = args
+
+    def __call__(self):
+        L.call("fb_conv_gemm", C.byref(self.args))
+
+
+def _weight_box_rows(n_total, n_tile):
+    return n_tile
+
+
+class Conv2dPlan:
+    """Forward / dgrad / wgrad launches of one bias-free Conv2d (k in {1,3}, stride in {1,2}, pad (k-1)/2) on NHWC data.
+
+    x_hi/x_lo : [n,h,w,cin] bf16 planes (conv input; for the stem: the im2col patches with cin=64, k=1)
+    y         : [n,ho,wo,cout] fp32 (forward output)
+    dy        : [n,ho,wo,cout] bf16 (output gradient)
+    dx        : [n,h,w,cin] fp32 (input gradient) or None if no dgrad is needed
+    wf/wd     : weight operand matrices (hi, lo) made by fb_weight_prep
+    """
+
+    def __init__(self, n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
+                 dx_accumulate=False, split=True):
+        assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
+        assert not (k == 1 and stride == 2)
+        self.n, self.h, self.w, self.cin, self.cout, self.k, self.stride = n, h, w, cin, cout, k, stride
+        ho, wo = h // stride, w // stride
+        self.ho, self.wo = ho, wo
+        taps = k * k
+        self.taps = taps
+        planes = 2 if (split and x_lo is not None) else 1
+        wplanes = 2 if (split and wf_lo is not None) else 1
+        tile = pixel_tile(ho, wo)
+        cb_in, cb_out = cin // 64, cout // 64
+
+        # ---- activation maps over the conv input, indexed [phase * planes + plane]
+        nph = 4 if stride == 2 else 1
+        xs = MapSet(nph * planes)
+        for p in range(nph):
+            for pl, t in enumerate((x_hi, x_lo)[:planes]):
+                encode_act(xs, p * planes + pl, t, n, h, w, cin, tile, phase=(p // 2, p % 2) if stride == 2 else None)
+        self.x_maps = xs
+
+        def tap_geom(kh, kw):
+            if k == 1:
+                return 0, 0, 0
+            if stride == 1:
+                return 0, kh - 1, kw - 1
+            (ph, dh), (pw, dw) = _s2_tap(kh), _s2_tap(kw)
+            return ph * 2 + pw, dh, dw
+
+        # ---- forward
+        m_tiles = n * (ho // tile[1]) if tile[2] == 1 else -(-n // tile[2])
+        n_tile = choose_n_tile(m_tiles, cout)
+        bs = MapSet(wplanes)
+        for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
+            encode_mat(bs, pl, t, taps * cin, cout, n_tile)
+        combos = [(0, 0)]
+        if planes == 2 and wplanes == 2:
+            combos = [(0, 0), (0, 1), (1, 0)]
+        elif planes == 2:
+            combos = [(0, 0), (1, 0)]
+        elif wplanes == 2:
+            combos = [(0, 0), (0, 1)]
+        steps = []
+        for kh in range(k):
+            for kw in range(k):
+                phase, dh, dw = tap_geom(kh, kw)
+                for (ap, bp) in combos:
+                    steps.append((phase * planes + ap, bp, dh, dw, (kh * k + kw) * cin))
+        self.fwd = ConvGemm(xs, bs, steps, cb_in, tile, ho, n, cout, y, 0, (ho * wo * cout, wo * cout, cout), False,
+                            n_tile=n_tile)
+
+        # ---- dgrad
+        self.dgrads = []
+        if dx is not None:
+            dys = MapSet(1)
+            encode_act(dys, 0, dy, n, ho, wo, cout, tile)
+            m_tiles_d = m_tiles
+            n_tile_d = choose_n_tile(m_tiles_d * (4 if stride == 2 else 1), cin)
+            ds = MapSet(wplanes)
+            for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
+                encode_mat(ds, pl, t, taps * cout, cin, n_tile_d)
+            if stride == 1:
+                steps = []
+                for kh in range(k):
+                    for kw in range(k):
+                        dh, dw = (1 - kh, 1 - kw) if k == 3 else (0, 0)
+                        for bp in range(wplanes):
+                            steps.append((0, bp, dh, dw, (kh * k + kw) * cout))
+                self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, 0,
+                                            (h * w * cin, w * cin, cin), dx_accumulate, n_tile=n_tile_d))
+            else:
+                # stride 2: output pixel (2i+ph, 2j+pw) gathers taps kh with (ph + 1 - kh) even: ho = i + (ph+1-kh)/2
+                def taps_for(par):
+                    return [(1, 0)] if par == 0 else [(0, 1), (2, 0)]  # (k index, shift in the dY grid)
+
+                for ph in range(2):
+                    for pw in range(2):
+                        steps = []
+                        for kh, dh in taps_for(ph):
+                            for kw, dw in taps_for(pw):
+                                for bp in range(wplanes):
+                                    steps.append((0, bp, dh, dw, (kh * 3 + kw) * cout))
+                        self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, (ph * w + pw) * cin,
+                                                    (h * w * cin, 2 * w * cin, 2 * cin), dx_accumulate,
+                                                    n_tile=n_tile_d))
+            self.dy_maps_d = dys
+
+        # ---- wgrad
+        wa = L.WgradArgs()
+        dym = MapSet(1)
+        encode_act(dym, 0, dy, n, ho, wo, cout, tile)
+        self.dy_map_w = dym
+        wa.host_dy_map, wa.host_x_maps = dym.addr, xs.addr
+        wa.n_x_maps, wa.planes = xs.n, planes
+        wa.n_taps, wa.cblocks = taps, cb_in
+        for kh in range(k):
+            for kw in range(k):
+                phase, dh, dw = tap_geom(kh, kw)
+                wa.taps[kh * k + kw] = L.WgradTap(phase, dh, dw, 0)
+        n_slots = taps * cb_in
+        spc = 8
+        if n_slots <= 8:
+            spc = n_slots
+        elif n_slots == 9:
+            spc = 3
+        co_tiles = -(-cout // 128)
+        groups = -(-n_slots // spc)
+        n_pixblocks = m_tiles
+        splits = max(1, min(n_pixblocks, NUM_SMS // (co_tiles * groups)))
+        wa.slots_per_cta = spc
+        wa.cout, wa.cin = cout, cin
+        wa.tile_w, wa.tile_h, wa.tile_n = tile
+        wa.grid_h, wa.grid_n = ho, n
+        wa.splits = splits
+        need = splits * cout * taps * cin
+        if partial.numel() < need:
+            raise RuntimeError(f"wgrad workspace too small: {partial.numel()} < {need}")
+        self.partial = partial
+        wa.partial = partial.data_ptr()
+        self.wargs = wa
+        self.splits = splits
+
+    @staticmethod
+    def partial_elems(n, h, w, cin, cout, k, stride):
+        ho, wo = h // stride, w // stride
+        tile = pixel_tile(ho, wo)
+        m_tiles = n * (ho // tile[1]) if tile[2] == 1 else -(-n // tile[2])
+        taps = k * k
+        n_slots = taps * (cin // 64)
+        spc = n_slots if n_slots <= 8 else (3 if n_slots == 9 else 8)
+        splits = max(1, min(m_tiles, NUM_SMS // ((-(-cout // 128)) * (-(-n_slots // spc)))))
+        return splits * cout * taps * cin
+
+    def forward(self):
+        self.fwd()
+
+    def dgrad(self):
+        for d in self.dgrads:
+            d()
+
+    def wgrad(self, g_oihw, cin_real=None, mode=0):
+        """partial sums -> fixed-order reduction -> g (OIHW fp32 view of the flat gradient buffer)."""
+        L.call("fb_conv_wgrad", C.byref(self.wargs))
+        cin_real = cin_real or self.cin
+        L.call("fb_wgrad_finalize", self.partial.data_ptr(), self.splits, self.cout, cin_real,
+               self.taps if mode == 0 else 9, self.cin, mode, g_oihw.data_ptr())
+
+
+# ---- thin wrappers of the layer kernels ------------------------------------------------------------------------------
+
+def weight_prep(w_oihw, cout, cin, taps, wf_hi, wf_lo, wd_hi=None, wd_lo=None):
+    L.call("fb_weight_prep", w_oihw.data_ptr(), cout, cin, taps, wf_hi.data_ptr(), L.ptr(wf_lo), wf_hi.stride(0),
+           L.ptr(wd_hi), L.ptr(wd_lo), wd_hi.stride(0) if wd_hi is not None else 0)
+
+
+def stem_im2col(x, labels, perm, cursor, first, n, p_hi, p_lo, labels_out):
+    L.call("fb_stem_im2col", x.data_ptr(), L.ptr(labels), L.ptr(perm), L.ptr(cursor), first, n, p_hi.data_ptr(),
+           L.ptr(p_lo), L.ptr(labels_out))
+
+
+def bn_stats(y, P, Cc, ws, mean, rstd, running_mean, running_var, momentum=0.1, eps=1e-5):
+    L.call("fb_bn_stats", y.data_ptr(), P, Cc, ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(), L.ptr(running_mean),
+           L.ptr(running_var), momentum, eps)
+
+
+def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, second=None, res=None):
+    a = L.BnApplyArgs()
+    a.y, a.mean, a.rstd, a.gamma, a.beta = (t.data_ptr() for t in (y, mean, rstd, gamma, beta))
+    if second is not None:
+        a.y2, a.mean2, a.rstd2, a.gamma2, a.beta2 = (t.data_ptr() for t in second)
+    if res is not None:
+        a.res_hi, a.res_lo = res[0].data_ptr(), L.ptr(res[1])
+    a.relu, a.P, a.C = int(relu), P, Cc
+    a.out_hi, a.out_lo = out_hi.data_ptr(), L.ptr(out_lo)
+    L.call("fb_bn_apply", C.byref(a))
+
+
+def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dz_accumulate=False):
+    a = L.BnBwdArgs()
+    a.dA, a.mask_hi, a.y, a.mean, a.rstd, a.gamma = dA.data_ptr(), L.ptr(mask_hi), y.data_ptr(), mean.data_ptr(), \
+        rstd.data_ptr(), gamma.data_ptr()
+    a.P, a.C, a.ws = P, Cc, ws.data_ptr()
+    a.dgamma, a.dbeta, a.dy_bf16 = dgamma.data_ptr(), dbeta.data_ptr(), dy.data_ptr()
+    a.dz_out, a.dz_accumulate = L.ptr(dz_out), int(dz_accumulate)
+    L.call("fb_bn_bwd", C.byref(a))
+
+
+def avgpool2_fwd(in_hi, in_lo, n, h, w, c, out_hi, out_lo):
+    L.call("fb_avgpool2_fwd", in_hi.data_ptr(), L.ptr(in_lo), n, h, w, c, out_hi.data_ptr(), L.ptr(out_lo))
+
+
+def avgpool2_bwd(dP, n, h, w, c, dX, accumulate=False):
+    L.call("fb_avgpool2_bwd", dP.data_ptr(), n, h, w, c, dX.data_ptr(), int(accumulate))
+
+
+def head_fwd_bwd(a_hi, a_lo, n, hw, c, fc_w, fc_b, labels, classes, smoothing, ws, scal, loss_slot, correct_slot, d_fcw,
+                 d_fcb, dA):
+    L.call("fb_head_fwd_bwd", a_hi.data_ptr(), L.ptr(a_lo), n, hw, c, fc_w.data_ptr(), fc_b.data_ptr(),
+           labels.data_ptr(), classes, smoothing, ws.data_ptr(), scal.data_ptr(), loss_slot, correct_slot,
+           d_fcw.data_ptr(), d_fcb.data_ptr(), dA.data_ptr())
+
+
+def flat_sqnorm(x, n, ws, scal, slot):
+    L.call("fb_flat_sqnorm", x.data_ptr(), n, ws.data_ptr(), scal.data_ptr(), slot)
+
+
+def fd_perturb(theta, g, n, bs, eps, scal, sq_slot, eps_slot, norms_out, cursor, theta_p):
+    L.call("fb_fd_perturb", theta.data_ptr(), g.data_ptr(), n, bs, eps, scal.data_ptr(), sq_slot, eps_slot,
+           L.ptr(norms_out), L.ptr(cursor), theta_p.data_ptr())
+
+
+def fd_combine(g, g2, avg, n, scal, eps_slot, cf, cursor, count0, write_g, cf_slot=-1):
+    L.call("fb_fd_combine", g.data_ptr(), g2.data_ptr(), L.ptr(avg), n, scal.data_ptr(), eps_slot, cf, cf_slot,
+           L.ptr(cursor), count0, int(write_g))
+
+
+def mean_accumulate(g, avg, n, cursor, count0):
+    L.call("fb_mean_accumulate", g.data_ptr(), avg.data_ptr(), n, L.ptr(cursor), count0)
+
+
+def cursor_add(cursor, delta):
+    L.call("fb_cursor_add", cursor.data_ptr(), delta)
+
+
+def flat_scale(x, n, alpha):
+    L.call("fb_flat_scale", x.data_ptr(), n, alpha)

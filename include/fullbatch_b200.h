@@ -1,0 +1,190 @@
+/*
+ * fullbatch_b200 -- C ABI of the B200 (sm_100a) kernels behind the full-batch gradient-regularised step.
+ *
+ * The reference (JonasGeiping/fullbatchtraining) has no native/FFI layer: its hot path is Python calling torch ops.
+ * This header introduces the boundary UNDER the three Python call sites the reference exposes for the path
+ * (SURVEY.md 8b).  Each entry point names the reference code whose device work it replaces (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t value or an FB_ERR_* code otherwise; fb_last_error() has text;
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation, no allocation;
+ *   - pointers are device pointers unless the name says host; sizes are elements unless the name says bytes;
+ *   - activations are NHWC; "hi"/"lo" are the two bf16 planes of a split fp32 value (x ~= hi + lo), lo may be NULL
+ *     (plain-bf16 mode); conv outputs and activation gradients are fp32 NHWC; output gradients fed to the tensor
+ *     cores (dY) are plain bf16;
+ *   - unsupported shapes return FB_ERR_UNSUPPORTED: there is NO fallback path.
+ */
+#ifndef FULLBATCH_B200_H
+#define FULLBATCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ERR_BAD_ARG 1001
+#define FB_ERR_UNSUPPORTED 1002
+#define FB_ERR_DRIVER 1003
+
+#define FB_TMAP_BYTES 128 /* sizeof(CUtensorMap) */
+#define FB_MAX_TAP_STEPS 32
+#define FB_MAX_A_MAPS 8
+#define FB_MAX_B_MAPS 2
+#define FB_MAX_WGRAD_TAPS 9
+
+int fb_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+int fb_last_error(char* buf, size_t n);
+
+/* ---- TMA descriptors (host side; written into caller-owned 128-byte, 64-byte aligned blobs) -------------------- */
+
+/* 4-D bf16 view (c, w, h, n) of an NHWC activation plane (or of one stride-2 phase of it): extents and element strides
+ * of w/h/n (c is contiguous); box = box_c x box_w x box_h x box_n, SWIZZLE_128B (box_c must be 64), OOB -> 0. */
+int fb_tmap_encode_act4d(void* host_blob, const void* base, int c, int w, int h, int n, int64_t stride_w,
+                         int64_t stride_h, int64_t stride_n, int box_c, int box_w, int box_h, int box_n);
+/* 2-D bf16 row-major matrix [rows][k] with row stride `ld` elements; box = box_k(64) x box_rows, SWIZZLE_128B. */
+int fb_tmap_encode_mat2d(void* host_blob, const void* base, int k, int rows, int64_t ld, int box_k, int box_rows);
+
+/* ---- convolutions as tcgen05 implicit GEMMs -------------------------------------------------------------------- */
+
+/* One K-segment of the implicit GEMM: A box = activation map `a_map` shifted by (dh, dw) pixels, B columns start at
+ * b_k0 in weight map `b_map`; the segment runs over `cblocks` 64-channel blocks. */
+typedef struct {
+  int8_t a_map, b_map, dh, dw;
+  int32_t b_k0;
+} fb_tap_step;
+
+/* out[pixel, n_off + 0..n_total) (+)= sum_steps sum_cblocks  A_step[pixel tile, 64] * B_step[n_tile rows, 64]^T
+ * Used for: conv forward (resnets.py:69-73,206-210,285-291 -> cuDNN fprop), dgrad of stride-1 and stride-2 convs
+ * (autograd, training.py:82 / modules.py:230), 1x1 shortcut convs and the im2col'ed stem.
+ * The 128-pixel M tile is the TMA box tile_w x tile_h x tile_n of the OUTPUT pixel grid (width == tile_w). */
+typedef struct {
+  const void* host_a_maps; /* n_a_maps x 128 B */
+  const void* host_b_maps; /* n_b_maps x 128 B */
+  int32_t n_a_maps, n_b_maps;
+  int32_t n_steps, cblocks;
+  fb_tap_step steps[FB_MAX_TAP_STEPS];
+  int32_t tile_w, tile_h, tile_n; /* product must be 128 */
+  int32_t grid_h, grid_n;         /* rows and images of the output pixel grid */
+  int32_t n_total, n_tile;        /* GEMM N (output channels) and the per-CTA N tile: 64, 128 or 256 */
+  float* out;                     /* fp32; element (n,h,w,c) at out + n*out_sn + h*out_sh + w*out_sw + c */
+  int64_t out_sn, out_sh, out_sw;
+  int32_t accumulate; /* 0: overwrite, 1: out += result */
+} fb_conv_gemm_args;
+int fb_conv_gemm(const fb_conv_gemm_args* args, void* stream);
+
+typedef struct {
+  int8_t phase, dh, dw, pad;
+} fb_wgrad_tap;
+
+/* Weight gradient: partial[split][co][tap*cin + ci] = sum_{pixels of split} dY[pixel, co] * X[pixel + tap shift, ci]
+ * (autograd wgrad, training.py:82 / modules.py:230).  X maps are indexed [phase * planes + plane]. */
+typedef struct {
+  const void* host_dy_map; /* 1 x 128 B */
+  const void* host_x_maps; /* n_x_maps x 128 B */
+  int32_t n_x_maps, planes;
+  int32_t n_taps, cblocks;
+  fb_wgrad_tap taps[FB_MAX_WGRAD_TAPS];
+  int32_t slots_per_cta; /* accumulators (tap, ci-block pairs) per CTA: 1..8 */
+  int32_t cout, cin;     /* cin = 64*cblocks; row length of partial = n_taps*cin */
+  int32_t tile_w, tile_h, tile_n;
+  int32_t grid_h, grid_n; /* dY pixel grid */
+  int32_t splits;         /* split-K over 128-pixel blocks */
+  float* partial;         /* [splits][cout][n_taps*cin] fp32 */
+} fb_wgrad_args;
+int fb_conv_wgrad(const fb_wgrad_args* args, void* stream);
+
+/* Sum split-K partials in a fixed order and scatter to the reference layout (OIHW, training/utils.py:34 order).
+ * mode 0: partial columns are tap*cin_stored + ci  -> g[co][ci][tap];  mode 1: columns already ci*taps + tap. */
+int fb_wgrad_finalize(const float* partial, int splits, int cout, int cin, int taps, int cin_stored, int mode,
+                      float* g_oihw, void* stream);
+
+/* fp32 OIHW conv weight -> bf16 hi/lo GEMM operands: wf[co][tap][ci] (forward / wgrad order) and wd[ci][tap][co]
+ * (dgrad); lo pointers may be NULL.  wd_* may be NULL (first layer needs no dgrad).  ld_f / ld_d: row strides. */
+int fb_weight_prep(const float* w_oihw, int cout, int cin, int taps, void* wf_hi, void* wf_lo, int64_t ld_f,
+                   void* wd_hi, void* wd_lo, int64_t ld_d, void* stream);
+
+/* ---- bandwidth-bound layer kernels ----------------------------------------------------------------------------- */
+
+/* x [n,3,32,32] fp32 NCHW (optionally gathered through perm[first + i]) -> 3x3/pad-1 patches [n*1024][64] bf16 hi/lo,
+ * column = ci*9 + kh*3 + kw (27 used).  `first` is read from *first_dev if first_dev != NULL (device-side microbatch
+ * cursor).  labels_out[i] = labels[perm ? perm[first+i] : first+i]. */
+int fb_stem_im2col(const float* x, const int64_t* labels, const int64_t* perm, const int32_t* first_dev, int64_t first,
+                   int n, void* patches_hi, void* patches_lo, int64_t* labels_out, void* stream);
+
+/* Train-mode BatchNorm statistics over y[P][C] (resnets.py:71 / torch.nn.BatchNorm2d): mean, rstd = 1/sqrt(var+eps)
+ * (biased var) and the running-stat EMA with unbiased variance.  ws: >= 2*C*1024 floats. */
+int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* mean, float* rstd, float* running_mean,
+                float* running_var, float momentum, float eps, void* stream);
+
+/* out = [relu]( bn(y) + [bn2(y2)] + [res] ) written as bf16 hi/lo planes (BasicBlock.forward resnets.py:214-230). */
+typedef struct {
+  const float *y, *mean, *rstd, *gamma, *beta;
+  const float *y2, *mean2, *rstd2, *gamma2, *beta2; /* optional second normalised branch (downsample), NULL if none */
+  const void *res_hi, *res_lo;                      /* optional identity residual (bf16 planes) */
+  int32_t relu;
+  int64_t P;
+  int32_t C;
+  void *out_hi, *out_lo;
+} fb_bn_apply_args;
+int fb_bn_apply(const fb_bn_apply_args* args, void* stream);
+
+/* BatchNorm(+ReLU) backward.  dz = dA * [mask_hi > 0] (mask_hi NULL: no ReLU).  Writes dgamma/dbeta (fp32, C each),
+ * dY as bf16 (tensor-core operand), and optionally dz as fp32 (`dz_out`, the identity-branch gradient; if
+ * dz_accumulate != 0 it is added to dz_out instead of overwriting).  ws: >= 2*C*1024 floats. */
+typedef struct {
+  const float* dA;
+  const void* mask_hi;
+  const float *y, *mean, *rstd, *gamma;
+  int64_t P;
+  int32_t C;
+  float* ws;
+  float *dgamma, *dbeta;
+  void* dy_bf16;
+  float* dz_out;
+  int32_t dz_accumulate;
+} fb_bn_bwd_args;
+int fb_bn_bwd(const fb_bn_bwd_args* args, void* stream);
+
+/* AvgPool2d(2) on bf16 hi/lo planes (downsample 'C', resnets.py:147-152) and its backward (dX = up(dP)/4). */
+int fb_avgpool2_fwd(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi, void* out_lo,
+                    void* stream);
+int fb_avgpool2_bwd(const float* dP, int n, int h, int w, int c, float* dX, int accumulate, void* stream);
+
+/* Global average pool + Linear + LabelSmoothCrossEntropyLoss + accuracy + their backward
+ * (resnets.py:106-107,183-186; modules.py:96-101; training.py:79-80).  Adds mean loss to scal[loss_slot] and the
+ * correct count to scal[correct_slot]; writes d(fc.weight), d(fc.bias) and dA [n][hw][c] fp32.  ws >= n*(c+32). */
+int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw, int c, const float* fc_w, const float* fc_b,
+                    const int64_t* labels, int classes, float smoothing, float* ws, float* scal, int loss_slot,
+                    int correct_slot, float* d_fcw, float* d_fcb, float* dA, void* stream);
+
+/* ---- flat-buffer (multi-tensor) kernels: GradRegularizer._forward_differences + running mean --------------------- */
+
+/* out[slot] = sum x^2 over n fp32 elements, deterministic two-stage reduction (training.py:162, modules.py:223).
+ * ws >= 1024 doubles. */
+int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, void* stream);
+
+/* eps_n = eps / sqrt(sum (bs*g)^2) from scal[sq_slot]; theta_p = theta + eps_n * (bs * g) (modules.py:217-226);
+ * stores eps_n in scal[eps_slot] and, if norms_out != NULL, scal[sq_slot] into norms_out[*cursor] (training.py:162). */
+int fb_fd_perturb(const float* theta, const float* g, int64_t n, float block_strength, float eps, float* scal,
+                  int sq_slot, int eps_slot, float* norms_out, const int32_t* cursor, float* theta_p, void* stream);
+
+/* g_reg = g + cf * (g2 - g) / eps_n (modules.py:232-240), cf = scal[cf_slot] if cf_slot >= 0 (device-resident lr/4, so
+ * that a captured CUDA graph survives learning-rate changes) else the `cf` argument; if avg != NULL:
+ * avg += (g_reg - avg) / (count0 + *cursor + 1) (training.py:45-47,168); if write_g: g <- g_reg. */
+int fb_fd_combine(float* g, const float* g2, float* avg, int64_t n, const float* scal, int eps_slot, float cf,
+                  int cf_slot, const int32_t* cursor, int32_t count0, int write_g, void* stream);
+/* avg += (g - avg) / (count0 + *cursor + 1) without regulariser (GradRegularizer._pass, modules.py:177-178) */
+int fb_mean_accumulate(const float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0, void* stream);
+/* *cursor += delta  (device-side microbatch cursor, so that a captured CUDA graph can be replayed per microbatch) */
+int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream);
+/* x *= alpha over n elements (rank-weighting before the all-reduce, training/utils.py:31-41) */
+int fb_flat_scale(float* x, int64_t n, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FULLBATCH_B200_H */
