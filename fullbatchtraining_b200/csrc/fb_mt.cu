@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restrict__ partial, int nblocks,
-                                                           float* __restrict__ scal, int slot) {
+                                                           float* __restrict__ scal, int slot,
+                                                           float* __restrict__ norms_out,
+                                                           const int* __restrict__ cursor) {
   __shared__ double red[8];
   double d = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += blockDim.x) d += partial[i];
@@ -50,20 +52,17 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restr
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += red[i];
     scal[slot] = float(s);
+    if (norms_out) norms_out[cursor ? *cursor : 0] = float(s);
   }
 }
 
 __global__ void __launch_bounds__(256) fd_perturb_kernel(const float* __restrict__ theta, const float* __restrict__ g,
                                                          long long n, float bs, float eps, float* __restrict__ scal,
-                                                         int sq_slot, int eps_slot, float* __restrict__ norms_out,
-                                                         const int* __restrict__ cursor, float* __restrict__ theta_p) {
+                                                         int sq_slot, int eps_slot, float* __restrict__ theta_p) {
   const float n2 = scal[sq_slot];
   // modules.py:223: eps / sqrt(sum (bs*g)^2)
   const float eps_n = eps / sqrtf(bs * bs * n2);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    scal[eps_slot] = eps_n;
-    if (norms_out) norms_out[cursor ? *cursor : 0] = n2;
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[eps_slot] = eps_n;
   const long long n4 = n / 4;
   const float4* t4 = reinterpret_cast<const float4*>(theta);
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -120,25 +119,25 @@ static int flat_grid(long long n) {
 
 using namespace fb;
 
-extern "C" int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, void* stream) {
+extern "C" int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, float* norms_out,
+                              const int32_t* cursor, void* stream) {
   FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm: bad arguments");
   FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fb_flat_sqnorm: x must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sqnorm_partial_kernel<<<kSqBlocks, 256, 0, st>>>(x, n, ws);
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, kSqBlocks, scal, slot);
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, kSqBlocks, scal, slot, norms_out, cursor);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int fb_fd_perturb(const float* theta, const float* g, int64_t n, float block_strength, float eps, float* scal,
-                             int sq_slot, int eps_slot, float* norms_out, const int32_t* cursor, float* theta_p,
-                             void* stream) {
+                             int sq_slot, int eps_slot, float* theta_p, void* stream) {
   FB_REQUIRE(theta && g && scal && theta_p && n > 0, "fb_fd_perturb: bad arguments");
   FB_REQUIRE(((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) |
                reinterpret_cast<uintptr_t>(theta_p)) & 15) == 0,
              "fb_fd_perturb: buffers must be 16-byte aligned");
   fd_perturb_kernel<<<flat_grid(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, g, n, block_strength, eps, scal, sq_slot, eps_slot, norms_out, cursor, theta_p);
+      theta, g, n, block_strength, eps, scal, sq_slot, eps_slot, theta_p);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,388 @@
+"""Whole-microbatch executor of the full-batch gradient-regularised step on one B200.
+
+Replaces the device work of ``_accumulate_full_gradient`` (reference fullbatch/training/training.py:121-185) and
+``GradRegularizer._forward_differences`` (fullbatch/models/modules.py:211-241):
+
+  per microbatch k (a replay of ONE captured CUDA graph, no host synchronisation):
+    im2col of the microbatch (stem)                                              [fb_stem_im2col]
+    pass 1: forward / loss / backward at theta           -> g      (flat fp32)   [tcgen05 convs + layer kernels]
+    n2 = |g|^2 -> grad_norms[k]; eps_n = eps / (bs*sqrt(n2)); theta' = theta + eps_n*bs*g   [fb_flat_sqnorm, fb_fd_perturb]
+    pass 2: forward / loss / backward at theta'          -> g2
+    g_reg = g + (lr/4) (g2 - g)/eps_n ; avg += (g_reg - avg)/(k+1)               [fb_fd_combine]
+
+Persistent state (allocated once, kernels never allocate):
+  theta, theta', g, g2, avg : flat fp32 buffers in model.parameters() order (= training/utils.py:34 order);
+                              the model's parameters are re-pointed to views of ``theta`` so optimizers update it in place
+  per conv: bf16 hi/lo GEMM operands of the weights, refreshed from theta / theta' at the start of each pass
+  per layer: fp32 conv output, bf16 hi/lo activation planes, fp32 activation gradient, bf16 output gradient
+
+theta itself is never modified by the regulariser, so the reference's "restore from a clone" (modules.py:237-238) is
+exact by construction.
+"""
+import torch
+
+from . import ops
+from .models import ResNet, ResidualBlock
+
+S_N2, S_EPS, S_LOSS, S_CORRECT, S_LOSS2, S_CORRECT2, S_CF = 0, 1, 2, 3, 4, 5, 6
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class Act:
+    """An activation tensor [n,h,w,c]: bf16 hi/lo planes (+ fp32 gradient buffer when it needs one)."""
+
+    def __init__(self, n, h, w, c, split, device, grad=True):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        self.hi = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16)
+        self.lo = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16) if split else None
+        self.grad = torch.zeros(n, h, w, c, device=device, dtype=torch.float32) if grad else None
+
+    @property
+    def P(self):
+        return self.n * self.h * self.w
+
+
+class Unit:
+    """conv (bias-free) + BatchNorm: buffers, descriptors and parameter offsets."""
+
+    def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, dx_accumulate, needs_dx=True, stem=False):
+        dev, split = eng.device, eng.split
+        self.conv_name, self.bn_name, self.x, self.stem = conv_name, bn_name, x, stem
+        self.cin, self.cout, self.k, self.stride = x.c, cout, k, stride
+        n, h, w = x.n, x.h, x.w
+        self.ho, self.wo = h // stride, w // stride
+        self.P = n * self.ho * self.wo
+        self.y = torch.zeros(n, self.ho, self.wo, cout, device=dev)
+        self.dy = torch.zeros(n, self.ho, self.wo, cout, device=dev, dtype=torch.bfloat16)
+        self.mean = torch.zeros(cout, device=dev)
+        self.rstd = torch.zeros(cout, device=dev)
+        taps = k * k
+        self.taps = taps
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.wf_hi = torch.zeros(cout, taps * x.c, **bf)
+        self.wf_lo = torch.zeros(cout, taps * x.c, **bf) if split else None
+        self.wd_hi = torch.zeros(x.c, taps * cout, **bf) if needs_dx else None
+        self.wd_lo = torch.zeros(x.c, taps * cout, **bf) if (needs_dx and split) else None
+        need = ops.Conv2dPlan.partial_elems(n, h, w, x.c, cout, k, stride)
+        eng.partial_elems = max(eng.partial_elems, need)
+        self.args = (n, h, w, x.c, cout, k, stride)
+        self.dx_accumulate, self.needs_dx = dx_accumulate, needs_dx
+        self.plan = None
+
+    def finish(self, eng):
+        self.plan = ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
+                                   self.x.grad if self.needs_dx else None, self.wf_hi, self.wf_lo, self.wd_hi,
+                                   self.wd_lo, eng.partial, dx_accumulate=self.dx_accumulate, split=eng.split)
+
+
+class Block:
+    def __init__(self):
+        self.units = []
+        self.ds = None          # downsample Unit
+        self.pooled = None      # Act: AvgPool2d(stride) of the block input (stride-2 downsample only)
+        self.x = None
+        self.out = None
+
+
+class FullBatchEngine:
+    """Runs the per-microbatch gradient + finite-difference regulariser on the sm_100a kernels.
+
+    precision: "split"  -- activations and weights enter the tensor cores as bf16 hi+lo pairs (3 MMAs forward,
+                           2 dgrad, 2 wgrad; ~16 mantissa bits per operand): the parity mode;
+               "bf16"   -- plain bf16 operands (1 MMA each): the fast mode, cannot resolve the FD perturbation.
+    """
+
+    def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None):
+        if not isinstance(model, ResNet):
+            raise RuntimeError("FullBatchEngine needs a model built by fullbatchtraining_b200.construct_model "
+                               "(there is no fallback path)")
+        if precision not in ("split", "bf16"):
+            raise ValueError(f"unknown precision {precision!r}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("FullBatchEngine needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device(device or "cuda")
+        self.model = model.to(self.device, torch.float32)
+        self.mb = int(microbatch)
+        self.split = precision == "split"
+        self.precision = precision
+        self.smoothing = float(label_smoothing)
+        self.classes = model.fc.out_features
+        self.partial_elems = 0
+        dev = self.device
+
+        # ---- flat parameter buffers, parameters() order
+        self.names, self.offsets, self.shapes = [], {}, {}
+        off = 0
+        for name, p in self.model.named_parameters():
+            self.names.append(name)
+            self.offsets[name] = off
+            self.shapes[name] = tuple(p.shape)
+            off += p.numel()
+        self.numel = off
+        pad = (-off) % 4
+        self.theta = torch.zeros(off + pad, device=dev)[:off]
+        self.theta_p = torch.zeros(off + pad, device=dev)[:off]
+        self.g = torch.zeros(off + pad, device=dev)[:off]
+        self.g2 = torch.zeros(off + pad, device=dev)[:off]
+        self.avg = torch.zeros(off + pad, device=dev)[:off]
+        with torch.no_grad():
+            for name, p in self.model.named_parameters():
+                o = self.offsets[name]
+                if o % 4 != 0:
+                    raise RuntimeError(f"parameter {name} is not 16-byte aligned in the flat buffer")
+                self.theta[o:o + p.numel()].copy_(p.reshape(-1))
+                p.data = self.theta[o:o + p.numel()].view(p.shape)
+        self.scal = torch.zeros(16, device=dev)
+        self.cursor = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.sq_ws = torch.zeros(1024, device=dev, dtype=torch.float64)
+        self.labels_mb = torch.zeros(self.mb, device=dev, dtype=torch.int64)
+
+        # ---- network plan
+        n = self.mb
+        self.patches = Act(n, 32, 32, 64, self.split, dev, grad=False)
+        stem_conv = self.model.stem[0]
+        if stem_conv.in_channels != 3 or stem_conv.out_channels != 64:
+            raise RuntimeError("the stem kernel expects 3 input channels and 64 output channels")
+        self.stem = Unit(self, "stem.0", "stem.1", self.patches, 64, 1, 1, False, needs_dx=False, stem=True)
+        self.a0 = Act(n, 32, 32, 64, self.split, dev)
+        self.stem.out = self.a0
+        self.blocks = []
+        cur = self.a0
+        max_c = 64
+        for s, stage in enumerate(self.model.layers):
+            for b, mod in enumerate(stage):
+                assert isinstance(mod, ResidualBlock)
+                blk = Block()
+                blk.x = cur
+                pre = f"layers.{s}.{b}"
+                x = cur
+                pairs = mod.conv_bn_pairs()
+                for i, (cn, bnn) in enumerate(pairs):
+                    conv = getattr(mod, cn)
+                    k, st = conv.kernel_size[0], conv.stride[0]
+                    u = Unit(self, f"{pre}.{cn}", f"{pre}.{bnn}", x, conv.out_channels, k, st, dx_accumulate=(i == 0))
+                    u.out = Act(x.n, u.ho, u.wo, conv.out_channels, self.split, dev)
+                    blk.units.append(u)
+                    x = u.out
+                    max_c = max(max_c, conv.out_channels)
+                if mod.downsample is not None:
+                    pool, dconv = mod.downsample[0], mod.downsample[1]
+                    ps = pool.kernel_size if isinstance(pool.kernel_size, int) else pool.kernel_size[0]
+                    src = cur
+                    if ps == 2:
+                        blk.pooled = Act(cur.n, cur.h // 2, cur.w // 2, cur.c, self.split, dev)
+                        src = blk.pooled
+                    elif ps != 1:
+                        raise RuntimeError(f"AvgPool2d({ps}) in the shortcut is not supported")
+                    blk.ds = Unit(self, f"{pre}.downsample.1", f"{pre}.downsample.2", src, dconv.out_channels, 1, 1,
+                                  dx_accumulate=False)
+                blk.out = x
+                self.blocks.append(blk)
+                cur = x
+        self.last = cur
+        self.partial = torch.zeros(self.partial_elems, device=dev)
+        self.bn_ws = torch.zeros(2 * max_c * 1024, device=dev)
+        self.head_ws = torch.zeros(n * (cur.c + 32), device=dev)
+        self.units = [self.stem] + [u for blk in self.blocks for u in (blk.units + ([blk.ds] if blk.ds else []))]
+        for u in self.units:
+            u.finish(self)
+        self._bn_modules = dict(self.model.named_modules())
+        self._graphs = {}
+        self.grad_norms = None
+        self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _view(self, flat, name):
+        o = self.offsets[name]
+        n = 1
+        for d in self.shapes[name]:
+            n *= d
+        return flat[o:o + n]
+
+    def _bn_buffers(self, bn_name):
+        m = self._bn_modules[bn_name]
+        return m.running_mean, m.running_var
+
+    def _weight_prep(self, P):
+        for u in self.units:
+            w = self._view(P, u.conv_name + ".weight")
+            if u.stem:
+                ops.weight_prep(w, 64, 3, 9, u.wf_hi, u.wf_lo)
+            else:
+                ops.weight_prep(w, u.cout, u.cin, u.taps, u.wf_hi, u.wf_lo, u.wd_hi, u.wd_lo)
+
+    def _unit_forward(self, u, P):
+        u.plan.forward()
+        rm, rv = self._bn_buffers(u.bn_name)
+        ops.bn_stats(u.y, u.P, u.cout, self.bn_ws, u.mean, u.rstd, rm, rv, BN_MOMENTUM, BN_EPS)
+
+    def _bn_params(self, u, P):
+        return self._view(P, u.bn_name + ".weight"), self._view(P, u.bn_name + ".bias")
+
+    def _forward(self, P, G, loss_slot, correct_slot):
+        self._weight_prep(P)
+        u = self.stem
+        self._unit_forward(u, P)
+        ga, be = self._bn_params(u, P)
+        ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, u.out.hi, u.out.lo, relu=True)
+        for blk in self.blocks:
+            last = len(blk.units) - 1
+            for i, u in enumerate(blk.units):
+                self._unit_forward(u, P)
+                if i < last:
+                    ga, be = self._bn_params(u, P)
+                    ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, u.out.hi, u.out.lo, relu=True)
+            u = blk.units[last]
+            ga, be = self._bn_params(u, P)
+            if blk.ds is not None:
+                d = blk.ds
+                if blk.pooled is not None:
+                    x = blk.x
+                    ops.avgpool2_fwd(x.hi, x.lo, x.n, x.h, x.w, x.c, blk.pooled.hi, blk.pooled.lo)
+                self._unit_forward(d, P)
+                ga2, be2 = self._bn_params(d, P)
+                ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, blk.out.hi, blk.out.lo, relu=True,
+                             second=(d.y, d.mean, d.rstd, ga2, be2))
+            else:
+                ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, blk.out.hi, blk.out.lo, relu=True,
+                             res=(blk.x.hi, blk.x.lo))
+        a = self.last
+        ops.head_fwd_bwd(a.hi, a.lo, a.n, a.h * a.w, a.c, self._view(P, "fc.weight"), self._view(P, "fc.bias"),
+                         self.labels_mb, self.classes, self.smoothing, self.head_ws, self.scal, loss_slot, correct_slot,
+                         self._view(G, "fc.weight"), self._view(G, "fc.bias"), a.grad)
+
+    def _unit_backward(self, u, P, G, dA, mask_hi, dz_out=None):
+        """BN(+ReLU) backward of `u` from dA, then wgrad and dgrad of its conv."""
+        ga, _ = self._bn_params(u, P)
+        ops.bn_bwd(dA, mask_hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
+                   self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out)
+        gw = self._view(G, u.conv_name + ".weight")
+        if u.stem:
+            u.plan.wgrad(gw, cin_real=3, mode=1)
+        else:
+            u.plan.wgrad(gw)
+            u.plan.dgrad()
+
+    def _backward(self, P, G):
+        for blk in reversed(self.blocks):
+            out = blk.out
+            last = len(blk.units) - 1
+            if blk.ds is not None:
+                # shortcut branch first: it overwrites the block-input gradient, the main branch accumulates into it
+                d = blk.ds
+                self._unit_backward(d, P, G, out.grad, out.hi)
+                if blk.pooled is not None:
+                    x = blk.x
+                    ops.avgpool2_bwd(blk.pooled.grad, x.n, x.h, x.w, x.c, x.grad, accumulate=False)
+                dz_out = None
+            else:
+                dz_out = blk.x.grad  # identity shortcut: dz of the last BN is the block-input gradient's first term
+            for i in range(last, -1, -1):
+                u = blk.units[i]
+                if i == last:
+                    self._unit_backward(u, P, G, out.grad, out.hi, dz_out=dz_out)
+                else:
+                    self._unit_backward(u, P, G, u.out.grad, u.out.hi)
+        self._unit_backward(self.stem, P, G, self.a0.grad, self.a0.hi)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g):
+        ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb, self.patches.hi,
+                        self.patches.lo, self.labels_mb)
+        self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
+        self._backward(self.theta, self.g)
+        ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_N2, self.grad_norms, self.cursor)
+        if block_strength != 0:
+            ops.fd_perturb(self.theta, self.g, self.numel, block_strength, eps, self.scal, S_N2, S_EPS, self.theta_p)
+            self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
+            self._backward(self.theta_p, self.g2)
+            ops.fd_combine(self.g, self.g2, self.avg if accumulate else None, self.numel, self.scal, S_EPS, 0.0,
+                           self.cursor, 0, write_g, cf_slot=S_CF)
+        elif accumulate:
+            ops.mean_accumulate(self.g, self.avg, self.numel, self.cursor, 0)
+        ops.cursor_add(self.cursor, 1)
+
+    def _program(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate=True, write_g=False,
+                 use_graph=True):
+        """Returns a callable running one microbatch; captured into a CUDA graph on first use."""
+        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
+               float(block_strength), float(eps), accumulate, write_g, self.grad_norms.data_ptr())
+        if not use_graph:
+            return lambda: self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps,
+                                                accumulate, write_g)
+        if key not in self._graphs:
+            state = self._save_state()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up launch (sets kernel attributes, loads modules) outside capture
+                self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g)
+            self._restore_state(state)
+            self._graphs[key] = (graph, (x_src, labels_src, perm))
+        return self._graphs[key][0].replay
+
+    def _save_state(self):
+        bufs = [b.clone() for b in self.model.buffers()]
+        return dict(avg=self.avg.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
+                    norms=self.grad_norms.clone(), g=self.g.clone())
+
+    def _restore_state(self, st):
+        self.avg.copy_(st["avg"])
+        self.scal.copy_(st["scal"])
+        self.cursor.copy_(st["cursor"])
+        self.grad_norms.copy_(st["norms"])
+        self.g.copy_(st["g"])
+        for b, s in zip(self.model.buffers(), st["bufs"]):
+            b.copy_(s)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def set_lr(self, lr):
+        """correction factor lr/4 of modules.py:214, kept on the device so captured graphs stay valid"""
+        self.scal[S_CF] = lr / 4
+
+    def begin_step(self, num_microbatches):
+        if self.grad_norms is None or self.grad_norms.numel() < num_microbatches:
+            self.grad_norms = torch.zeros(max(num_microbatches, 16), device=self.device)
+            self._graphs.clear()
+        self.grad_norms.zero_()
+        self.avg.zero_()
+        self.scal[S_LOSS:S_CORRECT2 + 1] = 0
+        self.cursor.zero_()
+
+    def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True):
+        """Full-batch accumulation over `count` consecutive microbatches of a device-resident dataset
+        X [N,3,32,32] fp32, Y [N] int64, starting at sample `first` (optionally through the index tensor `perm`).
+        Returns after enqueueing; results: self.avg (running mean), self.grad_norms[:count], loss/correct sums in scal."""
+        assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and Y.dtype == torch.int64
+        n_avail = (perm.numel() if perm is not None else X.shape[0]) - first
+        count = n_avail // self.mb if count is None else count
+        self.begin_step(count)
+        self.set_lr(lr)
+        run = self._program(X, Y, perm, first, True, block_strength, eps, use_graph=use_graph)
+        for _ in range(count):
+            run()
+        self.bn_passes += count * (2 if block_strength != 0 else 1)
+        return count
+
+    def results(self, count):
+        """Host read of the step scalars (one synchronisation): mean loss, correct count, grad_norms."""
+        s = self.scal.tolist()
+        return dict(loss=s[S_LOSS] / max(count, 1), correct=s[S_CORRECT], loss_sum=s[S_LOSS],
+                    grad_norms=self.grad_norms[:count].clone())
+
+    def sync_bn_counters(self):
+        """num_batches_tracked += number of train-mode passes (2 per microbatch with the regulariser)."""
+        if self.bn_passes:
+            for m in self.model.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.num_batches_tracked += self.bn_passes
+            self.bn_passes = 0
+
+    def grads_list(self, flat):
+        """Views of a flat buffer shaped like model.parameters()."""
+        return [self._view(flat, n).view(self.shapes[n]) for n in self.names]

@@ -72,8 +72,8 @@ _SIGNATURES = {
     "fb_avgpool2_fwd": ([vp, vp, i32, i32, i32, i32, vp, vp, vp], i32),
     "fb_avgpool2_bwd": ([vp, i32, i32, i32, i32, vp, i32, vp], i32),
     "fb_head_fwd_bwd": ([vp, vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, vp, i32, i32, vp, vp, vp, vp], i32),
-    "fb_flat_sqnorm": ([vp, i64, vp, vp, i32, vp], i32),
-    "fb_fd_perturb": ([vp, vp, i64, f32, f32, vp, i32, i32, vp, vp, vp, vp], i32),
+    "fb_flat_sqnorm": ([vp, i64, vp, vp, i32, vp, vp, vp], i32),
+    "fb_fd_perturb": ([vp, vp, i64, f32, f32, vp, i32, i32, vp, vp], i32),
     "fb_fd_combine": ([vp, vp, vp, i64, vp, i32, f32, i32, vp, i32, i32, vp], i32),
     "fb_mean_accumulate": ([vp, vp, i64, vp, i32, vp], i32),
     "fb_cursor_add": ([vp, i32, vp], i32),

@@ -323,13 +323,13 @@ def head_fwd_bwd(a_hi, a_lo, n, hw, c, fc_w, fc_b, labels, classes, smoothing, w
            d_fcw.data_ptr(), d_fcb.data_ptr(), dA.data_ptr())
 
 
-def flat_sqnorm(x, n, ws, scal, slot):
-    L.call("fb_flat_sqnorm", x.data_ptr(), n, ws.data_ptr(), scal.data_ptr(), slot)
+def flat_sqnorm(x, n, ws, scal, slot, norms_out=None, cursor=None):
+    L.call("fb_flat_sqnorm", x.data_ptr(), n, ws.data_ptr(), scal.data_ptr(), slot, L.ptr(norms_out), L.ptr(cursor))
 
 
-def fd_perturb(theta, g, n, bs, eps, scal, sq_slot, eps_slot, norms_out, cursor, theta_p):
+def fd_perturb(theta, g, n, bs, eps, scal, sq_slot, eps_slot, theta_p):
     L.call("fb_fd_perturb", theta.data_ptr(), g.data_ptr(), n, bs, eps, scal.data_ptr(), sq_slot, eps_slot,
-           L.ptr(norms_out), L.ptr(cursor), theta_p.data_ptr())
+           theta_p.data_ptr())
 
 
 def fd_combine(g, g2, avg, n, scal, eps_slot, cf, cursor, count0, write_g, cf_slot=-1):

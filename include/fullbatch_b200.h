@@ -163,14 +163,16 @@ int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw, int c, co
 
 /* ---- flat-buffer (multi-tensor) kernels: GradRegularizer._forward_differences + running mean --------------------- */
 
-/* out[slot] = sum x^2 over n fp32 elements, deterministic two-stage reduction (training.py:162, modules.py:223).
+/* scal[slot] = sum x^2 over n fp32 elements, deterministic two-stage reduction (training.py:162, modules.py:223);
+ * if norms_out != NULL the value is also stored in norms_out[*cursor] (grad_norms[k], training.py:162).
  * ws >= 1024 doubles. */
-int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, void* stream);
+int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, float* norms_out,
+                   const int32_t* cursor, void* stream);
 
 /* eps_n = eps / sqrt(sum (bs*g)^2) from scal[sq_slot]; theta_p = theta + eps_n * (bs * g) (modules.py:217-226);
- * stores eps_n in scal[eps_slot] and, if norms_out != NULL, scal[sq_slot] into norms_out[*cursor] (training.py:162). */
+ * stores eps_n in scal[eps_slot]. */
 int fb_fd_perturb(const float* theta, const float* g, int64_t n, float block_strength, float eps, float* scal,
-                  int sq_slot, int eps_slot, float* norms_out, const int32_t* cursor, float* theta_p, void* stream);
+                  int sq_slot, int eps_slot, float* theta_p, void* stream);
 
 /* g_reg = g + cf * (g2 - g) / eps_n (modules.py:232-240), cf = scal[cf_slot] if cf_slot >= 0 (device-resident lr/4, so
  * that a captured CUDA graph survives learning-rate changes) else the `cf` argument; if avg != NULL:

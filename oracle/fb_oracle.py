@@ -211,9 +211,9 @@ def full_batch_step(depth, p, buffers, X, Y, mb, lr, block_strength=0.5, eps=1e-
     acc_dtype = acc_dtype or X.dtype
     K = X.shape[0] // mb
     avg = [torch.zeros_like(v, dtype=acc_dtype) for v in p.values()]  # :123
-    grad_norms = torch.zeros(K, dtype=X.dtype)
-    step_loss = torch.zeros((), dtype=X.dtype)
-    step_preds = torch.zeros((), dtype=X.dtype)
+    grad_norms = torch.zeros(K, dtype=X.dtype, device=X.device)
+    step_loss = torch.zeros((), dtype=X.dtype, device=X.device)
+    step_preds = torch.zeros((), dtype=X.dtype, device=X.device)
     kept = []
     for k in range(K):
         idx = slice(k * mb, (k + 1) * mb) if order is None else order[k * mb:(k + 1) * mb]
@@ -244,10 +244,10 @@ def flat(tensors):
 def fingerprint(tensors, stride=997):
     """Compact, machine-independent fingerprint of a list of tensors: per-tensor L2 norms and sums, plus a strided
     sample of the flat vector.  Used for the committed goldens (full vectors are 45 MB each)."""
-    f = flat(tensors).double()
+    f = flat(tensors).double().cpu()
     return dict(
-        norms=torch.stack([t.double().norm() for t in tensors]).numpy(),
-        sums=torch.stack([t.double().sum() for t in tensors]).numpy(),
+        norms=torch.stack([t.double().norm() for t in tensors]).cpu().numpy(),
+        sums=torch.stack([t.double().sum() for t in tensors]).cpu().numpy(),
         sample=f[::stride].numpy().copy(),
         total_norm=float(f.norm()),
     )

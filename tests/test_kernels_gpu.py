@@ -323,12 +323,12 @@ def test_flat_fd_kernels():
     scal = torch.zeros(16, device=DEV)
     cursor = torch.tensor([2], device=DEV, dtype=torch.int32)
     norms = torch.zeros(8, device=DEV)
-    ops.flat_sqnorm(grad, n, ws, scal, 0)
+    ops.flat_sqnorm(grad, n, ws, scal, 0, norms, cursor)
     n2 = float(grad.double().pow(2).sum())
     assert abs(float(scal[0]) - n2) < 1e-6 * n2
     theta_p = torch.empty_like(theta)
     bs, eps, cf = 0.5, 1e-2, 0.2
-    ops.fd_perturb(theta, grad, n, bs, eps, scal, 0, 1, norms, cursor, theta_p)
+    ops.fd_perturb(theta, grad, n, bs, eps, scal, 0, 1, theta_p)
     eps_n = eps / (bs * n2 ** 0.5)
     assert abs(float(scal[1]) - eps_n) < 1e-6 * eps_n
     assert float(norms[2]) == float(scal[0])
