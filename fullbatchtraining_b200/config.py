@@ -1,0 +1,110 @@
+"""Config surface of the hot path with the reference's key names and defaults.
+
+The reference composes hydra YAML groups (config/cfg.yaml:9-20).  hydra is not a dependency here: ``default_cfg`` returns
+the same nested keys as an attribute dict (only the keys the path reads), ``load_yaml`` overlays
+reference-style YAML files, and ``apply_overrides`` accepts hydra-like ``a.b.c=value`` strings.  Defaults reproduce
+``hyp=gradreg`` on the default stack: config/hyp/gradreg.yaml, config/hyp/_default_hyperparams.yaml,
+config/hyp/optim/gd.yaml, config/impl/standard.yaml, config/data/CIFAR10.yaml, config/model/resnet18.yaml.
+"""
+import copy
+
+import yaml
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    return d
+
+
+_DEFAULT = dict(
+    name="fullbatch_b200", dryrun=False, seed=None, original_cwd=".",
+    data=dict(name="CIFAR10", size=50000, channels=3, classes=10, pixels=32, batch_size=128),
+    model=dict(name="ResNet18", depth=18, width=64, stem="CIFAR", convolution="Standard", nonlin_fn="ReLU",
+               normalization="BatchNorm2d", downsample="C", initialization="skip-residual"),
+    impl=dict(dtype="float", memory="contiguous", non_blocking=True, mixed_precision=False, accumulation_dtype="float",
+              validate_every_nth_step=100, checkpoint=dict(name=None, save_every_nth_step=1),
+              setup=dict(dist=False, world_size=1, backend="nccl"),
+              # B200-path switch (not in the reference): "split" = bf16 hi+lo tensor-core operands (parity mode),
+              # "bf16" = plain bf16 operands (fast mode)
+              precision="split"),
+    hyp=dict(template_name="fbgradreg", train_stochastic=False, shuffle=False, steps=3000, sub_batch=128,
+             optim=dict(name="Gradient Descent", lr=0.8, momentum=0.9, weight_decay=5e-4, dampening=0.0, nesterov=True,
+                        line_search="none"),
+             optim_modification=dict(name="none"), only_linear_layers_weight_decay=False,
+             scheduler="cosine-4000", warmup=400, grad_clip=0.25, batch_clip=None, grad_clip_norm=2,
+             grad_noise=dict(additive=None, multiplicative=None),
+             grad_reg=dict(norm=2, block_strength=0.5, acc_strength=0.0, eps=1e-2, implementation="forward-differences"),
+             label_smoothing=0.0, loss_modification=None, norm_bias=dict(strength=0.0, norm_type=1, bias=0),
+             evaluate_ema=False, eval_ema_momentum=0.99, train_switch_stochastic=None, train_semi_stochastic=False,
+             stop_at_full_training_accuracy=0, test_time_flips=False),
+    analysis=dict(type=None, check_every_nth_step=100, save_model_every_nth_step=None),
+)
+
+
+def default_cfg(overrides=None):
+    """Defaults of `hyp=gradreg`; ``overrides`` is a dict {"a.b": value} or a list of hydra-like "a.b=value" strings."""
+    cfg = to_attr(copy.deepcopy(_DEFAULT))
+    if isinstance(overrides, dict):
+        for key, val in overrides.items():
+            node = cfg
+            parts = key.split(".")
+            for p in parts[:-1]:
+                node = node.setdefault(p, AttrDict())
+            node[parts[-1]] = to_attr(val)
+    elif overrides:
+        apply_overrides(cfg, overrides)
+    return cfg
+
+
+def _merge(dst, src):
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = to_attr(v)
+
+
+def load_yaml(cfg, path, group=None):
+    """Overlay a reference-style YAML file; ``group`` (e.g. "hyp") nests it like a hydra config group.  hydra
+    ``defaults:`` lists are ignored (compose by calling load_yaml once per file)."""
+    with open(path) as f:
+        data = yaml.safe_load(f) or {}
+    data.pop("defaults", None)
+    target = cfg if group is None else cfg.setdefault(group, AttrDict())
+    _merge(target, data)
+    return cfg
+
+
+def _parse(raw):
+    if not isinstance(raw, str):
+        return raw
+    val = yaml.safe_load(raw)
+    if isinstance(val, str):  # YAML 1.1 reads "1e-2" as a string
+        try:
+            return float(val)
+        except ValueError:
+            return val
+    return to_attr(val)
+
+
+def apply_overrides(cfg, overrides):
+    for item in overrides:
+        key, _, raw = item.partition("=")
+        node = cfg
+        parts = key.split(".")
+        for p in parts[:-1]:
+            node = node.setdefault(p, AttrDict())
+        node[parts[-1]] = _parse(raw)
+    return cfg

@@ -13,7 +13,7 @@
 
 namespace fb {
 
-constexpr int kMaxChunks = 1000;
+constexpr int kMaxChunks = 592;  // 4 reduction blocks per SM
 typedef __nv_bfloat16 bf16;
 
 struct alignas(16) bf16x8 {
@@ -118,17 +118,42 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
   }
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, long long P,
-                                         float* __restrict__ mean, float* __restrict__ rstd,
-                                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                                         float momentum, float eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s1 += partial[(long long)k * 2 * C + c];
-    s2 += partial[(long long)k * 2 * C + C + c];
+// Second stage of the column reductions: block = 32 channels x 8 chunk lanes (fixed summation order -> deterministic).
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int chunks, int C, int c, int lane_k,
+                                                double& s1, double& s2) {
+  __shared__ double red[2][8][32];
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int k = lane_k; k < chunks; k += 8) {
+      a += partial[(long long)k * 2 * C + c];
+      b += partial[(long long)k * 2 * C + C + c];
+    }
   }
+  red[0][lane_k][threadIdx.x & 31] = a;
+  red[1][lane_k][threadIdx.x & 31] = b;
+  __syncthreads();
+  s1 = 0.0;
+  s2 = 0.0;
+  if (lane_k == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += red[0][j][threadIdx.x & 31];
+      s2 += red[1][j][threadIdx.x & 31];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
+                                                                long long P, float* __restrict__ mean,
+                                                                float* __restrict__ rstd,
+                                                                float* __restrict__ running_mean,
+                                                                float* __restrict__ running_var, float momentum,
+                                                                float eps) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_k = threadIdx.x >> 5;
+  double s1, s2;
+  reduce_partials(partial, chunks, C, c, lane_k, s1, s2);
+  if (lane_k != 0 || c >= C) return;
   const double m = s1 / double(P);
   double var = s2 / double(P) - m * m;
   var = var < 0.0 ? 0.0 : var;
@@ -142,16 +167,14 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int 
 }
 
 // coef[0][C] = sum dz / P, coef[1][C] = sum dz*xhat / P; dgamma = sum dz*xhat, dbeta = sum dz
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, long long P,
-                                       float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s1 += partial[(long long)k * 2 * C + c];
-    s2 += partial[(long long)k * 2 * C + C + c];
-  }
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
+                                                              long long P, float* __restrict__ coef,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_k = threadIdx.x >> 5;
+  double s1, s2;
+  reduce_partials(partial, chunks, C, c, lane_k, s1, s2);
+  if (lane_k != 0 || c >= C) return;
   dbeta[c] = float(s1);
   dgamma[c] = float(s2);
   coef[c] = float(s1 / double(P));
@@ -417,42 +440,60 @@ __global__ void __launch_bounds__(128) head_bwd_act_kernel(const float* __restri
   for (int p = 0; p < hw; ++p) dA[((long long)img * hw + p) * c + ch] = s;
 }
 
-// grid = c/128 (+ block 0 also reduces bias grad, loss, accuracy)
-__global__ void __launch_bounds__(128) head_bwd_param_kernel(const float* __restrict__ dlogits,
+// grid = c/32 (+ block 0 also reduces bias grad, loss, accuracy); block = 32 channels x 8 sample lanes
+__global__ void __launch_bounds__(256) head_bwd_param_kernel(const float* __restrict__ dlogits,
                                                              const float* __restrict__ pooled,
                                                              const float* __restrict__ loss_n,
                                                              const float* __restrict__ correct_n, int n, int c,
                                                              int classes, float* __restrict__ d_fcw,
                                                              float* __restrict__ d_fcb, float* __restrict__ scal,
                                                              int loss_slot, int correct_slot) {
-  const int ch = blockIdx.x * 128 + threadIdx.x;
+  __shared__ float red[8][kMaxClasses][33];
+  const int cl = threadIdx.x & 31, lane_n = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cl;
+  float acc[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
   if (ch < c) {
-    float acc[kMaxClasses];
-#pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
-    for (int i = 0; i < n; ++i) {
+    for (int i = lane_n; i < n; i += 8) {
       const float pv = pooled[(long long)i * c + ch];
+      const float4* dl = reinterpret_cast<const float4*>(dlogits + i * kMaxClasses);
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k)
-        if (k < classes) acc[k] += dlogits[i * kMaxClasses + k] * pv;
+      for (int q = 0; q < kMaxClasses / 4; ++q) {
+        const float4 d = dl[q];
+        acc[4 * q] += d.x * pv;
+        acc[4 * q + 1] += d.y * pv;
+        acc[4 * q + 2] += d.z * pv;
+        acc[4 * q + 3] += d.w * pv;
+      }
     }
+  }
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < classes) d_fcw[(long long)k * c + ch] = acc[k];
+  for (int k = 0; k < kMaxClasses; ++k) red[lane_n][k][cl] = acc[k];
+  __syncthreads();
+  // 256 threads -> (class, channel) pairs of this block: 16 x 32 = 512 outputs, two per thread
+  for (int o = threadIdx.x; o < kMaxClasses * 32; o += 256) {
+    const int k = o >> 5, cc = o & 31;
+    if (k < classes && blockIdx.x * 32 + cc < c) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += red[j][k][cc];
+      d_fcw[(long long)k * c + blockIdx.x * 32 + cc] = sum;
+    }
   }
   if (blockIdx.x == 0) {
     if (threadIdx.x < classes) {
-      float s = 0.f;
-      for (int i = 0; i < n; ++i) s += dlogits[i * kMaxClasses + threadIdx.x];
-      d_fcb[threadIdx.x] = s;
+      float sum = 0.f;
+      for (int i = 0; i < n; ++i) sum += dlogits[i * kMaxClasses + threadIdx.x];
+      d_fcb[threadIdx.x] = sum;
     } else if (threadIdx.x == 32) {
-      double s = 0.0;
-      for (int i = 0; i < n; ++i) s += loss_n[i];
-      scal[loss_slot] += float(s / double(n));
+      double sum = 0.0;
+      for (int i = 0; i < n; ++i) sum += loss_n[i];
+      scal[loss_slot] += float(sum / double(n));
     } else if (threadIdx.x == 64) {
-      float s = 0.f;
-      for (int i = 0; i < n; ++i) s += correct_n[i];
-      scal[correct_slot] += s;
+      float sum = 0.f;
+      for (int i = 0; i < n; ++i) sum += correct_n[i];
+      scal[correct_slot] += sum;
     }
   }
 }
@@ -492,7 +533,7 @@ extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* m
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, P, C, TX, rpc, ws);
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, chunks, C, P, mean, rstd, running_mean, running_var,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, chunks, C, P, mean, rstd, running_mean, running_var,
                                                             momentum, eps);
   FB_CUDA(cudaGetLastError());
   return 0;
@@ -519,7 +560,7 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   float* coef = a->ws + (long long)2 * a->C * kMaxChunks;
   bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, static_cast<const bf16*>(a->mask_hi), a->mean,
                                                               a->rstd, a->P, a->C, TX, rpc, a->ws);
-  bn_bwd_finalize_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->ws, chunks, a->C, a->P, coef, a->dgamma, a->dbeta);
+  bn_bwd_finalize_kernel<<<(a->C + 31) / 32, 256, 0, st>>>(a->ws, chunks, a->C, a->P, coef, a->dgamma, a->dbeta);
   bn_bwd_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, st>>>(*a, coef);
   FB_CUDA(cudaGetLastError());
   return 0;
@@ -573,7 +614,7 @@ extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw
       static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
       reinterpret_cast<const long long*>(labels), classes, smoothing, pooled, dlogits, loss_n, correct_n);
   head_bwd_act_kernel<<<dim3((c + 127) / 128, n), 128, 0, st>>>(dlogits, fc_w, hw, c, classes, dA);
-  head_bwd_param_kernel<<<(c + 127) / 128, 128, 0, st>>>(dlogits, pooled, loss_n, correct_n, n, c, classes, d_fcw, d_fcb,
+  head_bwd_param_kernel<<<(c + 31) / 32, 256, 0, st>>>(dlogits, pooled, loss_n, correct_n, n, c, classes, d_fcw, d_fcb,
                                                         scal, loss_slot, correct_slot);
   FB_CUDA(cudaGetLastError());
   return 0;

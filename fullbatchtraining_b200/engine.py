@@ -73,7 +73,8 @@ class Unit:
     def finish(self, eng):
         self.plan = ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
                                    self.x.grad if self.needs_dx else None, self.wf_hi, self.wf_lo, self.wd_hi,
-                                   self.wd_lo, eng.partial, dx_accumulate=self.dx_accumulate, split=eng.split)
+                                   self.wd_lo, eng.partial, dx_accumulate=self.dx_accumulate, split=eng.split,
+                                   alg_k=27 if self.stem else None)
 
 
 class Block:
@@ -190,6 +191,7 @@ class FullBatchEngine:
         self._bn_modules = dict(self.model.named_modules())
         self._graphs = {}
         self.grad_norms = None
+        self.norm_offset = 0
         self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
 
     # ------------------------------------------------------------------------------------------------------------
@@ -287,13 +289,18 @@ class FullBatchEngine:
         self._unit_backward(self.stem, P, G, self.a0.grad, self.a0.hi)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g):
+    def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g,
+                        mode="full"):
+        """mode "full": whole per-microbatch recipe; "raw": pass 1 only (training.py:76-83 + :162);
+        "reg": regulariser only, self.g already holds the raw gradient of this microbatch (modules.py:211-241)."""
         ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb, self.patches.hi,
                         self.patches.lo, self.labels_mb)
-        self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
-        self._backward(self.theta, self.g)
-        ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_N2, self.grad_norms, self.cursor)
-        if block_strength != 0:
+        if mode != "reg":
+            self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
+            self._backward(self.theta, self.g)
+        norms = self.grad_norms[self.norm_offset:] if self.norm_offset else self.grad_norms
+        ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_N2, norms, self.cursor)
+        if block_strength != 0 and mode != "raw":
             ops.fd_perturb(self.theta, self.g, self.numel, block_strength, eps, self.scal, S_N2, S_EPS, self.theta_p)
             self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
             self._backward(self.theta_p, self.g2)
@@ -304,24 +311,25 @@ class FullBatchEngine:
         ops.cursor_add(self.cursor, 1)
 
     def _program(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate=True, write_g=False,
-                 use_graph=True):
+                 use_graph=True, mode="full"):
         """Returns a callable running one microbatch; captured into a CUDA graph on first use."""
-        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
-               float(block_strength), float(eps), accumulate, write_g, self.grad_norms.data_ptr())
+        args = (x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g, mode)
         if not use_graph:
-            return lambda: self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps,
-                                                accumulate, write_g)
+            return lambda: self._microbatch_ops(*args)
+        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
+               float(block_strength), float(eps), accumulate, write_g, mode, self.grad_norms.data_ptr(),
+               self.norm_offset)
         if key not in self._graphs:
             state = self._save_state()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up launch (sets kernel attributes, loads modules) outside capture
-                self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g)
+                self._microbatch_ops(*args)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._microbatch_ops(x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g)
+                self._microbatch_ops(*args)
             self._restore_state(state)
             self._graphs[key] = (graph, (x_src, labels_src, perm))
         return self._graphs[key][0].replay
@@ -354,20 +362,114 @@ class FullBatchEngine:
         self.scal[S_LOSS:S_CORRECT2 + 1] = 0
         self.cursor.zero_()
 
-    def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True):
+    def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
+                            num_norms=None, norm_offset=0):
         """Full-batch accumulation over `count` consecutive microbatches of a device-resident dataset
         X [N,3,32,32] fp32, Y [N] int64, starting at sample `first` (optionally through the index tensor `perm`).
         Returns after enqueueing; results: self.avg (running mean), self.grad_norms[:count], loss/correct sums in scal."""
         assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and Y.dtype == torch.int64
         n_avail = (perm.numel() if perm is not None else X.shape[0]) - first
         count = n_avail // self.mb if count is None else count
-        self.begin_step(count)
+        self.begin_step(num_norms or count)
+        self.norm_offset = int(norm_offset)
         self.set_lr(lr)
         run = self._program(X, Y, perm, first, True, block_strength, eps, use_graph=use_graph)
         for _ in range(count):
             run()
         self.bn_passes += count * (2 if block_strength != 0 else 1)
         return count
+
+    def _stages(self):
+        if not hasattr(self, "_x_stage"):
+            self._x_stage = [torch.zeros(self.mb, 3, 32, 32, device=self.device) for _ in range(2)]
+            self._y_stage = [torch.zeros(self.mb, device=self.device, dtype=torch.int64) for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+        return self._x_stage, self._y_stage
+
+    def accumulate_stream(self, loader, lr, block_strength, eps, num_microbatches, use_graph=True, norm_offset=0):
+        """Full-batch accumulation over blocks (inputs [B,3,32,32], labels [B]) coming from a host-side iterable (the
+        reference's DataLoader protocol, training.py:148-152): every block is split into microbatches
+        (torch.chunk, training.py:155-156), copied host->device on a copy stream into one of two staging buffers and
+        consumed by a captured graph, so the copy of microbatch k+1 overlaps the compute of microbatch k."""
+        xs, ys = self._stages()
+        self.begin_step(num_microbatches)
+        self.norm_offset = int(norm_offset)
+        self.set_lr(lr)
+        runs = [self._program(xs[i], ys[i], None, 0, False, block_strength, eps, use_graph=use_graph) for i in range(2)]
+        main = torch.cuda.current_stream()
+        k = 0
+        h2d = 0
+        for inputs, labels in loader:
+            chunks = max(labels.shape[0] // self.mb, 1)
+            for xc, yc in zip(torch.chunk(inputs, chunks, dim=0), torch.chunk(labels, chunks, dim=0)):
+                if xc.shape[0] != self.mb:
+                    raise RuntimeError(f"microbatch of {xc.shape[0]} samples, engine built for {self.mb} (drop_last?)")
+                i = k & 1
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._stage_free[i])
+                    xs[i].copy_(xc, non_blocking=True)
+                    ys[i].copy_(yc, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+                main.wait_event(ready)
+                runs[i]()
+                self._stage_free[i].record(main)
+                h2d += xc.numel() * xc.element_size() + yc.numel() * yc.element_size()
+                k += 1
+        self.bn_passes += k * (2 if block_strength != 0 else 1)
+        self.h2d_bytes = h2d
+        return k
+
+    # ---- GradRegularizer / _compute_batched_gradient protocol ------------------------------------------------------
+    def microbatch_gradient(self, inputs, labels):
+        """training.py:76-83 on the device for one microbatch: fills self.g (raw gradient), returns (loss, correct)."""
+        xs, ys = self._stages()
+        xs[0].copy_(inputs)
+        ys[0].copy_(labels)
+        self.begin_step(1)
+        self._program(xs[0], ys[0], None, 0, False, 0.0, 0.0, accumulate=False, mode="raw")()
+        self.bn_passes += 1
+        return self.scal[S_LOSS], self.scal[S_CORRECT]
+
+    def regularize(self, inputs, labels, lr, block_strength, eps):
+        """modules.py:211-241: self.g (raw gradient of this microbatch) <- regularised gradient, in place."""
+        xs, ys = self._stages()
+        xs[0].copy_(inputs)
+        ys[0].copy_(labels)
+        if self.grad_norms is None:
+            self.begin_step(1)
+        self.cursor.zero_()
+        self.set_lr(lr)
+        self._program(xs[0], ys[0], None, 0, False, block_strength, eps, accumulate=False, write_g=True, mode="reg")()
+        self.bn_passes += 1
+
+    def load_grads(self, grads):
+        for name, gt in zip(self.names, grads):
+            v = self._view(self.g, name)
+            if gt.data_ptr() != v.data_ptr():
+                v.copy_(gt.reshape(-1))
+
+    def store_grads(self, grads):
+        for name, gt in zip(self.names, grads):
+            v = self._view(self.g, name)
+            if gt.data_ptr() != v.data_ptr():
+                gt.copy_(v.view(gt.shape))
+
+    # ---- multi-GPU: one all-reduce of the flat buffer per full-batch pass (training/utils.py:31-41) -----------------
+    def all_reduce_mean(self, local_count, global_count):
+        """avg holds the running mean over this rank's `local_count` microbatches; after this call every rank holds the
+        mean over all `global_count` microbatches (exactly the single-process result up to fp32 summation order).
+        The reference's own multi-process weighting (training.py:168 with num_machines > 1) is not a mean and is
+        deliberately not reproduced."""
+        import torch.distributed as dist
+
+        ops.flat_scale(self.avg, self.numel, float(local_count) / float(global_count))
+        dist.all_reduce(self.avg, op=dist.ReduceOp.SUM)
+        pack = torch.cat([self.scal[S_LOSS:S_CORRECT + 1], self.grad_norms])
+        dist.all_reduce(pack, op=dist.ReduceOp.SUM)
+        self.scal[S_LOSS:S_CORRECT + 1] = pack[:2]
+        self.grad_norms.copy_(pack[2:])
 
     def results(self, count):
         """Host read of the step scalars (one synchronisation): mean loss, correct count, grad_norms."""

@@ -13,6 +13,27 @@ from . import lib as L
 
 NUM_SMS = 148
 
+# Optional per-launch timing for bench.py's roofline: set PROFILE = [] to collect
+# (family, algorithmic work, unit, start event, end event) around every wrapped launch on the current stream.
+PROFILE = None
+LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
+_KERNELS_PER_CALL = {"fb_conv_gemm": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
+                     "fb_stem_im2col": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
+                     "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
+                     "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1}
+
+
+def _call(family, work, unit, name, *args):
+    LAUNCHES["count"] += _KERNELS_PER_CALL[name]
+    if PROFILE is None:
+        L.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.call(name, *args)
+    e1.record()
+    PROFILE.append((family, work, unit, e0, e1))
+
 
 def pixel_tile(h, w):
     """128-pixel TMA box (tile_w, tile_h, tile_n) over an [n, h, w] pixel grid; the box always spans full rows."""
@@ -101,9 +122,10 @@ class ConvGemm:
         args.out_sn, args.out_sh, args.out_sw = out_strides
         args.accumulate = int(accumulate)
         self.args = args
+        self.flops = 0.0  # algorithmic FLOPs of this launch (set by Conv2dPlan)
 
     def __call__(self):
-        L.call("fb_conv_gemm", C.byref(self.args))
+        _call("conv_gemm", self.flops, "flop", "fb_conv_gemm", C.byref(self.args))
 
 
 def _weight_box_rows(n_total, n_tile):
@@ -121,7 +143,7 @@ class Conv2dPlan:
     """
 
     def __init__(self, n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
-                 dx_accumulate=False, split=True):
+                 dx_accumulate=False, split=True, alg_k=None):
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.n, self.h, self.w, self.cin, self.cout, self.k, self.stride = n, h, w, cin, cout, k, stride
@@ -129,6 +151,8 @@ class Conv2dPlan:
         self.ho, self.wo = ho, wo
         taps = k * k
         self.taps = taps
+        # algorithmic FLOPs of one forward (= one dgrad = one wgrad): 2 * pixels * cout * K, K = taps*cin (27 for the stem)
+        self.alg_flops = 2.0 * n * ho * wo * cout * (alg_k or taps * cin)
         planes = 2 if (split and x_lo is not None) else 1
         wplanes = 2 if (split and wf_lo is not None) else 1
         tile = pixel_tile(ho, wo)
@@ -171,6 +195,7 @@ class Conv2dPlan:
                     steps.append((phase * planes + ap, bp, dh, dw, (kh * k + kw) * cin))
         self.fwd = ConvGemm(xs, bs, steps, cb_in, tile, ho, n, cout, y, 0, (ho * wo * cout, wo * cout, cout), False,
                             n_tile=n_tile)
+        self.fwd.flops = self.alg_flops
 
         # ---- dgrad
         self.dgrads = []
@@ -191,6 +216,7 @@ class Conv2dPlan:
                             steps.append((0, bp, dh, dw, (kh * k + kw) * cout))
                 self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, 0,
                                             (h * w * cin, w * cin, cin), dx_accumulate, n_tile=n_tile_d))
+                self.dgrads[-1].flops = self.alg_flops
             else:
                 # stride 2: output pixel (2i+ph, 2j+pw) gathers taps kh with (ph + 1 - kh) even: ho = i + (ph+1-kh)/2
                 def taps_for(par):
@@ -206,6 +232,7 @@ class Conv2dPlan:
                         self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, (ph * w + pw) * cin,
                                                     (h * w * cin, 2 * w * cin, 2 * cin), dx_accumulate,
                                                     n_tile=n_tile_d))
+                        self.dgrads[-1].flops = self.alg_flops * len(steps) / wplanes / 9.0
             self.dy_maps_d = dys
 
         # ---- wgrad
@@ -263,26 +290,31 @@ class Conv2dPlan:
 
     def wgrad(self, g_oihw, cin_real=None, mode=0):
         """partial sums -> fixed-order reduction -> g (OIHW fp32 view of the flat gradient buffer)."""
-        L.call("fb_conv_wgrad", C.byref(self.wargs))
+        _call("conv_wgrad", self.alg_flops, "flop", "fb_conv_wgrad", C.byref(self.wargs))
         cin_real = cin_real or self.cin
-        L.call("fb_wgrad_finalize", self.partial.data_ptr(), self.splits, self.cout, cin_real,
-               self.taps if mode == 0 else 9, self.cin, mode, g_oihw.data_ptr())
+        taps = self.taps if mode == 0 else 9
+        nbytes = 4.0 * self.cout * (self.splits * self.taps * self.cin + cin_real * taps)
+        _call("wgrad_finalize", nbytes, "byte", "fb_wgrad_finalize", self.partial.data_ptr(), self.splits, self.cout,
+              cin_real, taps, self.cin, mode, g_oihw.data_ptr())
 
 
 # ---- thin wrappers of the layer kernels ------------------------------------------------------------------------------
 
 def weight_prep(w_oihw, cout, cin, taps, wf_hi, wf_lo, wd_hi=None, wd_lo=None):
-    L.call("fb_weight_prep", w_oihw.data_ptr(), cout, cin, taps, wf_hi.data_ptr(), L.ptr(wf_lo), wf_hi.stride(0),
+    planes = (1 + (wf_lo is not None)) * (1 + (wd_hi is not None))
+    _call("weight_prep", cout * cin * taps * (4.0 + 2.0 * planes), "byte", "fb_weight_prep", w_oihw.data_ptr(), cout, cin,
+          taps, wf_hi.data_ptr(), L.ptr(wf_lo), wf_hi.stride(0),
            L.ptr(wd_hi), L.ptr(wd_lo), wd_hi.stride(0) if wd_hi is not None else 0)
 
 
 def stem_im2col(x, labels, perm, cursor, first, n, p_hi, p_lo, labels_out):
-    L.call("fb_stem_im2col", x.data_ptr(), L.ptr(labels), L.ptr(perm), L.ptr(cursor), first, n, p_hi.data_ptr(),
+    _call("stem_im2col", n * (3072 * 4.0 + 1024 * 64 * 2.0 * (1 + (p_lo is not None))), "byte", "fb_stem_im2col",
+          x.data_ptr(), L.ptr(labels), L.ptr(perm), L.ptr(cursor), first, n, p_hi.data_ptr(),
            L.ptr(p_lo), L.ptr(labels_out))
 
 
 def bn_stats(y, P, Cc, ws, mean, rstd, running_mean, running_var, momentum=0.1, eps=1e-5):
-    L.call("fb_bn_stats", y.data_ptr(), P, Cc, ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(), L.ptr(running_mean),
+    _call("bn_stats", 4.0 * P * Cc, "byte", "fb_bn_stats", y.data_ptr(), P, Cc, ws.data_ptr(), mean.data_ptr(), rstd.data_ptr(), L.ptr(running_mean),
            L.ptr(running_var), momentum, eps)
 
 
@@ -295,7 +327,9 @@ def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, secon
         a.res_hi, a.res_lo = res[0].data_ptr(), L.ptr(res[1])
     a.relu, a.P, a.C = int(relu), P, Cc
     a.out_hi, a.out_lo = out_hi.data_ptr(), L.ptr(out_lo)
-    L.call("fb_bn_apply", C.byref(a))
+    planes = 1 + (out_lo is not None)
+    per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes
+    _call("bn_apply", per_elem * P * Cc, "byte", "fb_bn_apply", C.byref(a))
 
 
 def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dz_accumulate=False):
@@ -305,45 +339,47 @@ def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_o
     a.P, a.C, a.ws = P, Cc, ws.data_ptr()
     a.dgamma, a.dbeta, a.dy_bf16 = dgamma.data_ptr(), dbeta.data_ptr(), dy.data_ptr()
     a.dz_out, a.dz_accumulate = L.ptr(dz_out), int(dz_accumulate)
-    L.call("fb_bn_bwd", C.byref(a))
+    # distinct tensors: dA, y (+ mask) in; dy (+ dz) out -- each counted once although the two-phase kernel reads twice
+    per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0)
+    _call("bn_bwd", per_elem * P * Cc, "byte", "fb_bn_bwd", C.byref(a))
 
 
 def avgpool2_fwd(in_hi, in_lo, n, h, w, c, out_hi, out_lo):
-    L.call("fb_avgpool2_fwd", in_hi.data_ptr(), L.ptr(in_lo), n, h, w, c, out_hi.data_ptr(), L.ptr(out_lo))
+    _call("misc", 0.0, "byte", "fb_avgpool2_fwd", in_hi.data_ptr(), L.ptr(in_lo), n, h, w, c, out_hi.data_ptr(), L.ptr(out_lo))
 
 
 def avgpool2_bwd(dP, n, h, w, c, dX, accumulate=False):
-    L.call("fb_avgpool2_bwd", dP.data_ptr(), n, h, w, c, dX.data_ptr(), int(accumulate))
+    _call("misc", 0.0, "byte", "fb_avgpool2_bwd", dP.data_ptr(), n, h, w, c, dX.data_ptr(), int(accumulate))
 
 
 def head_fwd_bwd(a_hi, a_lo, n, hw, c, fc_w, fc_b, labels, classes, smoothing, ws, scal, loss_slot, correct_slot, d_fcw,
                  d_fcb, dA):
-    L.call("fb_head_fwd_bwd", a_hi.data_ptr(), L.ptr(a_lo), n, hw, c, fc_w.data_ptr(), fc_b.data_ptr(),
+    _call("misc", 0.0, "byte", "fb_head_fwd_bwd", a_hi.data_ptr(), L.ptr(a_lo), n, hw, c, fc_w.data_ptr(), fc_b.data_ptr(),
            labels.data_ptr(), classes, smoothing, ws.data_ptr(), scal.data_ptr(), loss_slot, correct_slot,
            d_fcw.data_ptr(), d_fcb.data_ptr(), dA.data_ptr())
 
 
 def flat_sqnorm(x, n, ws, scal, slot, norms_out=None, cursor=None):
-    L.call("fb_flat_sqnorm", x.data_ptr(), n, ws.data_ptr(), scal.data_ptr(), slot, L.ptr(norms_out), L.ptr(cursor))
+    _call("misc", 0.0, "byte", "fb_flat_sqnorm", x.data_ptr(), n, ws.data_ptr(), scal.data_ptr(), slot, L.ptr(norms_out), L.ptr(cursor))
 
 
 def fd_perturb(theta, g, n, bs, eps, scal, sq_slot, eps_slot, theta_p):
-    L.call("fb_fd_perturb", theta.data_ptr(), g.data_ptr(), n, bs, eps, scal.data_ptr(), sq_slot, eps_slot,
+    _call("misc", 0.0, "byte", "fb_fd_perturb", theta.data_ptr(), g.data_ptr(), n, bs, eps, scal.data_ptr(), sq_slot, eps_slot,
            theta_p.data_ptr())
 
 
 def fd_combine(g, g2, avg, n, scal, eps_slot, cf, cursor, count0, write_g, cf_slot=-1):
-    L.call("fb_fd_combine", g.data_ptr(), g2.data_ptr(), L.ptr(avg), n, scal.data_ptr(), eps_slot, cf, cf_slot,
+    _call("misc", 0.0, "byte", "fb_fd_combine", g.data_ptr(), g2.data_ptr(), L.ptr(avg), n, scal.data_ptr(), eps_slot, cf, cf_slot,
            L.ptr(cursor), count0, int(write_g))
 
 
 def mean_accumulate(g, avg, n, cursor, count0):
-    L.call("fb_mean_accumulate", g.data_ptr(), avg.data_ptr(), n, L.ptr(cursor), count0)
+    _call("misc", 0.0, "byte", "fb_mean_accumulate", g.data_ptr(), avg.data_ptr(), n, L.ptr(cursor), count0)
 
 
 def cursor_add(cursor, delta):
-    L.call("fb_cursor_add", cursor.data_ptr(), delta)
+    _call("misc", 0.0, "byte", "fb_cursor_add", cursor.data_ptr(), delta)
 
 
 def flat_scale(x, n, alpha):
-    L.call("fb_flat_scale", x.data_ptr(), n, alpha)
+    _call("misc", 0.0, "byte", "fb_flat_scale", x.data_ptr(), n, alpha)

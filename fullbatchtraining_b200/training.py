@@ -1,0 +1,280 @@
+"""Reference-facing training routine: the drop-in for ``fullbatch.training.train`` (reference
+fullbatch/training/training.py:50-340) restricted to the hot path -- the full-batch closure with the per-microbatch
+finite-difference regulariser -- plus the SGD sanity branch (:241-286) through the same kernels.
+
+Structure mirrors the reference:
+
+    while step < cfg.hyp.steps:
+        def closure():                                   # training.py:226-234
+            loss = _accumulate_full_gradient()           # :121-185 -> engine (CUDA graph per microbatch, one all-reduce)
+            _modify_gradient_params()                    # :187-215 (global-norm clip)
+            return loss
+        optimizer.step(closure); scheduler.step()        # :237-238 (stock torch.optim.SGD, as in the reference)
+
+What is different on purpose: microbatch gradients never leave the device, the running mean lives in one flat fp32
+buffer whose views are ``param.grad`` (the reference does the same in its distributed branch,
+training/utils.py:36-41), and with several processes each rank owns a contiguous range of the single-process microbatch
+list and the result is the exact global mean (the reference's own multi-process weighting is not a mean).
+"""
+import logging
+import math
+import time
+from collections import defaultdict
+
+import torch
+
+from .engine import FullBatchEngine
+from .modules import GradRegularizer, LabelSmoothCrossEntropyLoss
+
+log = logging.getLogger("fullbatch_b200")
+
+
+def get_loss_fn(cfg_hyp, batch_size=None):
+    """training.py:391-413: label_smoothing not in [None, ""] selects LabelSmoothCrossEntropyLoss (also for 0.0)."""
+    if cfg_hyp.loss_modification is not None:
+        raise ValueError(f"Loss modification {cfg_hyp.loss_modification} is not on the B200 path.")
+    smoothing = cfg_hyp.label_smoothing if cfg_hyp.label_smoothing not in [None, ""] else 0.0
+    return LabelSmoothCrossEntropyLoss(smoothing=smoothing)
+
+
+def optim_interface(model, cfg_hyp):
+    """optimizers.py:10-93 for the configuration the path uses: ``Gradient Descent`` = torch.optim.SGD
+    (:25-28), scheduler cosine-4000 / cosine-decay / none (:75-87) and the linear warm-up wrapper (:89-91,
+    scheduler.py:57-66: lr = base*step/warmup up to `warmup`, the wrapped scheduler starts one step later)."""
+    if cfg_hyp.optim.name != "Gradient Descent" or cfg_hyp.optim.get("line_search", "none") != "none":
+        raise ValueError(f"Optimizer {cfg_hyp.optim.name} / line search is not on the B200 path (closure optimizers "
+                         "from the reference can be passed to train_with_optimizer).")
+    if cfg_hyp.optim_modification.name != "none":
+        raise ValueError("optim_modification is not on the B200 path")
+    params = {k: v for k, v in cfg_hyp.optim.items() if k not in ("name", "line_search")}
+    optimizer = torch.optim.SGD(model.parameters(), **params)
+    warmup = int(cfg_hyp.warmup or 0)
+    sched = cfg_hyp.scheduler
+
+    def after(t):
+        if sched == "cosine-4000":
+            return (1 + math.cos(math.pi * t / 4000)) / 2
+        if sched == "cosine-decay":
+            return (1 + math.cos(math.pi * t / cfg_hyp.steps)) / 2
+        if sched in ["", " ", None]:
+            return 1.0
+        raise ValueError(f"Invalid scheduler {sched} provided.")
+
+    def factor(step):
+        if warmup > 0:
+            return step / warmup if step <= warmup else after(step - warmup - 1)
+        return after(step)
+
+    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, factor)
+    return optimizer, scheduler
+
+
+def _resident_dataset(loader, device):
+    """If the loader iterates a TensorDataset sequentially, keep the whole dataset in HBM (50k CIFAR images = 614 MB)."""
+    ds = getattr(loader, "dataset", None)
+    sampler = getattr(loader, "sampler", None)
+    if isinstance(ds, torch.utils.data.TensorDataset) and isinstance(sampler, torch.utils.data.SequentialSampler):
+        X, Y = ds.tensors
+        return X.to(device=device, dtype=torch.float32).contiguous(), Y.to(device=device, dtype=torch.long).contiguous()
+    return None
+
+
+class Trainer:
+    """State of one ``train`` call; ``step()`` is one iteration of the reference's main loop (training.py:219-339)."""
+
+    def __init__(self, model, trainloader, validloader, setup, cfg):
+        model.train()
+        self.model, self.trainloader, self.validloader, self.setup, self.cfg = model, trainloader, validloader, setup, cfg
+        self.optimizer, self.scheduler = optim_interface(model, cfg.hyp)
+        self.stats = defaultdict(list)
+        self.device = torch.device(setup["device"])
+        if str(cfg.impl.accumulation_dtype) not in ("float", "float32") or \
+                setup.get("dtype", torch.float32) != torch.float32:
+            raise ValueError("the B200 path keeps fp32 master weights and fp32 accumulation "
+                             "(impl.dtype / impl.accumulation_dtype must be float)")
+        if cfg.impl.mixed_precision:
+            raise ValueError("impl.mixed_precision is not on the B200 path; use impl.precision = split | bf16")
+        if cfg.hyp.batch_clip is not None or cfg.hyp.norm_bias.strength > 0 or cfg.hyp.grad_reg.acc_strength != 0:
+            raise ValueError("batch_clip / norm_bias / acc_strength are not on the B200 path yet")
+        self.mb = min(cfg.data.batch_size, cfg.hyp.sub_batch)
+        self.num_blocks = len(trainloader)
+        self.num_chunks = max(cfg.data.batch_size // cfg.hyp.sub_batch, 1)
+        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.rank = torch.distributed.get_rank() if self.dist else 0
+        self.world = torch.distributed.get_world_size() if self.dist else 1
+        loss_fn = get_loss_fn(cfg.hyp, cfg.data.batch_size)
+        self.engine = FullBatchEngine(model, self.mb, precision=cfg.impl.get("precision", "split"),
+                                      label_smoothing=loss_fn.smoothing, device=self.device)
+        self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **cfg.hyp.grad_reg, mixed_precision=False,
+                                       engine=self.engine)
+        self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps
+        self.resident = _resident_dataset(trainloader, self.device) if cfg.impl.get("resident_dataset", True) else None
+        # microbatches per full-batch pass (training.py:65-66,146).  A resident dataset is sharded here by contiguous
+        # microbatch ranges; a streamed loader is taken as this rank's shard already (impl.setup.sharded_loader).
+        local = self.num_blocks * self.num_chunks
+        if self.resident is not None or self.world == 1:
+            self.K = local
+            self.k0, self.k1 = (self.rank * local) // self.world, ((self.rank + 1) * local) // self.world
+        else:
+            if not cfg.impl.setup.get("sharded_loader", False):
+                raise RuntimeError("multi-process training needs a TensorDataset loader (sharded on the device) or "
+                                   "impl.setup.sharded_loader=True with one loader per rank")
+            counts = torch.zeros(self.world, device=self.device, dtype=torch.int64)
+            counts[self.rank] = local
+            torch.distributed.all_reduce(counts)
+            self.K = int(counts.sum())
+            self.k0 = int(counts[:self.rank].sum())
+            self.k1 = self.k0 + local
+        self.step_count = 0
+
+    # training.py:121-185
+    def _accumulate_full_gradient(self):
+        t0 = time.time()
+        eng, cfg, stats = self.engine, self.cfg, self.stats
+        lr = self.optimizer.param_groups[0]["lr"]
+        if self.resident is not None:
+            local = eng.accumulate_resident(self.resident[0], self.resident[1], lr, self.bs, self.eps,
+                                            first=self.k0 * self.mb, count=self.k1 - self.k0, num_norms=self.K,
+                                            norm_offset=self.k0)
+        else:
+            local = eng.accumulate_stream(self.trainloader, lr, self.bs, self.eps, self.K, norm_offset=self.k0)
+        if self.dist:
+            eng.all_reduce_mean(local, self.K)
+        for p, g in zip(self.model.parameters(), eng.grads_list(eng.avg)):
+            p.grad = g  # training.py:183 / training/utils.py:40
+        res = eng.results(self.K)  # the only host synchronisation of the step (training.py:110-115 has several)
+        # _record_stats, training.py:85-119
+        for idx, entry in enumerate(res["grad_norms"].sqrt().tolist()):
+            stats[f"grad_norm_train_{idx}"] += [entry]
+        param_norm = float(eng.theta.double().pow(2).sum())
+        full_grad_norm = float(res["grad_norms"].mean())
+        full_loss = res["loss"] + 0.5 * cfg.hyp.optim.get("weight_decay", 0.0) * param_norm
+        if self.bs != 0:
+            full_loss += lr / 4 * self.bs * full_grad_norm
+        stats["train_loss"] += [res["loss"]]
+        stats["train_acc"] += [res["correct"] / (self.K * self.mb)]
+        stats["train_time"] += [time.time() - t0]
+        stats["param_norm"] += [param_norm]
+        stats["grad_norm"] += [math.sqrt(full_grad_norm)]
+        stats["full_loss"] += [full_loss]
+        return torch.as_tensor(res["loss"], device=self.device)
+
+    @torch.no_grad()
+    def _modify_gradient_params(self):
+        """training.py:187-215 (global clip only; next-row item f1 fuses this into the flat-buffer sweeps)."""
+        cfg, eng, stats = self.cfg, self.engine, self.stats
+        if cfg.hyp.grad_clip is not None:
+            norm_type = float(cfg.hyp.grad_clip_norm)
+            grad_norm = eng.avg.abs().max() if norm_type == float("inf") else torch.norm(eng.avg, norm_type)
+            stats["preclip_gradnorm"] += [grad_norm.item()]
+            if grad_norm > cfg.hyp.grad_clip:
+                eng.avg.mul_(cfg.hyp.grad_clip / (grad_norm + 1e-6))
+                stats["clipped_step"] += [1]
+            else:
+                stats["clipped_step"] += [0]
+
+    def _sgd_epoch(self):
+        """training.py:241-286: one optimizer step per block through the same kernels (regulariser per block)."""
+        eng, cfg, stats = self.engine, self.cfg, self.stats
+        acc = dict(loss=0.0, preds=0.0)
+        datapoints = 0
+        t0 = time.time()
+        for inputs, labels in self.trainloader:
+            inputs = inputs.to(device=self.device, dtype=torch.float32, non_blocking=True)
+            labels = labels.to(device=self.device, dtype=torch.long, non_blocking=True)
+            if inputs.shape[0] != self.mb:
+                continue
+            datapoints += labels.shape[0]
+
+            def closure():
+                loss, correct = eng.microbatch_gradient(inputs, labels)
+                loss, correct = float(loss), float(correct)
+                if self.bs != 0:
+                    eng.regularize(inputs, labels, self.optimizer.param_groups[0]["lr"], self.bs, self.eps)
+                if self.dist:
+                    torch.distributed.all_reduce(eng.g)  # training.py:268-270 (SUM, no division, as the reference)
+                for p, g in zip(self.model.parameters(), eng.grads_list(eng.g)):
+                    p.grad = g
+                if cfg.hyp.grad_clip is not None:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), cfg.hyp.grad_clip,
+                                                   norm_type=float(cfg.hyp.grad_clip_norm))
+                acc["loss"] += loss
+                acc["preds"] += correct
+                return torch.as_tensor(loss, device=self.device)
+
+            self.optimizer.step(closure)
+        stats["train_loss"] += [acc["loss"] / max(self.num_blocks, 1)]
+        stats["train_acc"] += [acc["preds"] / max(datapoints, 1)]
+        stats["train_time"] += [time.time() - t0]
+
+    def step(self, validate=True):
+        cfg = self.cfg
+        self.model.train()
+        if not cfg.hyp.train_stochastic:
+            def gradient_evaluation():  # training.py:226-234
+                loss = self._accumulate_full_gradient()
+                self._modify_gradient_params()
+                return loss
+
+            self.optimizer.step(gradient_evaluation)
+            self.scheduler.step()
+        else:
+            self._sgd_epoch()
+            self.scheduler.step()
+        self.step_count += 1
+        self.engine.sync_bn_counters()
+        step = self.step_count
+        if validate and self.validloader is not None and (step % cfg.impl.validate_every_nth_step == 0
+                                                          or step == cfg.hyp.steps or cfg.dryrun or step == 1):
+            evaluate(self.model, self.validloader, self.stats, self.setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun)
+        if self.rank == 0:
+            log.info(status_message(self.optimizer, self.stats, step))
+        return self.stats["train_loss"][-1]
+
+
+def train(model, trainloader, validloader, setup, cfg):
+    """Drop-in for ``fullbatch.training.train`` (training.py:50): trains `model` (built by ``construct_model``) and
+    returns ``stats`` with the reference's keys."""
+    trainer = Trainer(model, trainloader, validloader, setup, cfg)
+    while trainer.step_count < cfg.hyp.steps:
+        loss = trainer.step()
+        if not math.isfinite(loss):  # training.py:314-317
+            log.info("Nonfinite loss in train loss. Stopping ...")
+            break
+        if cfg.dryrun:
+            break
+    return trainer.stats
+
+
+@torch.no_grad()
+def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False):
+    """training.py:343-388: eval-mode forward over the validation loader (plain PyTorch; not on the hot path)."""
+    loss_fn = torch.nn.CrossEntropyLoss()
+    model.eval()
+    device = torch.device(setup["device"])
+    if stats is None:
+        stats = defaultdict(list)
+    step_loss, step_preds, datapoints = 0.0, 0.0, 0
+    for inputs, labels in dataloader:
+        inputs = inputs.to(device=device, dtype=torch.float32)
+        labels = labels.to(device=device, dtype=torch.long)
+        datapoints += labels.shape[0]
+        outputs = model(inputs)
+        step_loss += loss_fn(outputs, labels).item() * labels.shape[0]
+        step_preds += (outputs.argmax(dim=-1) == labels).float().sum().item()
+        if dryrun:
+            break
+    stats["valid_loss"] += [step_loss / max(datapoints, 1)]
+    stats["valid_acc"] += [step_preds / max(datapoints, 1)]
+    model.train()
+    return stats
+
+
+def status_message(optimizer, stats, step):
+    """training.py:416-426."""
+    def last(key):
+        return stats[key][-1] if len(stats[key]) > 0 else float("nan")
+
+    return (f'Step: {step:<4}| lr: {optimizer.param_groups[0]["lr"]:.4f} | Time: {last("train_time"):4.2f}s |'
+            f'TRAIN loss {last("train_loss"):7.4f} | TRAIN Acc: {last("train_acc"):7.2%} |'
+            f'VAL loss {last("valid_loss"):7.4f} | VAL Acc: {last("valid_acc"):7.2%} |')

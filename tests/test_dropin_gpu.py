@@ -1,0 +1,153 @@
+"""Drop-in surface on the B200: GradRegularizer call protocol (reference fullbatch/models/modules.py:346-348,211-241),
+Trainer/train (fullbatch/training/training.py:50-340) with resident and host-streamed data, SGD sanity branch."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from fullbatchtraining_b200 import construct_model  # noqa: E402
+from fullbatchtraining_b200.config import default_cfg  # noqa: E402
+from fullbatchtraining_b200.data import HostBlockLoader  # noqa: E402
+from fullbatchtraining_b200.modules import GradRegularizer, LabelSmoothCrossEntropyLoss  # noqa: E402
+from fullbatchtraining_b200.training import Trainer, train  # noqa: E402
+from oracle import fb_oracle as O  # noqa: E402
+
+DEV = torch.device("cuda")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def fresh(depth=18):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    return construct_model(dict(name=f"ResNet{depth}", depth=depth), 3, 10)
+
+
+def test_gradregularizer_call_protocol():
+    model = fresh().to(DEV)
+    mb = 16
+    X, Y = O.synthetic_cifar(mb)
+    X, Y = X.to(DEV), Y.to(DEV)
+    optimizer = torch.optim.SGD(model.parameters(), lr=0.8)
+    loss_fn = LabelSmoothCrossEntropyLoss(0.0)
+    # raw gradient by plain autograd, as in the reference README (README.md:36-44)
+    model.train()
+    grads = torch.autograd.grad(loss_fn(model(X), Y), list(model.parameters()))
+    grads = [g.clone() for g in grads]
+    raw = [g.clone() for g in grads]
+    theta_before = [p.detach().clone() for p in model.parameters()]
+    gradreg = GradRegularizer(model, optimizer, loss_fn, block_strength=0.5, eps=1e-2, implementation="finite_diff",
+                              microbatch=mb)
+    assert gradreg.create_graph is False
+    out = gradreg(grads, X, Y, None)
+    assert out is grads  # in place, same list (modules.py:240-241)
+    for p, q in zip(model.parameters(), theta_before):
+        assert torch.equal(p.detach(), q)  # parameters restored exactly (modules.py:237-238)
+    # oracle: forward differences in fp64 starting from the same raw gradient
+    p64 = {k: v.detach().double() for k, v in model.named_parameters()}
+    b64 = {k: (v.detach().clone() if v.dtype == torch.long else v.detach().double()) for k, v in model.named_buffers()}
+    net = O.OracleResNet(18, b64, update_running_stats=False)
+    ref, _, _ = O.forward_differences(net, p64, [g.double() for g in raw], X.double(), Y, 0.8, 0.5, 1e-2)
+    err = rel(O.flat(grads), O.flat(ref))
+    assert err < 0.5, err  # FD term divides operand rounding by eps_n; fp32 itself is ~5e-2 here
+    cos = float((O.flat(grads).double() * O.flat(ref)).sum() / (O.flat(grads).double().norm() * O.flat(ref).norm()))
+    assert cos > 0.98
+
+
+def test_gradregularizer_rejects_unknown_implementation():
+    model = fresh()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    with pytest.raises(ValueError):
+        GradRegularizer(model, opt, None, block_strength=0.5, implementation="nonsense")
+    with pytest.raises(ValueError):
+        GradRegularizer(model, opt, None, block_strength=0.5, implementation="central-differences")
+    g = GradRegularizer(model, opt, None, block_strength=0.0, acc_strength=0.0, implementation="nonsense")
+    grads = [torch.zeros(1)]
+    assert g(grads, None, None, None) is grads  # _pass, modules.py:151-153
+
+
+def _cfg(mb, **extra):
+    o = {"data.batch_size": mb, "hyp.sub_batch": mb, "hyp.warmup": 0, "hyp.steps": 1, "hyp.grad_clip": None}
+    o.update(extra)
+    return default_cfg(o)
+
+
+def test_train_one_step_matches_oracle_and_stream_equals_resident():
+    mb, n = 16, 48
+    X, Y = O.synthetic_cifar(n)
+    setup = dict(device=DEV, dtype=torch.float32)
+    # resident: a TensorDataset loader like the oracle harness builds (data_preparation.py:56-72)
+    ds = torch.utils.data.TensorDataset(X, Y)
+    sampler = torch.utils.data.SequentialSampler(ds)
+    loader = torch.utils.data.DataLoader(ds, batch_size=mb, sampler=sampler, drop_last=True)
+    model = fresh()
+    p64 = {k: v.detach().to(DEV, torch.float64) for k, v in model.named_parameters()}
+    b64 = {k: (v.detach().to(DEV) if v.dtype == torch.long else v.detach().to(DEV, torch.float64))
+           for k, v in model.named_buffers()}
+    stats = train(model, loader, None, setup, _cfg(mb))
+    ref = O.full_batch_step(18, p64, b64, X.to(DEV).double(), Y.to(DEV), mb, lr=0.8, block_strength=0.5, eps=1e-2)
+    assert stats["train_loss"][0] == pytest.approx(float(ref["loss"]), rel=1e-4)
+    assert stats["train_acc"][0] == pytest.approx(float(ref["correct"]) / n)
+    assert stats["grad_norm"][0] == pytest.approx(math.sqrt(float(ref["grad_norms"].mean())), rel=1e-2)
+    full = float(ref["loss"]) + 0.5 * 5e-4 * float(ref["param_norm"]) + 0.8 / 4 * 0.5 * float(ref["grad_norms"].mean())
+    assert stats["full_loss"][0] == pytest.approx(full, rel=1e-2)
+    for k in range(3):
+        assert f"grad_norm_train_{k}" in stats
+    # the SGD update used the accumulated gradient: theta1 = theta0 - lr * (g + wd*theta0)  (nesterov, first step:
+    # buf = d, d + momentum*buf = 1.9 d)
+    g = O.flat(ref["avg"])
+    th0 = O.flat(list(p64.values()))
+    th1 = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+    d = g + 5e-4 * th0
+    expect = th0 - 0.8 * 1.9 * d
+    assert rel(th1 - th0, expect - th0) < 0.3
+    # host-streamed blocks give bit-identical accumulation
+    model_a, model_b = fresh(), fresh()
+    ta = Trainer(model_a, loader, None, setup, _cfg(mb))
+    tb = Trainer(model_b, HostBlockLoader(X, Y, mb), None, setup, _cfg(mb, **{"impl.resident_dataset": False}))
+    assert ta.resident is not None and tb.resident is None
+    ta._accumulate_full_gradient()
+    tb._accumulate_full_gradient()
+    assert torch.equal(ta.engine.avg, tb.engine.avg)
+    assert tb.engine.h2d_bytes == n * (3 * 32 * 32 * 4 + 8)
+
+
+def test_grad_clip_and_lr_schedule():
+    mb, n = 16, 32
+    X, Y = O.synthetic_cifar(n)
+    loader = HostBlockLoader(X, Y, mb)
+    cfg = _cfg(mb, **{"hyp.grad_clip": 0.25, "hyp.warmup": 2, "hyp.steps": 3})
+    model = fresh()
+    trainer = Trainer(model, loader, None, dict(device=DEV, dtype=torch.float32), cfg)
+    lrs = []
+    for _ in range(3):
+        lrs.append(trainer.optimizer.param_groups[0]["lr"])
+        trainer.step(validate=False)
+    # scheduler.py:57-66: lr = base * step / warmup during warm-up, base afterwards (cosine-4000 starts one step later)
+    assert lrs == pytest.approx([0.0, 0.4, 0.8])
+    assert trainer.stats["clipped_step"] == [1, 1, 1]
+    assert float(trainer.engine.avg.norm()) == pytest.approx(0.25, rel=1e-3)
+    assert all(math.isfinite(v) for v in trainer.stats["train_loss"])
+
+
+def test_sgd_sanity_branch_runs_through_the_same_kernels():
+    mb, n = 16, 64
+    X, Y = O.synthetic_cifar(n)
+    loader = HostBlockLoader(X, Y, mb)
+    cfg = _cfg(mb, **{"hyp.train_stochastic": True, "hyp.grad_reg.block_strength": 0.0, "hyp.optim.lr": 0.05,
+                      "hyp.steps": 2, "hyp.grad_clip": None})
+    model = fresh()
+    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    stats = train(model, loader, None, dict(device=DEV, dtype=torch.float32), cfg)
+    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu()
+    assert len(stats["train_loss"]) == 2 and all(math.isfinite(v) for v in stats["train_loss"])
+    assert not torch.equal(before, after)
+    assert stats["train_loss"][1] < 50

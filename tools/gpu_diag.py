@@ -15,6 +15,7 @@ GROUPS = {
     "conv_wgrad": ["tests/test_kernels_gpu.py", "-k", "conv_wgrad"],
     "stem": ["tests/test_kernels_gpu.py", "-k", "stem"],
     "engine": ["tests/test_engine_gpu.py"],
+    "dropin": ["tests/test_dropin_gpu.py"],
 }
 
 
