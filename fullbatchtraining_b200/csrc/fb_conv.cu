@@ -1,10 +1,12 @@
 // Convolutions of the full-batch step as tcgen05 implicit GEMMs (sm_100a).
 //
-//   conv_gemm_kernel : out[128-pixel tile, N_TILE] = sum_steps A_step * B_step^T
+//   conv_gemm_kernel : out[128-pixel tile, N_TILE] = sum_taps sum_cblocks A * B^T, persistent CTAs (one per SM),
 //                      A = NHWC activation boxes fetched by 4-D TMA with a per-tap spatial shift (halo / padding comes
 //                      from TMA out-of-bounds zero fill), B = weight rows, both K-major SWIZZLE_128B tiles, fp32
-//                      accumulation in TMEM.  Serves conv forward, dgrad (stride 1 and the 4 phases of stride 2),
-//                      1x1 convs and the im2col'ed stem.  bf16 hi/lo operand splitting is expressed as extra steps.
+//                      accumulation in double-buffered TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//                      Serves conv forward, dgrad (stride 1 and the 4 phases of stride 2), 1x1 convs and the
+//                      im2col'ed stem.  A pipeline stage holds the hi and lo bf16 planes of both operands; the
+//                      hi*hi + hi*lo + lo*hi products are three MMA groups on the same stage.
 //   wgrad_kernel     : partial[co, (tap,ci)] = sum_pixels dY[pixel, co] * X[pixel + tap, ci]; both operands are
 //                      MN-major (the channel dimension is contiguous in NHWC), split-K over 128-pixel blocks,
 //                      up to 8 (tap, ci-block) accumulators of 64 TMEM columns per CTA.
@@ -75,24 +77,25 @@ static int encode(void* blob, const void* base, int rank, const cuuint64_t* dims
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// conv_gemm_kernel
+// conv_gemm_kernel: persistent, warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), double-buffered TMEM
 // ---------------------------------------------------------------------------------------------------------------
 struct alignas(64) ConvGemmKParams {
   CUtensorMap a_maps[FB_MAX_A_MAPS];
   CUtensorMap b_maps[FB_MAX_B_MAPS];
-  fb_tap_step steps[FB_MAX_TAP_STEPS];
-  int n_steps, cblocks;
+  fb_tap taps[FB_MAX_TAPS];
+  int n_taps, cblocks;
   int tile_w, tile_h, tile_n;
   int grid_h, grid_n;
-  int n_total;
+  int m_tiles, n_tiles;
   float* out;
   long long out_sn, out_sh, out_sw;
   int accumulate;
 };
 
-constexpr int kTileM = 128;                   // pixels per CTA tile == UMMA M
-constexpr int kBlockK = 64;                   // bf16 elements per K block == one 128-byte swizzle row
+constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
+constexpr int kBlockK = 64;                        // bf16 elements per K block == one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KiB
+constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, int grid_h, int& n0, int& h0) {
   if (tile_n == 1) {
@@ -105,16 +108,30 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
   }
 }
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int PA, int PB>
+struct ConvGemmCfg {
+  static constexpr int kBBytes = N_TILE * kBlockK * 2;
+  static constexpr int kStageBytes = PA * kATileBytes + PB * kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * N_TILE;
+  // operand-plane combinations accumulated into one tile: x*w ~= xh*wh + xh*wl + xl*wh (the lo*lo term is dropped)
+  static constexpr int kCombos = (PA == 2 && PB == 2) ? 3 : (PA * PB);
+  static_assert(kStages >= 2, "stage does not fit twice into shared memory");
+};
+
+template <int N_TILE, int PA, int PB>
 __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
-  constexpr int B_BYTES = N_TILE * kBlockK * 2;
-  constexpr int STAGE_BYTES = kATileBytes + B_BYTES;
+  using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
+  constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,55 +141,80 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, N_TILE);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  int n0, h0;
-  tile_origin(blockIdx.x, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-  const int n_tile0 = blockIdx.y * N_TILE;
-  const int total = p.n_steps * p.cblocks;
+  const int k_iters = p.n_taps * p.cblocks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 1);
-        const fb_tap_step st = p.steps[it / p.cblocks];
-        const int cb = it % p.cblocks;
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(sa, &p.a_maps[st.a_map], &full_bar[s], cb * kBlockK, st.dw, h0 + st.dh, n0);
-        tma_load_2d(sa + kATileBytes, &p.b_maps[st.b_map], &full_bar[s], st.b_k0 + cb * kBlockK, n_tile0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, h0;
+        tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+        const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const fb_tap tap = p.taps[t];
+          for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, 1);
+            uint8_t* st = smem + s * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+#pragma unroll
+            for (int pl = 0; pl < PA; ++pl)
+              tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
+                          h0 + tap.dh, n0);
+#pragma unroll
+            for (int pl = 0; pl < PB; ++pl)
+              tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
+                          tap.b_k0 + cb * kBlockK, n_tile0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, N_TILE, 0, 0);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph, 2);
+      int it = 0, tile_i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+        const int buf = tile_i & 1;
+        mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_base = a_base + kATileBytes;
+        const uint32_t tmem_d = tmem_base + buf * N_TILE;
+        for (int ki = 0; ki < k_iters; ++ki, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1, 2);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + PA * kATileBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0);
+          for (int c = 0; c < Cfg::kCombos; ++c) {
+            // combos: (a0,b0), then (a0,b1) if PB == 2, then (a1,b0) if PA == 2
+            const int ap = (PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0;
+            const int bp = (PB == 2 && c == 1) ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_base + ap * kATileBytes + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(b_base + bp * Cfg::kBBytes + k * 32, 16, 1024);
+              tc_mma_bf16(tmem_d, da, db, idesc, (ki | c | k) != 0);
+            }
+          }
+          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&empty_bar[s]);
+        tc_commit(&acc_full[buf]);
       }
-      tc_commit(accum_bar);
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global (fp32 NHWC) ----------------
@@ -181,47 +223,69 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     const int w = r % p.tile_w;
     const int h = (r / p.tile_w) % p.tile_h;
     const int n = r / (p.tile_w * p.tile_h);
-    const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
-    float* dst = p.out + (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw +
-                 n_tile0;
-    mbar_wait(accum_bar, 0, 3);
-    tc_fence_after();
+    int tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      int n0, h0;
+      tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+      const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
+      float* dst = p.out + (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw +
+                   n_tile0;
+      const int buf = tile_i & 1;
+      mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (valid) {
-        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+      for (int c = 0; c < N_TILE / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + buf * N_TILE + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          if (p.accumulate) {
-            const float4 e = d4[j];
-            o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if (p.accumulate) {
+              const float4 e = d4[j];
+              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
+            d4[j] = o;
           }
-          d4[j] = o;
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, N_TILE);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int N_TILE, int STAGES>
-static int launch_conv_gemm(const ConvGemmKParams& kp, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kATileBytes + N_TILE * kBlockK * 2) + 1024 + 256;
+template <int N_TILE, int PA, int PB>
+static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
   static bool configured = false;
   if (!configured) {
-    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
     configured = true;
   }
-  conv_gemm_kernel<N_TILE, STAGES><<<grid, 192, smem, stream>>>(kp);
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  conv_gemm_kernel<N_TILE, PA, PB><<<grid, 192, Cfg::kSmemBytes, stream>>>(kp);
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int N_TILE>
+static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStream_t stream) {
+  if (pa == 2 && pb == 2) return launch_conv_gemm<N_TILE, 2, 2>(kp, stream);
+  if (pa == 1 && pb == 2) return launch_conv_gemm<N_TILE, 1, 2>(kp, stream);
+  if (pa == 1 && pb == 1) return launch_conv_gemm<N_TILE, 1, 1>(kp, stream);
+  set_error("fb_conv_gemm: unsupported operand planes (%d, %d)", pa, pb);
+  return FB_ERR_UNSUPPORTED;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -453,6 +517,72 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// all conv weights of the network in ONE launch: table of per-layer descriptors, block -> layer by binary search
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weight_prep_tile(const float* __restrict__ w, int cout, int cin, int taps, int co0,
+                                                 int ci0, __nv_bfloat16* __restrict__ wf_hi,
+                                                 __nv_bfloat16* __restrict__ wf_lo, long long ld_f,
+                                                 __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo,
+                                                 long long ld_d, float* wtile) {
+  const int row_len = 32 * taps;
+  const int pitch = row_len + 1;
+  for (int i = threadIdx.x; i < 32 * row_len; i += blockDim.x) {
+    const int co = i / row_len, r = i % row_len;
+    wtile[co * pitch + r] = w[((long long)(co0 + co) * cin + ci0) * taps + r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {  // two ci per thread -> 4-byte stores
+    const int ci = (i % 16) * 2, tap = (i / 16) % taps, co = i / (16 * taps);
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(wtile[co * pitch + ci * taps + tap], h0, l0);
+    split_bf16(wtile[co * pitch + (ci + 1) * taps + tap], h1, l1);
+    const long long o = (long long)(co0 + co) * ld_f + (long long)tap * cin + ci0 + ci;
+    *reinterpret_cast<__nv_bfloat162*>(wf_hi + o) = __halves2bfloat162(h0, h1);
+    if (wf_lo) *reinterpret_cast<__nv_bfloat162*>(wf_lo + o) = __halves2bfloat162(l0, l1);
+  }
+  if (wd_hi) {
+    for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {
+      const int co = (i % 16) * 2, tap = (i / 16) % taps, ci = i / (16 * taps);
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(wtile[co * pitch + ci * taps + tap], h0, l0);
+      split_bf16(wtile[(co + 1) * pitch + ci * taps + tap], h1, l1);
+      const long long o = (long long)(ci0 + ci) * ld_d + (long long)tap * cout + co0 + co;
+      *reinterpret_cast<__nv_bfloat162*>(wd_hi + o) = __halves2bfloat162(h0, h1);
+      if (wd_lo) *reinterpret_cast<__nv_bfloat162*>(wd_lo + o) = __halves2bfloat162(l0, l1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) weight_prep_multi_kernel(const float* __restrict__ theta,
+                                                                const fb_wprep_entry* __restrict__ table, int n) {
+  extern __shared__ float wtile[];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {  // last entry with block_start <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const fb_wprep_entry e = table[lo];
+  const int b = blockIdx.x - e.block_start;
+  const float* w = theta + e.w_offset;
+  if (e.cin % 32 != 0) {  // stem: wf[co][k] = w[co][k], k = ci*taps + tap
+    const int k = e.cin * e.taps;
+    __nv_bfloat16* wf_hi = static_cast<__nv_bfloat16*>(e.wf_hi);
+    __nv_bfloat16* wf_lo = static_cast<__nv_bfloat16*>(e.wf_lo);
+    for (int i = b * 256 + threadIdx.x; i < e.cout * k; i += e.n_blocks * 256) {
+      __nv_bfloat16 h, l;
+      split_bf16(w[i], h, l);
+      wf_hi[(i / k) * e.ld_f + i % k] = h;
+      if (wf_lo) wf_lo[(i / k) * e.ld_f + i % k] = l;
+    }
+    return;
+  }
+  const int ci_blocks = e.cin / 32;
+  weight_prep_tile(w, e.cout, e.cin, e.taps, (b / ci_blocks) * 32, (b % ci_blocks) * 32,
+                   static_cast<__nv_bfloat16*>(e.wf_hi), static_cast<__nv_bfloat16*>(e.wf_lo), e.ld_f,
+                   static_cast<__nv_bfloat16*>(e.wd_hi), static_cast<__nv_bfloat16*>(e.wd_lo), e.ld_d, wtile);
+}
+
 // small-cin (stem) variant: wf[co][k] = w[co][k], k = ci*taps + tap, row stride ld_f (padding columns stay untouched)
 __global__ void weight_prep_direct_kernel(const float* __restrict__ w, int cout, int k, __nv_bfloat16* __restrict__ wf_hi,
                                           __nv_bfloat16* __restrict__ wf_lo, long long ld_f) {
@@ -511,19 +641,18 @@ extern "C" int fb_tmap_encode_mat2d(void* host_blob, const void* base, int k, in
 
 extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   FB_REQUIRE(a && a->host_a_maps && a->host_b_maps && a->out, "fb_conv_gemm: null pointer");
-  FB_REQUIRE(a->n_a_maps >= 1 && a->n_a_maps <= FB_MAX_A_MAPS && a->n_b_maps >= 1 && a->n_b_maps <= FB_MAX_B_MAPS,
-             "fb_conv_gemm: map counts out of range (%d, %d)", a->n_a_maps, a->n_b_maps);
-  FB_REQUIRE(a->n_steps >= 1 && a->n_steps <= FB_MAX_TAP_STEPS && a->cblocks >= 1, "fb_conv_gemm: bad step count %d",
-             a->n_steps);
+  FB_REQUIRE(a->a_planes >= 1 && a->a_planes <= 2 && a->b_planes >= 1 && a->b_planes <= 2 && a->n_phases >= 1 &&
+                 a->n_phases * a->a_planes <= FB_MAX_A_MAPS,
+             "fb_conv_gemm: plane / phase counts out of range (%d, %d, %d)", a->a_planes, a->b_planes, a->n_phases);
+  FB_REQUIRE(a->n_taps >= 1 && a->n_taps <= FB_MAX_TAPS && a->cblocks >= 1, "fb_conv_gemm: bad tap count %d", a->n_taps);
   FB_REQUIRE(a->tile_w * a->tile_h * a->tile_n == 128, "fb_conv_gemm: tile %dx%dx%d is not 128 pixels", a->tile_w,
              a->tile_h, a->tile_n);
   FB_REQUIRE(a->tile_n == 1 ? (a->grid_h % a->tile_h == 0) : (a->tile_h == a->grid_h),
              "fb_conv_gemm: tile does not divide the pixel grid (grid_h %d, tile_h %d, tile_n %d)", a->grid_h, a->tile_h,
              a->tile_n);
-  for (int i = 0; i < a->n_steps; ++i)
-    FB_REQUIRE(a->steps[i].a_map >= 0 && a->steps[i].a_map < a->n_a_maps && a->steps[i].b_map >= 0 &&
-                   a->steps[i].b_map < a->n_b_maps,
-               "fb_conv_gemm: step %d references a missing map", i);
+  for (int i = 0; i < a->n_taps; ++i)
+    FB_REQUIRE(a->taps[i].phase >= 0 && a->taps[i].phase < a->n_phases, "fb_conv_gemm: tap %d references a missing map",
+               i);
   if (!(a->n_tile == 64 || a->n_tile == 128 || a->n_tile == 256) || a->n_total % a->n_tile != 0) {
     set_error("fb_conv_gemm: unsupported n_tile %d for n_total %d", a->n_tile, a->n_total);
     return FB_ERR_UNSUPPORTED;
@@ -533,35 +662,28 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
              "fb_conv_gemm: output must be 16-byte aligned with strides multiple of 4");
   ConvGemmKParams kp;
   memset(&kp, 0, sizeof(kp));
-  memcpy(kp.a_maps, a->host_a_maps, size_t(a->n_a_maps) * FB_TMAP_BYTES);
-  memcpy(kp.b_maps, a->host_b_maps, size_t(a->n_b_maps) * FB_TMAP_BYTES);
-  memcpy(kp.steps, a->steps, sizeof(fb_tap_step) * a->n_steps);
-  kp.n_steps = a->n_steps;
+  memcpy(kp.a_maps, a->host_a_maps, size_t(a->n_phases * a->a_planes) * FB_TMAP_BYTES);
+  memcpy(kp.b_maps, a->host_b_maps, size_t(a->b_planes) * FB_TMAP_BYTES);
+  memcpy(kp.taps, a->taps, sizeof(fb_tap) * a->n_taps);
+  kp.n_taps = a->n_taps;
   kp.cblocks = a->cblocks;
   kp.tile_w = a->tile_w;
   kp.tile_h = a->tile_h;
   kp.tile_n = a->tile_n;
   kp.grid_h = a->grid_h;
   kp.grid_n = a->grid_n;
-  kp.n_total = a->n_total;
+  kp.m_tiles = (a->tile_n == 1) ? a->grid_n * (a->grid_h / a->tile_h) : (a->grid_n + a->tile_n - 1) / a->tile_n;
+  kp.n_tiles = a->n_total / a->n_tile;
   kp.out = a->out;
   kp.out_sn = a->out_sn;
   kp.out_sh = a->out_sh;
   kp.out_sw = a->out_sw;
   kp.accumulate = a->accumulate;
-  const int m_tiles = (a->tile_n == 1) ? a->grid_n * (a->grid_h / a->tile_h) : (a->grid_n + a->tile_n - 1) / a->tile_n;
-  dim3 grid(m_tiles, a->n_total / a->n_tile, 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // FB_GEMM_DEEP=1: one CTA per SM with a deep TMA ring; default: two co-resident CTAs per SM with shallower rings,
-  // so that one CTA's TMEM->global epilogue overlaps the other CTA's MMA main loop.
-  static const bool deep = [] {
-    const char* e = getenv("FB_GEMM_DEEP");
-    return e && e[0] == '1';
-  }();
   switch (a->n_tile) {
-    case 64: return deep ? launch_conv_gemm<64, 8>(kp, grid, st) : launch_conv_gemm<64, 4>(kp, grid, st);
-    case 128: return deep ? launch_conv_gemm<128, 6>(kp, grid, st) : launch_conv_gemm<128, 3>(kp, grid, st);
-    default: return launch_conv_gemm<256, 4>(kp, grid, st);
+    case 64: return dispatch_conv_gemm<64>(kp, a->a_planes, a->b_planes, st);
+    case 128: return dispatch_conv_gemm<128>(kp, a->a_planes, a->b_planes, st);
+    default: return dispatch_conv_gemm<256>(kp, a->a_planes, a->b_planes, st);
   }
 }
 
@@ -645,6 +767,15 @@ extern "C" int fb_weight_prep(const float* w_oihw, int cout, int cin, int taps, 
                                                 static_cast<__nv_bfloat16*>(wd_hi), static_cast<__nv_bfloat16*>(wd_lo),
                                                 ld_d);
   }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_weight_prep_multi(const float* theta, const fb_wprep_entry* table_dev, int n_entries, int total_blocks,
+                                    void* stream) {
+  FB_REQUIRE(theta && table_dev && n_entries > 0 && total_blocks > 0, "fb_weight_prep_multi: bad arguments");
+  const size_t smem = size_t(32) * (32 * 9 + 1) * sizeof(float);
+  weight_prep_multi_kernel<<<total_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(theta, table_dev, n_entries);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

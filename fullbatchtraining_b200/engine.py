@@ -60,21 +60,24 @@ class Unit:
         taps = k * k
         self.taps = taps
         bf = dict(device=dev, dtype=torch.bfloat16)
-        self.wf_hi = torch.zeros(cout, taps * x.c, **bf)
-        self.wf_lo = torch.zeros(cout, taps * x.c, **bf) if split else None
-        self.wd_hi = torch.zeros(x.c, taps * cout, **bf) if needs_dx else None
-        self.wd_lo = torch.zeros(x.c, taps * cout, **bf) if (needs_dx and split) else None
+        # two sets of bf16 GEMM operands: [0] from theta (refreshed once per step), [1] from theta' (every microbatch)
+        self.w = []
+        for _ in range(2):
+            self.w.append((torch.zeros(cout, taps * x.c, **bf),
+                           torch.zeros(cout, taps * x.c, **bf) if split else None,
+                           torch.zeros(x.c, taps * cout, **bf) if needs_dx else None,
+                           torch.zeros(x.c, taps * cout, **bf) if (needs_dx and split) else None))
         need = ops.Conv2dPlan.partial_elems(n, h, w, x.c, cout, k, stride)
         eng.partial_elems = max(eng.partial_elems, need)
         self.args = (n, h, w, x.c, cout, k, stride)
         self.dx_accumulate, self.needs_dx = dx_accumulate, needs_dx
-        self.plan = None
+        self.plans = None
 
     def finish(self, eng):
-        self.plan = ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
-                                   self.x.grad if self.needs_dx else None, self.wf_hi, self.wf_lo, self.wd_hi,
-                                   self.wd_lo, eng.partial, dx_accumulate=self.dx_accumulate, split=eng.split,
-                                   alg_k=27 if self.stem else None)
+        self.plans = [ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
+                                     self.x.grad if self.needs_dx else None, *self.w[i], eng.partial,
+                                     dx_accumulate=self.dx_accumulate, split=eng.split,
+                                     alg_k=27 if self.stem else None) for i in range(2)]
 
 
 class Block:
@@ -188,6 +191,11 @@ class FullBatchEngine:
         self.units = [self.stem] + [u for blk in self.blocks for u in (blk.units + ([blk.ds] if blk.ds else []))]
         for u in self.units:
             u.finish(self)
+        self.wprep = []
+        for i in range(2):
+            entries = [(self.offsets[u.conv_name + ".weight"], 64 if u.stem else u.cout, 3 if u.stem else u.cin,
+                        9 if u.stem else u.taps, *u.w[i]) for u in self.units]
+            self.wprep.append(ops.WeightPrepTable(entries, dev))
         self._bn_modules = dict(self.model.named_modules())
         self._graphs = {}
         self.grad_norms = None
@@ -206,16 +214,8 @@ class FullBatchEngine:
         m = self._bn_modules[bn_name]
         return m.running_mean, m.running_var
 
-    def _weight_prep(self, P):
-        for u in self.units:
-            w = self._view(P, u.conv_name + ".weight")
-            if u.stem:
-                ops.weight_prep(w, 64, 3, 9, u.wf_hi, u.wf_lo)
-            else:
-                ops.weight_prep(w, u.cout, u.cin, u.taps, u.wf_hi, u.wf_lo, u.wd_hi, u.wd_lo)
-
     def _unit_forward(self, u, P):
-        u.plan.forward()
+        u.plans[self._pass].forward()
         rm, rv = self._bn_buffers(u.bn_name)
         ops.bn_stats(u.y, u.P, u.cout, self.bn_ws, u.mean, u.rstd, rm, rv, BN_MOMENTUM, BN_EPS)
 
@@ -223,7 +223,9 @@ class FullBatchEngine:
         return self._view(P, u.bn_name + ".weight"), self._view(P, u.bn_name + ".bias")
 
     def _forward(self, P, G, loss_slot, correct_slot):
-        self._weight_prep(P)
+        self._pass = 0 if P is self.theta else 1
+        if self._pass == 1:
+            self.wprep[1](P)  # operands of theta' = theta + eps_n*v; those of theta are refreshed once per step
         u = self.stem
         self._unit_forward(u, P)
         ga, be = self._bn_params(u, P)
@@ -260,11 +262,12 @@ class FullBatchEngine:
         ops.bn_bwd(dA, mask_hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
                    self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out)
         gw = self._view(G, u.conv_name + ".weight")
+        plan = u.plans[self._pass]
         if u.stem:
-            u.plan.wgrad(gw, cin_real=3, mode=1)
+            plan.wgrad(gw, cin_real=3, mode=1)
         else:
-            u.plan.wgrad(gw)
-            u.plan.dgrad()
+            plan.wgrad(gw)
+            plan.dgrad()
 
     def _backward(self, P, G):
         for blk in reversed(self.blocks):
@@ -361,6 +364,7 @@ class FullBatchEngine:
         self.avg.zero_()
         self.scal[S_LOSS:S_CORRECT2 + 1] = 0
         self.cursor.zero_()
+        self.wprep[0](self.theta)  # theta is constant during the step: pass-1 operands once, not per microbatch
 
     def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
                             num_norms=None, norm_offset=0):
@@ -441,6 +445,7 @@ class FullBatchEngine:
             self.begin_step(1)
         self.cursor.zero_()
         self.set_lr(lr)
+        self._pass = 1
         self._program(xs[0], ys[0], None, 0, False, block_strength, eps, accumulate=False, write_g=True, mode="reg")()
         self.bn_passes += 1
 

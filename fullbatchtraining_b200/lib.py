@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfullbatch_b200.so")
 
 FB_TMAP_BYTES = 128
-FB_MAX_TAP_STEPS = 32
+FB_MAX_TAPS = 9
 FB_MAX_A_MAPS = 8
 FB_MAX_B_MAPS = 2
 FB_MAX_WGRAD_TAPS = 9
@@ -23,13 +23,13 @@ i64 = C.c_int64
 f32 = C.c_float
 
 
-class TapStep(C.Structure):
-    _fields_ = [("a_map", C.c_int8), ("b_map", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("b_k0", i32)]
+class Tap(C.Structure):
+    _fields_ = [("phase", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("pad", C.c_int8), ("b_k0", i32)]
 
 
 class ConvGemmArgs(C.Structure):
-    _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("n_a_maps", i32), ("n_b_maps", i32), ("n_steps", i32),
-                ("cblocks", i32), ("steps", TapStep * FB_MAX_TAP_STEPS), ("tile_w", i32), ("tile_h", i32),
+    _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("n_phases", i32), ("a_planes", i32), ("b_planes", i32),
+                ("n_taps", i32), ("cblocks", i32), ("taps", Tap * FB_MAX_TAPS), ("tile_w", i32), ("tile_h", i32),
                 ("tile_n", i32), ("grid_h", i32), ("grid_n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32)]
 
@@ -43,6 +43,11 @@ class WgradArgs(C.Structure):
                 ("cblocks", i32), ("taps", WgradTap * FB_MAX_WGRAD_TAPS), ("slots_per_cta", i32), ("cout", i32),
                 ("cin", i32), ("tile_w", i32), ("tile_h", i32), ("tile_n", i32), ("grid_h", i32), ("grid_n", i32),
                 ("splits", i32), ("partial", vp)]
+
+
+class WprepEntry(C.Structure):
+    _fields_ = [("w_offset", i64), ("cout", i32), ("cin", i32), ("taps", i32), ("block_start", i32), ("n_blocks", i32),
+                ("pad", i32), ("wf_hi", vp), ("wf_lo", vp), ("wd_hi", vp), ("wd_lo", vp), ("ld_f", i64), ("ld_d", i64)]
 
 
 class BnApplyArgs(C.Structure):
@@ -65,6 +70,7 @@ _SIGNATURES = {
     "fb_conv_wgrad": ([C.POINTER(WgradArgs), vp], i32),
     "fb_wgrad_finalize": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "fb_weight_prep": ([vp, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp], i32),
+    "fb_weight_prep_multi": ([vp, vp, i32, i32, vp], i32),
     "fb_stem_im2col": ([vp, vp, vp, vp, i64, i32, vp, vp, vp, vp], i32),
     "fb_bn_stats": ([vp, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp], i32),
     "fb_bn_apply": ([C.POINTER(BnApplyArgs), vp], i32),

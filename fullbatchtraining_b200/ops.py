@@ -17,7 +17,7 @@ NUM_SMS = 148
 # (family, algorithmic work, unit, start event, end event) around every wrapped launch on the current stream.
 PROFILE = None
 LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
-_KERNELS_PER_CALL = {"fb_conv_gemm": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
+_KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
                      "fb_stem_im2col": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
                      "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1}
@@ -101,22 +101,20 @@ def _s2_tap(k):
 class ConvGemm:
     """One launch of fb_conv_gemm with frozen arguments (descriptors are encoded once)."""
 
-    def __init__(self, a_maps, b_maps, steps, cblocks, tile, grid_h, grid_n, n_total, out, out_off, out_strides,
-                 accumulate, n_tile=None):
+    def __init__(self, a_maps, b_maps, n_phases, a_planes, b_planes, taps, cblocks, tile, grid_h, grid_n, n_total, out,
+                 out_off, out_strides, accumulate, n_tile):
         self.a_maps, self.b_maps = a_maps, b_maps
         args = L.ConvGemmArgs()
         args.host_a_maps, args.host_b_maps = a_maps.addr, b_maps.addr
-        args.n_a_maps, args.n_b_maps = a_maps.n, b_maps.n
-        if len(steps) > L.FB_MAX_TAP_STEPS:
-            raise RuntimeError("too many tap steps")
-        args.n_steps, args.cblocks = len(steps), cblocks
-        for i, (am, bm, dh, dw, k0) in enumerate(steps):
-            args.steps[i] = L.TapStep(am, bm, dh, dw, k0)
+        args.n_phases, args.a_planes, args.b_planes = n_phases, a_planes, b_planes
+        if len(taps) > L.FB_MAX_TAPS:
+            raise RuntimeError("too many taps")
+        args.n_taps, args.cblocks = len(taps), cblocks
+        for i, (phase, dh, dw, k0) in enumerate(taps):
+            args.taps[i] = L.Tap(phase, dh, dw, 0, k0)
         args.tile_w, args.tile_h, args.tile_n = tile
         args.grid_h, args.grid_n = grid_h, grid_n
-        m_tiles = grid_n * (grid_h // tile[1]) if tile[2] == 1 else -(-grid_n // tile[2])
-        args.n_total = n_total
-        args.n_tile = n_tile or choose_n_tile(m_tiles, n_total)
+        args.n_total, args.n_tile = n_total, n_tile
         self.out = out
         args.out = out.data_ptr() + out_off * 4
         args.out_sn, args.out_sh, args.out_sw = out_strides
@@ -180,21 +178,15 @@ class Conv2dPlan:
         bs = MapSet(wplanes)
         for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
             encode_mat(bs, pl, t, taps * cin, cout, n_tile)
-        combos = [(0, 0)]
-        if planes == 2 and wplanes == 2:
-            combos = [(0, 0), (0, 1), (1, 0)]
-        elif planes == 2:
-            combos = [(0, 0), (1, 0)]
-        elif wplanes == 2:
-            combos = [(0, 0), (0, 1)]
-        steps = []
+        if planes != wplanes:
+            raise RuntimeError("activation and weight operands must both be split or both be plain bf16")
+        ftaps = []
         for kh in range(k):
             for kw in range(k):
                 phase, dh, dw = tap_geom(kh, kw)
-                for (ap, bp) in combos:
-                    steps.append((phase * planes + ap, bp, dh, dw, (kh * k + kw) * cin))
-        self.fwd = ConvGemm(xs, bs, steps, cb_in, tile, ho, n, cout, y, 0, (ho * wo * cout, wo * cout, cout), False,
-                            n_tile=n_tile)
+                ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
+        self.fwd = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, n, cout, y, 0,
+                            (ho * wo * cout, wo * cout, cout), False, n_tile)
         self.fwd.flops = self.alg_flops
 
         # ---- dgrad
@@ -208,14 +200,13 @@ class Conv2dPlan:
             for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
                 encode_mat(ds, pl, t, taps * cout, cin, n_tile_d)
             if stride == 1:
-                steps = []
+                dtaps = []
                 for kh in range(k):
                     for kw in range(k):
                         dh, dw = (1 - kh, 1 - kw) if k == 3 else (0, 0)
-                        for bp in range(wplanes):
-                            steps.append((0, bp, dh, dw, (kh * k + kw) * cout))
-                self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, 0,
-                                            (h * w * cin, w * cin, cin), dx_accumulate, n_tile=n_tile_d))
+                        dtaps.append((0, dh, dw, (kh * k + kw) * cout))
+                self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, n, cin, dx, 0,
+                                            (h * w * cin, w * cin, cin), dx_accumulate, n_tile_d))
                 self.dgrads[-1].flops = self.alg_flops
             else:
                 # stride 2: output pixel (2i+ph, 2j+pw) gathers taps kh with (ph + 1 - kh) even: ho = i + (ph+1-kh)/2
@@ -224,15 +215,14 @@ class Conv2dPlan:
 
                 for ph in range(2):
                     for pw in range(2):
-                        steps = []
+                        dtaps = []
                         for kh, dh in taps_for(ph):
                             for kw, dw in taps_for(pw):
-                                for bp in range(wplanes):
-                                    steps.append((0, bp, dh, dw, (kh * 3 + kw) * cout))
-                        self.dgrads.append(ConvGemm(dys, ds, steps, cb_out, tile, ho, n, cin, dx, (ph * w + pw) * cin,
-                                                    (h * w * cin, 2 * w * cin, 2 * cin), dx_accumulate,
-                                                    n_tile=n_tile_d))
-                        self.dgrads[-1].flops = self.alg_flops * len(steps) / wplanes / 9.0
+                                dtaps.append((0, dh, dw, (kh * 3 + kw) * cout))
+                        self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, n, cin, dx,
+                                                    (ph * w + pw) * cin, (h * w * cin, 2 * w * cin, 2 * cin),
+                                                    dx_accumulate, n_tile_d))
+                        self.dgrads[-1].flops = self.alg_flops * len(dtaps) / 9.0
             self.dy_maps_d = dys
 
         # ---- wgrad
@@ -305,6 +295,29 @@ def weight_prep(w_oihw, cout, cin, taps, wf_hi, wf_lo, wd_hi=None, wd_lo=None):
     _call("weight_prep", cout * cin * taps * (4.0 + 2.0 * planes), "byte", "fb_weight_prep", w_oihw.data_ptr(), cout, cin,
           taps, wf_hi.data_ptr(), L.ptr(wf_lo), wf_hi.stride(0),
            L.ptr(wd_hi), L.ptr(wd_lo), wd_hi.stride(0) if wd_hi is not None else 0)
+
+
+class WeightPrepTable:
+    """Device table for fb_weight_prep_multi: entries = (w_offset, cout, cin, taps, wf_hi, wf_lo, wd_hi, wd_lo)."""
+
+    def __init__(self, entries, device):
+        arr = (L.WprepEntry * len(entries))()
+        block, nbytes = 0, 0.0
+        for i, (off, cout, cin, taps, wf_hi, wf_lo, wd_hi, wd_lo) in enumerate(entries):
+            nb = (cout // 32) * (cin // 32) if cin % 32 == 0 else 4
+            arr[i] = L.WprepEntry(off, cout, cin, taps, block, nb, 0, wf_hi.data_ptr(), L.ptr(wf_lo), L.ptr(wd_hi),
+                                  L.ptr(wd_lo), wf_hi.stride(0), wd_hi.stride(0) if wd_hi is not None else 0)
+            block += nb
+            planes = (1 + (wf_lo is not None)) * (1 + (wd_hi is not None))
+            nbytes += cout * cin * taps * (4.0 + 2.0 * planes)
+        self.keep = entries
+        self.n, self.blocks, self.nbytes = len(entries), block, nbytes
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = raw.to(device)
+
+    def __call__(self, theta):
+        _call("weight_prep", self.nbytes, "byte", "fb_weight_prep_multi", theta.data_ptr(), self.table.data_ptr(), self.n,
+              self.blocks)
 
 
 def stem_im2col(x, labels, perm, cursor, first, n, p_hi, p_lo, labels_out):

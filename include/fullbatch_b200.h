@@ -30,7 +30,7 @@ extern "C" {
 #define FB_ERR_DRIVER 1003
 
 #define FB_TMAP_BYTES 128 /* sizeof(CUtensorMap) */
-#define FB_MAX_TAP_STEPS 32
+#define FB_MAX_TAPS 9
 #define FB_MAX_A_MAPS 8
 #define FB_MAX_B_MAPS 2
 #define FB_MAX_WGRAD_TAPS 9
@@ -50,23 +50,25 @@ int fb_tmap_encode_mat2d(void* host_blob, const void* base, int k, int rows, int
 
 /* ---- convolutions as tcgen05 implicit GEMMs -------------------------------------------------------------------- */
 
-/* One K-segment of the implicit GEMM: A box = activation map `a_map` shifted by (dh, dw) pixels, B columns start at
- * b_k0 in weight map `b_map`; the segment runs over `cblocks` 64-channel blocks. */
+/* One filter tap of the implicit GEMM: the A box is fetched from activation phase map `phase` shifted by (dh, dw)
+ * pixels; the tap's weights start at column b_k0 of the weight matrix and run over `cblocks` 64-channel blocks. */
 typedef struct {
-  int8_t a_map, b_map, dh, dw;
+  int8_t phase, dh, dw, pad;
   int32_t b_k0;
-} fb_tap_step;
+} fb_tap;
 
-/* out[pixel, n_off + 0..n_total) (+)= sum_steps sum_cblocks  A_step[pixel tile, 64] * B_step[n_tile rows, 64]^T
+/* out[pixel, 0..n_total) (+)= sum_taps sum_cblocks  A_tap[pixel tile, 64] * B_tap[n_tile rows, 64]^T
  * Used for: conv forward (resnets.py:69-73,206-210,285-291 -> cuDNN fprop), dgrad of stride-1 and stride-2 convs
  * (autograd, training.py:82 / modules.py:230), 1x1 shortcut convs and the im2col'ed stem.
- * The 128-pixel M tile is the TMA box tile_w x tile_h x tile_n of the OUTPUT pixel grid (width == tile_w). */
+ * The 128-pixel M tile is the TMA box tile_w x tile_h x tile_n of the OUTPUT pixel grid (width == tile_w).
+ * a_planes / b_planes = 2: operands are bf16 hi+lo pairs, accumulated as hi*hi + hi*lo + lo*hi (a=2,b=2) or
+ * a*b_hi + a*b_lo (a=1,b=2).  A maps are indexed [phase * a_planes + plane], B maps [plane]. */
 typedef struct {
-  const void* host_a_maps; /* n_a_maps x 128 B */
-  const void* host_b_maps; /* n_b_maps x 128 B */
-  int32_t n_a_maps, n_b_maps;
-  int32_t n_steps, cblocks;
-  fb_tap_step steps[FB_MAX_TAP_STEPS];
+  const void* host_a_maps; /* n_phases * a_planes x 128 B */
+  const void* host_b_maps; /* b_planes x 128 B */
+  int32_t n_phases, a_planes, b_planes;
+  int32_t n_taps, cblocks;
+  fb_tap taps[FB_MAX_TAPS];
   int32_t tile_w, tile_h, tile_n; /* product must be 128 */
   int32_t grid_h, grid_n;         /* rows and images of the output pixel grid */
   int32_t n_total, n_tile;        /* GEMM N (output channels) and the per-CTA N tile: 64, 128 or 256 */
@@ -106,6 +108,19 @@ int fb_wgrad_finalize(const float* partial, int splits, int cout, int cin, int t
  * (dgrad); lo pointers may be NULL.  wd_* may be NULL (first layer needs no dgrad).  ld_f / ld_d: row strides. */
 int fb_weight_prep(const float* w_oihw, int cout, int cin, int taps, void* wf_hi, void* wf_lo, int64_t ld_f,
                    void* wd_hi, void* wd_lo, int64_t ld_d, void* stream);
+
+/* All conv weights of the network in one launch.  Table entries live in device memory; entry i owns the blocks
+ * [block_start, block_start + n_blocks) with n_blocks = (cout/32)*(cin/32) (or any count >= 1 for the stem, cin < 32). */
+typedef struct {
+  int64_t w_offset; /* element offset of the OIHW weight inside theta */
+  int32_t cout, cin, taps;
+  int32_t block_start, n_blocks;
+  int32_t pad;
+  void *wf_hi, *wf_lo, *wd_hi, *wd_lo; /* lo / wd pointers may be NULL */
+  int64_t ld_f, ld_d;
+} fb_wprep_entry;
+int fb_weight_prep_multi(const float* theta, const fb_wprep_entry* table_dev, int n_entries, int total_blocks,
+                         void* stream);
 
 /* ---- bandwidth-bound layer kernels ----------------------------------------------------------------------------- */
 
