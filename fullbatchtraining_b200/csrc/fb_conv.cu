@@ -304,7 +304,7 @@ struct alignas(64) WgradKParams {
 };
 
 constexpr int kWgAStages = 2;
-constexpr int kWgBStages = 6;
+constexpr int kWgBStages = 9;
 constexpr int kWgABytes = 2 * kATileBytes;  // two 64-channel chunks of dY: [chunk][128 pixels][64 co]
 constexpr int kWgBBytes = kATileBytes;      // [128 pixels][64 ci]
 constexpr int kWgTmemCols = 512;
@@ -444,6 +444,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 // ---------------------------------------------------------------------------------------------------------------
 // wgrad finalize: deterministic split-K reduction + scatter to OIHW
 // ---------------------------------------------------------------------------------------------------------------
+// fixed-order sum over split-K partials with 8 loads in flight
+__device__ __forceinline__ float sum_splits(const float* __restrict__ src, int splits, long long stride) {
+  float acc = 0.f;
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = src[(s + j) * stride];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j];
+  }
+  for (; s < splits; ++s) acc += src[s * stride];
+  return acc;
+}
+
 // block = (co, 32-wide ci block); blockDim = 32 * taps
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int taps,
                                       int cin_stored, int mode, float* __restrict__ g) {
@@ -458,7 +473,7 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
     float acc = 0.f;
     if (ci0 + cil < cin) {
       const float* src = partial + (long long)co * k_total + tap * cin_stored + ci0 + cil;
-      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+      acc = sum_splits(src, splits, split_stride);
     }
     tile[cil * taps + tap] = acc;
     __syncthreads();
@@ -469,8 +484,7 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
     const int col = ci0 * taps + t;
     if (col < cin * taps) {
       const float* src = partial + (long long)co * k_total + col;
-      float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+      const float acc = sum_splits(src, splits, split_stride);
       g[(long long)co * cin * taps + col] = acc;
     }
   }

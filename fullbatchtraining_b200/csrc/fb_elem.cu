@@ -13,7 +13,7 @@
 
 namespace fb {
 
-constexpr int kMaxChunks = 592;  // 4 reduction blocks per SM
+constexpr int kMaxChunks = 296;  // 2 reduction blocks per SM
 typedef __nv_bfloat16 bf16;
 
 struct alignas(16) bf16x8 {
@@ -62,8 +62,56 @@ __device__ __forceinline__ void store8_bf16(bf16* dst, long long off, const floa
 
 // ---------------------------------------------------------------------------------------------------------------
 // Per-channel column reductions over a [P][C] fp32 matrix: shared skeleton for BN statistics and BN backward.
-// Block = 256 threads = TX float4-columns x TY rows; grid = (chunks, column slabs).  partial[chunk][2][C].
+// Block = 256 threads = TX float4-columns x TY rows; grid = (chunks, column slabs) -> partial[chunk][2][C].
+// The LAST block to finish (atomic ticket) reduces the partials in a fixed order and finalises, so the whole reduction
+// is one launch and still deterministic.
 // ---------------------------------------------------------------------------------------------------------------
+struct BnFinalize {
+  long long P;
+  int chunks;
+  // forward (statistics)
+  float *mean_out, *rstd_out, *running_mean, *running_var;
+  float momentum, eps;
+  // backward
+  float *coef, *dgamma, *dbeta;
+};
+
+// Second stage: block = 8 channels x 32 lanes; lane l sums chunks l, l+32, ... (independent loads in flight), lanes
+// are combined by a fixed shuffle tree -> deterministic.
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int C, BnFinalize f) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int k = lane; k < f.chunks; k += 32) {
+      s1 += partial[(long long)k * 2 * C + c];
+      s2 += partial[(long long)k * 2 * C + C + c];
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane != 0 || c >= C) return;
+  if (!BWD) {
+    const double m = s1 / double(f.P);
+    double var = s2 / double(f.P) - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    f.mean_out[c] = float(m);
+    f.rstd_out[c] = float(1.0 / sqrt(var + double(f.eps)));
+    if (f.running_mean) {
+      const double unbiased = f.P > 1 ? var * double(f.P) / double(f.P - 1) : var;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(m);
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
+    }
+  } else {
+    f.dbeta[c] = float(s1);
+    f.dgamma[c] = float(s2);
+    f.coef[c] = float(s1 / double(f.P));
+    f.coef[C + c] = float(s2 / double(f.P));
+  }
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ y, const float* __restrict__ dA,
                                                         const bf16* __restrict__ mask, const float* __restrict__ mean,
@@ -80,6 +128,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     mu = *reinterpret_cast<const float4*>(mean + c);
     rs = *reinterpret_cast<const float4*>(rstd + c);
   }
+#pragma unroll 8
   for (long long r = r0 + ty; r < r1; r += TY) {
     const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
     if (!BWD) {
@@ -116,69 +165,6 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(dst + c) = s1;
     *reinterpret_cast<float4*>(dst + C + c) = s2;
   }
-}
-
-// Second stage of the column reductions: block = 32 channels x 8 chunk lanes (fixed summation order -> deterministic).
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int chunks, int C, int c, int lane_k,
-                                                double& s1, double& s2) {
-  __shared__ double red[2][8][32];
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (int k = lane_k; k < chunks; k += 8) {
-      a += partial[(long long)k * 2 * C + c];
-      b += partial[(long long)k * 2 * C + C + c];
-    }
-  }
-  red[0][lane_k][threadIdx.x & 31] = a;
-  red[1][lane_k][threadIdx.x & 31] = b;
-  __syncthreads();
-  s1 = 0.0;
-  s2 = 0.0;
-  if (lane_k == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1 += red[0][j][threadIdx.x & 31];
-      s2 += red[1][j][threadIdx.x & 31];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
-                                                                long long P, float* __restrict__ mean,
-                                                                float* __restrict__ rstd,
-                                                                float* __restrict__ running_mean,
-                                                                float* __restrict__ running_var, float momentum,
-                                                                float eps) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_k = threadIdx.x >> 5;
-  double s1, s2;
-  reduce_partials(partial, chunks, C, c, lane_k, s1, s2);
-  if (lane_k != 0 || c >= C) return;
-  const double m = s1 / double(P);
-  double var = s2 / double(P) - m * m;
-  var = var < 0.0 ? 0.0 : var;
-  mean[c] = float(m);
-  rstd[c] = float(1.0 / sqrt(var + double(eps)));
-  if (running_mean) {
-    const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(m);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
-  }
-}
-
-// coef[0][C] = sum dz / P, coef[1][C] = sum dz*xhat / P; dgamma = sum dz*xhat, dbeta = sum dz
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C,
-                                                              long long P, float* __restrict__ coef,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_k = threadIdx.x >> 5;
-  double s1, s2;
-  reduce_partials(partial, chunks, C, c, lane_k, s1, s2);
-  if (lane_k != 0 || c >= C) return;
-  dbeta[c] = float(s1);
-  dgamma[c] = float(s2);
-  coef[c] = float(s1 / double(P));
-  coef[C + c] = float(s2 / double(P));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -532,9 +518,17 @@ extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* m
     return FB_ERR_UNSUPPORTED;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BnFinalize fin = {};
+  fin.P = P;
+  fin.chunks = chunks;
+  fin.mean_out = mean;
+  fin.rstd_out = rstd;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.momentum = momentum;
+  fin.eps = eps;
   bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, P, C, TX, rpc, ws);
-  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, chunks, C, P, mean, rstd, running_mean, running_var,
-                                                            momentum, eps);
+  bn_finalize_kernel<false><<<(C + 7) / 8, 256, 0, st>>>(ws, C, fin);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -558,9 +552,15 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* coef = a->ws + (long long)2 * a->C * kMaxChunks;
+  BnFinalize fin = {};
+  fin.P = a->P;
+  fin.chunks = chunks;
+  fin.coef = coef;
+  fin.dgamma = a->dgamma;
+  fin.dbeta = a->dbeta;
   bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, static_cast<const bf16*>(a->mask_hi), a->mean,
                                                               a->rstd, a->P, a->C, TX, rpc, a->ws);
-  bn_bwd_finalize_kernel<<<(a->C + 31) / 32, 256, 0, st>>>(a->ws, chunks, a->C, a->P, coef, a->dgamma, a->dbeta);
+  bn_finalize_kernel<true><<<(a->C + 7) / 8, 256, 0, st>>>(a->ws, a->C, fin);
   bn_bwd_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, st>>>(*a, coef);
   FB_CUDA(cudaGetLastError());
   return 0;

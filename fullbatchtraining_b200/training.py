@@ -69,6 +69,11 @@ def optim_interface(model, cfg_hyp):
     return optimizer, scheduler
 
 
+def shard_range(rank, world, num_microbatches):
+    """Contiguous range [k0, k1) of the single-process microbatch list owned by `rank` (sizes differ by at most 1)."""
+    return (rank * num_microbatches) // world, ((rank + 1) * num_microbatches) // world
+
+
 def _resident_dataset(loader, device):
     """If the loader iterates a TensorDataset sequentially, keep the whole dataset in HBM (50k CIFAR images = 614 MB)."""
     ds = getattr(loader, "dataset", None)
@@ -114,7 +119,7 @@ class Trainer:
         local = self.num_blocks * self.num_chunks
         if self.resident is not None or self.world == 1:
             self.K = local
-            self.k0, self.k1 = (self.rank * local) // self.world, ((self.rank + 1) * local) // self.world
+            self.k0, self.k1 = shard_range(self.rank, self.world, local)
         else:
             if not cfg.impl.setup.get("sharded_loader", False):
                 raise RuntimeError("multi-process training needs a TensorDataset loader (sharded on the device) or "

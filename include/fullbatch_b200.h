@@ -131,7 +131,7 @@ int fb_stem_im2col(const float* x, const int64_t* labels, const int64_t* perm, c
                    int n, void* patches_hi, void* patches_lo, int64_t* labels_out, void* stream);
 
 /* Train-mode BatchNorm statistics over y[P][C] (resnets.py:71 / torch.nn.BatchNorm2d): mean, rstd = 1/sqrt(var+eps)
- * (biased var) and the running-stat EMA with unbiased variance.  ws: >= 2*C*1024 floats. */
+ * (biased var) and the running-stat EMA with unbiased variance.  ws: >= 2*C*1024 floats of scratch. */
 int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* mean, float* rstd, float* running_mean,
                 float* running_var, float momentum, float eps, void* stream);
 
@@ -149,7 +149,7 @@ int fb_bn_apply(const fb_bn_apply_args* args, void* stream);
 
 /* BatchNorm(+ReLU) backward.  dz = dA * [mask_hi > 0] (mask_hi NULL: no ReLU).  Writes dgamma/dbeta (fp32, C each),
  * dY as bf16 (tensor-core operand), and optionally dz as fp32 (`dz_out`, the identity-branch gradient; if
- * dz_accumulate != 0 it is added to dz_out instead of overwriting).  ws: >= 2*C*1024 floats. */
+ * dz_accumulate != 0 it is added to dz_out instead of overwriting).  ws: >= 2*C*1024 floats of scratch. */
 typedef struct {
   const float* dA;
   const void* mask_hi;

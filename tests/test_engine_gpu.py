@@ -65,7 +65,8 @@ def dump(name, d):
     print(name, json.dumps(d))
 
 
-@pytest.mark.parametrize("depth,mb,n", [(18, 16, 32), (18, 128, 256)], ids=["r18_mb16", "r18_mb128"])
+@pytest.mark.parametrize("depth,mb,n", [(18, 16, 32), (18, 128, 256), (152, 8, 16)],
+                         ids=["r18_mb16", "r18_mb128", "r152_mb8"])
 def test_full_batch_step_matches_oracle(depth, mb, n):
     model, params, buffers, X, Y = setup_case(depth, mb, n)
     ref64, buf64 = oracle_run(depth, params, buffers, X, Y, mb, torch.float64)
@@ -94,14 +95,24 @@ def test_full_batch_step_matches_oracle(depth, mb, n):
     rep.update(e_new_raw=rel(raw, O.flat(k64["raw"])), e32_raw=rel(O.flat(k32["raw"]), O.flat(k64["raw"])),
                e_new_reg=rel(reg, O.flat(k64["reg"])), e32_reg=rel(O.flat(k32["reg"]), O.flat(k64["reg"])),
                cos_raw=cos(raw, O.flat(k64["raw"])), cos_reg=cos(reg, O.flat(k64["reg"])))
+    # scalar outputs: bounded by a multiple of the fp32 reference's own deviation from fp64 (ResNet-152 at batch 8 is so
+    # ill-conditioned at initialisation that fp32 itself is 9% / 90% off in the raw / regularised gradient)
+    l64, l32 = float(ref64["loss"]), float(ref32["loss"])
+    gn64, gn32 = ref64["grad_norms"].double().cpu(), ref32["grad_norms"].double().cpu()
+    e32_loss = abs(l32 - l64) / abs(l64)
+    e32_gn = float(((gn32 - gn64).abs() / gn64).max())
+    rep.update(e32_loss=e32_loss, e32_grad_norms=e32_gn,
+               e_new_loss=abs(res["loss"] - l64) / abs(l64),
+               e_new_grad_norms=float(((res["grad_norms"].double().cpu() - gn64).abs() / gn64).max()))
     dump(f"r{depth}_mb{mb}_n{n}", rep)
-    assert abs(res["loss"] - float(ref64["loss"])) < 1e-4 * abs(float(ref64["loss"]))
+    assert rep["e_new_loss"] <= max(1e-4, RATIO_RAW * e32_loss)
+    assert rep["e_new_grad_norms"] <= max(2e-2, RATIO_RAW * e32_gn)
     assert res["correct"] == float(ref64["correct"])
-    assert torch.allclose(res["grad_norms"].double().cpu(), ref64["grad_norms"].double().cpu(), rtol=2e-2)
     assert rep["e_new_raw"] <= RATIO_RAW * max(rep["e32_raw"], FLOOR_RAW)
     assert rep["e_new_reg"] <= RATIO_REG * max(rep["e32_reg"], FLOOR_REG)
     assert e_new <= RATIO_REG * max(e32, FLOOR_REG)
-    assert rep["cos_avg"] > 0.98
+    if e32 < 0.2:
+        assert rep["cos_avg"] > 0.98
 
 
 def test_running_stats_and_determinism():
@@ -148,3 +159,18 @@ def test_no_regulariser_pass_is_plain_mean():
     ref = O.full_batch_step(depth, p, b, X.double(), Y, mb, lr=0.8, block_strength=0.0)
     assert rel(eng.avg, O.flat(ref["avg"])) < 2e-2  # mb=16: fp32 floor ~2.5e-3, split ~1e-2
     assert K == 2
+
+
+def test_shuffled_order_through_permutation():
+    """hyp.shuffle (data_preparation.py:53-54): microbatches are gathered through an index tensor on the device."""
+    depth, mb, n = 18, 16, 48
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(3)).to(DEV)
+    eng = FullBatchEngine(model, mb, precision="split")
+    K = eng.accumulate_resident(X, Y, 0.8, 0.5, 1e-2, perm=perm)
+    p = {k: v.to(DEV, torch.float64) for k, v in params.items()}
+    b = {k: (v.to(DEV) if v.dtype == torch.long else v.to(DEV, torch.float64)) for k, v in buffers.items()}
+    ref = O.full_batch_step(depth, p, b, X.double(), Y, mb, order=perm, **HYP)
+    assert K == 3
+    assert abs(eng.results(K)["loss"] - float(ref["loss"])) < 1e-4 * float(ref["loss"])
+    assert rel(eng.avg, O.flat(ref["avg"])) < RATIO_REG * 0.08

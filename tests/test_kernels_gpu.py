@@ -192,7 +192,7 @@ def test_stem_im2col_and_stem_conv():
 def test_bn_stats(P, Cc):
     g = torch.Generator(device="cuda").manual_seed(P + Cc)
     y = torch.randn(P, Cc, device=DEV, generator=g) * 2 + 0.5
-    ws = torch.empty(2 * Cc * 1024, device=DEV)
+    ws = torch.zeros(2 * Cc * 1024, device=DEV)  # zero-initialised: holds the block ticket
     mean, rstd = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
     rm, rv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
     ops.bn_stats(y, P, Cc, ws, mean, rstd, rm, rv)
@@ -217,7 +217,7 @@ def test_bn_apply_and_backward(variant):
     beta2 = torch.randn(Cc, device=DEV, generator=g) * 0.1
     res = torch.randn(P, Cc, device=DEV, generator=g)
     res_hi, res_lo = split(res)
-    ws = torch.empty(2 * Cc * 1024, device=DEV)
+    ws = torch.zeros(2 * Cc * 1024, device=DEV)  # zero-initialised: holds the block ticket
     mean, rstd = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
     mean2, rstd2 = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
     ops.bn_stats(y, P, Cc, ws, mean, rstd, None, None)
