@@ -170,28 +170,48 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // BN apply (+ second normalised branch, + residual, + ReLU) -> bf16 hi/lo
 // ---------------------------------------------------------------------------------------------------------------
+// Per-thread channel parameters are loop invariant: the grid stride (gridDim.x * 2048 elements) is a multiple of C for
+// every channel count of the ResNet family (C | 2048), so they are loaded once per thread.
+struct BnAffine {
+  float mu[8], scale[8], shift[8];
+  __device__ __forceinline__ void load(const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                       int c) {
+    float rs[8], ga[8];
+    load8(mean + c, mu);
+    load8(rstd + c, rs);
+    load8(gamma + c, ga);
+    load8(beta + c, shift);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) scale[j] = rs[j] * ga[j];
+  }
+};
+
 __global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
   const long long total8 = a.P * a.C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
-       i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool invariant = (stride * 8) % a.C == 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  BnAffine p1, p2;
+  if (i < total8) {
+    const int c = int((i * 8) % a.C);
+    p1.load(a.mean, a.rstd, a.gamma, a.beta, c);
+    if (a.y2) p2.load(a.mean2, a.rstd2, a.gamma2, a.beta2, c);
+  }
+  for (; i < total8; i += stride) {
     const long long off = i * 8;
-    const int c = int(off % a.C);
-    float y[8], mu[8], rs[8], ga[8], be[8], o[8];
+    if (!invariant) {
+      const int c = int(off % a.C);
+      p1.load(a.mean, a.rstd, a.gamma, a.beta, c);
+      if (a.y2) p2.load(a.mean2, a.rstd2, a.gamma2, a.beta2, c);
+    }
+    float y[8], o[8];
     load8(a.y + off, y);
-    load8(a.mean + c, mu);
-    load8(a.rstd + c, rs);
-    load8(a.gamma + c, ga);
-    load8(a.beta + c, be);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (y[j] - mu[j]) * (rs[j] * ga[j]) + be[j];
+    for (int j = 0; j < 8; ++j) o[j] = (y[j] - p1.mu[j]) * p1.scale[j] + p1.shift[j];
     if (a.y2) {
       load8(a.y2 + off, y);
-      load8(a.mean2 + c, mu);
-      load8(a.rstd2 + c, rs);
-      load8(a.gamma2 + c, ga);
-      load8(a.beta2 + c, be);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (y[j] - mu[j]) * (rs[j] * ga[j]) + be[j];
+      for (int j = 0; j < 8; ++j) o[j] += (y[j] - p2.mu[j]) * p2.scale[j] + p2.shift[j];
     }
     if (a.res_hi) {
       float rh[8];
@@ -216,13 +236,31 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
 // ---------------------------------------------------------------------------------------------------------------
 // BN backward apply: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) -> bf16; optional dz (fp32) output
 // ---------------------------------------------------------------------------------------------------------------
+struct BnBwdCoef {
+  float mu[8], rs[8], grs[8], c1[8], c2[8];
+  __device__ __forceinline__ void load(const fb_bn_bwd_args& a, const float* coef, int c) {
+    float ga[8];
+    load8(a.mean + c, mu);
+    load8(a.rstd + c, rs);
+    load8(a.gamma + c, ga);
+    load8(coef + c, c1);
+    load8(coef + a.C + c, c2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) grs[j] = ga[j] * rs[j];
+  }
+};
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, const float* __restrict__ coef) {
   const long long total8 = a.P * a.C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
-       i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool invariant = (stride * 8) % a.C == 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  BnBwdCoef p;
+  if (i < total8) p.load(a, coef, int((i * 8) % a.C));
+  for (; i < total8; i += stride) {
     const long long off = i * 8;
-    const int c = int(off % a.C);
-    float d[8], y[8], mu[8], rs[8], ga[8], c1[8], c2[8], o[8];
+    if (!invariant) p.load(a, coef, int(off % a.C));
+    float d[8], y[8], o[8];
     load8(a.dA + off, d);
     if (a.mask_hi) {
       float m[8];
@@ -231,15 +269,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, con
       for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
     }
     load8(a.y + off, y);
-    load8(a.mean + c, mu);
-    load8(a.rstd + c, rs);
-    load8(a.gamma + c, ga);
-    load8(coef + c, c1);
-    load8(coef + a.C + c, c2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xhat = (y[j] - mu[j]) * rs[j];
-      o[j] = (ga[j] * rs[j]) * (d[j] - c1[j] - xhat * c2[j]);
+      const float xhat = (y[j] - p.mu[j]) * p.rs[j];
+      o[j] = p.grs[j] * (d[j] - p.c1[j] - xhat * p.c2[j]);
     }
     store8_bf16(static_cast<bf16*>(a.dy_bf16), off, o);
     if (a.dz_out) {
