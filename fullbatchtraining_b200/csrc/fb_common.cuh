@@ -160,7 +160,55 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// same, 16 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue store of a 32-row x 16-column fp32 block that a warp holds one ROW per lane (the tcgen05.ld 32x32b layout).
+// Writing it straight from registers makes every store instruction touch 32 different rows (32 half-filled sectors);
+// instead the block is transposed through a per-warp shared-memory patch (32 x 20 floats, conflict free) so that one
+// instruction writes 8 rows x 64 contiguous bytes (16 full sectors).  row_off / valid describe THIS lane's row.
+constexpr int kEpiPitch = 20;                       // floats per staged row
+constexpr int kEpiWarpFloats = 32 * kEpiPitch;      // 2560 B per warp
+__device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
+                                                  bool valid, int col0, bool accumulate, int lane) {
+  float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int sub = lane >> 2;
+  const int c4 = (lane & 3) * 4;
+  float4* d[4];
+  float4 e[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // all read-modify-write loads first: four independent requests in flight
+    const int row = i * 8 + sub;
+    const long long off = __shfl_sync(0xffffffffu, row_off, row);
+    ok[i] = __shfl_sync(0xffffffffu, valid ? 1 : 0, row) != 0;
+    d[i] = reinterpret_cast<float4*>(base + off + col0 + c4);
+    e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (accumulate && ok[i]) e[i] = *d[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + sub;
+    float4 o = *reinterpret_cast<const float4*>(stage + row * kEpiPitch + c4);
+    o.x += e[i].x; o.y += e[i].y; o.z += e[i].z; o.w += e[i].w;
+    if (ok[i]) *d[i] = o;
+  }
+  __syncwarp();
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

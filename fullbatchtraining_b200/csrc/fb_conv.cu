@@ -95,7 +95,8 @@ struct alignas(64) ConvGemmKParams {
 constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
 constexpr int kBlockK = 64;                        // bf16 elements per K block == one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KiB
-constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int kEpiStageBytes = 4 * kEpiWarpFloats * 4;     // 4 epilogue warps x 32 x 20 floats
+constexpr int kSmemBudget = 227 * 1024 - 2048 - kEpiStageBytes;
 
 __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, int grid_h, int& n0, int& h0) {
   if (tile_n == 1) {
@@ -114,10 +115,16 @@ struct ConvGemmCfg {
   static constexpr int kStageBytes = PA * kATileBytes + PB * kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kTmemCols = 2 * N_TILE;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 + 256;
+  // An SS-mode tcgen05.mma re-reads its 128x16 A tile from shared memory (~64 clocks) whatever N is, so N = 64
+  // instructions run the tensor pipe at half rate.  With split weights and a 64-wide tile the hi and lo B tiles are
+  // adjacent in the stage: ONE N = 128 instruction computes A*[B_hi;B_lo]^T into two 64-column halves that the epilogue
+  // adds ("stacked" mode; it also picks up the tiny lo*lo term).
+  static constexpr bool kStack = (PB == 2 && N_TILE == 64);
+  static constexpr int kUmmaN = kStack ? 128 : N_TILE;
+  static constexpr int kTmemCols = 2 * kUmmaN;
   // operand-plane combinations accumulated into one tile: x*w ~= xh*wh + xh*wl + xl*wh (the lo*lo term is dropped)
-  static constexpr int kCombos = (PA == 2 && PB == 2) ? 3 : (PA * PB);
+  static constexpr int kCombos = kStack ? PA : ((PA == 2 && PB == 2) ? 3 : (PA * PB));
   static_assert(kStages >= 2, "stage does not fit twice into shared memory");
 };
 
@@ -127,7 +134,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
@@ -186,13 +194,13 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
       int it = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
         const int buf = tile_i & 1;
         mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * N_TILE;
+        const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
         for (int ki = 0; ki < k_iters; ++ki, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1, 2);
@@ -201,9 +209,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
           const uint32_t b_base = a_base + PA * kATileBytes;
 #pragma unroll
           for (int c = 0; c < Cfg::kCombos; ++c) {
-            // combos: (a0,b0), then (a0,b1) if PB == 2, then (a1,b0) if PA == 2
-            const int ap = (PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0;
-            const int bp = (PB == 2 && c == 1) ? 1 : 0;
+            // stacked: combo c = A plane c against [B_hi;B_lo]; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
+            const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
+            const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               const uint64_t da = make_smem_desc_sw128(a_base + ap * kATileBytes + k * 32, 16, 1024);
@@ -217,41 +225,39 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       }
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global (fp32 NHWC) ----------------
+    // ---------------- epilogue: TMEM -> registers -> smem transpose -> coalesced global stores (fp32 NHWC) ----------
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const int w = r % p.tile_w;
     const int h = (r / p.tile_w) % p.tile_h;
     const int n = r / (p.tile_w * p.tile_h);
+    float* stage = epi_stage + q * kEpiWarpFloats;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       int n0, h0;
       tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
       const int n_tile0 = (tile % p.n_tiles) * N_TILE;
       const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
-      float* dst = p.out + (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw +
-                   n_tile0;
+      const long long row_off =
+          (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw + n_tile0;
       const int buf = tile_i & 1;
       mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < N_TILE / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + buf * N_TILE + c * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+      for (int c = 0; c < N_TILE / 16; ++c) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kUmmaN + c * 16;
+        tmem_ld_32x16(taddr, v);
+        if (Cfg::kStack) {
+          uint32_t v2[16];
+          tmem_ld_32x16(taddr + 64, v2);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            if (p.accumulate) {
-              const float4 e = d4[j];
-              o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-            }
-            d4[j] = o;
-          }
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
         }
+        warp_store_rows16(stage, v, p.out, row_off, valid, c * 16, p.accumulate != 0, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -289,6 +295,292 @@ static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// conv3x3_kernel: 3x3 / stride 1 / pad 1 convolutions (forward and dgrad) on feature maps whose rows are >= 1024 bytes
+// of one 64-channel block (W >= 8 pixels) and whose 256-pixel tiles are whole image rows.
+//
+// The generic kernel re-fetches the A box once per filter tap (9x).  Here the producer fetches, per column shift
+// dw in {-1,0,1} and 64-channel block, ONE haloed box of (2*TH + 2) image rows (TH = 128 / W rows per 128-pixel half);
+// the three row shifts dh are then 1024-byte-aligned VIEWS of that box (offset (dh+1) * W * 128 bytes), so the
+// SWIZZLE_128B pattern is preserved and no data is moved.  A CTA tile is 256 pixels = two UMMA M=128 halves that share
+// every weight tile.  Traffic per MMA-clock drops from ~125 to ~57 bytes (N_TILE 64) / ~37 bytes (N_TILE 128).
+// ---------------------------------------------------------------------------------------------------------------
+// Optional in-kernel cycle accounting of CTA 0 (FB_KERNEL_DEBUG=1): where do the producer / MMA / epilogue roles wait?
+__device__ long long g_dbg[32];
+
+struct alignas(64) Conv3x3KParams {
+  CUtensorMap a_maps[2];  // [plane]: box = 64 ch x W x (2*TH+2) rows x 1 image
+  CUtensorMap b_maps[2];  // [plane]: box = 64 x N_TILE weight rows
+  int b_k0[3][3];         // [dw+1][dh+1] -> first K column of that tap in the weight matrix
+  int cblocks;
+  int w, h, n;            // feature map and images
+  int th;                 // rows per 128-pixel half
+  int n_tiles;
+  float* out;
+  long long out_sn, out_sh, out_sw;
+  int accumulate;
+  int debug;
+};
+
+#define FB_DBG_WAIT(slot, call)                      \
+  do {                                               \
+    if (dbg) {                                       \
+      const long long _t = clock64();                \
+      call;                                          \
+      dbg_acc[slot & 1] += clock64() - _t;           \
+    } else {                                         \
+      call;                                          \
+    }                                                \
+  } while (0)
+
+template <int N_TILE, int PA, int PB>
+struct Conv3x3Cfg {
+  static constexpr int kBBytes = N_TILE * kBlockK * 2;
+  static constexpr int kBStageBytes = PB * kBBytes;
+  static constexpr int kAStages = 2;
+  static constexpr bool kStack = (PB == 2 && N_TILE == 64);  // see ConvGemmCfg
+  static constexpr int kUmmaN = kStack ? 128 : N_TILE;
+  static constexpr int kCombos = kStack ? PA : ((PA == 2 && PB == 2) ? 3 : (PA * PB));
+  static constexpr int kTmemCols = 4 * kUmmaN;  // 2 halves x 2 buffers
+};
+
+template <int N_TILE, int PA, int PB>
+__global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__ Conv3x3KParams p, int a_box_bytes,
+                                                         int b_stages) {
+  using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage_bytes = PA * a_box_bytes;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kAStages * a_stage_bytes;
+  float* epi_stage = reinterpret_cast<float*>(smem_b + b_stages * Cfg::kBStageBytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + b_stages * Cfg::kBStageBytes + kEpiStageBytes);
+  uint64_t* a_empty = a_full + Cfg::kAStages;
+  uint64_t* b_full = a_empty + Cfg::kAStages;
+  uint64_t* b_empty = b_full + 8;
+  uint64_t* acc_full = b_empty + 8;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.h / (2 * p.th);
+  const int m_tiles = p.n * tiles_per_img;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int row_bytes = p.w * 128;          // one image row of one 64-channel block
+  const int half_bytes = p.th * row_bytes;  // 128 pixels = 16 KiB
+  const bool dbg = p.debug && blockIdx.x == 0;
+  const long long t_start = clock64();
+  long long dbg_acc[2] = {0, 0};  // register accumulators (slot parity), flushed once per role
+  long long dbg_issue = 0, dbg_acc_empty = 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int n0 = mt / tiles_per_img, h0 = (mt % tiles_per_img) * 2 * p.th;
+        const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+        for (int dwi = 0; dwi < 3; ++dwi) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            const int as = ia % Cfg::kAStages;
+            FB_DBG_WAIT(0, mbar_wait(&a_empty[as], ((ia / Cfg::kAStages) & 1) ^ 1, 21));
+            mbar_arrive_expect_tx(&a_full[as], a_stage_bytes);
+#pragma unroll
+            for (int pl = 0; pl < PA; ++pl)
+              tma_load_4d(smem_a + as * a_stage_bytes + pl * a_box_bytes, &p.a_maps[pl], &a_full[as], cb * kBlockK,
+                          dwi - 1, h0 - 1, n0);
+            ++ia;
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const int bs = ib % b_stages;
+              FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 22));
+              mbar_arrive_expect_tx(&b_full[bs], Cfg::kBStageBytes);
+#pragma unroll
+              for (int pl = 0; pl < PB; ++pl)
+                tma_load_2d(smem_b + bs * Cfg::kBStageBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &b_full[bs],
+                            p.b_k0[dwi][dhi] + cb * kBlockK, n_tile0);
+              ++ib;
+            }
+          }
+        }
+      }
+      if (dbg) {
+        g_dbg[0] += dbg_acc[0];
+        g_dbg[1] += dbg_acc[1];
+        g_dbg[10] += clock64() - t_start;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
+      int ia = 0, ib = 0, tile_i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+        const int buf = tile_i & 1;
+        {
+          const long long _t = clock64();
+          mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 24);
+          dbg_acc_empty += clock64() - _t;
+        }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 2 * Cfg::kUmmaN;
+        bool first = true;
+        for (int dwi = 0; dwi < 3; ++dwi) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            const int as = ia % Cfg::kAStages;
+            FB_DBG_WAIT(2, mbar_wait(&a_full[as], (ia / Cfg::kAStages) & 1, 23));
+            const uint32_t a_base = smem_u32(smem_a + as * a_stage_bytes);
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const int bs = ib % b_stages;
+              FB_DBG_WAIT(3, mbar_wait(&b_full[bs], (ib / b_stages) & 1, 25));
+              tc_fence_after();
+              const uint32_t b_base = smem_u32(smem_b + bs * Cfg::kBStageBytes);
+              const long long t_issue = dbg ? clock64() : 0;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t a_view = a_base + dhi * row_bytes + half * half_bytes;
+#pragma unroll
+                for (int c = 0; c < Cfg::kCombos; ++c) {
+                  const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
+                  const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(a_view + ap * a_box_bytes + k * 32, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(b_base + bp * Cfg::kBBytes + k * 32, 16, 1024);
+                    tc_mma_bf16(tmem_d + half * Cfg::kUmmaN, da, db, idesc, (first && c == 0 && k == 0) ? 0u : 1u);
+                  }
+                }
+              }
+              first = false;
+              tc_commit(&b_empty[bs]);
+              if (dbg) dbg_issue += clock64() - t_issue;
+              ++ib;
+            }
+            tc_commit(&a_empty[as]);
+            ++ia;
+          }
+        }
+        tc_commit(&acc_full[buf]);
+      }
+      if (dbg) {
+        g_dbg[2] += dbg_acc[0];
+        g_dbg[3] += dbg_acc[1];
+        g_dbg[4] += dbg_acc_empty;
+        g_dbg[5] += clock64() - t_start;  // MMA role total
+        g_dbg[9] += tile_i;
+        g_dbg[11] += dbg_issue;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int w = r % p.w;
+    const int hr = r / p.w;
+    const bool edbg = dbg && warp == 2 && lane == 0;
+    int tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int mt = tile / p.n_tiles;
+      const int n0 = mt / tiles_per_img, h0 = (mt % tiles_per_img) * 2 * p.th;
+      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+      const int buf = tile_i & 1;
+      {
+        const long long _t = clock64();
+        mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 26);
+        dbg_acc[0] += clock64() - _t;
+      }
+      const long long t_epi = clock64();
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const long long row_off = (long long)n0 * p.out_sn + (long long)(h0 + half * p.th + hr) * p.out_sh +
+                                  (long long)w * p.out_sw + n_tile0;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / 16; ++c) {
+          uint32_t v[16];
+          const uint32_t taddr =
+              tmem_base + (uint32_t(q * 32) << 16) + buf * 2 * Cfg::kUmmaN + half * Cfg::kUmmaN + c * 16;
+          tmem_ld_32x16(taddr, v);
+          if (Cfg::kStack) {
+            uint32_t v2[16];
+            tmem_ld_32x16(taddr + 64, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          } else {
+            tmem_ld_wait();
+          }
+          warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      dbg_acc[1] += clock64() - t_epi;
+    }
+    if (edbg) {
+      g_dbg[6] += dbg_acc[0];
+      g_dbg[7] += dbg_acc[1];
+      g_dbg[8] += clock64() - t_start;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int N_TILE, int PA, int PB>
+static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
+  using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
+  const int a_box_bytes = (2 * kp.th + 2) * kp.w * 128;
+  const int a_bytes = Cfg::kAStages * PA * a_box_bytes;
+  int b_stages = (kSmemBudget - 1024 - a_bytes) / Cfg::kBStageBytes;  // kSmemBudget already excludes the epilogue patch
+  if (b_stages > 8) b_stages = 8;
+  if (b_stages < 2) {
+    set_error("fb_conv3x3: tile does not fit into shared memory (W %d, N_TILE %d)", kp.w, N_TILE);
+    return FB_ERR_UNSUPPORTED;
+  }
+  const int smem = a_bytes + b_stages * Cfg::kBStageBytes + kEpiStageBytes + 1024 + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    FB_CUDA(cudaFuncSetAttribute(conv3x3_kernel<N_TILE, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int tiles = kp.n * (kp.h / (2 * kp.th)) * kp.n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  conv3x3_kernel<N_TILE, PA, PB><<<grid, 192, smem, stream>>>(kp, a_box_bytes, b_stages);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N_TILE>
+static int dispatch_conv3x3(const Conv3x3KParams& kp, int pa, int pb, cudaStream_t stream) {
+  if (pa == 2 && pb == 2) return launch_conv3x3<N_TILE, 2, 2>(kp, stream);
+  if (pa == 1 && pb == 2) return launch_conv3x3<N_TILE, 1, 2>(kp, stream);
+  if (pa == 1 && pb == 1) return launch_conv3x3<N_TILE, 1, 1>(kp, stream);
+  set_error("fb_conv3x3: unsupported operand planes (%d, %d)", pa, pb);
+  return FB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // wgrad_kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct alignas(64) WgradKParams {
@@ -304,7 +596,7 @@ struct alignas(64) WgradKParams {
 };
 
 constexpr int kWgAStages = 2;
-constexpr int kWgBStages = 9;
+constexpr int kWgBStages = 8;              // 16 KiB X tiles; a ring stage is `planes` consecutive tiles
 constexpr int kWgABytes = 2 * kATileBytes;  // two 64-channel chunks of dY: [chunk][128 pixels][64 co]
 constexpr int kWgBBytes = kATileBytes;      // [128 pixels][64 ci]
 constexpr int kWgTmemCols = 512;
@@ -314,7 +606,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kWgAStages * kWgABytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kWgBBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem_b + kWgBStages * kWgBBytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kWgBBytes + kEpiStageBytes);
   uint64_t* a_empty = a_full + kWgAStages;
   uint64_t* b_full = a_empty + kWgAStages;
   uint64_t* b_empty = b_full + kWgBStages;
@@ -346,6 +639,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int n_slots_total = p.n_taps * p.cblocks;
   const int n_slots = min(p.slots_per_cta, n_slots_total - slot0);
   const int split = blockIdx.z;
+  const int b_stages = kWgBStages / p.planes;
   const int pb0 = int((long long)split * p.n_pixblocks / p.splits);
   const int pb1 = int((long long)(split + 1) * p.n_pixblocks / p.splits);
   const bool two_chunks = (co0 + 64) < p.cout;
@@ -364,46 +658,44 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         tma_load_4d(sa, &p.dy_map, &a_full[as], co0, 0, h0, n0);
         if (two_chunks) tma_load_4d(sa + kATileBytes, &p.dy_map, &a_full[as], co0 + 64, 0, h0, n0);
         ++ia;
-        for (int j = 0; j < n_slots; ++j) {
+        for (int j = 0; j < n_slots; ++j, ++ib) {
           const int s = slot0 + j;
           const fb_wgrad_tap tap = p.taps[s % p.n_taps];
           const int cb = s / p.n_taps;
-          for (int pl = 0; pl < p.planes; ++pl) {
-            const int bs = ib % kWgBStages;
-            mbar_wait(&b_empty[bs], ((ib / kWgBStages) & 1) ^ 1, 12);
-            mbar_arrive_expect_tx(&b_full[bs], kWgBBytes);
-            tma_load_4d(smem_b + bs * kWgBBytes, &p.x_maps[tap.phase * p.planes + pl], &b_full[bs], cb * kBlockK,
-                        tap.dw, h0 + tap.dh, n0);
-            ++ib;
-          }
+          const int bs = ib % b_stages;
+          mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 12);
+          mbar_arrive_expect_tx(&b_full[bs], p.planes * kWgBBytes);
+          for (int pl = 0; pl < p.planes; ++pl)
+            tma_load_4d(smem_b + (bs * p.planes + pl) * kWgBBytes, &p.x_maps[tap.phase * p.planes + pl], &b_full[bs],
+                        cb * kBlockK, tap.dw, h0 + tap.dh, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      // both operands MN-major; the hi and lo X tiles of a stage are adjacent, so ONE instruction with N = 64*planes
+      // computes dY^T*[X_hi, X_lo] into two 64-column halves that the epilogue adds (an SS-mode MMA re-reads its
+      // 128x16 A tile per instruction, N = 64 would run the tensor pipe at half rate)
+      const uint32_t idesc = make_idesc_bf16(128, 64 * p.planes, 1, 1);
       int ia = 0, ib = 0;
       for (int pb = pb0; pb < pb1; ++pb) {
         const int as = ia % kWgAStages;
         mbar_wait(&a_full[as], (ia / kWgAStages) & 1, 13);
         const uint32_t a_base = smem_u32(smem_a + as * kWgABytes);
-        for (int j = 0; j < n_slots; ++j) {
-          for (int pl = 0; pl < p.planes; ++pl) {
-            const int bs = ib % kWgBStages;
-            mbar_wait(&b_full[bs], (ib / kWgBStages) & 1, 14);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(smem_b + bs * kWgBBytes);
+        for (int j = 0; j < n_slots; ++j, ++ib) {
+          const int bs = ib % b_stages;
+          mbar_wait(&b_full[bs], (ib / b_stages) & 1, 14);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(smem_b + bs * p.planes * kWgBBytes);
 #pragma unroll
-            for (int k = 0; k < kTileM / 16; ++k) {
-              // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO),
-              // groups of 8 pixel rows are 1024 bytes apart (SBO)
-              const uint64_t da = make_smem_desc_sw128(a_base + k * 2048, kATileBytes, 1024);
-              const uint64_t db = make_smem_desc_sw128(b_base + k * 2048, kATileBytes, 1024);
-              tc_mma_bf16(tmem_base + j * 64, da, db, idesc, (pb != pb0 || pl != 0 || k != 0) ? 1u : 0u);
-            }
-            tc_commit(&b_empty[bs]);
-            ++ib;
+          for (int k = 0; k < kTileM / 16; ++k) {
+            // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO),
+            // groups of 8 pixel rows are 1024 bytes apart (SBO)
+            const uint64_t da = make_smem_desc_sw128(a_base + k * 2048, kATileBytes, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_base + k * 2048, kATileBytes, 1024);
+            tc_mma_bf16(tmem_base + j * 64 * p.planes, da, db, idesc, (pb != pb0 || k != 0) ? 1u : 0u);
           }
+          tc_commit(&b_empty[bs]);
         }
         tc_commit(&a_empty[as]);
         ++ia;
@@ -414,7 +706,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
     const bool valid = co < p.cout;
-    float* row = p.partial + ((long long)split * p.cout + co) * k_total;
+    const long long row_off = ((long long)split * p.cout + co) * k_total;
     mbar_wait(accum_bar, 0, 15);
     tc_fence_after();
     for (int j = 0; j < n_slots; ++j) {
@@ -422,17 +714,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       const int tap = s % p.n_taps;
       const int cb = s / p.n_taps;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + j * 64 + c * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(row + tap * p.cin + cb * kBlockK + c * 32);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + j * 64 * p.planes + c * 16;
+        tmem_ld_32x16(taddr, v);
+        if (p.planes == 2) {
+          uint32_t v2[16];
+          tmem_ld_32x16(taddr + 64, v2);
+          tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
-            d4[t] = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
-                                __uint_as_float(v[4 * t + 3]));
+          for (int t = 0; t < 16; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + __uint_as_float(v2[t]));
+        } else {
+          tmem_ld_wait();
         }
+        warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.partial, row_off, valid,
+                          tap * p.cin + cb * kBlockK + c * 16, false, lane);
       }
     }
   }
@@ -701,13 +997,54 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   }
 }
 
+extern "C" int fb_conv3x3(const fb_conv3x3_args* a, void* stream) {
+  FB_REQUIRE(a && a->host_a_maps && a->host_b_maps && a->out, "fb_conv3x3: null pointer");
+  FB_REQUIRE(a->a_planes >= 1 && a->a_planes <= 2 && a->b_planes >= 1 && a->b_planes <= 2, "fb_conv3x3: bad planes");
+  if (a->w < 8 || a->w > 128 || 128 % a->w != 0 || a->h % (2 * (128 / a->w)) != 0) {
+    set_error("fb_conv3x3: feature map %dx%d not supported by the haloed 256-pixel tiling", a->h, a->w);
+    return FB_ERR_UNSUPPORTED;
+  }
+  if (!(a->n_tile == 64 || a->n_tile == 128) || a->n_total % a->n_tile != 0) {
+    set_error("fb_conv3x3: unsupported n_tile %d for n_total %d", a->n_tile, a->n_total);
+    return FB_ERR_UNSUPPORTED;
+  }
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->out_sn % 4 == 0 && a->out_sh % 4 == 0 &&
+                 a->out_sw % 4 == 0,
+             "fb_conv3x3: output must be 16-byte aligned with strides multiple of 4");
+  Conv3x3KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  memcpy(kp.a_maps, a->host_a_maps, size_t(a->a_planes) * FB_TMAP_BYTES);
+  memcpy(kp.b_maps, a->host_b_maps, size_t(a->b_planes) * FB_TMAP_BYTES);
+  memcpy(kp.b_k0, a->b_k0, sizeof(kp.b_k0));
+  kp.cblocks = a->cblocks;
+  kp.w = a->w;
+  kp.h = a->h;
+  kp.n = a->n;
+  kp.th = 128 / a->w;
+  kp.n_tiles = a->n_total / a->n_tile;
+  kp.out = a->out;
+  kp.out_sn = a->out_sn;
+  kp.out_sh = a->out_sh;
+  kp.out_sw = a->out_sw;
+  kp.accumulate = a->accumulate;
+  static const bool debug = [] {
+    const char* e = getenv("FB_KERNEL_DEBUG");
+    return e && e[0] == '1';
+  }();
+  kp.debug = debug ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->n_tile == 64) return dispatch_conv3x3<64>(kp, a->a_planes, a->b_planes, st);
+  return dispatch_conv3x3<128>(kp, a->a_planes, a->b_planes, st);
+}
+
 extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
   FB_REQUIRE(a && a->host_dy_map && a->host_x_maps && a->partial, "fb_conv_wgrad: null pointer");
   FB_REQUIRE(a->planes >= 1 && a->planes <= 2 && a->n_x_maps >= a->planes && a->n_x_maps <= FB_MAX_A_MAPS,
              "fb_conv_wgrad: bad planes/maps (%d, %d)", a->planes, a->n_x_maps);
   FB_REQUIRE(a->n_taps >= 1 && a->n_taps <= FB_MAX_WGRAD_TAPS && a->cblocks >= 1 && a->cin == 64 * a->cblocks,
              "fb_conv_wgrad: bad taps/cblocks/cin (%d, %d, %d)", a->n_taps, a->cblocks, a->cin);
-  FB_REQUIRE(a->slots_per_cta >= 1 && a->slots_per_cta <= 8, "fb_conv_wgrad: slots_per_cta must be 1..8");
+  FB_REQUIRE(a->slots_per_cta >= 1 && a->slots_per_cta * a->planes <= 8,
+             "fb_conv_wgrad: slots_per_cta * planes must be in 1..8 (512 TMEM columns)");
   FB_REQUIRE(a->tile_w * a->tile_h * a->tile_n == 128, "fb_conv_wgrad: tile is not 128 pixels");
   FB_REQUIRE(a->tile_n == 1 ? (a->grid_h % a->tile_h == 0) : (a->tile_h == a->grid_h),
              "fb_conv_wgrad: tile does not divide the pixel grid");
@@ -739,7 +1076,7 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
   kp.partial = a->partial;
   const int n_slots_total = a->n_taps * a->cblocks;
   dim3 grid((a->cout + 127) / 128, (n_slots_total + a->slots_per_cta - 1) / a->slots_per_cta, a->splits);
-  constexpr int smem = kWgAStages * kWgABytes + kWgBStages * kWgBBytes + 1024 + 256;
+  constexpr int smem = kWgAStages * kWgABytes + kWgBStages * kWgBBytes + kEpiStageBytes + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     FB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -791,5 +1128,16 @@ extern "C" int fb_weight_prep_multi(const float* theta, const fb_wprep_entry* ta
   const size_t smem = size_t(32) * (32 * 9 + 1) * sizeof(float);
   weight_prep_multi_kernel<<<total_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(theta, table_dev, n_entries);
   FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* development aid: read (and clear) the in-kernel cycle counters of fb_conv3x3 (FB_KERNEL_DEBUG=1) */
+extern "C" int fb_debug_counters(long long* host32, int clear) {
+  FB_CUDA(cudaDeviceSynchronize());
+  FB_CUDA(cudaMemcpyFromSymbol(host32, g_dbg, sizeof(long long) * 32));
+  if (clear) {
+    long long zero[32] = {0};
+    FB_CUDA(cudaMemcpyToSymbol(g_dbg, zero, sizeof(zero)));
+  }
   return 0;
 }

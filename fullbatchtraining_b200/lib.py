@@ -34,6 +34,12 @@ class ConvGemmArgs(C.Structure):
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32)]
 
 
+class Conv3x3Args(C.Structure):
+    _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("a_planes", i32), ("b_planes", i32), ("b_k0", (i32 * 3) * 3),
+                ("cblocks", i32), ("w", i32), ("h", i32), ("n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
+                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32)]
+
+
 class WgradTap(C.Structure):
     _fields_ = [("phase", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("pad", C.c_int8)]
 
@@ -67,6 +73,7 @@ _SIGNATURES = {
     "fb_tmap_encode_act4d": ([vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32], i32),
     "fb_tmap_encode_mat2d": ([vp, vp, i32, i32, i64, i32, i32], i32),
     "fb_conv_gemm": ([C.POINTER(ConvGemmArgs), vp], i32),
+    "fb_conv3x3": ([C.POINTER(Conv3x3Args), vp], i32),
     "fb_conv_wgrad": ([C.POINTER(WgradArgs), vp], i32),
     "fb_wgrad_finalize": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "fb_weight_prep": ([vp, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp], i32),
@@ -84,6 +91,7 @@ _SIGNATURES = {
     "fb_mean_accumulate": ([vp, vp, i64, vp, i32, vp], i32),
     "fb_cursor_add": ([vp, i32, vp], i32),
     "fb_flat_scale": ([vp, i64, f32, vp], i32),
+    "fb_debug_counters": ([vp, i32], i32),
 }
 
 EXPORTS = tuple(_SIGNATURES)

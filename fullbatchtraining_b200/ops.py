@@ -6,6 +6,7 @@ plain-bf16 mode); conv outputs / activation gradients fp32 NHWC; dY bf16 NHWC; G
 wf[cout][tap*cin + ci] and wd[cin][tap*cout + co].
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -17,7 +18,7 @@ NUM_SMS = 148
 # (family, algorithmic work, unit, start event, end event) around every wrapped launch on the current stream.
 PROFILE = None
 LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
-_KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
+_KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv3x3": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
                      "fb_stem_im2col": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
                      "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1}
@@ -86,11 +87,26 @@ def encode_mat(ms, i, mat, k, rows, box_rows):
     ms.keep.append(mat)
 
 
-def choose_n_tile(m_tiles, n_total):
-    for nt in (256, 128, 64):
-        if n_total % nt == 0 and m_tiles * (n_total // nt) >= NUM_SMS:
-            return nt
-    return 64
+def choose_n_tile(m_tiles, n_total, a_planes=2, b_planes=2):
+    """N tile of the generic GEMM by a small cost model: waves of the persistent grid x tensor-pipe clocks per K=16
+    step of one tile.  An SS-mode MMA costs max(64, N/2) clocks (the 128x16 A tile is re-read from shared memory per
+    instruction), a 64-wide tile with split weights issues `a_planes` stacked N=128 instructions, otherwise one
+    instruction per operand-plane combination."""
+    combos = 3 if (a_planes == 2 and b_planes == 2) else a_planes * b_planes
+    best, best_cost = 64, None
+    for nt in (64, 128, 256):
+        if n_total % nt != 0:
+            continue
+        if nt == 64 and b_planes == 2:
+            clocks = a_planes * 64
+        else:
+            clocks = combos * max(64, nt // 2)
+        tiles = m_tiles * (n_total // nt)
+        waves = -(-tiles // NUM_SMS)
+        cost = waves * clocks
+        if best_cost is None or cost < best_cost or (cost == best_cost and nt > best):
+            best, best_cost = nt, cost
+    return best
 
 
 def _s2_tap(k):
@@ -126,8 +142,45 @@ class ConvGemm:
         _call("conv_gemm", self.flops, "flop", "fb_conv_gemm", C.byref(self.args))
 
 
-def _weight_box_rows(n_total, n_tile):
-    return n_tile
+def halo_eligible(h, w, k, stride):
+    """3x3 / stride-1 convs whose 256-pixel tiles are whole image rows of >= 1024 bytes use the haloed-box kernel."""
+    if os.environ.get("FB_DISABLE_HALO") == "1":
+        return False
+    return k == 3 and stride == 1 and w in (16, 32, 64, 128) and h % (256 // w) == 0
+
+
+class Conv3x3:
+    """One launch of fb_conv3x3 (haloed A boxes, 256-pixel tiles) with frozen arguments."""
+
+    def __init__(self, planes_a, planes_b, n, h, w, c_k, n_total, b_k0, out, accumulate):
+        """planes_a: list of NHWC bf16 planes [n,h,w,c_k]; planes_b: list of weight matrices [n_total][9*c_k]."""
+        th = 128 // w
+        n_tile = 128 if n_total % 128 == 0 else 64
+        self.a_maps = MapSet(len(planes_a))
+        for i, t in enumerate(planes_a):
+            encode_act(self.a_maps, i, t, n, h, w, c_k, (w, 2 * th + 2, 1))
+        self.b_maps = MapSet(len(planes_b))
+        for i, t in enumerate(planes_b):
+            encode_mat(self.b_maps, i, t, 9 * c_k, n_total, n_tile)
+        a = L.Conv3x3Args()
+        a.host_a_maps, a.host_b_maps = self.a_maps.addr, self.b_maps.addr
+        a.a_planes, a.b_planes = len(planes_a), len(planes_b)
+        for i in range(3):
+            for j in range(3):
+                a.b_k0[i][j] = b_k0[i][j]
+        a.cblocks = c_k // 64
+        a.w, a.h, a.n = w, h, n
+        a.n_total, a.n_tile = n_total, n_tile
+        self.out = out
+        a.out = out.data_ptr()
+        a.out_sn, a.out_sh, a.out_sw = h * w * n_total, w * n_total, n_total
+        a.accumulate = int(accumulate)
+        self.args = a
+        self.flops = 0.0
+
+    def __call__(self):
+        _call("conv_gemm", self.flops, "flop", "fb_conv3x3", C.byref(self.args))
+
 
 
 class Conv2dPlan:
@@ -174,7 +227,7 @@ class Conv2dPlan:
 
         # ---- forward
         m_tiles = n * (ho // tile[1]) if tile[2] == 1 else -(-n // tile[2])
-        n_tile = choose_n_tile(m_tiles, cout)
+        n_tile = choose_n_tile(m_tiles, cout, planes, wplanes)
         bs = MapSet(wplanes)
         for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
             encode_mat(bs, pl, t, taps * cin, cout, n_tile)
@@ -185,8 +238,14 @@ class Conv2dPlan:
             for kw in range(k):
                 phase, dh, dw = tap_geom(kh, kw)
                 ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
-        self.fwd = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, n, cout, y, 0,
-                            (ho * wo * cout, wo * cout, cout), False, n_tile)
+        halo = halo_eligible(h, w, k, stride)
+        if halo:
+            # b_k0[dw+1][dh+1]: forward tap (kh, kw) reads input pixel (h + kh - 1, w + kw - 1)
+            fk0 = [[(dhi * 3 + dwi) * cin for dhi in range(3)] for dwi in range(3)]
+            self.fwd = Conv3x3([x_hi, x_lo][:planes], [wf_hi, wf_lo][:wplanes], n, h, w, cin, cout, fk0, y, False)
+        else:
+            self.fwd = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, n, cout, y, 0,
+                                (ho * wo * cout, wo * cout, cout), False, n_tile)
         self.fwd.flops = self.alg_flops
 
         # ---- dgrad
@@ -195,11 +254,16 @@ class Conv2dPlan:
             dys = MapSet(1)
             encode_act(dys, 0, dy, n, ho, wo, cout, tile)
             m_tiles_d = m_tiles
-            n_tile_d = choose_n_tile(m_tiles_d * (4 if stride == 2 else 1), cin)
+            n_tile_d = choose_n_tile(m_tiles_d, cin, 1, wplanes)
             ds = MapSet(wplanes)
             for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
                 encode_mat(ds, pl, t, taps * cout, cin, n_tile_d)
-            if stride == 1:
+            if halo:
+                # dgrad tap (kh, kw) reads dY pixel (h + 1 - kh, w + 1 - kw): dh = 1 - kh, dw = 1 - kw
+                dk0 = [[((2 - dhi) * 3 + (2 - dwi)) * cout for dhi in range(3)] for dwi in range(3)]
+                self.dgrads.append(Conv3x3([dy], [wd_hi, wd_lo][:wplanes], n, h, w, cout, cin, dk0, dx, dx_accumulate))
+                self.dgrads[-1].flops = self.alg_flops
+            elif stride == 1:
                 dtaps = []
                 for kh in range(k):
                     for kw in range(k):
@@ -238,11 +302,7 @@ class Conv2dPlan:
                 phase, dh, dw = tap_geom(kh, kw)
                 wa.taps[kh * k + kw] = L.WgradTap(phase, dh, dw, 0)
         n_slots = taps * cb_in
-        spc = 8
-        if n_slots <= 8:
-            spc = n_slots
-        elif n_slots == 9:
-            spc = 3
+        spc = self._slots_per_cta(n_slots, planes)
         co_tiles = -(-cout // 128)
         groups = -(-n_slots // spc)
         n_pixblocks = m_tiles
@@ -261,15 +321,27 @@ class Conv2dPlan:
         self.splits = splits
 
     @staticmethod
-    def partial_elems(n, h, w, cin, cout, k, stride):
+    def _slots_per_cta(n_slots, planes):
+        """(tap, ci-block) accumulators per CTA: each takes 64*planes of the 512 TMEM columns."""
+        cap = 8 // planes
+        if n_slots <= cap:
+            return n_slots
+        return 3 if n_slots == 9 else cap
+
+    @staticmethod
+    def partial_elems(n, h, w, cin, cout, k, stride, planes=2):
+        """Upper bound of the split-K workspace (fp32 elements) over both operand modes."""
         ho, wo = h // stride, w // stride
         tile = pixel_tile(ho, wo)
         m_tiles = n * (ho // tile[1]) if tile[2] == 1 else -(-n // tile[2])
         taps = k * k
         n_slots = taps * (cin // 64)
-        spc = n_slots if n_slots <= 8 else (3 if n_slots == 9 else 8)
-        splits = max(1, min(m_tiles, NUM_SMS // ((-(-cout // 128)) * (-(-n_slots // spc)))))
-        return splits * cout * taps * cin
+        worst = 0
+        for pl in (1, 2):
+            spc = Conv2dPlan._slots_per_cta(n_slots, pl)
+            splits = max(1, min(m_tiles, NUM_SMS // ((-(-cout // 128)) * (-(-n_slots // spc)))))
+            worst = max(worst, splits)
+        return worst * cout * taps * cin
 
     def forward(self):
         self.fwd()

@@ -78,6 +78,25 @@ typedef struct {
 } fb_conv_gemm_args;
 int fb_conv_gemm(const fb_conv_gemm_args* args, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution (forward or dgrad) with haloed A boxes: per column shift dw one box of
+ * (2*TH + 2) rows is fetched and the three row shifts are aligned views of it; a CTA tile is 256 pixels (two M=128
+ * halves sharing every weight tile).  Requires W in {8,16,32,64,128}, H % (256/W) == 0.  A maps: [plane], box =
+ * 64 x W x (256/W + 2) x 1; B maps: [plane], box = 64 x n_tile.  b_k0[dw+1][dh+1] = first weight column of the tap
+ * that reads input pixel (h+dh, w+dw).  Same output conventions as fb_conv_gemm. */
+typedef struct {
+  const void* host_a_maps;
+  const void* host_b_maps;
+  int32_t a_planes, b_planes;
+  int32_t b_k0[3][3];
+  int32_t cblocks;
+  int32_t w, h, n;
+  int32_t n_total, n_tile; /* n_tile: 64 or 128 */
+  float* out;
+  int64_t out_sn, out_sh, out_sw;
+  int32_t accumulate;
+} fb_conv3x3_args;
+int fb_conv3x3(const fb_conv3x3_args* args, void* stream);
+
 typedef struct {
   int8_t phase, dh, dw, pad;
 } fb_wgrad_tap;
@@ -90,7 +109,7 @@ typedef struct {
   int32_t n_x_maps, planes;
   int32_t n_taps, cblocks;
   fb_wgrad_tap taps[FB_MAX_WGRAD_TAPS];
-  int32_t slots_per_cta; /* accumulators (tap, ci-block pairs) per CTA: 1..8 */
+  int32_t slots_per_cta; /* accumulators (tap, ci-block pairs) per CTA: slots_per_cta * planes <= 8 */
   int32_t cout, cin;     /* cin = 64*cblocks; row length of partial = n_taps*cin */
   int32_t tile_w, tile_h, tile_n;
   int32_t grid_h, grid_n; /* dY pixel grid */
@@ -200,6 +219,10 @@ int fb_mean_accumulate(const float* g, float* avg, int64_t n, const int32_t* cur
 int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream);
 /* x *= alpha over n elements (rank-weighting before the all-reduce, training/utils.py:31-41) */
 int fb_flat_scale(float* x, int64_t n, float alpha, void* stream);
+
+/* Development aid: with FB_KERNEL_DEBUG=1 fb_conv3x3 accumulates per-role wait cycles of CTA 0 in 32 device counters;
+ * this call synchronises the device, copies them to host32[32] and optionally clears them. */
+int fb_debug_counters(long long* host32, int clear);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,22 @@ CONV_CASES = [
     (4, 4, 4, 512, 512, 3, 1),      # tile_n = 8 > n: out-of-bounds images are zero-filled and masked
     (16, 8, 8, 256, 512, 3, 2),
     (32, 8, 8, 64, 256, 1, 1),      # bottleneck 1x1 expansion, N tile 256
+    (2, 32, 32, 128, 64, 3, 1),     # haloed-box kernel, 2 channel blocks
+    (3, 16, 16, 64, 256, 3, 1),     # haloed-box kernel, 2 N tiles, odd image count
 ]
+
+
+@pytest.fixture(params=["halo", "generic"], autouse=True)
+def conv_path(request, monkeypatch):
+    """3x3/stride-1 convs on 16x16 and 32x32 maps run through the haloed-box kernel by default; the generic per-tap
+    kernel must stay correct for the same shapes (it serves every other shape)."""
+    if request.param == "generic":
+        if "conv" not in request.node.name:
+            pytest.skip("only conv tests depend on the conv path")
+        monkeypatch.setenv("FB_DISABLE_HALO", "1")
+    else:
+        monkeypatch.delenv("FB_DISABLE_HALO", raising=False)
+    return request.param
 
 
 def operands(c, use_split):
