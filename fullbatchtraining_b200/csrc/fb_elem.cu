@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ y, const float* __restrict__ dA,
+                                                        const float* __restrict__ dA2,
                                                         const bf16* __restrict__ mask, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, long long P, int C, int TX,
                                                         int rows_per_chunk, float* __restrict__ partial) {
@@ -136,6 +137,10 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
       s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
     } else {
       float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
+      if (dA2) {
+        const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
+        d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+      }
       if (mask) {
         const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
         const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
@@ -262,6 +267,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, con
     if (!invariant) p.load(a, coef, int(off % a.C));
     float d[8], y[8], o[8];
     load8(a.dA + off, d);
+    if (a.dA2) {
+      float d2[8];
+      load8(a.dA2 + off, d2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += d2[j];
+    }
     if (a.mask_hi) {
       float m[8];
       load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
@@ -284,6 +295,280 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, con
       }
       store8(a.dz_out + off, d);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused BatchNorm kernels: statistics -> finalize -> apply in ONE persistent launch with two grid-wide barriers.
+// All blocks are co-resident (grid <= 2 per SM, checked on the host), so a spin barrier on a global counter is safe; it
+// is bounded and traps instead of hanging.  Every block applies to the same rows it reduced, so the second pass over
+// Y / dA / mask is served by L2 (the largest ResNet-18 tensors are 33 MB, L2 is 126 MB) instead of HBM, and the two
+// extra launches per BatchNorm disappear.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("[fb] grid barrier timeout: block %d target %u have %u\n", blockIdx.x, target, *counter);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// after the last barrier: the last block to leave resets the counters for the next launch
+__device__ __forceinline__ void grid_barrier_release(unsigned int* counters) {
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counters + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      counters[0] = 0u;
+      counters[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+struct BnFusedFwdArgs {
+  fb_bn_apply_args ap;           // y, gamma, beta, (y2, gamma2, beta2), residual, relu, P, C, outputs; mean/rstd = outputs
+  float *mean, *rstd, *mean2, *rstd2;
+  float *running_mean, *running_var, *running_mean2, *running_var2;
+  float momentum, eps;
+  float* partial;                // [grid][2 branches][2][C]
+  unsigned int* counters;        // [2], zero on entry
+  int rows_per_block;
+};
+
+// column sums of one branch over rows [r0, r1): partial[2][C] of this block
+template <bool BWD>
+__device__ __forceinline__ void block_column_sums(const float* __restrict__ y, const float* __restrict__ dA,
+                                                  const float* __restrict__ dA2, const bf16* __restrict__ mask,
+                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                  long long r0, long long r1, int C, float* __restrict__ out,
+                                                  float4 (*red)[256]) {
+  const int c4 = C / 4;
+  const int TX = c4 < 256 ? c4 : 256;
+  const int TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  for (int slab = 0; slab < c4 / TX; ++slab) {
+    const int c = (slab * TX + tx) * 4;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, mu = s1, rs = s1;
+    if (BWD) {
+      mu = *reinterpret_cast<const float4*>(mean + c);
+      rs = *reinterpret_cast<const float4*>(rstd + c);
+    }
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += TY) {
+      const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
+      if (!BWD) {
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+        s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
+      } else {
+        float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
+        if (dA2) {
+          const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
+          d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+        }
+        if (mask) {
+          const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
+          const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
+          const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
+          d.x = m01.x > 0.f ? d.x : 0.f;
+          d.y = m01.y > 0.f ? d.y : 0.f;
+          d.z = m23.x > 0.f ? d.z : 0.f;
+          d.w = m23.y > 0.f ? d.w : 0.f;
+        }
+        s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+        s2.x += d.x * (v.x - mu.x) * rs.x;
+        s2.y += d.y * (v.y - mu.y) * rs.y;
+        s2.z += d.z * (v.z - mu.z) * rs.z;
+        s2.w += d.w * (v.w - mu.w) * rs.w;
+      }
+    }
+    __syncthreads();
+    red[0][threadIdx.x] = s1;
+    red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (ty == 0) {
+      for (int j = 1; j < TY; ++j) {
+        const float4 a = red[0][j * TX + tx], b = red[1][j * TX + tx];
+        s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+        s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+      }
+      *reinterpret_cast<float4*>(out + c) = s1;
+      *reinterpret_cast<float4*>(out + C + c) = s2;
+    }
+  }
+}
+
+// fixed-order reduction of the per-block partials of channel c by one warp (lane = block index mod 32)
+__device__ __forceinline__ void warp_reduce_partials(const float* __restrict__ partial, long long block_stride, int nblk,
+                                                     int C, int c, int lane, double& s1, double& s2) {
+  s1 = 0.0;
+  s2 = 0.0;
+#pragma unroll 4
+  for (int k = lane; k < nblk; k += 32) {
+    s1 += __ldcg(partial + (long long)k * block_stride + c);
+    s2 += __ldcg(partial + (long long)k * block_stride + C + c);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+}
+
+__global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) {
+  __shared__ float4 red[2][256];
+  const fb_bn_apply_args& ap = a.ap;
+  const int C = ap.C;
+  const long long P = ap.P;
+  const int branches = ap.y2 ? 2 : 1;
+  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+  const long long r1 = min(P, r0 + a.rows_per_block);
+  const long long block_stride = (long long)branches * 2 * C;
+  float* mine = a.partial + blockIdx.x * block_stride;
+  // ---- phase 1: per-block column sums
+  block_column_sums<false>(ap.y, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine, red);
+  if (ap.y2) block_column_sums<false>(ap.y2, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine + 2 * C, red);
+  grid_barrier(a.counters, gridDim.x);
+  // ---- finalize: one warp per channel, spread over the blocks
+  {
+    const int lane = threadIdx.x & 31;
+    const int total = branches * C;
+    for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += gridDim.x * 8) {
+      const int br = item / C, c = item % C;
+      double s1, s2;
+      warp_reduce_partials(a.partial + br * 2 * C, block_stride, gridDim.x, C, c, lane, s1, s2);
+      if (lane == 0) {
+        const double m = s1 / double(P);
+        double var = s2 / double(P) - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        (br ? a.mean2 : a.mean)[c] = float(m);
+        (br ? a.rstd2 : a.rstd)[c] = float(1.0 / sqrt(var + double(a.eps)));
+        float* rm = br ? a.running_mean2 : a.running_mean;
+        float* rv = br ? a.running_var2 : a.running_var;
+        if (rm) {
+          const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
+          rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * float(m);
+          rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * float(unbiased);
+        }
+      }
+    }
+  }
+  grid_barrier(a.counters, 2 * gridDim.x);
+  grid_barrier_release(a.counters);
+  // ---- phase 2: normalise the rows this block reduced (L2 hits)
+  const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
+  const bool invariant = (256 * 8) % C == 0;
+  long long i = e0 + threadIdx.x;
+  BnAffine p1, p2;
+  if (i < e1 && invariant) {
+    const int c = int((i * 8) % C);
+    p1.load(a.mean, a.rstd, ap.gamma, ap.beta, c);
+    if (ap.y2) p2.load(a.mean2, a.rstd2, ap.gamma2, ap.beta2, c);
+  }
+  for (; i < e1; i += 256) {
+    const long long off = i * 8;
+    if (!invariant) {
+      const int c = int(off % C);
+      p1.load(a.mean, a.rstd, ap.gamma, ap.beta, c);
+      if (ap.y2) p2.load(a.mean2, a.rstd2, ap.gamma2, ap.beta2, c);
+    }
+    float y[8], o[8];
+    load8(ap.y + off, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (y[j] - p1.mu[j]) * p1.scale[j] + p1.shift[j];
+    if (ap.y2) {
+      load8(ap.y2 + off, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += (y[j] - p2.mu[j]) * p2.scale[j] + p2.shift[j];
+    }
+    if (ap.res_hi) {
+      float rh[8];
+      load8_bf16(static_cast<const bf16*>(ap.res_hi) + off, rh);
+      if (ap.res_lo) {
+        float rl[8];
+        load8_bf16(static_cast<const bf16*>(ap.res_lo) + off, rl);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rh[j] += rl[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += rh[j];
+    }
+    if (ap.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    store8_split(static_cast<bf16*>(ap.out_hi), static_cast<bf16*>(ap.out_lo), off, o);
+  }
+}
+
+struct BnFusedBwdArgs {
+  fb_bn_bwd_args bw;       // dA, dA2, mask, y, mean, rstd, gamma, P, C, ws, dgamma, dbeta, dy, dz_out
+  float* partial;          // [grid][2][C]
+  float* coef;             // [2][C]
+  unsigned int* counters;  // [2]
+  int rows_per_block;
+};
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) {
+  __shared__ float4 red[2][256];
+  const fb_bn_bwd_args& bw = a.bw;
+  const int C = bw.C;
+  const long long P = bw.P;
+  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+  const long long r1 = min(P, r0 + a.rows_per_block);
+  const long long block_stride = 2LL * C;
+  block_column_sums<true>(bw.y, bw.dA, bw.dA2, static_cast<const bf16*>(bw.mask_hi), bw.mean, bw.rstd, r0, r1, C,
+                          a.partial + blockIdx.x * block_stride, red);
+  grid_barrier(a.counters, gridDim.x);
+  {
+    const int lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < C; c += gridDim.x * 8) {
+      double s1, s2;
+      warp_reduce_partials(a.partial, block_stride, gridDim.x, C, c, lane, s1, s2);
+      if (lane == 0) {
+        bw.dbeta[c] = float(s1);
+        bw.dgamma[c] = float(s2);
+        a.coef[c] = float(s1 / double(P));
+        a.coef[C + c] = float(s2 / double(P));
+      }
+    }
+  }
+  grid_barrier(a.counters, 2 * gridDim.x);
+  grid_barrier_release(a.counters);
+  const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
+  const bool invariant = (256 * 8) % C == 0;
+  long long i = e0 + threadIdx.x;
+  BnBwdCoef p;
+  if (i < e1 && invariant) p.load(bw, a.coef, int((i * 8) % C));
+  for (; i < e1; i += 256) {
+    const long long off = i * 8;
+    if (!invariant) p.load(bw, a.coef, int(off % C));
+    float d[8], y[8], o[8];
+    load8(bw.dA + off, d);
+    if (bw.dA2) {
+      float d2[8];
+      load8(bw.dA2 + off, d2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += d2[j];
+    }
+    if (bw.mask_hi) {
+      float m[8];
+      load8_bf16(static_cast<const bf16*>(bw.mask_hi) + off, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
+    }
+    load8(bw.y + off, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (y[j] - p.mu[j]) * p.rs[j];
+      o[j] = p.grs[j] * (d[j] - p.c1[j] - xhat * p.c2[j]);
+    }
+    store8_bf16(static_cast<bf16*>(bw.dy_bf16), off, o);
+    if (bw.dz_out) store8(bw.dz_out + off, d);
   }
 }
 
@@ -560,7 +845,8 @@ extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* m
   fin.running_var = running_var;
   fin.momentum = momentum;
   fin.eps = eps;
-  bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, P, C, TX, rpc, ws);
+  bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, P, C, TX,
+                                                               rpc, ws);
   bn_finalize_kernel<false><<<(C + 7) / 8, 256, 0, st>>>(ws, C, fin);
   FB_CUDA(cudaGetLastError());
   return 0;
@@ -591,8 +877,8 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   fin.coef = coef;
   fin.dgamma = a->dgamma;
   fin.dbeta = a->dbeta;
-  bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, static_cast<const bf16*>(a->mask_hi), a->mean,
-                                                              a->rstd, a->P, a->C, TX, rpc, a->ws);
+  bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, a->dA2, static_cast<const bf16*>(a->mask_hi),
+                                                              a->mean, a->rstd, a->P, a->C, TX, rpc, a->ws);
   bn_finalize_kernel<true><<<(a->C + 7) / 8, 256, 0, st>>>(a->ws, a->C, fin);
   bn_bwd_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, st>>>(*a, coef);
   FB_CUDA(cudaGetLastError());
@@ -649,6 +935,79 @@ extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw
   head_bwd_act_kernel<<<dim3((c + 127) / 128, n), 128, 0, st>>>(dlogits, fc_w, hw, c, classes, dA);
   head_bwd_param_kernel<<<(c + 31) / 32, 256, 0, st>>>(dlogits, pooled, loss_n, correct_n, n, c, classes, d_fcw, d_fcb,
                                                         scal, loss_slot, correct_slot);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int fused_geometry(long long P, int C, int& grid, int& rows_per_block) {
+  if (C % 8 != 0) return FB_ERR_UNSUPPORTED;
+  const int c4 = C / 4;
+  const int TX = c4 < 256 ? c4 : 256;
+  if (256 % TX != 0 || c4 % TX != 0) return FB_ERR_UNSUPPORTED;
+  const int TY = 256 / TX;
+  // every block must own whole groups of TY rows and an element range that keeps the channel offset thread-invariant:
+  // rows_per_block is a multiple of lcm(TY, 2048 / C)
+  int unit = TY;
+  const int inv = (2048 % C == 0) ? 2048 / C : 1;
+  if (inv > unit) unit = inv;
+  long long units = (P + unit - 1) / unit;
+  long long g = units < 2 * kNumSMs ? units : 2 * kNumSMs;
+  long long upb = (units + g - 1) / g;
+  rows_per_block = int(upb * unit);
+  grid = int((P + rows_per_block - 1) / rows_per_block);
+  return 0;
+}
+
+extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, float* rstd2_out, float* running_mean,
+                               float* running_var, float* running_mean2, float* running_var2, float momentum,
+                               float eps, float* ws, void* stream) {
+  FB_REQUIRE(ap && ap->y && ap->mean && ap->rstd && ap->gamma && ap->beta && ap->out_hi && ws,
+             "fb_bn_fwd_fused: null pointer");
+  FB_REQUIRE(!ap->y2 || (mean2_out && rstd2_out && ap->gamma2 && ap->beta2), "fb_bn_fwd_fused: second branch incomplete");
+  int grid, rpb;
+  if (fused_geometry(ap->P, ap->C, grid, rpb)) {
+    set_error("fb_bn_fwd_fused: unsupported channel count %d", ap->C);
+    return FB_ERR_UNSUPPORTED;
+  }
+  BnFusedFwdArgs a;
+  a.ap = *ap;
+  a.mean = const_cast<float*>(ap->mean);
+  a.rstd = const_cast<float*>(ap->rstd);
+  a.mean2 = mean2_out;
+  a.rstd2 = rstd2_out;
+  a.ap.mean2 = mean2_out;
+  a.ap.rstd2 = rstd2_out;
+  a.running_mean = running_mean;
+  a.running_var = running_var;
+  a.running_mean2 = running_mean2;
+  a.running_var2 = running_var2;
+  a.momentum = momentum;
+  a.eps = eps;
+  a.counters = reinterpret_cast<unsigned int*>(ws);
+  a.partial = ws + 4;
+  a.rows_per_block = rpb;
+  bn_fwd_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
+  FB_REQUIRE(bw && bw->dA && bw->y && bw->mean && bw->rstd && bw->gamma && bw->ws && bw->dgamma && bw->dbeta &&
+                 bw->dy_bf16,
+             "fb_bn_bwd_fused: null pointer");
+  FB_REQUIRE(!bw->dz_accumulate, "fb_bn_bwd_fused: dz_accumulate is not supported");
+  int grid, rpb;
+  if (fused_geometry(bw->P, bw->C, grid, rpb)) {
+    set_error("fb_bn_bwd_fused: unsupported channel count %d", bw->C);
+    return FB_ERR_UNSUPPORTED;
+  }
+  BnFusedBwdArgs a;
+  a.bw = *bw;
+  a.counters = reinterpret_cast<unsigned int*>(bw->ws);
+  a.partial = bw->ws + 4;
+  a.coef = a.partial + (long long)2 * bw->C * 2 * kNumSMs;
+  a.rows_per_block = rpb;
+  bn_bwd_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

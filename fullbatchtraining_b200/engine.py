@@ -37,6 +37,13 @@ class Act:
         self.hi = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16)
         self.lo = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16) if split else None
         self.grad = torch.zeros(n, h, w, c, device=device, dtype=torch.float32) if grad else None
+        # second addend of the gradient (shortcut branch of the consuming block); consumers read grad + grad2, so no
+        # GEMM epilogue ever has to read-modify-write
+        self.grad2 = None
+
+    def add_grad2(self):
+        self.grad2 = torch.zeros_like(self.grad)
+        return self.grad2
 
     @property
     def P(self):
@@ -46,7 +53,8 @@ class Act:
 class Unit:
     """conv (bias-free) + BatchNorm: buffers, descriptors and parameter offsets."""
 
-    def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, dx_accumulate, needs_dx=True, stem=False):
+    def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, dx_accumulate=False, needs_dx=True, stem=False,
+                 dx_target=None):
         dev, split = eng.device, eng.split
         self.conv_name, self.bn_name, self.x, self.stem = conv_name, bn_name, x, stem
         self.cin, self.cout, self.k, self.stride = x.c, cout, k, stride
@@ -71,11 +79,13 @@ class Unit:
         eng.partial_elems = max(eng.partial_elems, need)
         self.args = (n, h, w, x.c, cout, k, stride)
         self.dx_accumulate, self.needs_dx = dx_accumulate, needs_dx
+        self.dx_target = dx_target  # fp32 buffer receiving the input gradient (default: x.grad)
         self.plans = None
 
     def finish(self, eng):
         self.plans = [ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
-                                     self.x.grad if self.needs_dx else None, *self.w[i], eng.partial,
+                                     (self.dx_target if self.dx_target is not None else self.x.grad)
+                                     if self.needs_dx else None, *self.w[i], eng.partial,
                                      dx_accumulate=self.dx_accumulate, split=eng.split,
                                      alg_k=27 if self.stem else None) for i in range(2)]
 
@@ -165,22 +175,23 @@ class FullBatchEngine:
                 for i, (cn, bnn) in enumerate(pairs):
                     conv = getattr(mod, cn)
                     k, st = conv.kernel_size[0], conv.stride[0]
-                    u = Unit(self, f"{pre}.{cn}", f"{pre}.{bnn}", x, conv.out_channels, k, st, dx_accumulate=(i == 0))
+                    u = Unit(self, f"{pre}.{cn}", f"{pre}.{bnn}", x, conv.out_channels, k, st)
                     u.out = Act(x.n, u.ho, u.wo, conv.out_channels, self.split, dev)
                     blk.units.append(u)
                     x = u.out
                     max_c = max(max_c, conv.out_channels)
+                cur.add_grad2()  # shortcut-branch gradient of this block's input
                 if mod.downsample is not None:
                     pool, dconv = mod.downsample[0], mod.downsample[1]
                     ps = pool.kernel_size if isinstance(pool.kernel_size, int) else pool.kernel_size[0]
-                    src = cur
+                    src, target = cur, cur.grad2
                     if ps == 2:
                         blk.pooled = Act(cur.n, cur.h // 2, cur.w // 2, cur.c, self.split, dev)
-                        src = blk.pooled
+                        src, target = blk.pooled, None
                     elif ps != 1:
                         raise RuntimeError(f"AvgPool2d({ps}) in the shortcut is not supported")
                     blk.ds = Unit(self, f"{pre}.downsample.1", f"{pre}.downsample.2", src, dconv.out_channels, 1, 1,
-                                  dx_accumulate=False)
+                                  dx_target=target)
                 blk.out = x
                 self.blocks.append(blk)
                 cur = x
@@ -214,53 +225,54 @@ class FullBatchEngine:
         m = self._bn_modules[bn_name]
         return m.running_mean, m.running_var
 
-    def _unit_forward(self, u, P):
-        u.plans[self._pass].forward()
-        rm, rv = self._bn_buffers(u.bn_name)
-        ops.bn_stats(u.y, u.P, u.cout, self.bn_ws, u.mean, u.rstd, rm, rv, BN_MOMENTUM, BN_EPS)
-
     def _bn_params(self, u, P):
         return self._view(P, u.bn_name + ".weight"), self._view(P, u.bn_name + ".bias")
+
+    def _bn_forward(self, u, P, out, relu=True, second=None, res=None):
+        """fused train-mode BatchNorm of unit `u` (statistics, running-stat EMA, normalise, add, ReLU) -> `out` planes"""
+        ga, be = self._bn_params(u, P)
+        sec = None
+        if second is not None:
+            ga2, be2 = self._bn_params(second, P)
+            sec = (second.y, second.mean, second.rstd, ga2, be2, *self._bn_buffers(second.bn_name))
+        ops.bn_fwd_fused(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, out.hi, out.lo, self.bn_ws,
+                         running=self._bn_buffers(u.bn_name), relu=relu, second=sec, res=res, momentum=BN_MOMENTUM,
+                         eps=BN_EPS)
 
     def _forward(self, P, G, loss_slot, correct_slot):
         self._pass = 0 if P is self.theta else 1
         if self._pass == 1:
             self.wprep[1](P)  # operands of theta' = theta + eps_n*v; those of theta are refreshed once per step
         u = self.stem
-        self._unit_forward(u, P)
-        ga, be = self._bn_params(u, P)
-        ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, u.out.hi, u.out.lo, relu=True)
+        u.plans[self._pass].forward()
+        self._bn_forward(u, P, u.out)
         for blk in self.blocks:
             last = len(blk.units) - 1
             for i, u in enumerate(blk.units):
-                self._unit_forward(u, P)
+                u.plans[self._pass].forward()
                 if i < last:
-                    ga, be = self._bn_params(u, P)
-                    ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, u.out.hi, u.out.lo, relu=True)
+                    self._bn_forward(u, P, u.out)
             u = blk.units[last]
-            ga, be = self._bn_params(u, P)
             if blk.ds is not None:
                 d = blk.ds
                 if blk.pooled is not None:
                     x = blk.x
                     ops.avgpool2_fwd(x.hi, x.lo, x.n, x.h, x.w, x.c, blk.pooled.hi, blk.pooled.lo)
-                self._unit_forward(d, P)
-                ga2, be2 = self._bn_params(d, P)
-                ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, blk.out.hi, blk.out.lo, relu=True,
-                             second=(d.y, d.mean, d.rstd, ga2, be2))
+                d.plans[self._pass].forward()
+                self._bn_forward(u, P, blk.out, second=d)
             else:
-                ops.bn_apply(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, blk.out.hi, blk.out.lo, relu=True,
-                             res=(blk.x.hi, blk.x.lo))
+                self._bn_forward(u, P, blk.out, res=(blk.x.hi, blk.x.lo))
         a = self.last
         ops.head_fwd_bwd(a.hi, a.lo, a.n, a.h * a.w, a.c, self._view(P, "fc.weight"), self._view(P, "fc.bias"),
                          self.labels_mb, self.classes, self.smoothing, self.head_ws, self.scal, loss_slot, correct_slot,
                          self._view(G, "fc.weight"), self._view(G, "fc.bias"), a.grad)
 
-    def _unit_backward(self, u, P, G, dA, mask_hi, dz_out=None):
-        """BN(+ReLU) backward of `u` from dA, then wgrad and dgrad of its conv."""
+    def _unit_backward(self, u, P, G, act, dz_out=None):
+        """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
         ga, _ = self._bn_params(u, P)
-        ops.bn_bwd(dA, mask_hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
-                   self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out)
+        ops.bn_bwd_fused(act.grad, act.hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
+                         self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out,
+                         dA2=act.grad2)
         gw = self._view(G, u.conv_name + ".weight")
         plan = u.plans[self._pass]
         if u.stem:
@@ -274,22 +286,22 @@ class FullBatchEngine:
             out = blk.out
             last = len(blk.units) - 1
             if blk.ds is not None:
-                # shortcut branch first: it overwrites the block-input gradient, the main branch accumulates into it
+                # shortcut branch: its input gradient goes to the block input's second gradient buffer (grad2)
                 d = blk.ds
-                self._unit_backward(d, P, G, out.grad, out.hi)
+                self._unit_backward(d, P, G, out)
                 if blk.pooled is not None:
                     x = blk.x
-                    ops.avgpool2_bwd(blk.pooled.grad, x.n, x.h, x.w, x.c, x.grad, accumulate=False)
+                    ops.avgpool2_bwd(blk.pooled.grad, x.n, x.h, x.w, x.c, x.grad2, accumulate=False)
                 dz_out = None
             else:
-                dz_out = blk.x.grad  # identity shortcut: dz of the last BN is the block-input gradient's first term
+                dz_out = blk.x.grad2  # identity shortcut: dz of the last BN is the shortcut gradient
             for i in range(last, -1, -1):
                 u = blk.units[i]
                 if i == last:
-                    self._unit_backward(u, P, G, out.grad, out.hi, dz_out=dz_out)
+                    self._unit_backward(u, P, G, out, dz_out=dz_out)
                 else:
-                    self._unit_backward(u, P, G, u.out.grad, u.out.hi)
-        self._unit_backward(self.stem, P, G, self.a0.grad, self.a0.hi)
+                    self._unit_backward(u, P, G, u.out)
+        self._unit_backward(self.stem, P, G, self.a0)
 
     # ------------------------------------------------------------------------------------------------------------
     def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g,

@@ -63,7 +63,7 @@ class BnApplyArgs(C.Structure):
 
 
 class BnBwdArgs(C.Structure):
-    _fields_ = [("dA", vp), ("mask_hi", vp), ("y", vp), ("mean", vp), ("rstd", vp), ("gamma", vp), ("P", i64), ("C", i32),
+    _fields_ = [("dA", vp), ("dA2", vp), ("mask_hi", vp), ("y", vp), ("mean", vp), ("rstd", vp), ("gamma", vp), ("P", i64), ("C", i32),
                 ("ws", vp), ("dgamma", vp), ("dbeta", vp), ("dy_bf16", vp), ("dz_out", vp), ("dz_accumulate", i32)]
 
 
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "fb_bn_stats": ([vp, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp], i32),
     "fb_bn_apply": ([C.POINTER(BnApplyArgs), vp], i32),
     "fb_bn_bwd": ([C.POINTER(BnBwdArgs), vp], i32),
+    "fb_bn_fwd_fused": ([C.POINTER(BnApplyArgs), vp, vp, vp, vp, vp, vp, f32, f32, vp, vp], i32),
+    "fb_bn_bwd_fused": ([C.POINTER(BnBwdArgs), vp], i32),
     "fb_avgpool2_fwd": ([vp, vp, i32, i32, i32, i32, vp, vp, vp], i32),
     "fb_avgpool2_bwd": ([vp, i32, i32, i32, i32, vp, i32, vp], i32),
     "fb_head_fwd_bwd": ([vp, vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, vp, i32, i32, vp, vp, vp, vp], i32),

@@ -19,7 +19,7 @@ NUM_SMS = 148
 PROFILE = None
 LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
 _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv3x3": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
-                     "fb_stem_im2col": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
+                     "fb_stem_im2col": 1, "fb_bn_fwd_fused": 1, "fb_bn_bwd_fused": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
                      "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1}
 
@@ -417,16 +417,50 @@ def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, secon
     _call("bn_apply", per_elem * P * Cc, "byte", "fb_bn_apply", C.byref(a))
 
 
-def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dz_accumulate=False):
+def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dz_accumulate=False, dA2=None):
     a = L.BnBwdArgs()
-    a.dA, a.mask_hi, a.y, a.mean, a.rstd, a.gamma = dA.data_ptr(), L.ptr(mask_hi), y.data_ptr(), mean.data_ptr(), \
-        rstd.data_ptr(), gamma.data_ptr()
+    a.dA, a.dA2, a.mask_hi, a.y, a.mean, a.rstd, a.gamma = dA.data_ptr(), L.ptr(dA2), L.ptr(mask_hi), y.data_ptr(), \
+        mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
     a.P, a.C, a.ws = P, Cc, ws.data_ptr()
     a.dgamma, a.dbeta, a.dy_bf16 = dgamma.data_ptr(), dbeta.data_ptr(), dy.data_ptr()
     a.dz_out, a.dz_accumulate = L.ptr(dz_out), int(dz_accumulate)
     # distinct tensors: dA, y (+ mask) in; dy (+ dz) out -- each counted once although the two-phase kernel reads twice
-    per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0)
+    per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0) + \
+        (4.0 if dA2 is not None else 0.0)
     _call("bn_bwd", per_elem * P * Cc, "byte", "fb_bn_bwd", C.byref(a))
+
+
+def bn_fwd_fused(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, ws, running=None, relu=True, second=None, res=None,
+                 momentum=0.1, eps=1e-5):
+    """Train-mode BatchNorm statistics + normalise (+ second normalised branch / residual) + ReLU in one launch.
+    second = (y2, mean2, rstd2, gamma2, beta2, running_mean2, running_var2)."""
+    a = L.BnApplyArgs()
+    a.y, a.mean, a.rstd, a.gamma, a.beta = (t.data_ptr() for t in (y, mean, rstd, gamma, beta))
+    m2 = r2 = rm2 = rv2 = None
+    if second is not None:
+        y2, m2, r2, g2, b2, rm2, rv2 = second
+        a.y2, a.mean2, a.rstd2, a.gamma2, a.beta2 = (t.data_ptr() for t in (y2, m2, r2, g2, b2))
+    if res is not None:
+        a.res_hi, a.res_lo = res[0].data_ptr(), L.ptr(res[1])
+    a.relu, a.P, a.C = int(relu), P, Cc
+    a.out_hi, a.out_lo = out_hi.data_ptr(), L.ptr(out_lo)
+    planes = 1 + (out_lo is not None)
+    per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes
+    rm, rv = running if running is not None else (None, None)
+    _call("bn_fwd", per_elem * P * Cc, "byte", "fb_bn_fwd_fused", C.byref(a), L.ptr(m2), L.ptr(r2), L.ptr(rm), L.ptr(rv),
+          L.ptr(rm2), L.ptr(rv2), momentum, eps, ws.data_ptr())
+
+
+def bn_bwd_fused(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None):
+    a = L.BnBwdArgs()
+    a.dA, a.dA2, a.mask_hi, a.y, a.mean, a.rstd, a.gamma = dA.data_ptr(), L.ptr(dA2), L.ptr(mask_hi), y.data_ptr(), \
+        mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
+    a.P, a.C, a.ws = P, Cc, ws.data_ptr()
+    a.dgamma, a.dbeta, a.dy_bf16 = dgamma.data_ptr(), dbeta.data_ptr(), dy.data_ptr()
+    a.dz_out, a.dz_accumulate = L.ptr(dz_out), 0
+    per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0) + \
+        (4.0 if dA2 is not None else 0.0)
+    _call("bn_bwd", per_elem * P * Cc, "byte", "fb_bn_bwd_fused", C.byref(a))
 
 
 def avgpool2_fwd(in_hi, in_lo, n, h, w, c, out_hi, out_lo):

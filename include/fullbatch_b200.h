@@ -166,11 +166,12 @@ typedef struct {
 } fb_bn_apply_args;
 int fb_bn_apply(const fb_bn_apply_args* args, void* stream);
 
-/* BatchNorm(+ReLU) backward.  dz = dA * [mask_hi > 0] (mask_hi NULL: no ReLU).  Writes dgamma/dbeta (fp32, C each),
+/* BatchNorm(+ReLU) backward.  dz = (dA + dA2) * [mask_hi > 0] (mask_hi NULL: no ReLU; dA2 NULL: no second addend).  Writes dgamma/dbeta (fp32, C each),
  * dY as bf16 (tensor-core operand), and optionally dz as fp32 (`dz_out`, the identity-branch gradient; if
  * dz_accumulate != 0 it is added to dz_out instead of overwriting).  ws: >= 2*C*1024 floats of scratch. */
 typedef struct {
   const float* dA;
+  const float* dA2; /* optional second addend of the incoming gradient (shortcut branch), NULL if none */
   const void* mask_hi;
   const float *y, *mean, *rstd, *gamma;
   int64_t P;
@@ -182,6 +183,15 @@ typedef struct {
   int32_t dz_accumulate;
 } fb_bn_bwd_args;
 int fb_bn_bwd(const fb_bn_bwd_args* args, void* stream);
+
+/* Fused variants (one persistent launch with two grid-wide barriers: statistics -> finalize -> apply; the second pass
+ * over the tensors is served by L2).  fb_bn_fwd_fused = fb_bn_stats (for y, and for y2 if given) + fb_bn_apply: it
+ * WRITES args->mean / args->rstd (and mean2_out / rstd2_out).  fb_bn_bwd_fused = fb_bn_bwd without dz_accumulate.
+ * ws: >= 2*C*1024 floats, the first 16 bytes ZERO on first use (self-resetting barrier counters). */
+int fb_bn_fwd_fused(const fb_bn_apply_args* args, float* mean2_out, float* rstd2_out, float* running_mean,
+                    float* running_var, float* running_mean2, float* running_var2, float momentum, float eps, float* ws,
+                    void* stream);
+int fb_bn_bwd_fused(const fb_bn_bwd_args* args, void* stream);
 
 /* AvgPool2d(2) on bf16 hi/lo planes (downsample 'C', resnets.py:147-152) and its backward (dX = up(dP)/4). */
 int fb_avgpool2_fwd(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi, void* out_lo,

@@ -365,3 +365,80 @@ def test_flat_fd_kernels():
     x = grad.clone()
     ops.flat_scale(x, n, 0.25)
     assert torch.equal(x, grad * 0.25)
+
+
+def test_bn_bwd_second_addend():
+    """dA2: the shortcut-branch gradient is added on the fly (no read-modify-write in a GEMM epilogue)."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    P, Cc = 2048, 64
+    y = torch.randn(P, Cc, device=DEV, generator=g)
+    gamma = torch.rand(Cc, device=DEV, generator=g) + 0.5
+    a1 = torch.randn(P, Cc, device=DEV, generator=g)
+    a2 = torch.randn(P, Cc, device=DEV, generator=g)
+    mask = torch.randn(P, Cc, device=DEV, generator=g).to(torch.bfloat16)
+    ws = torch.zeros(2 * Cc * 1024, device=DEV)
+    mean, rstd = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
+    ops.bn_stats(y, P, Cc, ws, mean, rstd, None, None)
+    outs = []
+    for dA, dA2 in ((a1, a2), (a1 + a2, None)):
+        dgamma, dbeta = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
+        dy = torch.empty(P, Cc, device=DEV, dtype=torch.bfloat16)
+        dz = torch.empty(P, Cc, device=DEV)
+        ops.bn_bwd(dA, mask, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=dz, dA2=dA2)
+        outs.append((dgamma, dbeta, dy.float(), dz))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("P,Cc,variant", [(131072, 64, "residual"), (32768, 128, "dual"), (2048, 512, "plain"),
+                                          (512, 2048, "plain"), (1000, 128, "residual"), (8192, 256, "dual")])
+def test_bn_fused_kernels_match_unfused(P, Cc, variant):
+    """fb_bn_fwd_fused / fb_bn_bwd_fused (one persistent launch, grid barriers) against the three-launch kernels."""
+    g = torch.Generator(device="cuda").manual_seed(P + Cc)
+    y = torch.randn(P, Cc, device=DEV, generator=g) * 1.5 + 0.3
+    y2 = torch.randn(P, Cc, device=DEV, generator=g)
+    gamma = torch.rand(Cc, device=DEV, generator=g) + 0.5
+    beta = torch.randn(Cc, device=DEV, generator=g) * 0.1
+    gamma2 = torch.rand(Cc, device=DEV, generator=g) + 0.5
+    beta2 = torch.randn(Cc, device=DEV, generator=g) * 0.1
+    res_hi, res_lo = split(torch.randn(P, Cc, device=DEV, generator=g))
+    ws = torch.zeros(2 * Cc * 1024, device=DEV)
+    ws2 = torch.zeros(2 * Cc * 1024, device=DEV)
+    # reference: unfused kernels
+    mean, rstd, mean2, rstd2 = (torch.empty(Cc, device=DEV) for _ in range(4))
+    rm, rv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
+    ops.bn_stats(y, P, Cc, ws, mean, rstd, rm, rv)
+    ops.bn_stats(y2, P, Cc, ws, mean2, rstd2, None, None)
+    o_hi, o_lo = torch.empty(P, Cc, device=DEV, dtype=torch.bfloat16), torch.empty(P, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(y, mean, rstd, gamma, beta, P, Cc, o_hi, o_lo, relu=True,
+                 second=(y2, mean2, rstd2, gamma2, beta2) if variant == "dual" else None,
+                 res=(res_hi, res_lo) if variant == "residual" else None)
+    # fused
+    fmean, frstd, fmean2, frstd2 = (torch.empty(Cc, device=DEV) for _ in range(4))
+    frm, frv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
+    frm2, frv2 = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
+    f_hi, f_lo = torch.empty_like(o_hi), torch.empty_like(o_lo)
+    for _ in range(2):  # twice: the barrier counters must reset themselves
+        frm.zero_(); frv.fill_(1)
+        ops.bn_fwd_fused(y, fmean, frstd, gamma, beta, P, Cc, f_hi, f_lo, ws2, running=(frm, frv), relu=True,
+                         second=(y2, fmean2, frstd2, gamma2, beta2, frm2, frv2) if variant == "dual" else None,
+                         res=(res_hi, res_lo) if variant == "residual" else None)
+    assert rel_err(fmean, mean) < 1e-6 and rel_err(frstd, rstd) < 1e-6
+    assert rel_err(frm, rm) < 1e-6 and rel_err(frv, rv) < 1e-6
+    got, ref = f_hi.double() + f_lo.double(), o_hi.double() + o_lo.double()
+    assert rel_err(got, ref) < 2e-5
+    # backward
+    dA = torch.randn(P, Cc, device=DEV, generator=g)
+    dA2 = torch.randn(P, Cc, device=DEV, generator=g)
+    outs = []
+    for fused in (False, True):
+        dgamma, dbeta = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
+        dy = torch.empty(P, Cc, device=DEV, dtype=torch.bfloat16)
+        dz = torch.empty(P, Cc, device=DEV)
+        fn = ops.bn_bwd_fused if fused else ops.bn_bwd
+        for _ in range(2 if fused else 1):
+            fn(dA, o_hi, y, mean, rstd, gamma, P, Cc, ws2 if fused else ws, dgamma, dbeta, dy, dz_out=dz, dA2=dA2)
+        outs.append((dgamma, dbeta, dy.float(), dz))
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5 and rel_err(outs[1][1], outs[0][1]) < 1e-5
+    assert rel_err(outs[1][2], outs[0][2]) < 1e-2   # bf16 outputs: last-bit differences from the reduction order
+    assert torch.equal(outs[1][3], outs[0][3])
