@@ -593,6 +593,7 @@ struct alignas(64) WgradKParams {
   int grid_h, grid_n;
   int splits, n_pixblocks;
   float* partial;
+  int debug;
 };
 
 constexpr int kWgAStages = 2;
@@ -644,6 +645,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int pb1 = int((long long)(split + 1) * p.n_pixblocks / p.splits);
   const bool two_chunks = (co0 + 64) < p.cout;
   const int k_total = p.n_taps * p.cin;
+  const bool dbg = p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const long long t_start = clock64();
+  long long dbg_acc[2] = {0, 0}, dbg_issue = 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         int n0, h0;
         tile_origin(pb, p.tile_h, p.tile_n, p.grid_h, n0, h0);
         const int as = ia % kWgAStages;
-        mbar_wait(&a_empty[as], ((ia / kWgAStages) & 1) ^ 1, 11);
+        FB_DBG_WAIT(0, mbar_wait(&a_empty[as], ((ia / kWgAStages) & 1) ^ 1, 11));
         uint8_t* sa = smem_a + as * kWgABytes;
         mbar_arrive_expect_tx(&a_full[as], two_chunks ? kWgABytes : kATileBytes);
         tma_load_4d(sa, &p.dy_map, &a_full[as], co0, 0, h0, n0);
@@ -663,12 +667,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
           const fb_wgrad_tap tap = p.taps[s % p.n_taps];
           const int cb = s / p.n_taps;
           const int bs = ib % b_stages;
-          mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 12);
+          FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 12));
           mbar_arrive_expect_tx(&b_full[bs], p.planes * kWgBBytes);
           for (int pl = 0; pl < p.planes; ++pl)
             tma_load_4d(smem_b + (bs * p.planes + pl) * kWgBBytes, &p.x_maps[tap.phase * p.planes + pl], &b_full[bs],
                         cb * kBlockK, tap.dw, h0 + tap.dh, n0);
         }
+      }
+      if (dbg) {
+        g_dbg[0] += dbg_acc[0];
+        g_dbg[1] += dbg_acc[1];
+        g_dbg[10] += clock64() - t_start;
       }
     }
   } else if (warp == 1) {
@@ -680,12 +689,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       int ia = 0, ib = 0;
       for (int pb = pb0; pb < pb1; ++pb) {
         const int as = ia % kWgAStages;
-        mbar_wait(&a_full[as], (ia / kWgAStages) & 1, 13);
+        FB_DBG_WAIT(0, mbar_wait(&a_full[as], (ia / kWgAStages) & 1, 13));
         const uint32_t a_base = smem_u32(smem_a + as * kWgABytes);
         for (int j = 0; j < n_slots; ++j, ++ib) {
           const int bs = ib % b_stages;
-          mbar_wait(&b_full[bs], (ib / b_stages) & 1, 14);
+          FB_DBG_WAIT(1, mbar_wait(&b_full[bs], (ib / b_stages) & 1, 14));
           tc_fence_after();
+          const long long t_issue = dbg ? clock64() : 0;
           const uint32_t b_base = smem_u32(smem_b + bs * p.planes * kWgBBytes);
 #pragma unroll
           for (int k = 0; k < kTileM / 16; ++k) {
@@ -696,18 +706,29 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             tc_mma_bf16(tmem_base + j * 64 * p.planes, da, db, idesc, (pb != pb0 || k != 0) ? 1u : 0u);
           }
           tc_commit(&b_empty[bs]);
+          if (dbg) dbg_issue += clock64() - t_issue;
         }
         tc_commit(&a_empty[as]);
         ++ia;
       }
       tc_commit(accum_bar);
+      if (dbg) {
+        g_dbg[2] += dbg_acc[0];
+        g_dbg[3] += dbg_acc[1];
+        g_dbg[5] += clock64() - t_start;
+        g_dbg[9] += pb1 - pb0;
+        g_dbg[11] += dbg_issue;
+      }
     }
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
     const bool valid = co < p.cout;
     const long long row_off = ((long long)split * p.cout + co) * k_total;
+    const bool edbg = dbg && warp == 2 && lane == 0;
     mbar_wait(accum_bar, 0, 15);
+    const long long t_epi = clock64();
+    if (edbg) g_dbg[6] += t_epi - t_start;
     tc_fence_after();
     for (int j = 0; j < n_slots; ++j) {
       const int s = slot0 + j;
@@ -730,6 +751,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.partial, row_off, valid,
                           tap * p.cin + cb * kBlockK + c * 16, false, lane);
       }
+    }
+    if (edbg) {
+      g_dbg[7] += clock64() - t_epi;
+      g_dbg[8] += clock64() - t_start;
     }
   }
   tc_fence_before();
@@ -1074,6 +1099,13 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
   kp.splits = a->splits;
   kp.n_pixblocks = n_pixblocks;
   kp.partial = a->partial;
+  {
+    static const bool debug = [] {
+      const char* e = getenv("FB_KERNEL_DEBUG");
+      return e && e[0] == '1';
+    }();
+    kp.debug = debug ? 1 : 0;
+  }
   const int n_slots_total = a->n_taps * a->cblocks;
   dim3 grid((a->cout + 127) / 128, (n_slots_total + a->slots_per_cta - 1) / a->slots_per_cta, a->splits);
   constexpr int smem = kWgAStages * kWgABytes + kWgBStages * kWgBBytes + kEpiStageBytes + 1024 + 256;

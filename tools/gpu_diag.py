@@ -25,7 +25,7 @@ def main():
     summary = {}
     for g in groups:
         t0 = time.time()
-        cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--timeout", "300", "-p", "no:cacheprovider"] + GROUPS[g]
+        cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--timeout", "600", "--durations=8", "-p", "no:cacheprovider"] + GROUPS[g]
         try:
             r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
             out, code = r.stdout + r.stderr, r.returncode

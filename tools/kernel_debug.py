@@ -35,7 +35,8 @@ def run(n, h, w, cin, cout, split, what):
     partial = torch.empty(ops.Conv2dPlan.partial_elems(n, h, w, cin, cout, 3, 1), device=DEV)
     plan = ops.Conv2dPlan(n, h, w, cin, cout, 3, 1, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
                           dx_accumulate=True, split=split)
-    fn = plan.forward if what == "fwd" else plan.dgrad
+    gw = torch.empty(cout, cin, 3, 3, device=DEV)
+    fn = {"fwd": plan.forward, "dgrad": plan.dgrad, "wgrad": lambda: plan.wgrad(gw)}[what]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -56,6 +57,10 @@ def run(n, h, w, cin, cout, split, what):
 
 
 if __name__ == "__main__":
+    for shape in [(128, 32, 32, 64, 64), (128, 16, 16, 128, 128), (128, 8, 8, 256, 256), (128, 4, 4, 512, 512)]:
+        run(*shape, True, "wgrad")
+    run(128, 8, 8, 256, 256, True, "fwd")
+    run(128, 4, 4, 512, 512, True, "fwd")
     run(128, 32, 32, 64, 64, True, "fwd")
     run(128, 32, 32, 64, 64, True, "dgrad")
     run(128, 16, 16, 128, 128, True, "fwd")
