@@ -173,3 +173,62 @@ extern "C" int fb_flat_scale(float* x, int64_t n, float alpha, void* stream) {
   FB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The step right after the path: global-norm clip (training.py:198-211) + torch.optim.SGD with
+// weight decay / momentum / dampening / Nesterov (optimizers.py:25-28) + sum theta^2 for _record_stats (training.py:92)
+// as ONE sweep over the flat buffers.  The clip coefficient is derived on the device from scal[norm_slot] (= |g|^2
+// from fb_flat_sqnorm), so the optimizer step needs no host synchronisation.
+//   d = g * coef + wd * theta ; buf = first ? d : momentum * buf + (1 - dampening) * d ; d = nesterov ? d + momentum*buf
+//   : buf ; theta -= lr * d            (torch/optim/sgd.py, _single_tensor_sgd, same operation order)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ theta, float* __restrict__ g,
+                                                       float* __restrict__ buf, long long n,
+                                                       const float* __restrict__ scal, int norm_slot, float clip,
+                                                       float lr, float momentum, float dampening, float wd,
+                                                       int nesterov, int first, int write_clipped_grad,
+                                                       double* __restrict__ partial) {
+  __shared__ double red[8];
+  float coef = 1.f;
+  if (clip > 0.f) {
+    const float norm = sqrtf(scal[norm_slot]);
+    if (norm > clip) coef = clip / (norm + 1e-6f);  // training.py:207
+  }
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float t = theta[i];
+    float d = g[i] * coef;
+    if (write_clipped_grad) g[i] = d;  // param.grad is clipped in place by the reference
+    if (wd != 0.f) d = d + wd * t;
+    if (momentum != 0.f) {
+      float b = first ? d : momentum * buf[i] + (1.f - dampening) * d;
+      buf[i] = b;
+      d = nesterov ? d + momentum * b : b;
+    }
+    t = t - lr * d;
+    theta[i] = t;
+    acc += t * t;
+  }
+  double s = warp_sum(double(acc));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    partial[blockIdx.x] = tot;
+  }
+}
+
+extern "C" int fb_sgd_step(float* theta, float* grad, float* momentum_buf, int64_t n, float* scal, int norm_slot,
+                           float clip, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                           int first_step, int write_clipped_grad, double* ws, int param_norm_slot, void* stream) {
+  FB_REQUIRE(theta && grad && scal && ws && n > 0, "fb_sgd_step: bad arguments");
+  FB_REQUIRE(momentum == 0.f || momentum_buf, "fb_sgd_step: momentum needs a buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = flat_grid(n) < kSqBlocks ? flat_grid(n) : kSqBlocks;
+  sgd_step_kernel<<<blocks, 256, 0, st>>>(theta, grad, momentum_buf, n, scal, norm_slot, clip, lr, momentum, dampening,
+                                          weight_decay, nesterov, first_step, write_clipped_grad, ws);
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, blocks, scal, param_norm_slot, nullptr, nullptr);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "fb_mean_accumulate": ([vp, vp, i64, vp, i32, vp], i32),
     "fb_cursor_add": ([vp, i32, vp], i32),
     "fb_flat_scale": ([vp, i64, f32, vp], i32),
+    "fb_sgd_step": ([vp, vp, vp, i64, vp, i32, f32, f32, f32, f32, f32, i32, i32, i32, vp, i32, vp], i32),
     "fb_debug_counters": ([vp, i32], i32),
 }
 

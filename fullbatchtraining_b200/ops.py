@@ -21,7 +21,7 @@ LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_
 _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv3x3": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
                      "fb_stem_im2col": 1, "fb_bn_fwd_fused": 1, "fb_bn_bwd_fused": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
-                     "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1}
+                     "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1, "fb_sgd_step": 2}
 
 
 def _call(family, work, unit, name, *args):
@@ -502,3 +502,9 @@ def cursor_add(cursor, delta):
 
 def flat_scale(x, n, alpha):
     _call("misc", 0.0, "byte", "fb_flat_scale", x.data_ptr(), n, alpha)
+
+
+def sgd_step(theta, grad, buf, n, scal, norm_slot, clip, lr, momentum, dampening, wd, nesterov, first, write_grad, ws,
+             param_norm_slot):
+    _call("misc", 0.0, "byte", "fb_sgd_step", theta.data_ptr(), grad.data_ptr(), L.ptr(buf), n, scal.data_ptr(), norm_slot,
+          clip, lr, momentum, dampening, wd, int(nesterov), int(first), int(write_grad), ws.data_ptr(), param_norm_slot)

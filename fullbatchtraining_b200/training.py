@@ -25,6 +25,7 @@ import torch
 
 from .engine import FullBatchEngine
 from .modules import GradRegularizer, LabelSmoothCrossEntropyLoss
+from .optim import FlatSGD, S_GNORM, S_PNORM
 
 log = logging.getLogger("fullbatch_b200")
 
@@ -37,7 +38,7 @@ def get_loss_fn(cfg_hyp, batch_size=None):
     return LabelSmoothCrossEntropyLoss(smoothing=smoothing)
 
 
-def optim_interface(model, cfg_hyp):
+def optim_interface(model, cfg_hyp, fused=False):
     """optimizers.py:10-93 for the configuration the path uses: ``Gradient Descent`` = torch.optim.SGD
     (:25-28), scheduler cosine-4000 / cosine-decay / none (:75-87) and the linear warm-up wrapper (:89-91,
     scheduler.py:57-66: lr = base*step/warmup up to `warmup`, the wrapped scheduler starts one step later)."""
@@ -47,7 +48,10 @@ def optim_interface(model, cfg_hyp):
     if cfg_hyp.optim_modification.name != "none":
         raise ValueError("optim_modification is not on the B200 path")
     params = {k: v for k, v in cfg_hyp.optim.items() if k not in ("name", "line_search")}
-    optimizer = torch.optim.SGD(model.parameters(), **params)
+    if fused:
+        optimizer = FlatSGD(model.parameters(), **params)  # clip + SGD + param norm in one device sweep
+    else:
+        optimizer = torch.optim.SGD(model.parameters(), **params)
     warmup = int(cfg_hyp.warmup or 0)
     sched = cfg_hyp.scheduler
 
@@ -90,7 +94,11 @@ class Trainer:
     def __init__(self, model, trainloader, validloader, setup, cfg):
         model.train()
         self.model, self.trainloader, self.validloader, self.setup, self.cfg = model, trainloader, validloader, setup, cfg
-        self.optimizer, self.scheduler = optim_interface(model, cfg.hyp)
+        # impl.fused_optimizer (default on): FlatSGD = clip + SGD + param norm as one sweep over the flat buffers;
+        # off: stock torch.optim.SGD and the torch clip of training.py:198-211
+        self.fused_opt = bool(cfg.impl.get("fused_optimizer", True)) and not cfg.hyp.train_stochastic and \
+            (cfg.hyp.grad_clip is None or float(cfg.hyp.grad_clip_norm) == 2.0)
+        self.optimizer, self.scheduler = optim_interface(model, cfg.hyp, fused=self.fused_opt)
         self.stats = defaultdict(list)
         self.device = torch.device(setup["device"])
         if str(cfg.impl.accumulation_dtype) not in ("float", "float32") or \
@@ -113,6 +121,8 @@ class Trainer:
         self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **cfg.hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps
+        if self.fused_opt:
+            self.optimizer.bind(self.engine, cfg.hyp.grad_clip)
         self.resident = _resident_dataset(trainloader, self.device) if cfg.impl.get("resident_dataset", True) else None
         # microbatches per full-batch pass (training.py:65-66,146).  A resident dataset is sharded here by contiguous
         # microbatch ranges; a streamed loader is taken as this rank's shard already (impl.setup.sharded_loader).
@@ -151,7 +161,10 @@ class Trainer:
         # _record_stats, training.py:85-119
         for idx, entry in enumerate(res["grad_norms"].sqrt().tolist()):
             stats[f"grad_norm_train_{idx}"] += [entry]
-        param_norm = float(eng.theta.double().pow(2).sum())
+        if self.fused_opt and self.step_count > 0:
+            param_norm = float(eng.scal[S_PNORM])  # left on the device by the previous FlatSGD step
+        else:
+            param_norm = float(eng.theta.double().pow(2).sum())
         full_grad_norm = float(res["grad_norms"].mean())
         full_loss = res["loss"] + 0.5 * cfg.hyp.optim.get("weight_decay", 0.0) * param_norm
         if self.bs != 0:
@@ -168,6 +181,8 @@ class Trainer:
     def _modify_gradient_params(self):
         """training.py:187-215 (global clip only; next-row item f1 fuses this into the flat-buffer sweeps)."""
         cfg, eng, stats = self.cfg, self.engine, self.stats
+        if self.fused_opt:
+            return  # FlatSGD.step clips on the device; the statistics are read after the step
         if cfg.hyp.grad_clip is not None:
             norm_type = float(cfg.hyp.grad_clip_norm)
             grad_norm = eng.avg.abs().max() if norm_type == float("inf") else torch.norm(eng.avg, norm_type)
@@ -222,6 +237,10 @@ class Trainer:
                 return loss
 
             self.optimizer.step(gradient_evaluation)
+            if self.fused_opt and cfg.hyp.grad_clip is not None:
+                gnorm = math.sqrt(float(self.engine.scal[S_GNORM]))
+                self.stats["preclip_gradnorm"] += [gnorm]
+                self.stats["clipped_step"] += [1 if gnorm > cfg.hyp.grad_clip else 0]
             self.scheduler.step()
         else:
             self._sgd_epoch()

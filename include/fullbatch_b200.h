@@ -230,6 +230,14 @@ int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream);
 /* x *= alpha over n elements (rank-weighting before the all-reduce, training/utils.py:31-41) */
 int fb_flat_scale(float* x, int64_t n, float alpha, void* stream);
 
+/* The step right after the path as one sweep: clip by the global L2 norm (coef from
+ * scal[norm_slot] = |g|^2, training.py:198-211; clip <= 0 disables), torch.optim.SGD update with weight decay,
+ * momentum, dampening, Nesterov (optimizers.py:25-28, same operation order as torch/optim/sgd.py) and
+ * scal[param_norm_slot] = sum theta_new^2 (training.py:92).  ws >= 1024 doubles. */
+int fb_sgd_step(float* theta, float* grad, float* momentum_buf, int64_t n, float* scal, int norm_slot, float clip,
+                float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                int write_clipped_grad, double* ws, int param_norm_slot, void* stream);
+
 /* Development aid: with FB_KERNEL_DEBUG=1 fb_conv3x3 accumulates per-role wait cycles of CTA 0 in 32 device counters;
  * this call synchronises the device, copies them to host32[32] and optionally clears them. */
 int fb_debug_counters(long long* host32, int clear);

@@ -151,3 +151,36 @@ def test_sgd_sanity_branch_runs_through_the_same_kernels():
     assert len(stats["train_loss"]) == 2 and all(math.isfinite(v) for v in stats["train_loss"])
     assert not torch.equal(before, after)
     assert stats["train_loss"][1] < 50
+
+
+def test_flat_sgd_matches_torch_sgd_with_clip():
+    """FlatSGD (fb_sgd_step: clip + weight decay + Nesterov momentum in one sweep) against torch.optim.SGD +
+    the reference's clip (training.py:198-211) on the same gradients, three steps."""
+    from fullbatchtraining_b200.engine import FullBatchEngine
+    from fullbatchtraining_b200.optim import FlatSGD, S_GNORM, S_PNORM
+
+    model = fresh()
+    eng = FullBatchEngine(model, 16)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    kw = dict(lr=0.8, momentum=0.9, dampening=0.0, weight_decay=5e-4, nesterov=True)
+    opt = FlatSGD(model.parameters(), **kw).bind(eng, grad_clip=0.25)
+    ref = torch.optim.SGD(ref_params, **kw)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for step in range(3):
+        grad = torch.randn(eng.numel, device=DEV, generator=g) * (1e-3 if step == 1 else 1e-2)
+        eng.avg.copy_(grad)
+        norm = grad.norm()
+        clipped = grad * (0.25 / (norm + 1e-6)) if norm > 0.25 else grad
+        off = 0
+        for p in ref_params:
+            p.grad = clipped[off:off + p.numel()].view_as(p).clone()
+            off += p.numel()
+        ref.step()
+        opt.step()
+        flat_ref = torch.cat([p.detach().reshape(-1) for p in ref_params])
+        assert rel(eng.theta, flat_ref) < 1e-6
+        assert float(eng.scal[S_GNORM]) == pytest.approx(float(norm) ** 2, rel=1e-5)
+        assert float(eng.scal[S_PNORM]) == pytest.approx(float(flat_ref.double().pow(2).sum()), rel=1e-5)
+        assert rel(eng.avg, clipped) < 1e-6  # param.grad clipped in place like the reference
+    sd = opt.state_dict()
+    assert "momentum_buffer" in sd["state"][0]
