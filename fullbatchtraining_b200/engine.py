@@ -19,6 +19,8 @@ Persistent state (allocated once, kernels never allocate):
 theta itself is never modified by the regulariser, so the reference's "restore from a clone" (modules.py:237-238) is
 exact by construction.
 """
+import os
+
 import torch
 
 from . import ops
@@ -209,6 +211,8 @@ class FullBatchEngine:
             self.wprep.append(ops.WeightPrepTable(entries, dev))
         self._bn_modules = dict(self.model.named_modules())
         self._graphs = {}
+        # FB_WGRAD_STREAM=0 disables the side stream (everything in one stream)
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "1") == "1" else None
         self.grad_norms = None
         self.norm_offset = 0
         self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
@@ -275,10 +279,16 @@ class FullBatchEngine:
                          dA2=act.grad2)
         gw = self._view(G, u.conv_name + ".weight")
         plan = u.plans[self._pass]
-        if u.stem:
-            plan.wgrad(gw, cin_real=3, mode=1)
+        # wgrad (+ its split-K reduction) only feeds the flat gradient: it runs on a side stream, concurrently with the
+        # dgrad -> BatchNorm-backward chain of the layers below (fork here, join at the end of the backward pass)
+        if self.wgrad_stream is not None:
+            main = torch.cuda.current_stream()
+            self.wgrad_stream.wait_stream(main)
+            with torch.cuda.stream(self.wgrad_stream):
+                plan.wgrad(gw, cin_real=3, mode=1) if u.stem else plan.wgrad(gw)
         else:
-            plan.wgrad(gw)
+            plan.wgrad(gw, cin_real=3, mode=1) if u.stem else plan.wgrad(gw)
+        if not u.stem:
             plan.dgrad()
 
     def _backward(self, P, G):
@@ -302,6 +312,8 @@ class FullBatchEngine:
                 else:
                     self._unit_backward(u, P, G, u.out)
         self._unit_backward(self.stem, P, G, self.a0)
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join: g is complete, activations are free
 
     # ------------------------------------------------------------------------------------------------------------
     def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g,
