@@ -34,6 +34,37 @@ int check_cuda(cudaError_t e, const char* what);
 constexpr int kNumSMs = 148;
 
 // ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The ~300 dependent kernels of a microbatch are short (10-50 us), so launch
+// latency and per-kernel prologues (barrier init, TMEM allocation, descriptor fetch) matter.  Kernels launched through
+// launch_pdl() may start while their predecessor in the stream is still draining; they run their prologue, then
+// griddep_wait() blocks until the predecessor grid has completed and its memory is visible -- every such kernel calls
+// it before its first global access, so stream semantics are unchanged.  griddep_launch() lets the successor start
+// early; kernels with grid-wide spin barriers never call it (their successor must not take SM resources before all
+// of their own blocks are resident).  The launch attribute is opt-in (FB_PDL=1): on B200 the measured gain for this
+// workload is within noise, so the default keeps plain stream serialisation (the instructions are then no-ops).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // shared-memory / mbarrier
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

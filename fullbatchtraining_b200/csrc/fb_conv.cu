@@ -30,6 +30,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FB_PDL");  // opt-in: measured gain on B200 is within noise
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("%s failed: %s", what, cudaGetErrorString(e));
@@ -160,6 +167,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();    // everything above overlapped the predecessor's tail
+  griddep_launch();
 
   const int k_iters = p.n_taps * p.cblocks;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -280,8 +289,7 @@ static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
   }
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  conv_gemm_kernel<N_TILE, PA, PB><<<grid, 192, Cfg::kSmemBytes, stream>>>(kp);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, kp));
   return 0;
 }
 
@@ -383,6 +391,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
 
   const int tiles_per_img = p.h / (2 * p.th);
   const int m_tiles = p.n * tiles_per_img;
@@ -566,8 +576,7 @@ static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
   }
   const int tiles = kp.n * (kp.h / (2 * kp.th)) * kp.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  conv3x3_kernel<N_TILE, PA, PB><<<grid, 192, smem, stream>>>(kp, a_box_bytes, b_stages);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), smem, stream, kp, a_box_bytes, b_stages));
   return 0;
 }
 
@@ -634,6 +643,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
 
   const int co0 = blockIdx.x * 128;
   const int slot0 = blockIdx.y * p.slots_per_cta;
@@ -784,6 +795,8 @@ __device__ __forceinline__ float sum_splits(const float* __restrict__ src, int s
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int taps,
                                       int cin_stored, int mode, float* __restrict__ g) {
   __shared__ float tile[32 * 9];
+  griddep_wait();
+  griddep_launch();
   const int co = blockIdx.y;
   const int ci0 = blockIdx.x * 32;
   const int t = threadIdx.x;
@@ -892,6 +905,8 @@ __device__ __forceinline__ void weight_prep_tile(const float* __restrict__ w, in
 __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const float* __restrict__ theta,
                                                                 const fb_wprep_entry* __restrict__ table, int n) {
   extern __shared__ float wtile[];
+  griddep_wait();
+  griddep_launch();
   int lo = 0, hi = n - 1;
   while (lo < hi) {  // last entry with block_start <= blockIdx.x
     const int mid = (lo + hi + 1) >> 1;
@@ -1114,8 +1129,7 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
     FB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(kp);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(wgrad_kernel, grid, dim3(192), smem, static_cast<cudaStream_t>(stream), kp));
   return 0;
 }
 
@@ -1125,9 +1139,8 @@ extern "C" int fb_wgrad_finalize(const float* partial, int splits, int cout, int
   FB_REQUIRE(taps == 1 || taps == 9, "fb_wgrad_finalize: taps must be 1 or 9");
   FB_REQUIRE(mode == 1 || cin % 32 == 0, "fb_wgrad_finalize: cin must be a multiple of 32 in mode 0");
   dim3 grid((cin + 31) / 32, cout);
-  wgrad_finalize_kernel<<<grid, 32 * taps, 0, static_cast<cudaStream_t>(stream)>>>(partial, splits, cout, cin, taps,
-                                                                                   cin_stored, mode, g_oihw);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(wgrad_finalize_kernel, grid, dim3(32 * taps), 0, static_cast<cudaStream_t>(stream), partial, splits,
+                     cout, cin, taps, cin_stored, mode, g_oihw));
   return 0;
 }
 
@@ -1158,8 +1171,8 @@ extern "C" int fb_weight_prep_multi(const float* theta, const fb_wprep_entry* ta
                                     void* stream) {
   FB_REQUIRE(theta && table_dev && n_entries > 0 && total_blocks > 0, "fb_weight_prep_multi: bad arguments");
   const size_t smem = size_t(32) * (32 * 9 + 1) * sizeof(float);
-  weight_prep_multi_kernel<<<total_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(theta, table_dev, n_entries);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(weight_prep_multi_kernel, dim3(total_blocks), dim3(256), smem, static_cast<cudaStream_t>(stream),
+                     theta, table_dev, n_entries));
   return 0;
 }
 

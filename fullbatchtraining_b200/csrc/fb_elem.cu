@@ -420,6 +420,7 @@ __device__ __forceinline__ void warp_reduce_partials(const float* __restrict__ p
 }
 
 __global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) {
+  griddep_wait();
   __shared__ float4 red[2][256];
   const fb_bn_apply_args& ap = a.ap;
   const int C = ap.C;
@@ -514,6 +515,7 @@ struct BnFusedBwdArgs {
 };
 
 __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) {
+  griddep_wait();
   __shared__ float4 red[2][256];
   const fb_bn_bwd_args& bw = a.bw;
   const int C = bw.C;
@@ -577,6 +579,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int n, int h, int w,
                                     int c, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  griddep_wait();
+  griddep_launch();
   const int ho = h / 2, wo = w / 2;
   const long long total8 = (long long)n * ho * wo * c / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
@@ -613,6 +617,8 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* 
 
 __global__ void avgpool2_bwd_kernel(const float* __restrict__ dP, int n, int h, int w, int c, float* __restrict__ dX,
                                     int accumulate) {
+  griddep_wait();
+  griddep_launch();
   const int ho = h / 2, wo = w / 2;
   const long long total4 = (long long)n * h * w * c / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
@@ -641,6 +647,8 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, const long long*
                                    const long long* __restrict__ perm, const int* __restrict__ first_dev,
                                    long long first, int n, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
                                    long long* __restrict__ labels_out) {
+  griddep_wait();
+  griddep_launch();
   if (first_dev) first += (long long)(*first_dev) * n;
   const long long total = (long long)n * 1024 * 8;  // 8 groups of 8 columns per pixel
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -681,6 +689,8 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ 
                                                        float smoothing, float* __restrict__ pooled,
                                                        float* __restrict__ dlogits, float* __restrict__ loss_n,
                                                        float* __restrict__ correct_n) {
+  griddep_wait();
+  griddep_launch();
   extern __shared__ float sp[];  // c floats + classes logits
   float* logits = sp + c;
   const int img = blockIdx.x;
@@ -735,6 +745,8 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(128) head_bwd_act_kernel(const float* __restrict__ dlogits,
                                                            const float* __restrict__ fc_w, int hw, int c, int classes,
                                                            float* __restrict__ dA) {
+  griddep_wait();
+  griddep_launch();
   const int ch = blockIdx.x * 128 + threadIdx.x;
   const int img = blockIdx.y;
   if (ch >= c) return;
@@ -752,6 +764,8 @@ __global__ void __launch_bounds__(256) head_bwd_param_kernel(const float* __rest
                                                              int classes, float* __restrict__ d_fcw,
                                                              float* __restrict__ d_fcb, float* __restrict__ scal,
                                                              int loss_slot, int correct_slot) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[8][kMaxClasses][33];
   const int cl = threadIdx.x & 31, lane_n = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
@@ -888,18 +902,16 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
 extern "C" int fb_avgpool2_fwd(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi,
                                void* out_lo, void* stream) {
   FB_REQUIRE(in_hi && out_hi && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "fb_avgpool2_fwd: bad arguments");
-  avgpool2_fwd_kernel<<<stream_grid((long long)n * h * w * c / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(in_hi), static_cast<const bf16*>(in_lo), n, h, w, c, static_cast<bf16*>(out_hi),
-      static_cast<bf16*>(out_lo));
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(avgpool2_fwd_kernel, dim3(stream_grid((long long)n * h * w * c / 32)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), static_cast<const bf16*>(in_hi), static_cast<const bf16*>(in_lo),
+                     n, h, w, c, static_cast<bf16*>(out_hi), static_cast<bf16*>(out_lo)));
   return 0;
 }
 
 extern "C" int fb_avgpool2_bwd(const float* dP, int n, int h, int w, int c, float* dX, int accumulate, void* stream) {
   FB_REQUIRE(dP && dX && h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "fb_avgpool2_bwd: bad arguments");
-  avgpool2_bwd_kernel<<<stream_grid((long long)n * h * w * c / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dP, n, h, w, c, dX, accumulate);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(avgpool2_bwd_kernel, dim3(stream_grid((long long)n * h * w * c / 4)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), dP, n, h, w, c, dX, accumulate));
   return 0;
 }
 
@@ -908,10 +920,11 @@ extern "C" int fb_stem_im2col(const float* x, const int64_t* labels, const int64
                               void* stream) {
   FB_REQUIRE(x && patches_hi && n > 0, "fb_stem_im2col: bad arguments");
   FB_REQUIRE(!labels_out || labels, "fb_stem_im2col: labels_out needs labels");
-  stem_im2col_kernel<<<stream_grid((long long)n * 1024 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<const long long*>(labels), reinterpret_cast<const long long*>(perm), first_dev, first, n,
-      static_cast<bf16*>(patches_hi), static_cast<bf16*>(patches_lo), reinterpret_cast<long long*>(labels_out));
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(stem_im2col_kernel, dim3(stream_grid((long long)n * 1024 * 8)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), x, reinterpret_cast<const long long*>(labels),
+                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, n,
+                     static_cast<bf16*>(patches_hi), static_cast<bf16*>(patches_lo),
+                     reinterpret_cast<long long*>(labels_out)));
   return 0;
 }
 
@@ -929,13 +942,14 @@ extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw
   float* dlogits = pooled + (long long)n * c;
   float* loss_n = dlogits + (long long)n * kMaxClasses;
   float* correct_n = loss_n + n;
-  head_fwd_kernel<<<n, 128, (c + kMaxClasses) * sizeof(float), st>>>(
-      static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
-      reinterpret_cast<const long long*>(labels), classes, smoothing, pooled, dlogits, loss_n, correct_n);
-  head_bwd_act_kernel<<<dim3((c + 127) / 128, n), 128, 0, st>>>(dlogits, fc_w, hw, c, classes, dA);
-  head_bwd_param_kernel<<<(c + 31) / 32, 256, 0, st>>>(dlogits, pooled, loss_n, correct_n, n, c, classes, d_fcw, d_fcb,
-                                                        scal, loss_slot, correct_slot);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(head_fwd_kernel, dim3(n), dim3(128), (c + kMaxClasses) * sizeof(float), st,
+                     static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
+                     reinterpret_cast<const long long*>(labels), classes, smoothing, pooled, dlogits, loss_n, correct_n));
+  FB_CUDA(launch_pdl(head_bwd_act_kernel, dim3((c + 127) / 128, n), dim3(128), 0, st, (const float*)dlogits, fc_w, hw, c,
+                     classes, dA));
+  FB_CUDA(launch_pdl(head_bwd_param_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)dlogits,
+                     (const float*)pooled, (const float*)loss_n, (const float*)correct_n, n, c, classes, d_fcw, d_fcb, scal,
+                     loss_slot, correct_slot));
   return 0;
 }
 
@@ -986,8 +1000,7 @@ extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, flo
   a.counters = reinterpret_cast<unsigned int*>(ws);
   a.partial = ws + 4;
   a.rows_per_block = rpb;
-  bn_fwd_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(bn_fwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }
 
@@ -1007,7 +1020,6 @@ extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
   a.partial = bw->ws + 4;
   a.coef = a.partial + (long long)2 * bw->C * 2 * kNumSMs;
   a.rows_per_block = rpb;
-  bn_bwd_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }

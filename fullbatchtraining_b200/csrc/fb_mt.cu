@@ -16,6 +16,8 @@ constexpr int kSqBlocks = 1024;
 
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ x, long long n,
                                                              double* __restrict__ partial) {
+  griddep_wait();
+  griddep_launch();
   __shared__ double red[8];
   float acc = 0.f;
   const long long n4 = n / 4;
@@ -42,6 +44,8 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restr
                                                            float* __restrict__ scal, int slot,
                                                            float* __restrict__ norms_out,
                                                            const int* __restrict__ cursor) {
+  griddep_wait();
+  griddep_launch();
   __shared__ double red[8];
   double d = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += blockDim.x) d += partial[i];
@@ -59,6 +63,8 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restr
 __global__ void __launch_bounds__(256) fd_perturb_kernel(const float* __restrict__ theta, const float* __restrict__ g,
                                                          long long n, float bs, float eps, float* __restrict__ scal,
                                                          int sq_slot, int eps_slot, float* __restrict__ theta_p) {
+  griddep_wait();
+  griddep_launch();
   const float n2 = scal[sq_slot];
   // modules.py:223: eps / sqrt(sum (bs*g)^2)
   const float eps_n = eps / sqrtf(bs * bs * n2);
@@ -84,6 +90,8 @@ __global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ g, 
                                                          const float* __restrict__ scal, int eps_slot, float cf,
                                                          int cf_slot, const int* __restrict__ cursor, int count0,
                                                          int write_g) {
+  griddep_wait();
+  griddep_launch();
   const float eps_n = REG ? scal[eps_slot] : 1.f;
   if (REG && cf_slot >= 0) cf = scal[cf_slot];
   const int count = count0 + (cursor ? *cursor : 0) + 1;
@@ -102,7 +110,11 @@ __global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ g, 
   }
 }
 
-__global__ void cursor_add_kernel(int* cursor, int delta) { *cursor += delta; }
+__global__ void cursor_add_kernel(int* cursor, int delta) {
+  griddep_wait();
+  griddep_launch();
+  *cursor += delta;
+}
 
 __global__ void __launch_bounds__(256) flat_scale_kernel(float* __restrict__ x, long long n, float alpha) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -124,9 +136,9 @@ extern "C" int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal
   FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm: bad arguments");
   FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fb_flat_sqnorm: x must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sqnorm_partial_kernel<<<kSqBlocks, 256, 0, st>>>(x, n, ws);
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, kSqBlocks, scal, slot, norms_out, cursor);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(sqnorm_partial_kernel, dim3(kSqBlocks), dim3(256), 0, st, x, (long long)n, ws));
+  FB_CUDA(launch_pdl(sqnorm_final_kernel, dim3(1), dim3(256), 0, st, (const double*)ws, kSqBlocks, scal, slot, norms_out,
+                     (const int*)cursor));
   return 0;
 }
 
@@ -136,34 +148,31 @@ extern "C" int fb_fd_perturb(const float* theta, const float* g, int64_t n, floa
   FB_REQUIRE(((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) |
                reinterpret_cast<uintptr_t>(theta_p)) & 15) == 0,
              "fb_fd_perturb: buffers must be 16-byte aligned");
-  fd_perturb_kernel<<<flat_grid(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, g, n, block_strength, eps, scal, sq_slot, eps_slot, theta_p);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(fd_perturb_kernel, dim3(flat_grid(n / 4 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), theta,
+                     g, (long long)n, block_strength, eps, scal, sq_slot, eps_slot, theta_p));
   return 0;
 }
 
 extern "C" int fb_fd_combine(float* g, const float* g2, float* avg, int64_t n, const float* scal, int eps_slot, float cf,
                              int cf_slot, const int32_t* cursor, int32_t count0, int write_g, void* stream) {
   FB_REQUIRE(g && g2 && scal && n > 0, "fb_fd_combine: bad arguments");
-  fd_combine_kernel<true><<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, g2, avg, n, scal, eps_slot, cf, cf_slot, cursor, count0, write_g);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(fd_combine_kernel<true>, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g, g2,
+                     avg, (long long)n, scal, eps_slot, cf, cf_slot, (const int*)cursor, (int)count0, write_g));
   return 0;
 }
 
 extern "C" int fb_mean_accumulate(const float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0,
                                   void* stream) {
   FB_REQUIRE(g && avg && n > 0, "fb_mean_accumulate: bad arguments");
-  fd_combine_kernel<false><<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      const_cast<float*>(g), nullptr, avg, n, nullptr, 0, 0.f, -1, cursor, count0, 0);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(fd_combine_kernel<false>, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                     const_cast<float*>(g), (const float*)nullptr, avg, (long long)n, (const float*)nullptr, 0, 0.f, -1,
+                     (const int*)cursor, (int)count0, 0));
   return 0;
 }
 
 extern "C" int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream) {
   FB_REQUIRE(cursor, "fb_cursor_add: null pointer");
-  cursor_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(cursor, delta);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(cursor_add_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), (int*)cursor, (int)delta));
   return 0;
 }
 
