@@ -241,3 +241,125 @@ extern "C" int fb_sgd_step(float* theta, float* grad, float* momentum_buf, int64
   FB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generalised variants for the rest of the hyp.grad_reg surface:
+//   acc_strength  : v = bs*g + acc*pre_grads                       (modules.py:217-221, training.py:128-142)
+//   central diffs : theta +- 0.5*eps_n*v, vhp = (g+ - g-)/eps_n    (modules.py:266-300)
+//   batch_clip    : per-microbatch L2 clip before the running mean (training/utils.py:4-19, training.py:166-168)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sqnorm_axpby_partial_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ y, float a, float b,
+                                                                   long long n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  griddep_wait();
+  griddep_launch();
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = a * x[i] + (y ? b * y[i] : 0.f);
+    acc += v * v;
+  }
+  double d = warp_sum(double(acc));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) fd_perturb_ex_kernel(const float* __restrict__ theta, const float* __restrict__ g,
+                                                            const float* __restrict__ pre, long long n, float bs,
+                                                            float acc, float eps, float scale, float* __restrict__ scal,
+                                                            int vsq_slot, int eps_slot, float* __restrict__ theta_p) {
+  griddep_wait();
+  griddep_launch();
+  const float eps_n = eps / sqrtf(scal[vsq_slot]);  // scal[vsq_slot] = sum v^2
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[eps_slot] = eps_n;
+  const float step = scale * eps_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = bs * g[i] + (pre ? acc * pre[i] : 0.f);
+    theta_p[i] = theta[i] + step * v;
+  }
+}
+
+__global__ void __launch_bounds__(256) fd_combine_ex_kernel(float* __restrict__ g, const float* __restrict__ g_plus,
+                                                            const float* __restrict__ g_minus, float* __restrict__ avg,
+                                                            long long n, const float* __restrict__ scal, int eps_slot,
+                                                            float cf, int cf_slot, const int* __restrict__ cursor,
+                                                            int count0, int write_g) {
+  griddep_wait();
+  griddep_launch();
+  const float eps_n = scal[eps_slot];
+  if (cf_slot >= 0) cf = scal[cf_slot];
+  const int count = count0 + (cursor ? *cursor : 0) + 1;
+  const float inv = float(1.0 / double(count));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float h = (g_plus[i] - g_minus[i]) / eps_n;  // modules.py:292-293
+    const float gr = g[i] + cf * h;                    // modules.py:299
+    if (write_g) g[i] = gr;
+    if (avg) {
+      const float a = avg[i];
+      avg[i] = a + (gr - a) * inv;
+    }
+  }
+}
+
+// avg += (coef*g - avg)/count with coef = clip/(norm+1e-6) if norm > clip (norm = sqrt(scal[norm_slot]));
+// scal[clipped_slot] += 1 when the microbatch was clipped; g is scaled in place like the reference does.
+__global__ void __launch_bounds__(256) mean_accumulate_clip_kernel(float* __restrict__ g, float* __restrict__ avg,
+                                                                   long long n, const int* __restrict__ cursor,
+                                                                   int count0, float* __restrict__ scal, int norm_slot,
+                                                                   float clip, int clipped_slot) {
+  griddep_wait();
+  griddep_launch();
+  const float norm = sqrtf(scal[norm_slot]);
+  const bool clipped = norm > clip;
+  const float coef = clipped ? clip / (norm + 1e-6f) : 1.f;
+  const int count = count0 + (cursor ? *cursor : 0) + 1;
+  const float inv = float(1.0 / double(count));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * coef;
+    if (clipped) g[i] = gr;
+    const float a = avg[i];
+    avg[i] = a + (gr - a) * inv;
+  }
+  if (clipped && blockIdx.x == 0 && threadIdx.x == 0) scal[clipped_slot] += 1.f;
+}
+
+extern "C" int fb_flat_sqnorm_axpby(const float* x, const float* y, float a, float b, int64_t n, double* ws, float* scal,
+                                    int slot, void* stream) {
+  FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm_axpby: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FB_CUDA(launch_pdl(sqnorm_axpby_partial_kernel, dim3(kSqBlocks), dim3(256), 0, st, x, y, a, b, (long long)n, ws));
+  FB_CUDA(launch_pdl(sqnorm_final_kernel, dim3(1), dim3(256), 0, st, (const double*)ws, kSqBlocks, scal, slot,
+                     (float*)nullptr, (const int*)nullptr));
+  return 0;
+}
+
+extern "C" int fb_fd_perturb_ex(const float* theta, const float* g, const float* pre, int64_t n, float block_strength,
+                                float acc_strength, float eps, float scale, float* scal, int vsq_slot, int eps_slot,
+                                float* theta_p, void* stream) {
+  FB_REQUIRE(theta && g && scal && theta_p && n > 0, "fb_fd_perturb_ex: bad arguments");
+  FB_CUDA(launch_pdl(fd_perturb_ex_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), theta, g,
+                     pre, (long long)n, block_strength, acc_strength, eps, scale, scal, vsq_slot, eps_slot, theta_p));
+  return 0;
+}
+
+extern "C" int fb_fd_combine_ex(float* g, const float* g_plus, const float* g_minus, float* avg, int64_t n,
+                                const float* scal, int eps_slot, float cf, int cf_slot, const int32_t* cursor,
+                                int32_t count0, int write_g, void* stream) {
+  FB_REQUIRE(g && g_plus && g_minus && scal && n > 0, "fb_fd_combine_ex: bad arguments");
+  FB_CUDA(launch_pdl(fd_combine_ex_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g, g_plus,
+                     g_minus, avg, (long long)n, scal, eps_slot, cf, cf_slot, (const int*)cursor, (int)count0, write_g));
+  return 0;
+}
+
+extern "C" int fb_mean_accumulate_clip(float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0,
+                                       float* scal, int norm_slot, float clip, int clipped_slot, void* stream) {
+  FB_REQUIRE(g && avg && scal && n > 0 && clip > 0.f, "fb_mean_accumulate_clip: bad arguments");
+  FB_CUDA(launch_pdl(mean_accumulate_clip_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g,
+                     avg, (long long)n, (const int*)cursor, (int)count0, scal, norm_slot, clip, clipped_slot));
+  return 0;
+}

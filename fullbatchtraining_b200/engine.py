@@ -27,6 +27,12 @@ from . import ops
 from .models import ResNet, ResidualBlock
 
 S_N2, S_EPS, S_LOSS, S_CORRECT, S_LOSS2, S_CORRECT2, S_CF = 0, 1, 2, 3, 4, 5, 6
+S_VSQ, S_CLIPPED, S_REGSQ = 9, 10, 11  # (7, 8 are used by optim.FlatSGD)
+
+# hyp.grad_reg.implementation -> device recipe.  `forward-differences-legacy` (modules.py:243-264) perturbs along g
+# instead of bs*g and scales the correction by bs: the same update up to rounding, so it shares the forward recipe.
+IMPLEMENTATIONS = {"finite_diff": "forward", "forward-differences": "forward", "forward-differences-legacy": "forward",
+                   "central-differences": "central"}
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -317,35 +323,80 @@ class FullBatchEngine:
 
     # ------------------------------------------------------------------------------------------------------------
     def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g,
-                        mode="full"):
+                        mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
         """mode "full": whole per-microbatch recipe; "raw": pass 1 only (training.py:76-83 + :162);
-        "reg": regulariser only, self.g already holds the raw gradient of this microbatch (modules.py:211-241)."""
+        "reg": regulariser only, self.g already holds the raw gradient of this microbatch (modules.py:211-241).
+        impl "forward" | "central" (modules.py:211-241 / :266-300); acc: acc_strength with self.pre as pre_grads;
+        batch_clip: per-microbatch L2 clip before the running mean (training.py:166-168); target "avg" | "pre"
+        (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into self.pre)."""
+        dst = self.avg if target == "avg" else self.pre
         ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb, self.patches.hi,
                         self.patches.lo, self.labels_mb)
         if mode != "reg":
             self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
             self._backward(self.theta, self.g)
-        norms = self.grad_norms[self.norm_offset:] if self.norm_offset else self.grad_norms
+        norms = None
+        if target == "avg":
+            norms = self.grad_norms[self.norm_offset:] if self.norm_offset else self.grad_norms
         ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_N2, norms, self.cursor)
-        if block_strength != 0 and mode != "raw":
-            ops.fd_perturb(self.theta, self.g, self.numel, block_strength, eps, self.scal, S_N2, S_EPS, self.theta_p)
-            self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
-            self._backward(self.theta_p, self.g2)
-            ops.fd_combine(self.g, self.g2, self.avg if accumulate else None, self.numel, self.scal, S_EPS, 0.0,
-                           self.cursor, 0, write_g, cf_slot=S_CF)
+        regularise = (block_strength != 0 or acc != 0) and mode != "raw"
+        fused_mean = dst if (accumulate and batch_clip is None) else None
+        if regularise:
+            if impl == "forward" and acc == 0:
+                ops.fd_perturb(self.theta, self.g, self.numel, block_strength, eps, self.scal, S_N2, S_EPS, self.theta_p)
+                self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
+                self._backward(self.theta_p, self.g2)
+                ops.fd_combine(self.g, self.g2, fused_mean, self.numel, self.scal, S_EPS, 0.0, self.cursor, 0,
+                               write_g or batch_clip is not None, cf_slot=S_CF)
+            else:
+                pre = self.pre if acc != 0 else None
+                ops.flat_sqnorm_axpby(self.g, pre, block_strength, acc, self.numel, self.sq_ws, self.scal, S_VSQ)
+                if impl == "forward":
+                    ops.fd_perturb_ex(self.theta, self.g, pre, self.numel, block_strength, acc, eps, 1.0, self.scal,
+                                      S_VSQ, S_EPS, self.theta_p)
+                    self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
+                    self._backward(self.theta_p, self.g2)
+                    ops.fd_combine(self.g, self.g2, fused_mean, self.numel, self.scal, S_EPS, 0.0, self.cursor, 0,
+                                   write_g or batch_clip is not None, cf_slot=S_CF)
+                else:
+                    for scale, gbuf in ((0.5, self.g2), (-0.5, self._g3())):
+                        ops.fd_perturb_ex(self.theta, self.g, pre, self.numel, block_strength, acc, eps, scale,
+                                          self.scal, S_VSQ, S_EPS, self.theta_p)
+                        self._forward(self.theta_p, gbuf, S_LOSS2, S_CORRECT2)
+                        self._backward(self.theta_p, gbuf)
+                    ops.fd_combine_ex(self.g, self.g2, self._g3(), fused_mean, self.numel, self.scal, S_EPS, 0.0,
+                                      self.cursor, 0, write_g or batch_clip is not None, cf_slot=S_CF)
+            if accumulate and batch_clip is not None:
+                ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_REGSQ)
+                ops.mean_accumulate_clip(self.g, dst, self.numel, self.cursor, 0, self.scal, S_REGSQ, batch_clip,
+                                         S_CLIPPED)
         elif accumulate:
-            ops.mean_accumulate(self.g, self.avg, self.numel, self.cursor, 0)
+            if batch_clip is not None:
+                ops.mean_accumulate_clip(self.g, dst, self.numel, self.cursor, 0, self.scal, S_N2, batch_clip, S_CLIPPED)
+            else:
+                ops.mean_accumulate(self.g, dst, self.numel, self.cursor, 0)
         ops.cursor_add(self.cursor, 1)
 
+    def _g3(self):
+        if not hasattr(self, "g3"):
+            self.g3 = torch.zeros_like(self.g)
+        return self.g3
+
     def _program(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate=True, write_g=False,
-                 use_graph=True, mode="full"):
+                 use_graph=True, mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
         """Returns a callable running one microbatch; captured into a CUDA graph on first use."""
-        args = (x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g, mode)
+        if acc != 0 or target == "pre":
+            if not hasattr(self, "pre"):
+                self.pre = torch.zeros_like(self.g)
+        if impl == "central":
+            self._g3()
+        args = (x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g, mode, impl, acc,
+                batch_clip, target)
         if not use_graph:
             return lambda: self._microbatch_ops(*args)
         key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
-               float(block_strength), float(eps), accumulate, write_g, mode, self.grad_norms.data_ptr(),
-               self.norm_offset)
+               float(block_strength), float(eps), accumulate, write_g, mode, impl, float(acc), batch_clip, target,
+               self.grad_norms.data_ptr(), self.norm_offset)
         if key not in self._graphs:
             state = self._save_state()
             side = torch.cuda.Stream()
@@ -364,7 +415,8 @@ class FullBatchEngine:
     def _save_state(self):
         bufs = [b.clone() for b in self.model.buffers()]
         return dict(avg=self.avg.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
-                    norms=self.grad_norms.clone(), g=self.g.clone())
+                    norms=self.grad_norms.clone(), g=self.g.clone(),
+                    pre=self.pre.clone() if hasattr(self, "pre") else None)
 
     def _restore_state(self, st):
         self.avg.copy_(st["avg"])
@@ -372,6 +424,8 @@ class FullBatchEngine:
         self.cursor.copy_(st["cursor"])
         self.grad_norms.copy_(st["norms"])
         self.g.copy_(st["g"])
+        if st["pre"] is not None:
+            self.pre.copy_(st["pre"])
         for b, s in zip(self.model.buffers(), st["bufs"]):
             b.copy_(s)
 
@@ -387,24 +441,40 @@ class FullBatchEngine:
         self.grad_norms.zero_()
         self.avg.zero_()
         self.scal[S_LOSS:S_CORRECT2 + 1] = 0
+        self.scal[S_CLIPPED] = 0
         self.cursor.zero_()
         self.wprep[0](self.theta)  # theta is constant during the step: pass-1 operands once, not per microbatch
 
     def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
-                            num_norms=None, norm_offset=0):
+                            num_norms=None, norm_offset=0, implementation="forward-differences", acc_strength=0.0,
+                            batch_clip=None):
         """Full-batch accumulation over `count` consecutive microbatches of a device-resident dataset
         X [N,3,32,32] fp32, Y [N] int64, starting at sample `first` (optionally through the index tensor `perm`).
         Returns after enqueueing; results: self.avg (running mean), self.grad_norms[:count], loss/correct sums in scal."""
         assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and Y.dtype == torch.int64
         n_avail = (perm.numel() if perm is not None else X.shape[0]) - first
         count = n_avail // self.mb if count is None else count
+        impl = IMPLEMENTATIONS[implementation]
         self.begin_step(num_norms or count)
         self.norm_offset = int(norm_offset)
         self.set_lr(lr)
-        run = self._program(X, Y, perm, first, True, block_strength, eps, use_graph=use_graph)
+        if acc_strength != 0:
+            # training.py:128-142: extra sweep for the mean raw gradient (pre_grads); single GPU only for now
+            self.pre = torch.zeros_like(self.g) if not hasattr(self, "pre") else self.pre.zero_()
+            pre_run = self._program(X, Y, perm, first, True, 0.0, eps, use_graph=use_graph, mode="raw", impl=impl,
+                                    batch_clip=batch_clip, target="pre")
+            for _ in range(count):
+                pre_run()
+            self.bn_passes += count
+            self.scal[S_LOSS:S_CORRECT2 + 1] = 0
+            self.scal[S_CLIPPED] = 0
+            self.cursor.zero_()
+        run = self._program(X, Y, perm, first, True, block_strength, eps, use_graph=use_graph, impl=impl,
+                            acc=acc_strength, batch_clip=batch_clip)
         for _ in range(count):
             run()
-        self.bn_passes += count * (2 if block_strength != 0 else 1)
+        regularised = block_strength != 0 or acc_strength != 0
+        self.bn_passes += count * ((3 if impl == "central" else 2) if regularised else 1)
         return count
 
     def _stages(self):
@@ -460,8 +530,10 @@ class FullBatchEngine:
         self.bn_passes += 1
         return self.scal[S_LOSS], self.scal[S_CORRECT]
 
-    def regularize(self, inputs, labels, lr, block_strength, eps):
-        """modules.py:211-241: self.g (raw gradient of this microbatch) <- regularised gradient, in place."""
+    def regularize(self, inputs, labels, lr, block_strength, eps, implementation="forward-differences",
+                   acc_strength=0.0):
+        """modules.py:211-300: self.g (raw gradient of this microbatch) <- regularised gradient, in place
+        (acc_strength uses self.pre, see load_pre)."""
         xs, ys = self._stages()
         xs[0].copy_(inputs)
         ys[0].copy_(labels)
@@ -470,8 +542,17 @@ class FullBatchEngine:
         self.cursor.zero_()
         self.set_lr(lr)
         self._pass = 1
-        self._program(xs[0], ys[0], None, 0, False, block_strength, eps, accumulate=False, write_g=True, mode="reg")()
-        self.bn_passes += 1
+        impl = IMPLEMENTATIONS[implementation]
+        self._program(xs[0], ys[0], None, 0, False, block_strength, eps, accumulate=False, write_g=True, mode="reg",
+                      impl=impl, acc=acc_strength)()
+        self.bn_passes += 2 if impl == "central" else 1
+
+    def load_pre(self, pre_grads):
+        """pre_grads (list shaped like model.parameters(), training.py:128-142) -> flat self.pre"""
+        if not hasattr(self, "pre"):
+            self.pre = torch.zeros_like(self.g)
+        for name, t in zip(self.names, pre_grads):
+            self._view(self.pre, name).copy_(t.reshape(-1))
 
     def load_grads(self, grads):
         for name, gt in zip(self.names, grads):
@@ -504,7 +585,7 @@ class FullBatchEngine:
         """Host read of the step scalars (one synchronisation): mean loss, correct count, grad_norms."""
         s = self.scal.tolist()
         return dict(loss=s[S_LOSS] / max(count, 1), correct=s[S_CORRECT], loss_sum=s[S_LOSS],
-                    grad_norms=self.grad_norms[:count].clone())
+                    grad_norms=self.grad_norms[:count].clone(), clipped_batches=int(s[S_CLIPPED]))
 
     def sync_bn_counters(self):
         """num_batches_tracked += number of train-mode passes (2 per microbatch with the regulariser)."""

@@ -93,6 +93,10 @@ _SIGNATURES = {
     "fb_mean_accumulate": ([vp, vp, i64, vp, i32, vp], i32),
     "fb_cursor_add": ([vp, i32, vp], i32),
     "fb_flat_scale": ([vp, i64, f32, vp], i32),
+    "fb_flat_sqnorm_axpby": ([vp, vp, f32, f32, i64, vp, vp, i32, vp], i32),
+    "fb_fd_perturb_ex": ([vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, i32, vp, vp], i32),
+    "fb_fd_combine_ex": ([vp, vp, vp, vp, i64, vp, i32, f32, i32, vp, i32, i32, vp], i32),
+    "fb_mean_accumulate_clip": ([vp, vp, i64, vp, i32, vp, i32, f32, i32, vp], i32),
     "fb_sgd_step": ([vp, vp, vp, i64, vp, i32, f32, f32, f32, f32, f32, i32, i32, i32, vp, i32, vp], i32),
     "fb_debug_counters": ([vp, i32], i32),
 }

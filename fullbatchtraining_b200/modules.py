@@ -13,8 +13,8 @@ import torch
 
 from .engine import FullBatchEngine
 
-ACCELERATED = ("finite_diff", "forward-differences")
-REFERENCE_ONLY = ("autograd-pen", "autograd", "central-differences", "complex-step", "forward-differences-legacy")
+ACCELERATED = ("finite_diff", "forward-differences", "forward-differences-legacy", "central-differences")
+REFERENCE_ONLY = ("autograd-pen", "autograd", "complex-step")
 
 
 class LabelSmoothCrossEntropyLoss(torch.nn.Module):
@@ -46,11 +46,10 @@ class GradRegularizer:
         elif implementation in ACCELERATED:
             if norm != 2:
                 raise ValueError("Only the 2-norm penalty is implemented by forward differences.")
-            if acc_strength != 0:
-                raise ValueError("acc_strength != 0 (pre_grads pre-pass, training.py:128-142) is not on the B200 path yet.")
             if mixed_precision:
                 raise ValueError("mixed_precision (fp16 autocast) is not on the B200 path; use impl.precision instead.")
-            self.forward = self._forward_differences
+            self.forward = self._finite_differences
+            self.implementation = implementation
         elif implementation in REFERENCE_ONLY:
             raise ValueError(f"Regularizer implementation {implementation} is not available on the B200 path "
                              f"(accelerated: {ACCELERATED}).")
@@ -73,11 +72,9 @@ class GradRegularizer:
     def _pass(self, grads, inputs, labels, pre_grads):
         return grads
 
-    def _forward_differences(self, grads, inputs, labels, pre_grads):
-        """modules.py:211-241 on the device: eps_n, theta' = theta + eps_n*bs*g, second forward/backward on the same
-        microbatch, g += (lr/4) (g' - g)/eps_n.  theta is never modified."""
-        if pre_grads is not None:
-            raise ValueError("pre_grads (acc_strength) are not supported on the B200 path")
+    def _finite_differences(self, grads, inputs, labels, pre_grads):
+        """modules.py:211-300 on the device: eps_n, theta' = theta +- eps_n*v with v = bs*g (+ acc*pre_grads), extra
+        forward/backward pass(es) on the same microbatch, g += (lr/4) * vhp.  theta is never modified."""
         if self._microbatch is None:
             self._microbatch = inputs.shape[0]
         eng = self.engine
@@ -85,7 +82,10 @@ class GradRegularizer:
             raise RuntimeError(f"GradRegularizer was built for microbatches of {eng.mb}, got {inputs.shape[0]}")
         lr = self.optimizer.param_groups[0]["lr"]  # modules.py:214, read at call time
         eng.load_grads(grads)
-        eng.regularize(inputs, labels, lr, self.block_strength, self.eps)
+        acc = self.acc_strength if pre_grads is not None else 0.0  # modules.py:219-221
+        if acc != 0:
+            eng.load_pre(pre_grads)
+        eng.regularize(inputs, labels, lr, self.block_strength, self.eps, self.implementation, acc)
         eng.store_grads(grads)
         return grads
 

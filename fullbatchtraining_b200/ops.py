@@ -21,7 +21,9 @@ LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_
 _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv3x3": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
                      "fb_stem_im2col": 1, "fb_bn_fwd_fused": 1, "fb_bn_bwd_fused": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
-                     "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1, "fb_sgd_step": 2}
+                     "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1, "fb_sgd_step": 2,
+                     "fb_flat_sqnorm_axpby": 2, "fb_fd_perturb_ex": 1, "fb_fd_combine_ex": 1,
+                     "fb_mean_accumulate_clip": 1}
 
 
 def _call(family, work, unit, name, *args):
@@ -508,3 +510,22 @@ def sgd_step(theta, grad, buf, n, scal, norm_slot, clip, lr, momentum, dampening
              param_norm_slot):
     _call("misc", 0.0, "byte", "fb_sgd_step", theta.data_ptr(), grad.data_ptr(), L.ptr(buf), n, scal.data_ptr(), norm_slot,
           clip, lr, momentum, dampening, wd, int(nesterov), int(first), int(write_grad), ws.data_ptr(), param_norm_slot)
+
+
+def flat_sqnorm_axpby(x, y, a, b, n, ws, scal, slot):
+    _call("misc", 0.0, "byte", "fb_flat_sqnorm_axpby", x.data_ptr(), L.ptr(y), a, b, n, ws.data_ptr(), scal.data_ptr(), slot)
+
+
+def fd_perturb_ex(theta, g, pre, n, bs, acc, eps, scale, scal, vsq_slot, eps_slot, theta_p):
+    _call("misc", 0.0, "byte", "fb_fd_perturb_ex", theta.data_ptr(), g.data_ptr(), L.ptr(pre), n, bs, acc, eps, scale,
+          scal.data_ptr(), vsq_slot, eps_slot, theta_p.data_ptr())
+
+
+def fd_combine_ex(g, g_plus, g_minus, avg, n, scal, eps_slot, cf, cursor, count0, write_g, cf_slot=-1):
+    _call("misc", 0.0, "byte", "fb_fd_combine_ex", g.data_ptr(), g_plus.data_ptr(), g_minus.data_ptr(), L.ptr(avg), n,
+          scal.data_ptr(), eps_slot, cf, cf_slot, L.ptr(cursor), count0, int(write_g))
+
+
+def mean_accumulate_clip(g, avg, n, cursor, count0, scal, norm_slot, clip, clipped_slot):
+    _call("misc", 0.0, "byte", "fb_mean_accumulate_clip", g.data_ptr(), avg.data_ptr(), n, L.ptr(cursor), count0,
+          scal.data_ptr(), norm_slot, clip, clipped_slot)

@@ -107,8 +107,10 @@ class Trainer:
                              "(impl.dtype / impl.accumulation_dtype must be float)")
         if cfg.impl.mixed_precision:
             raise ValueError("impl.mixed_precision is not on the B200 path; use impl.precision = split | bf16")
-        if cfg.hyp.batch_clip is not None or cfg.hyp.norm_bias.strength > 0 or cfg.hyp.grad_reg.acc_strength != 0:
-            raise ValueError("batch_clip / norm_bias / acc_strength are not on the B200 path yet")
+        if cfg.hyp.norm_bias.strength > 0:
+            raise ValueError("norm_bias is not on the B200 path yet")
+        if cfg.hyp.batch_clip is not None and float(cfg.hyp.grad_clip_norm) != 2.0:
+            raise ValueError("batch_clip is implemented for the 2-norm only")
         self.mb = min(cfg.data.batch_size, cfg.hyp.sub_batch)
         self.num_blocks = len(trainloader)
         self.num_chunks = max(cfg.data.batch_size // cfg.hyp.sub_batch, 1)
@@ -121,6 +123,8 @@ class Trainer:
         self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **cfg.hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps
+        self.acc = float(cfg.hyp.grad_reg.acc_strength)
+        self.impl = cfg.hyp.grad_reg.implementation if (self.bs != 0 or self.acc != 0) else "forward-differences"
         if self.fused_opt:
             self.optimizer.bind(self.engine, cfg.hyp.grad_clip)
         self.resident = _resident_dataset(trainloader, self.device) if cfg.impl.get("resident_dataset", True) else None
@@ -148,10 +152,16 @@ class Trainer:
         eng, cfg, stats = self.engine, self.cfg, self.stats
         lr = self.optimizer.param_groups[0]["lr"]
         if self.resident is not None:
+            if self.acc != 0 and self.world > 1:
+                raise RuntimeError("acc_strength with several processes is not implemented")
             local = eng.accumulate_resident(self.resident[0], self.resident[1], lr, self.bs, self.eps,
                                             first=self.k0 * self.mb, count=self.k1 - self.k0, num_norms=self.K,
-                                            norm_offset=self.k0)
+                                            norm_offset=self.k0, implementation=self.impl, acc_strength=self.acc,
+                                            batch_clip=cfg.hyp.batch_clip)
         else:
+            if self.acc != 0 or cfg.hyp.batch_clip is not None or self.impl == "central-differences":
+                raise RuntimeError("acc_strength / batch_clip / central-differences need a device-resident dataset "
+                                   "(TensorDataset loader)")
             local = eng.accumulate_stream(self.trainloader, lr, self.bs, self.eps, self.K, norm_offset=self.k0)
         if self.dist:
             eng.all_reduce_mean(local, self.K)
@@ -169,6 +179,10 @@ class Trainer:
         full_loss = res["loss"] + 0.5 * cfg.hyp.optim.get("weight_decay", 0.0) * param_norm
         if self.bs != 0:
             full_loss += lr / 4 * self.bs * full_grad_norm
+        if self.acc != 0:  # training.py:99-102
+            full_loss += lr / 4 * self.acc * float(eng.pre.double().pow(2).sum())
+        if cfg.hyp.batch_clip is not None:  # training.py:117-119 (a NameError in the reference as shipped)
+            stats["clipped_batches"] += [res["clipped_batches"]]
         stats["train_loss"] += [res["loss"]]
         stats["train_acc"] += [res["correct"] / (self.K * self.mb)]
         stats["train_time"] += [time.time() - t0]

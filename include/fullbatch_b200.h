@@ -230,6 +230,25 @@ int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream);
 /* x *= alpha over n elements (rank-weighting before the all-reduce, training/utils.py:31-41) */
 int fb_flat_scale(float* x, int64_t n, float alpha, void* stream);
 
+/* ---- generalised variants for the rest of hyp.grad_reg / hyp.batch_clip ---------------------- */
+/* scal[slot] = sum (a*x + b*y)^2 (y may be NULL): |v|^2 for v = bs*g + acc*pre_grads (modules.py:217-223) */
+int fb_flat_sqnorm_axpby(const float* x, const float* y, float a, float b, int64_t n, double* ws, float* scal, int slot,
+                         void* stream);
+/* eps_n = eps / sqrt(scal[vsq_slot]); theta_p = theta + scale*eps_n*(bs*g + acc*pre) (pre may be NULL).  scale = 1:
+ * forward differences with acc_strength (modules.py:217-226); scale = +-0.5: central differences (modules.py:279-286) */
+int fb_fd_perturb_ex(const float* theta, const float* g, const float* pre, int64_t n, float block_strength,
+                     float acc_strength, float eps, float scale, float* scal, int vsq_slot, int eps_slot, float* theta_p,
+                     void* stream);
+/* g_reg = g + cf*(g_plus - g_minus)/eps_n (central differences, modules.py:292-299); avg / cursor / write_g as in
+ * fb_fd_combine */
+int fb_fd_combine_ex(float* g, const float* g_plus, const float* g_minus, float* avg, int64_t n, const float* scal,
+                     int eps_slot, float cf, int cf_slot, const int32_t* cursor, int32_t count0, int write_g,
+                     void* stream);
+/* hyp.batch_clip (training/utils.py:4-19, training.py:166-168): g *= clip/(|g|+1e-6) if |g| = sqrt(scal[norm_slot]) >
+ * clip, scal[clipped_slot] += 1 in that case, then avg += (g - avg)/(count0 + *cursor + 1) */
+int fb_mean_accumulate_clip(float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0, float* scal,
+                            int norm_slot, float clip, int clipped_slot, void* stream);
+
 /* The step right after the path as one sweep: clip by the global L2 norm (coef from
  * scal[norm_slot] = |g|^2, training.py:198-211; clip <= 0 disables), torch.optim.SGD update with weight decay,
  * momentum, dampening, Nesterov (optimizers.py:25-28, same operation order as torch/optim/sgd.py) and

@@ -184,22 +184,58 @@ def microbatch_gradient(net, p, x, y, smoothing=0.0):
 
 
 @torch.no_grad()
-def forward_differences(net, p, grads, x, y, lr, block_strength, eps, smoothing=0.0):
-    """modules.py:211-241 with acc_strength == 0.  Returns (regularised grads, eps_n, hvp); ``p`` is unchanged."""
+def regularize(net, p, grads, x, y, lr, block_strength, eps, smoothing=0.0, implementation="forward-differences",
+               pre_grads=None, acc_strength=0.0):
+    """GradRegularizer.forward (modules.py:151-175 dispatch): returns (regularised grads, eps_n, hvp); ``p`` unchanged.
+
+    forward-differences         modules.py:211-241
+    forward-differences-legacy  modules.py:243-264  (v = g, cf *= block_strength: the same update up to rounding)
+    central-differences         modules.py:266-300  (theta +- 0.5*eps_n*v, three gradient evaluations in total)
+    acc_strength != 0 adds acc_strength * pre_grads to the direction v (modules.py:220-221, :273-274).
+    """
     cf = lr / 4  # :214
     names = list(p.keys())
-    vec = [g * block_strength for g in grads]  # :217
+    if implementation == "forward-differences-legacy":
+        vec = [g.clone() for g in grads]  # :247 (pre_grads are disregarded, :244)
+        cf = cf * block_strength  # :246
+    else:
+        vec = [g * block_strength for g in grads]  # :217
+        if pre_grads is not None:
+            vec = [v + acc_strength * q for v, q in zip(vec, pre_grads)]  # :220-221
     eps_n = eps / torch.stack([v.pow(2).sum() for v in vec]).sum().sqrt()  # :223
-    shifted = OrderedDict((k, p[k] + eps_n * v) for k, v in zip(names, vec))  # :226 (original kept -> exact restore :237)
-    g2, _, _ = microbatch_gradient(net, shifted, x, y, smoothing)  # :227-230
-    hvp = [(b - a) / eps_n for a, b in zip(grads, g2)]  # :232-234
-    out = [a + cf * h for a, h in zip(grads, hvp)]  # :240
+    if implementation in ("forward-differences", "forward-differences-legacy", "finite_diff"):
+        shifted = OrderedDict((k, p[k] + eps_n * v) for k, v in zip(names, vec))  # :226
+        g2, _, _ = microbatch_gradient(net, shifted, x, y, smoothing)  # :227-230
+        hvp = [(b - a) / eps_n for a, b in zip(grads, g2)]  # :232-234
+    elif implementation == "central-differences":
+        plus = OrderedDict((k, p[k] + 0.5 * eps_n * v) for k, v in zip(names, vec))  # :279
+        gp, _, _ = microbatch_gradient(net, plus, x, y, smoothing)
+        minus = OrderedDict((k, plus[k] - eps_n * v) for k, v in zip(names, vec))  # :286 (applied to the shifted params)
+        gm, _, _ = microbatch_gradient(net, minus, x, y, smoothing)
+        hvp = [(a - b) / eps_n for a, b in zip(gp, gm)]  # :292-293
+    else:
+        raise ValueError(f"Invalid spec. given for regularizer implementation: {implementation}")  # :175
+    out = [a + cf * h for a, h in zip(grads, hvp)]  # :240 / :299
     return out, eps_n, hvp
+
+
+def forward_differences(net, p, grads, x, y, lr, block_strength, eps, smoothing=0.0):
+    """modules.py:211-241 with acc_strength == 0."""
+    return regularize(net, p, grads, x, y, lr, block_strength, eps, smoothing, "forward-differences")
+
+
+def clip_gradient_list(grads, clip, eps=1e-6):
+    """training/utils.py:4-19 with grad_clip_norm = 2: in-place-equivalent global L2 clip; returns (grads, clipped?)."""
+    norm = torch.norm(torch.stack([torch.norm(g, 2) for g in grads]), 2)
+    if norm > clip:
+        return [g * (clip / (norm + eps)) for g in grads], 1
+    return grads, 0
 
 
 @torch.no_grad()
 def full_batch_step(depth, p, buffers, X, Y, mb, lr, block_strength=0.5, eps=1e-2, smoothing=0.0,
-                    acc_dtype=None, keep_microbatches=0, order=None):
+                    acc_dtype=None, keep_microbatches=0, order=None, implementation="forward-differences",
+                    acc_strength=0.0, batch_clip=None):
     """training.py:121-185, single process (num_machines = 1).
 
     X: [N,3,32,32], Y: [N] int64.  Microbatches are consecutive blocks of ``mb`` images, drop_last
@@ -210,23 +246,43 @@ def full_batch_step(depth, p, buffers, X, Y, mb, lr, block_strength=0.5, eps=1e-
     net = OracleResNet(depth, buffers)
     acc_dtype = acc_dtype or X.dtype
     K = X.shape[0] // mb
+
+    def batch(k):
+        idx = slice(k * mb, (k + 1) * mb) if order is None else order[k * mb:(k + 1) * mb]
+        return X[idx], Y[idx]
+
+    pre_grads = None
+    if acc_strength != 0:  # training.py:128-142: full extra sweep for the mean raw gradient
+        pre_grads = [torch.zeros_like(v, dtype=acc_dtype) for v in p.values()]
+        for k in range(K):
+            x, y = batch(k)
+            g, _, _ = microbatch_gradient(net, p, x, y, smoothing)
+            g = [t.to(acc_dtype) for t in g]
+            if batch_clip is not None:
+                g, _ = clip_gradient_list(g, batch_clip)
+            for a, t in zip(pre_grads, g):
+                a.add_(t - a, alpha=1 / (k + 1))
     avg = [torch.zeros_like(v, dtype=acc_dtype) for v in p.values()]  # :123
     grad_norms = torch.zeros(K, dtype=X.dtype, device=X.device)
     step_loss = torch.zeros((), dtype=X.dtype, device=X.device)
     step_preds = torch.zeros((), dtype=X.dtype, device=X.device)
     kept = []
+    clipped_batches = 0
     for k in range(K):
-        idx = slice(k * mb, (k + 1) * mb) if order is None else order[k * mb:(k + 1) * mb]
-        x, y = X[idx], Y[idx]
+        x, y = batch(k)
         g, loss, correct = microbatch_gradient(net, p, x, y, smoothing)  # :159
         grad_norms[k] = torch.stack([t.pow(2).sum() for t in g]).sum()  # :162
-        if block_strength != 0:
-            g_reg, eps_n, _ = forward_differences(net, p, g, x, y, lr, block_strength, eps, smoothing)  # :163
+        if block_strength != 0 or acc_strength != 0:
+            g_reg, eps_n, _ = regularize(net, p, g, x, y, lr, block_strength, eps, smoothing, implementation,
+                                         pre_grads, acc_strength)  # :163
         else:
             g_reg, eps_n = g, None  # modules.py:151-153,177-178 (_pass)
         if k < keep_microbatches:
             kept.append(dict(raw=g, reg=g_reg, loss=loss, correct=correct, eps_n=eps_n))
         g_acc = [t.to(acc_dtype) for t in g_reg]  # :165
+        if batch_clip is not None:  # :166-167
+            g_acc, c = clip_gradient_list(g_acc, batch_clip)
+            clipped_batches += c
         for a, t in zip(avg, g_acc):  # :45-47,168  (avg += (g - avg) / (k+1))
             t = t - a
             a.add_(t, alpha=1 / (k + 1))
@@ -234,7 +290,7 @@ def full_batch_step(depth, p, buffers, X, Y, mb, lr, block_strength=0.5, eps=1e-
         step_preds += correct
     param_norm = sum(v.pow(2).sum() for v in p.values())
     return dict(avg=avg, loss=step_loss / K, correct=step_preds, grad_norms=grad_norms, kept=kept, K=K,
-                param_norm=param_norm)
+                param_norm=param_norm, pre_grads=pre_grads, clipped_batches=clipped_batches)
 
 
 def flat(tensors):

@@ -28,6 +28,11 @@ CASES = {
     "r18_mb128_n256_f64": (18, 128, 256, "float64"),
     "r18_mb128_n256_f32": (18, 128, 256, "float32"),
     "r152_mb4_n8_f64": (152, 4, 8, "float64"),
+    # remaining hyp.grad_reg variants (modules.py:243-300, training.py:128-142); 5th entry = overrides
+    "r18_mb16_n48_f64_central": (18, 16, 48, "float64", dict(implementation="central-differences")),
+    "r18_mb16_n48_f64_legacy": (18, 16, 48, "float64", dict(implementation="forward-differences-legacy")),
+    "r18_mb16_n48_f64_acc": (18, 16, 48, "float64", dict(acc_strength=0.3)),
+    "r18_mb16_n48_f64_central_acc": (18, 16, 48, "float64", dict(implementation="central-differences", acc_strength=0.2)),
 }
 STRIDE = 4999
 HYP = dict(lr=0.8, block_strength=0.5, eps=1e-2)
@@ -39,10 +44,13 @@ def pack(prefix, fp, out):
 
 
 def make_case(name):
-    depth, mb, n, dts = CASES[name]
+    depth, mb, n, dts = CASES[name][:4]
+    extra = CASES[name][4] if len(CASES[name]) > 4 else {}
     dt = getattr(torch, dts)
     cfg = H.make_cfg(depth=depth, batch_size=mb, sub_batch=mb, grad_clip=None, warmup=0,
-                     accumulation_dtype="double" if dt == torch.float64 else "float", **HYP)
+                     accumulation_dtype="double" if dt == torch.float64 else "float",
+                     implementation=extra.get("implementation", "forward-differences"), **HYP)
+    cfg.hyp.grad_reg.acc_strength = extra.get("acc_strength", 0.0)
     model = H.construct_reference_model(cfg, seed=0, dtype=dt)
     X, Y = O.synthetic_cifar(n, dtype=dt)
     out = {}
@@ -60,7 +68,7 @@ def make_case(name):
     scalars = {k: float(v[0]) for k, v in stats.items() if len(v) and k in
                ("train_loss", "train_acc", "param_norm", "grad_norm", "full_loss")}
     scalars["grad_norm_train"] = [float(stats[f"grad_norm_train_{i}"][0]) for i in range(n // mb)]
-    meta = dict(case=name, depth=depth, mb=mb, n=n, dtype=dts, stride=STRIDE, hyp=HYP, scalars=scalars,
+    meta = dict(case=name, depth=depth, mb=mb, n=n, dtype=dts, stride=STRIDE, hyp=HYP, extra=extra, scalars=scalars,
                 torch=torch.__version__, threads=torch.get_num_threads(), reference_seconds=elapsed,
                 num_params=int(sum(p.numel() for p in model.parameters())))
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

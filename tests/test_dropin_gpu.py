@@ -68,7 +68,7 @@ def test_gradregularizer_rejects_unknown_implementation():
     with pytest.raises(ValueError):
         GradRegularizer(model, opt, None, block_strength=0.5, implementation="nonsense")
     with pytest.raises(ValueError):
-        GradRegularizer(model, opt, None, block_strength=0.5, implementation="central-differences")
+        GradRegularizer(model, opt, None, block_strength=0.5, implementation="autograd")  # double backward: not on the path
     g = GradRegularizer(model, opt, None, block_strength=0.0, acc_strength=0.0, implementation="nonsense")
     grads = [torch.zeros(1)]
     assert g(grads, None, None, None) is grads  # _pass, modules.py:151-153
@@ -184,3 +184,30 @@ def test_flat_sgd_matches_torch_sgd_with_clip():
         assert rel(eng.avg, clipped) < 1e-6  # param.grad clipped in place like the reference
     sd = opt.state_dict()
     assert "momentum_buffer" in sd["state"][0]
+
+
+def test_gradregularizer_central_differences_and_pre_grads():
+    """GradRegularizer(..., implementation='central-differences', acc_strength) with pre_grads (modules.py:266-300)."""
+    model = fresh().to(DEV)
+    mb = 16
+    X, Y = O.synthetic_cifar(mb)
+    X, Y = X.to(DEV), Y.to(DEV)
+    optimizer = torch.optim.SGD(model.parameters(), lr=0.8)
+    loss_fn = LabelSmoothCrossEntropyLoss(0.0)
+    model.train()
+    raw = [g.clone() for g in torch.autograd.grad(loss_fn(model(X), Y), list(model.parameters()))]
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    pre = [torch.randn(g.shape, device=DEV, generator=gen) * g.abs().mean() for g in raw]
+    gradreg = GradRegularizer(model, optimizer, loss_fn, block_strength=0.5, acc_strength=0.25, eps=1e-2,
+                              implementation="central-differences", microbatch=mb)
+    grads = [g.clone() for g in raw]
+    out = gradreg(grads, X, Y, pre)
+    assert out is grads
+    p64 = {k: v.detach().double() for k, v in model.named_parameters()}
+    b64 = {k: (v.detach().clone() if v.dtype == torch.long else v.detach().double()) for k, v in model.named_buffers()}
+    net = O.OracleResNet(18, b64, update_running_stats=False)
+    ref, _, _ = O.regularize(net, p64, [g.double() for g in raw], X.double(), Y, 0.8, 0.5, 1e-2, 0.0,
+                             "central-differences", [q.double() for q in pre], 0.25)
+    assert rel(O.flat(grads), O.flat(ref)) < 0.5
+    c = float((O.flat(grads).double() * O.flat(ref)).sum() / (O.flat(grads).double().norm() * O.flat(ref).norm()))
+    assert c > 0.98

@@ -175,3 +175,45 @@ def test_shuffled_order_through_permutation():
     assert K == 3
     assert abs(eng.results(K)["loss"] - float(ref["loss"])) < 1e-4 * float(ref["loss"])
     assert rel(eng.avg, O.flat(ref["avg"])) < RATIO_REG * 0.08
+
+
+VARIANTS = [
+    ("central", dict(implementation="central-differences")),
+    ("legacy", dict(implementation="forward-differences-legacy")),
+    ("acc", dict(acc_strength=0.3)),
+    ("central_acc", dict(implementation="central-differences", acc_strength=0.2)),
+    ("batch_clip", dict(batch_clip=5.0)),
+    ("acc_batch_clip", dict(acc_strength=0.3, batch_clip=5.0)),
+]
+
+
+@pytest.mark.parametrize("name,extra", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_grad_reg_variants_match_oracle(name, extra):
+    """The rest of the hyp.grad_reg / hyp.batch_clip surface (modules.py:243-300, training.py:128-142,166-168) on the
+    same kernels, against the oracle in fp64 with the fp32 oracle as noise floor."""
+    depth, mb, n = 18, 16, 48
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+
+    def oracle(dtype):
+        p = {k: v.to(DEV, dtype).clone() for k, v in params.items()}
+        b = {k: (v.to(DEV).clone() if v.dtype == torch.long else v.to(DEV, dtype).clone()) for k, v in buffers.items()}
+        return O.full_batch_step(depth, p, b, X.to(dtype), Y, mb, **HYP, **extra), b
+
+    ref64, buf64 = oracle(torch.float64)
+    ref32, _ = oracle(torch.float32)
+    eng = FullBatchEngine(model, mb, precision="split")
+    K = eng.accumulate_resident(X, Y, HYP["lr"], HYP["block_strength"], HYP["eps"], **extra)
+    eng.sync_bn_counters()
+    res = eng.results(K)
+    avg64 = O.flat(ref64["avg"])
+    e_new, e32 = rel(eng.avg, avg64), rel(O.flat(ref32["avg"]), avg64)
+    dump(f"variant_{name}", dict(e_new_avg=e_new, e32_avg=e32, cos=cos(eng.avg, avg64),
+                                 clipped=res["clipped_batches"], clipped64=ref64["clipped_batches"]))
+    assert e_new <= RATIO_REG * max(e32, FLOOR_REG)
+    assert cos(eng.avg, avg64) > 0.98
+    assert abs(res["loss"] - float(ref64["loss"])) < 1e-4 * float(ref64["loss"])
+    assert res["clipped_batches"] == ref64["clipped_batches"]
+    if "acc_strength" in extra:
+        assert rel(eng.pre, O.flat(ref64["pre_grads"])) < RATIO_RAW * FLOOR_RAW * 2
+    nbt = [b for k, b in model.named_buffers() if k.endswith("num_batches_tracked")][0]
+    assert int(nbt) == int(buf64["stem.1.num_batches_tracked"])  # 2 or 3 passes per microbatch (+1 for the pre-pass)

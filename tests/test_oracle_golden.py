@@ -28,6 +28,8 @@ def check_fp(z, prefix, tensors, stride, rtol):
 
 
 CASES = [("r18_mb16_n32_f64", 1e-9), ("r18_mb16_n32_f32", 5e-2), ("r152_mb4_n8_f64", 1e-9),
+         ("r18_mb16_n48_f64_central", 1e-9), ("r18_mb16_n48_f64_legacy", 1e-9), ("r18_mb16_n48_f64_acc", 1e-9),
+         ("r18_mb16_n48_f64_central_acc", 1e-9),
          pytest.param("r18_mb128_n256_f64", 1e-9, marks=pytest.mark.slow)]
 
 
@@ -41,7 +43,8 @@ def test_oracle_matches_reference_golden(golden_dir, name, rtol):
     # initialisation is bit-identical to the reference's construct_model under the same seed
     check_fp(z, "init", list(p.values()), meta["stride"], 1e-12 if dt == torch.float64 else 1e-6)
     X, Y = O.synthetic_cifar(meta["n"], dtype=dt)
-    out = O.full_batch_step(meta["depth"], p, b, X, Y, meta["mb"], keep_microbatches=2, **meta["hyp"])
+    extra = meta.get("extra", {})
+    out = O.full_batch_step(meta["depth"], p, b, X, Y, meta["mb"], keep_microbatches=2, **meta["hyp"], **extra)
     check_fp(z, "avg", out["avg"], meta["stride"], rtol)
     for i, kept in enumerate(out["kept"]):
         check_fp(z, f"mb{i}.raw", kept["raw"], meta["stride"], rtol)
@@ -56,6 +59,8 @@ def test_oracle_matches_reference_golden(golden_dir, name, rtol):
     # training.py:95-98 full_loss = loss + wd/2 |theta|^2 + lr/4*bs*mean(grad_norms)
     full = float(out["loss"]) + 0.5 * 5e-4 * float(out["param_norm"]) \
         + meta["hyp"]["lr"] / 4 * meta["hyp"]["block_strength"] * float(out["grad_norms"].mean())
+    if extra.get("acc_strength", 0.0) != 0:  # training.py:99-102
+        full += meta["hyp"]["lr"] / 4 * extra["acc_strength"] * float(sum(g.pow(2).sum() for g in out["pre_grads"]))
     assert full == pytest.approx(sc["full_loss"], rel=max(rtol, 1e-6))
 
 
