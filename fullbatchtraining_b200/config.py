@@ -30,7 +30,10 @@ def to_attr(d):
 
 _DEFAULT = dict(
     name="fullbatch_b200", dryrun=False, seed=None, original_cwd=".",
-    data=dict(name="CIFAR10", size=50000, channels=3, classes=10, pixels=32, batch_size=128),
+    data=dict(name="CIFAR10", size=50000, channels=3, classes=10, pixels=32, batch_size=128, normalize=True,
+              mean=[0.4914672374725342, 0.4822617471218109, 0.4467701315879822],
+              std=[0.24703224003314972, 0.24348513782024384, 0.26158785820007324],
+              augmentations_train=dict(RandomCrop=[32, 4], RandomHorizontalFlip=0.5), augmentations_val=None),
     model=dict(name="ResNet18", depth=18, width=64, stem="CIFAR", convolution="Standard", nonlin_fn="ReLU",
                normalization="BatchNorm2d", downsample="C", initialization="skip-residual"),
     impl=dict(dtype="float", memory="contiguous", non_blocking=True, mixed_precision=False, accumulation_dtype="float",

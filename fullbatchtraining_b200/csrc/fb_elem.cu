@@ -677,6 +677,58 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, const long long*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Same, fused with the reference's training augmentation for CIFAR (config/data/CIFAR10.yaml:22-26 applied by
+// torchvision in data_preparation.py:173-200): RandomCrop(32, padding=4) -> RandomHorizontalFlip -> ToTensor ->
+// Normalize(mean, std), evaluated on the fly from a device-resident uint8 HWC dataset.  aug[pos] = (dx, dy, flip, -)
+// holds this epoch's draws for the sample at position pos of the (optionally permuted) order: crop offsets 0..8 inside
+// the zero-padded 40x40 image and the flip bit; padded pixels are black BEFORE normalisation, exactly like torchvision.
+// ---------------------------------------------------------------------------------------------------------------
+struct AugNorm {
+  float mean[3], inv_std[3];
+};
+
+__global__ void stem_im2col_u8aug_kernel(const uint8_t* __restrict__ x, const long long* __restrict__ labels,
+                                         const long long* __restrict__ perm, const int* __restrict__ first_dev,
+                                         long long first, int n, const char4* __restrict__ aug, AugNorm nrm,
+                                         bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
+                                         long long* __restrict__ labels_out) {
+  griddep_wait();
+  griddep_launch();
+  if (first_dev) first += (long long)(*first_dev) * n;
+  const long long total = (long long)n * 1024 * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int grp = int(i & 7);
+    const long long pix = i >> 3;
+    const int w = int(pix & 31), h = int((pix >> 5) & 31);
+    const int img = int(pix >> 10);
+    const long long pos = first + img;
+    const long long src_img = perm ? perm[pos] : pos;
+    const char4 a = aug ? aug[pos] : make_char4(4, 4, 0, 0);
+    const uint8_t* xi = x + src_img * 3072;  // HWC
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = grp * 8 + j;
+      float val = 0.f;
+      if (k < 27) {
+        const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
+        const int hh = h + kh - 1, ww = w + kw - 1;  // pixel of the AUGMENTED image; outside -> conv zero padding
+        if (hh >= 0 && hh < 32 && ww >= 0 && ww < 32) {
+          const int wc = a.z ? 31 - ww : ww;          // flip acts on the cropped image
+          const int sh = hh + a.y - 4, sw = wc + a.x - 4;  // source pixel in the un-padded original
+          const float raw = (sh >= 0 && sh < 32 && sw >= 0 && sw < 32) ? float(xi[(sh * 32 + sw) * 3 + ci]) : 0.f;
+          val = (raw * (1.f / 255.f) - nrm.mean[ci]) * nrm.inv_std[ci];
+        }
+      }
+      v[j] = val;
+    }
+    store8_split(p_hi, p_lo, pix * 64 + grp * 8, v);
+    if (labels_out && grp == 0 && (pix & 1023) == 0) labels_out[img] = labels[src_img];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // head: global average pool -> linear -> label-smoothed cross entropy (+accuracy) and backward
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxClasses = 16;
@@ -1021,5 +1073,24 @@ extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
   a.coef = a.partial + (long long)2 * bw->C * 2 * kNumSMs;
   a.rows_per_block = rpb;
   FB_CUDA(launch_pdl(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
+  return 0;
+}
+
+extern "C" int fb_stem_im2col_u8aug(const uint8_t* x_hwc, const int64_t* labels, const int64_t* perm,
+                                    const int32_t* first_dev, int64_t first, int n, const int8_t* aug,
+                                    const float* mean3, const float* std3, void* patches_hi, void* patches_lo,
+                                    int64_t* labels_out, void* stream) {
+  FB_REQUIRE(x_hwc && patches_hi && mean3 && std3 && n > 0, "fb_stem_im2col_u8aug: bad arguments");
+  FB_REQUIRE(!labels_out || labels, "fb_stem_im2col_u8aug: labels_out needs labels");
+  AugNorm nrm;
+  for (int c = 0; c < 3; ++c) {
+    nrm.mean[c] = mean3[c];
+    nrm.inv_std[c] = 1.f / std3[c];
+  }
+  FB_CUDA(launch_pdl(stem_im2col_u8aug_kernel, dim3(stream_grid((long long)n * 1024 * 8)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), x_hwc, reinterpret_cast<const long long*>(labels),
+                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, n,
+                     reinterpret_cast<const char4*>(aug), nrm, static_cast<bf16*>(patches_hi),
+                     static_cast<bf16*>(patches_lo), reinterpret_cast<long long*>(labels_out)));
   return 0;
 }

@@ -220,6 +220,7 @@ class FullBatchEngine:
         # FB_WGRAD_STREAM=0 disables the side stream (everything in one stream)
         self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "1") == "1" else None
         self.grad_norms = None
+        self.aug_params, self.aug_mean, self.aug_std = None, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
         self.norm_offset = 0
         self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
 
@@ -330,8 +331,13 @@ class FullBatchEngine:
         batch_clip: per-microbatch L2 clip before the running mean (training.py:166-168); target "avg" | "pre"
         (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into self.pre)."""
         dst = self.avg if target == "avg" else self.pre
-        ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb, self.patches.hi,
-                        self.patches.lo, self.labels_mb)
+        if x_src.dtype == torch.uint8:  # raw HWC dataset: crop / flip / normalise fused into the im2col
+            ops.stem_im2col_u8aug(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb,
+                                  self.aug_params, self.aug_mean, self.aug_std, self.patches.hi, self.patches.lo,
+                                  self.labels_mb)
+        else:
+            ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb,
+                            self.patches.hi, self.patches.lo, self.labels_mb)
         if mode != "reg":
             self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
             self._backward(self.theta, self.g)
@@ -396,7 +402,8 @@ class FullBatchEngine:
             return lambda: self._microbatch_ops(*args)
         key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
                float(block_strength), float(eps), accumulate, write_g, mode, impl, float(acc), batch_clip, target,
-               self.grad_norms.data_ptr(), self.norm_offset)
+               self.grad_norms.data_ptr(), self.norm_offset,
+               None if self.aug_params is None else self.aug_params.data_ptr(), tuple(self.aug_mean), tuple(self.aug_std))
         if key not in self._graphs:
             state = self._save_state()
             side = torch.cuda.Stream()
@@ -430,6 +437,24 @@ class FullBatchEngine:
             b.copy_(s)
 
     # ------------------------------------------------------------------------------------------------------------
+    # ---- device-side data pipeline ---------------------------------------------------------
+    def set_normalization(self, mean, std):
+        """Normalize(mean, std) of config/data/CIFAR10.yaml:8-17 for uint8 datasets."""
+        self.aug_mean, self.aug_std = [float(v) for v in mean], [float(v) for v in std]
+
+    def draw_augmentation(self, num_samples, generator=None, crop_padding=4, flip=0.5):
+        """One epoch of RandomCrop(32, padding) + RandomHorizontalFlip(flip) draws, kept on the device in a persistent
+        int8 [num_samples, 4] buffer (dx, dy, flip, 0) indexed by position in the epoch order.  None disables."""
+        if self.aug_params is None or self.aug_params.shape[0] < num_samples:
+            self.aug_params = torch.zeros(num_samples, 4, device=self.device, dtype=torch.int8)
+            self._graphs.clear()
+        n = self.aug_params.shape[0]
+        off = torch.randint(0, 2 * crop_padding + 1, (n, 2), device=self.device, generator=generator)
+        flips = (torch.rand(n, device=self.device, generator=generator) < flip)
+        self.aug_params[:, 0:2] = off.to(torch.int8)
+        self.aug_params[:, 2] = flips.to(torch.int8)
+        return self.aug_params
+
     def set_lr(self, lr):
         """correction factor lr/4 of modules.py:214, kept on the device so captured graphs stay valid"""
         self.scal[S_CF] = lr / 4
@@ -451,7 +476,11 @@ class FullBatchEngine:
         """Full-batch accumulation over `count` consecutive microbatches of a device-resident dataset
         X [N,3,32,32] fp32, Y [N] int64, starting at sample `first` (optionally through the index tensor `perm`).
         Returns after enqueueing; results: self.avg (running mean), self.grad_norms[:count], loss/correct sums in scal."""
-        assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and Y.dtype == torch.int64
+        assert X.is_cuda and X.is_contiguous() and Y.dtype == torch.int64
+        if X.dtype == torch.uint8:
+            assert tuple(X.shape[1:]) == (32, 32, 3), "uint8 datasets are HWC [N,32,32,3]"
+        else:
+            assert X.dtype == torch.float32 and tuple(X.shape[1:]) == (3, 32, 32)
         n_avail = (perm.numel() if perm is not None else X.shape[0]) - first
         count = n_avail // self.mb if count is None else count
         impl = IMPLEMENTATIONS[implementation]

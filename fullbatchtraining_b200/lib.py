@@ -79,6 +79,7 @@ _SIGNATURES = {
     "fb_weight_prep": ([vp, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp], i32),
     "fb_weight_prep_multi": ([vp, vp, i32, i32, vp], i32),
     "fb_stem_im2col": ([vp, vp, vp, vp, i64, i32, vp, vp, vp, vp], i32),
+    "fb_stem_im2col_u8aug": ([vp, vp, vp, vp, i64, i32, vp, C.POINTER(f32), C.POINTER(f32), vp, vp, vp, vp], i32),
     "fb_bn_stats": ([vp, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp], i32),
     "fb_bn_apply": ([C.POINTER(BnApplyArgs), vp], i32),
     "fb_bn_bwd": ([C.POINTER(BnBwdArgs), vp], i32),

@@ -19,7 +19,7 @@ NUM_SMS = 148
 PROFILE = None
 LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
 _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv3x3": 1, "fb_conv_wgrad": 1, "fb_wgrad_finalize": 1, "fb_weight_prep": 1,
-                     "fb_stem_im2col": 1, "fb_bn_fwd_fused": 1, "fb_bn_bwd_fused": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
+                     "fb_stem_im2col": 1, "fb_stem_im2col_u8aug": 1, "fb_bn_fwd_fused": 1, "fb_bn_bwd_fused": 1, "fb_bn_stats": 2, "fb_bn_apply": 1, "fb_bn_bwd": 3, "fb_avgpool2_fwd": 1,
                      "fb_avgpool2_bwd": 1, "fb_head_fwd_bwd": 3, "fb_flat_sqnorm": 2, "fb_fd_perturb": 1,
                      "fb_fd_combine": 1, "fb_mean_accumulate": 1, "fb_cursor_add": 1, "fb_flat_scale": 1, "fb_sgd_step": 2,
                      "fb_flat_sqnorm_axpby": 2, "fb_fd_perturb_ex": 1, "fb_fd_combine_ex": 1,
@@ -398,6 +398,15 @@ def stem_im2col(x, labels, perm, cursor, first, n, p_hi, p_lo, labels_out):
     _call("stem_im2col", n * (3072 * 4.0 + 1024 * 64 * 2.0 * (1 + (p_lo is not None))), "byte", "fb_stem_im2col",
           x.data_ptr(), L.ptr(labels), L.ptr(perm), L.ptr(cursor), first, n, p_hi.data_ptr(),
            L.ptr(p_lo), L.ptr(labels_out))
+
+
+def stem_im2col_u8aug(x_u8, labels, perm, cursor, first, n, aug, mean, std, p_hi, p_lo, labels_out):
+    """x_u8: [N,32,32,3] uint8 on the device; aug: int8 [.,4] (dx, dy, flip, 0) per position or None; mean/std: 3 floats"""
+    m = (L.f32 * 3)(*[float(v) for v in mean])
+    sd = (L.f32 * 3)(*[float(v) for v in std])
+    _call("stem_im2col", n * (3072.0 + 1024 * 64 * 2.0 * (1 + (p_lo is not None))), "byte", "fb_stem_im2col_u8aug",
+          x_u8.data_ptr(), L.ptr(labels), L.ptr(perm), L.ptr(cursor), first, n, L.ptr(aug), m, sd, p_hi.data_ptr(),
+          L.ptr(p_lo), L.ptr(labels_out))
 
 
 def bn_stats(y, P, Cc, ws, mean, rstd, running_mean, running_var, momentum=0.1, eps=1e-5):

@@ -82,8 +82,11 @@ def _resident_dataset(loader, device):
     """If the loader iterates a TensorDataset sequentially, keep the whole dataset in HBM (50k CIFAR images = 614 MB)."""
     ds = getattr(loader, "dataset", None)
     sampler = getattr(loader, "sampler", None)
-    if isinstance(ds, torch.utils.data.TensorDataset) and isinstance(sampler, torch.utils.data.SequentialSampler):
+    ok_sampler = isinstance(sampler, (torch.utils.data.SequentialSampler, torch.utils.data.RandomSampler))
+    if isinstance(ds, torch.utils.data.TensorDataset) and ok_sampler:
         X, Y = ds.tensors
+        if X.dtype == torch.uint8:  # raw HWC images: normalisation / augmentation happen inside the stem kernel
+            return X.to(device=device).contiguous(), Y.to(device=device, dtype=torch.long).contiguous()
         return X.to(device=device, dtype=torch.float32).contiguous(), Y.to(device=device, dtype=torch.long).contiguous()
     return None
 
@@ -145,19 +148,48 @@ class Trainer:
             self.k0 = int(counts[:self.rank].sum())
             self.k1 = self.k0 + local
         self.step_count = 0
+        # device-side data pipeline: raw uint8 dataset + crop/flip/normalise fused into the stem,
+        # hyp.shuffle as a per-step device permutation (data_preparation.py:53-54)
+        self.data_gen = torch.Generator(device=self.device)
+        self.data_gen.manual_seed(int(cfg.seed) if cfg.get("seed") is not None else 0)
+        self.perm = None
+        self.augment = False
+        if self.resident is not None and self.resident[0].dtype == torch.uint8:
+            data = cfg.data
+            if data.get("normalize", True):
+                self.engine.set_normalization(data.mean, data.std)
+            aug = data.get("augmentations_train") or {}
+            unknown = set(aug.keys()) - {"RandomCrop", "RandomHorizontalFlip"}
+            if unknown:
+                raise ValueError(f"augmentations {sorted(unknown)} are not on the B200 path")
+            self.augment = len(aug) > 0
+            self.crop_pad = int(aug["RandomCrop"][1]) if "RandomCrop" in aug else 0
+            self.flip_p = float(aug.get("RandomHorizontalFlip", 0.0))
+
+    def _prepare_epoch(self):
+        if self.resident is None:
+            return
+        n = self.resident[0].shape[0]
+        if self.cfg.hyp.shuffle:
+            if self.perm is None:
+                self.perm = torch.zeros(n, device=self.device, dtype=torch.int64)
+            self.perm.copy_(torch.randperm(n, device=self.device, generator=self.data_gen))
+        if self.augment:
+            self.engine.draw_augmentation(n, self.data_gen, self.crop_pad, self.flip_p)
 
     # training.py:121-185
     def _accumulate_full_gradient(self):
         t0 = time.time()
         eng, cfg, stats = self.engine, self.cfg, self.stats
         lr = self.optimizer.param_groups[0]["lr"]
+        self._prepare_epoch()
         if self.resident is not None:
             if self.acc != 0 and self.world > 1:
                 raise RuntimeError("acc_strength with several processes is not implemented")
             local = eng.accumulate_resident(self.resident[0], self.resident[1], lr, self.bs, self.eps,
                                             first=self.k0 * self.mb, count=self.k1 - self.k0, num_norms=self.K,
                                             norm_offset=self.k0, implementation=self.impl, acc_strength=self.acc,
-                                            batch_clip=cfg.hyp.batch_clip)
+                                            batch_clip=cfg.hyp.batch_clip, perm=self.perm)
         else:
             if self.acc != 0 or cfg.hyp.batch_clip is not None or self.impl == "central-differences":
                 raise RuntimeError("acc_strength / batch_clip / central-differences need a device-resident dataset "

@@ -149,6 +149,15 @@ int fb_weight_prep_multi(const float* theta, const fb_wprep_entry* table_dev, in
 int fb_stem_im2col(const float* x, const int64_t* labels, const int64_t* perm, const int32_t* first_dev, int64_t first,
                    int n, void* patches_hi, void* patches_lo, int64_t* labels_out, void* stream);
 
+/* Same from a device-resident uint8 HWC dataset [N][32][32][3] with the reference's CIFAR training augmentation applied
+ * on the fly (config/data/CIFAR10.yaml:22-26 via torchvision, data_preparation.py:173-200): RandomCrop(32, padding 4)
+ * -> RandomHorizontalFlip -> ToTensor -> Normalize(mean, std).  aug (device, int8[.][4], may be NULL = no augmentation)
+ * holds (dx, dy, flip, 0) per POSITION of the epoch order: crop offsets 0..8 in the zero-padded 40x40 image.
+ * mean3 / std3 are host pointers. */
+int fb_stem_im2col_u8aug(const uint8_t* x_hwc, const int64_t* labels, const int64_t* perm, const int32_t* first_dev,
+                         int64_t first, int n, const int8_t* aug, const float* mean3, const float* std3,
+                         void* patches_hi, void* patches_lo, int64_t* labels_out, void* stream);
+
 /* Train-mode BatchNorm statistics over y[P][C] (resnets.py:71 / torch.nn.BatchNorm2d): mean, rstd = 1/sqrt(var+eps)
  * (biased var) and the running-stat EMA with unbiased variance.  ws: >= 2*C*1024 floats of scratch. */
 int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* mean, float* rstd, float* running_mean,

@@ -211,3 +211,39 @@ def test_gradregularizer_central_differences_and_pre_grads():
     assert rel(O.flat(grads), O.flat(ref)) < 0.5
     c = float((O.flat(grads).double() * O.flat(ref)).sum() / (O.flat(grads).double().norm() * O.flat(ref).norm()))
     assert c > 0.98
+
+
+def test_device_side_augmentation_and_shuffle_pipeline():
+    """uint8 HWC dataset kept in HBM: normalisation (+ crop / flip / per-step shuffle) happen inside the stem kernel.
+    Without augmentation and shuffling the step equals the float-dataset path; with them it runs and changes per step."""
+    mb, n = 16, 64
+    g = torch.Generator().manual_seed(4)
+    raw = torch.randint(0, 256, (n, 32, 32, 3), generator=g, dtype=torch.uint8)
+    Y = torch.randint(0, 10, (n,), generator=g)
+    cfg0 = _cfg(mb, **{"data.augmentations_train": None})
+    mean = torch.tensor(cfg0.data.mean)[None, :, None, None]
+    std = torch.tensor(cfg0.data.std)[None, :, None, None]
+    Xf = (raw.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    setup = dict(device=DEV, dtype=torch.float32)
+
+    def loader(x):
+        ds = torch.utils.data.TensorDataset(x, Y)
+        return torch.utils.data.DataLoader(ds, batch_size=mb, sampler=torch.utils.data.SequentialSampler(ds), drop_last=True)
+
+    ta = Trainer(fresh(), loader(raw), None, setup, cfg0)
+    tb = Trainer(fresh(), loader(Xf), None, setup, _cfg(mb))
+    assert ta.resident[0].dtype == torch.uint8 and not ta.augment
+    la, lb = ta._accumulate_full_gradient(), tb._accumulate_full_gradient()
+    assert float(la) == pytest.approx(float(lb), rel=1e-5)
+    assert rel(ta.engine.avg, tb.engine.avg) < 0.2  # same data up to 1 ulp of the normalisation; FD amplifies it
+    # augmentation + shuffle
+    cfg1 = _cfg(mb, **{"hyp.shuffle": True, "seed": 3})
+    tc = Trainer(fresh(), loader(raw), None, setup, cfg1)
+    assert tc.augment and tc.crop_pad == 4 and tc.flip_p == 0.5
+    l1 = float(tc._accumulate_full_gradient())
+    perm1, aug1 = tc.perm.clone(), tc.engine.aug_params.clone()
+    l2 = float(tc._accumulate_full_gradient())
+    assert math.isfinite(l1) and math.isfinite(l2)
+    assert not torch.equal(perm1, tc.perm) and not torch.equal(aug1, tc.engine.aug_params)
+    assert sorted(tc.perm.tolist()) == list(range(n))
+    assert int(tc.engine.aug_params[:, :2].max()) <= 8 and int(tc.engine.aug_params[:, :2].min()) >= 0

@@ -442,3 +442,48 @@ def test_bn_fused_kernels_match_unfused(P, Cc, variant):
     assert rel_err(outs[1][0], outs[0][0]) < 1e-5 and rel_err(outs[1][1], outs[0][1]) < 1e-5
     assert rel_err(outs[1][2], outs[0][2]) < 1e-2   # bf16 outputs: last-bit differences from the reduction order
     assert torch.equal(outs[1][3], outs[0][3])
+
+
+def test_stem_im2col_u8_augmentation_matches_torchvision_semantics():
+    """RandomCrop(32, padding=4) -> RandomHorizontalFlip -> ToTensor -> Normalize with GIVEN draws, fused into the stem
+    im2col, against the same pipeline spelled out with torch ops (data_preparation.py:173-200)."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    N, n = 40, 8
+    data = torch.randint(0, 256, (N, 32, 32, 3), device=DEV, generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 10, (N,), device=DEV, generator=g)
+    perm = torch.randperm(N, device=DEV, generator=g)
+    aug = torch.zeros(N, 4, device=DEV, dtype=torch.int8)
+    aug[:, 0:2] = torch.randint(0, 9, (N, 2), device=DEV, generator=g).to(torch.int8)
+    aug[:, 2] = (torch.rand(N, device=DEV, generator=g) < 0.5).to(torch.int8)
+    mean, std = [0.4914, 0.4822, 0.4465], [0.2470, 0.2435, 0.2616]
+    cursor = torch.tensor([2], device=DEV, dtype=torch.int32)
+    p_hi = torch.empty(n * 1024, 64, device=DEV, dtype=torch.bfloat16)
+    p_lo = torch.empty_like(p_hi)
+    lab = torch.empty(n, device=DEV, dtype=torch.int64)
+    first = 4
+    ops.stem_im2col_u8aug(data, labels, perm, cursor, first, n, aug, mean, std, p_hi, p_lo, lab)
+    pos = torch.arange(first + 2 * n, first + 3 * n, device=DEV)
+    idx = perm[pos]
+    assert torch.equal(lab, labels[idx])
+    imgs = []
+    for j in range(n):
+        img = data[idx[j]].permute(2, 0, 1).float()                     # PIL image -> CHW, still 0..255
+        padded = F.pad(img, (4, 4, 4, 4))                               # RandomCrop(32, padding=4): black border
+        dx, dy, fl = (int(v) for v in aug[pos[j], :3])
+        crop = padded[:, dy:dy + 32, dx:dx + 32]
+        if fl:
+            crop = torch.flip(crop, dims=[2])                           # RandomHorizontalFlip
+        t = crop / 255.0                                                # ToTensor
+        t = (t - torch.tensor(mean, device=DEV)[:, None, None]) / torch.tensor(std, device=DEV)[:, None, None]
+        imgs.append(t)
+    xb = torch.stack(imgs)
+    patches = F.unfold(xb, 3, padding=1).transpose(1, 2).reshape(n * 1024, 27)
+    got = p_hi.float() + p_lo.float()
+    assert float((got[:, :27] - patches).abs().max()) < 3e-5 * float(patches.abs().max())
+    assert float(got[:, 27:].abs().max()) == 0.0
+    # no augmentation (aug = None) = plain normalisation
+    ops.stem_im2col_u8aug(data, labels, None, None, 0, n, None, mean, std, p_hi, p_lo, lab)
+    x0 = (data[:n].permute(0, 3, 1, 2).float() / 255.0 - torch.tensor(mean, device=DEV)[None, :, None, None]) / \
+        torch.tensor(std, device=DEV)[None, :, None, None]
+    ref0 = F.unfold(x0, 3, padding=1).transpose(1, 2).reshape(n * 1024, 27)
+    assert float(((p_hi.float() + p_lo.float())[:, :27] - ref0).abs().max()) < 3e-5 * float(ref0.abs().max())
