@@ -39,6 +39,20 @@ class FlatSGD(torch.optim.Optimizer):
                 self.state[p]["momentum_buffer"] = v  # torch.optim.SGD state layout (views of the flat buffer)
         return self
 
+    def load_state_dict(self, state_dict):
+        """torch.optim.SGD checkpoints (training/utils.py:53-70): momentum buffers are copied INTO the flat buffer so its
+        per-parameter views stay the optimizer state."""
+        super().load_state_dict(state_dict)
+        if self._buf is not None and self.engine is not None:
+            group = self.param_groups[0]
+            for p, v in zip(group["params"], self.engine.grads_list(self._buf)):
+                loaded = self.state[p].get("momentum_buffer")
+                if loaded is not None:
+                    if loaded.data_ptr() != v.data_ptr():
+                        v.copy_(loaded.to(v.device))
+                    self._first = False
+                self.state[p]["momentum_buffer"] = v
+
     @torch.no_grad()
     def step(self, closure=None, grad=None):
         """closure() must leave the gradient in engine.avg (Trainer does); `grad` overrides the flat gradient buffer."""

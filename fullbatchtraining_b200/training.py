@@ -18,6 +18,7 @@ list and the result is the exact global mean (the reference's own 
 """
 import logging
 import math
+import os
 import time
 from collections import defaultdict
 
@@ -71,6 +72,34 @@ def optim_interface(model, cfg_hyp, fused=False):
 
     scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, factor)
     return optimizer, scheduler
+
+
+@torch.no_grad()
+def save_checkpoint(model, optimizer, scheduler, step, file):
+    """training/utils.py:43-51: the reference's 5-list [optim_state, model_state, scheduler_state, scaler_state, step]
+    (scaler_state is None: no fp16 grad scaling on this path), loadable by the reference's `_load_from_checkpoint` and
+    `hubconf.py:37-40` (state_dict keys and optimizer state layout are those of the reference model / torch SGD)."""
+    model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}  # params are views of the flat buffer
+    os.makedirs(os.path.dirname(os.path.abspath(file)), exist_ok=True)
+    torch.save([optimizer.state_dict(), model_state, scheduler.state_dict(), None, step], file)
+
+
+@torch.no_grad()
+def load_checkpoint(model, optimizer, scheduler, max_steps, device=None, file="checkpoints/fb.pth"):
+    """training/utils.py:53-70: returns the step to continue from (0 if no checkpoint exists); raises ValueError if the
+    checkpoint already reached max_steps."""
+    try:
+        optim_state, model_state, scheduler_state, _, step = torch.load(file, map_location=device)
+    except FileNotFoundError:
+        log.info("No existing checkpoint found. Starting to train from step 0.")
+        return 0
+    model.load_state_dict(model_state)  # copies into the existing (flat-buffer backed) parameters
+    optimizer.load_state_dict(optim_state)
+    scheduler.load_state_dict(scheduler_state)
+    if step >= max_steps:
+        raise ValueError("Maximum step size reached. Terminating computations.")
+    log.info(f"Existing checkpoint loaded successfully. Continuing to train from step {step}.")
+    return step
 
 
 def shard_range(rank, world, num_microbatches):
@@ -148,6 +177,12 @@ class Trainer:
             self.k0 = int(counts[:self.rank].sum())
             self.k1 = self.k0 + local
         self.step_count = 0
+        if cfg.impl.checkpoint.name is not None:  # training.py:60-63
+            self.checkpoint_file = os.path.join(cfg.original_cwd, "checkpoints", cfg.impl.checkpoint.name)
+            self.step_count = load_checkpoint(model, self.optimizer, self.scheduler, cfg.hyp.steps, device=self.device,
+                                              file=self.checkpoint_file)
+        else:
+            self.checkpoint_file = None
         # device-side data pipeline: raw uint8 dataset + crop/flip/normalise fused into the stem,
         # hyp.shuffle as a per-step device permutation (data_preparation.py:53-54)
         self.data_gen = torch.Generator(device=self.device)
@@ -299,6 +334,9 @@ class Trainer:
             evaluate(self.model, self.validloader, self.stats, self.setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun)
         if self.rank == 0:
             log.info(status_message(self.optimizer, self.stats, step))
+            if self.checkpoint_file is not None and ((step - 1) % cfg.impl.checkpoint.save_every_nth_step == 0
+                                                     or step >= cfg.hyp.steps):  # training.py:330-335
+                save_checkpoint(self.model, self.optimizer, self.scheduler, step, self.checkpoint_file)
         return self.stats["train_loss"][-1]
 
 
@@ -309,11 +347,39 @@ def train(model, trainloader, validloader, setup, cfg):
     while trainer.step_count < cfg.hyp.steps:
         loss = trainer.step()
         if not math.isfinite(loss):  # training.py:314-317
-            log.info("Nonfinite loss in train loss. Stopping ...")
+            log.info("Terminating iterations due to divergence of loss...")
+            break
+        n_full = cfg.hyp.stop_at_full_training_accuracy  # training.py:319-328
+        if n_full > 0 and min(trainer.stats["train_acc"][-n_full:]) == 1:
+            log.info("Terminating training after fitting all datapoints.")
+            if validloader is not None:
+                evaluate(model, validloader, trainer.stats, setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun)
             break
         if cfg.dryrun:
             break
     return trainer.stats
+
+
+def measure_implementation_noise(model, trainloader, validloader, setup, cfg):
+    """Drop-in for ``_measure_implementation_noise`` (training.py:429-600, the body of
+    measure_floating_point_accuracy.py:22-31): evaluate the full-batch gradient twice from the same state (parameters
+    AND BatchNorm buffers restored in between) and report the norms of the gradient and of the difference
+    (training.py:586-598).  The reference measures cuDNN / atomics nondeterminism on a GPU (0.0 on CPU); every reduction
+    on this path has a fixed order, so the expected drift is exactly 0."""
+    trainer = Trainer(model, trainloader, validloader, setup, cfg)
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    trainer._accumulate_full_gradient()
+    first = trainer.engine.avg.clone()
+    model.load_state_dict(state)
+    trainer._accumulate_full_gradient()
+    second = trainer.engine.avg
+    diff = (first - second).double()
+    ref = first.double()
+    report = dict(grad_linf=float(ref.abs().max()), grad_l2=float(ref.norm()), grad_l1=float(ref.abs().sum()),
+                  diff_linf=float(diff.abs().max()), diff_l2=float(diff.norm()), diff_l1=float(diff.abs().sum()))
+    log.info("Gradient  : Linf %(grad_linf).4e L2 %(grad_l2).4e L1 %(grad_l1).4e" % report)
+    log.info("Difference: Linf %(diff_linf).4e L2 %(diff_l2).4e L1 %(diff_l1).4e" % report)
+    return report
 
 
 @torch.no_grad()
@@ -322,6 +388,17 @@ def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False):
     loss_fn = torch.nn.CrossEntropyLoss()
     model.eval()
     device = torch.device(setup["device"])
+    if cfg_impl.setup.dist and torch.distributed.is_available() and torch.distributed.is_initialized():
+        # training.py:347-357: ranks see different microbatches, so BN running statistics are averaged first
+        bufs = [b for b in model.buffers()]
+        if bufs:
+            flat = torch.cat([b.data.reshape(-1).float() for b in bufs])
+            torch.distributed.all_reduce(flat)
+            flat /= cfg_impl.setup.world_size
+            off = 0
+            for b in bufs:
+                b.data.copy_(flat[off:off + b.numel()].view_as(b).to(b.dtype))
+                off += b.numel()
     if stats is None:
         stats = defaultdict(list)
     step_loss, step_preds, datapoints = 0.0, 0.0, 0
@@ -329,7 +406,10 @@ def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False):
         inputs = inputs.to(device=device, dtype=torch.float32)
         labels = labels.to(device=device, dtype=torch.long)
         datapoints += labels.shape[0]
-        outputs = model(inputs)
+        if cfg_hyp.test_time_flips:  # training.py:370-373
+            outputs = model(inputs).softmax(dim=1) + model(torch.flip(inputs, [3])).softmax(dim=1)
+        else:
+            outputs = model(inputs)
         step_loss += loss_fn(outputs, labels).item() * labels.shape[0]
         step_preds += (outputs.argmax(dim=-1) == labels).float().sum().item()
         if dryrun:

@@ -247,3 +247,44 @@ def test_device_side_augmentation_and_shuffle_pipeline():
     assert not torch.equal(perm1, tc.perm) and not torch.equal(aug1, tc.engine.aug_params)
     assert sorted(tc.perm.tolist()) == list(range(n))
     assert int(tc.engine.aug_params[:, :2].max()) <= 8 and int(tc.engine.aug_params[:, :2].min()) >= 0
+
+
+def test_checkpoint_roundtrip_in_reference_format(tmp_path):
+    """training/utils.py:43-70: 5-list checkpoint; resuming reproduces the uninterrupted run bit for bit."""
+    mb, n = 16, 32
+    X, Y = O.synthetic_cifar(n)
+    setup = dict(device=DEV, dtype=torch.float32)
+
+    def run(steps, name):
+        cfg = _cfg(mb, **{"hyp.steps": steps, "hyp.grad_clip": 0.25, "impl.checkpoint.name": name,
+                          "original_cwd": str(tmp_path), "hyp.warmup": 2})
+        model = fresh()
+        trainer = Trainer(model, HostBlockLoader(X, Y, mb), None, setup, cfg)
+        while trainer.step_count < steps:
+            trainer.step(validate=False)
+        return model, trainer
+
+    m_full, _ = run(3, None)            # uninterrupted
+    run(2, "ck.pth")                    # two steps, checkpointed
+    ck = torch.load(tmp_path / "checkpoints" / "ck.pth")
+    assert isinstance(ck, list) and len(ck) == 5 and ck[3] is None and ck[4] == 2
+    assert list(ck[1].keys()) == list(fresh().state_dict().keys())
+    assert "momentum_buffer" in ck[0]["state"][0]
+    m_res, t_res = run(3, "ck.pth")     # resumes at step 2, runs the third
+    assert t_res.stats["train_loss"] and len(t_res.stats["train_loss"]) == 1
+    a = torch.cat([p.detach().reshape(-1) for p in m_full.parameters()])
+    b = torch.cat([p.detach().reshape(-1) for p in m_res.parameters()])
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        run(2, "ck.pth")                # checkpoint is already at step 3 >= max_steps
+
+
+def test_measure_floating_point_accuracy_reports_zero_drift():
+    """measure_floating_point_accuracy.py / training.py:429-600: two evaluations from the same state."""
+    from fullbatchtraining_b200.training import measure_implementation_noise
+
+    mb, n = 16, 48
+    X, Y = O.synthetic_cifar(n)
+    rep = measure_implementation_noise(fresh(), HostBlockLoader(X, Y, mb), None, dict(device=DEV, dtype=torch.float32),
+                                       _cfg(mb))
+    assert rep["grad_l2"] > 0 and rep["diff_linf"] == 0.0 and rep["diff_l2"] == 0.0
