@@ -209,14 +209,28 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // instruction writes 8 rows x 64 contiguous bytes (16 full sectors).  row_off / valid describe THIS lane's row.
 constexpr int kEpiPitch = 20;                       // floats per staged row
 constexpr int kEpiWarpFloats = 32 * kEpiPitch;      // 2560 B per warp
+// If `stat` is given, the staged patch also yields per-column statistics of the 32 rows for the BatchNorm that follows
+// the convolution: lanes 0-15 add the column sums, lanes 16-31 the column sums of squares (column = lane & 15).
 __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
-                                                  bool valid, int col0, bool accumulate, int lane) {
+                                                  bool valid, int col0, bool accumulate, int lane,
+                                                  float* stat = nullptr) {
   float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                           __uint_as_float(v[4 * j + 3]));
   __syncwarp();
+  if (stat) {
+    const int col = lane & 15;
+    const bool sq = lane >= 16;
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float x = stage[r * kEpiPitch + col];
+      s += sq ? x * x : x;
+    }
+    *stat += s;
+  }
   const int sub = lane >> 2;
   const int c4 = (lane & 3) * 4;
   float4* d[4];

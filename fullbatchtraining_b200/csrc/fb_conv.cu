@@ -97,6 +97,8 @@ struct alignas(64) ConvGemmKParams {
   float* out;
   long long out_sn, out_sh, out_sw;
   int accumulate;
+  float* stats;  // optional [gridDim.x / n_tiles][2][n_total]: per-CTA column sums / sums of squares of the output
+  int n_total;
 };
 
 constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
@@ -113,6 +115,27 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
   } else {
     n0 = tile * tile_n;
     h0 = 0;
+  }
+}
+
+// Flush of the per-warp column statistics collected by the epilogue (BatchNorm statistics fused into the producing
+// convolution): the four epilogue warps combine through the staging patch and write one partial row
+// stats[row][0 = sum | 1 = sum of squares][channel].  acc[c] of lane l belongs to column c*16 + (l & 15).
+template <int N_TILE>
+__device__ __forceinline__ void flush_column_stats(float* epi_stage, const float (&acc)[N_TILE / 16], int q, int lane,
+                                                   float* stats, int row, int n_total, int n_tile0) {
+  float* sm = epi_stage + q * kEpiWarpFloats;  // [chunk][lane], N_TILE/16 * 32 <= 512 floats per warp
+#pragma unroll
+  for (int c = 0; c < N_TILE / 16; ++c) sm[c * 32 + lane] = acc[c];
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+  const int t = q * 32 + lane;
+  for (int idx = t; idx < 2 * N_TILE; idx += 128) {
+    const int which = idx / N_TILE, col = idx % N_TILE;
+    const int off = (col / 16) * 32 + (col % 16) + 16 * which;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) v += epi_stage[w * kEpiWarpFloats + off];
+    stats[((long long)row * 2 + which) * n_total + n_tile0 + col] = v;
   }
 }
 
@@ -241,6 +264,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     const int h = (r / p.tile_w) % p.tile_h;
     const int n = r / (p.tile_w * p.tile_h);
     float* stage = epi_stage + q * kEpiWarpFloats;
+    float col_acc[N_TILE / 16];
+#pragma unroll
+    for (int c = 0; c < N_TILE / 16; ++c) col_acc[c] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       int n0, h0;
@@ -266,12 +292,17 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         } else {
           tmem_ld_wait();
         }
-        warp_store_rows16(stage, v, p.out, row_off, valid, c * 16, p.accumulate != 0, lane);
+        warp_store_rows16(stage, v, p.out, row_off, valid, c * 16, p.accumulate != 0, lane,
+                          p.stats ? &col_acc[c] : nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    // host guarantees gridDim.x % n_tiles == 0 when stats are requested: this CTA only saw one N tile
+    if (p.stats)
+      flush_column_stats<N_TILE>(epi_stage, col_acc, q, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
+                                 (blockIdx.x % p.n_tiles) * N_TILE);
   }
   tc_fence_before();
   __syncthreads();
@@ -288,7 +319,8 @@ static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
     configured = true;
   }
   const int tiles = kp.m_tiles * kp.n_tiles;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;  // one N tile per CTA (see flush_column_stats)
   FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, kp));
   return 0;
 }
@@ -327,6 +359,8 @@ struct alignas(64) Conv3x3KParams {
   long long out_sn, out_sh, out_sw;
   int accumulate;
   int debug;
+  float* stats;  // optional per-CTA column statistics, see ConvGemmKParams
+  int n_total;
 };
 
 #define FB_DBG_WAIT(slot, call)                      \
@@ -506,6 +540,9 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
     const int w = r % p.w;
     const int hr = r / p.w;
     const bool edbg = dbg && warp == 2 && lane == 0;
+    float col_acc[N_TILE / 16];
+#pragma unroll
+    for (int c = 0; c < N_TILE / 16; ++c) col_acc[c] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       const int mt = tile / p.n_tiles;
@@ -538,7 +575,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
           } else {
             tmem_ld_wait();
           }
-          warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane);
+          warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane,
+                            p.stats ? &col_acc[c] : nullptr);
         }
       }
       tc_fence_before();
@@ -551,6 +589,9 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
       g_dbg[7] += dbg_acc[1];
       g_dbg[8] += clock64() - t_start;
     }
+    if (p.stats)
+      flush_column_stats<N_TILE>(epi_stage, col_acc, q, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
+                                 (blockIdx.x % p.n_tiles) * N_TILE);
   }
   tc_fence_before();
   __syncthreads();
@@ -575,7 +616,8 @@ static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
     configured = smem;
   }
   const int tiles = kp.n * (kp.h / (2 * kp.th)) * kp.n_tiles;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;
   FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), smem, stream, kp, a_box_bytes, b_stages));
   return 0;
 }
@@ -1029,6 +1071,9 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.out_sh = a->out_sh;
   kp.out_sw = a->out_sw;
   kp.accumulate = a->accumulate;
+  kp.stats = a->stats_out;
+  kp.n_total = a->n_total;
+  FB_REQUIRE(!a->stats_out || !a->accumulate, "fb_conv_gemm: column statistics need accumulate == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a->n_tile) {
     case 64: return dispatch_conv_gemm<64>(kp, a->a_planes, a->b_planes, st);
@@ -1072,6 +1117,9 @@ extern "C" int fb_conv3x3(const fb_conv3x3_args* a, void* stream) {
     return e && e[0] == '1';
   }();
   kp.debug = debug ? 1 : 0;
+  kp.stats = a->stats_out;
+  kp.n_total = a->n_total;
+  FB_REQUIRE(!a->stats_out || !a->accumulate, "fb_conv3x3: column statistics need accumulate == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->n_tile == 64) return dispatch_conv3x3<64>(kp, a->a_planes, a->b_planes, st);
   return dispatch_conv3x3<128>(kp, a->a_planes, a->b_planes, st);
@@ -1185,4 +1233,11 @@ extern "C" int fb_debug_counters(long long* host32, int clear) {
     FB_CUDA(cudaMemcpyToSymbol(g_dbg, zero, sizeof(zero)));
   }
   return 0;
+}
+
+extern "C" int fb_conv_stats_rows(int m_tiles, int n_tiles) {
+  const int tiles = m_tiles * n_tiles;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  grid = (grid / n_tiles) * n_tiles;
+  return grid / n_tiles;
 }

@@ -341,6 +341,10 @@ struct BnFusedFwdArgs {
   float* partial;                // [grid][2 branches][2][C]
   unsigned int* counters;        // [2], zero on entry
   int rows_per_block;
+  // statistics already reduced per CTA by the producing convolution's epilogue (fb_conv_gemm / fb_conv3x3 stats_out):
+  // [ext_rows][2][C] per branch; when given, phase 1 and the first barrier are skipped
+  const float *ext0, *ext1;
+  int ext_rows0, ext_rows1;
 };
 
 // column sums of one branch over rows [r0, r1): partial[2][C] of this block
@@ -430,10 +434,16 @@ __global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) 
   const long long r1 = min(P, r0 + a.rows_per_block);
   const long long block_stride = (long long)branches * 2 * C;
   float* mine = a.partial + blockIdx.x * block_stride;
-  // ---- phase 1: per-block column sums
-  block_column_sums<false>(ap.y, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine, red);
-  if (ap.y2) block_column_sums<false>(ap.y2, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine + 2 * C, red);
-  grid_barrier(a.counters, gridDim.x);
+  const bool external = a.ext0 != nullptr;
+  unsigned int barrier_target = gridDim.x;
+  if (!external) {
+    // ---- phase 1: per-block column sums
+    block_column_sums<false>(ap.y, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine, red);
+    if (ap.y2)
+      block_column_sums<false>(ap.y2, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine + 2 * C, red);
+    grid_barrier(a.counters, gridDim.x);
+    barrier_target = 2 * gridDim.x;
+  }
   // ---- finalize: one warp per channel, spread over the blocks
   {
     const int lane = threadIdx.x & 31;
@@ -441,7 +451,10 @@ __global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) 
     for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += gridDim.x * 8) {
       const int br = item / C, c = item % C;
       double s1, s2;
-      warp_reduce_partials(a.partial + br * 2 * C, block_stride, gridDim.x, C, c, lane, s1, s2);
+      if (external)
+        warp_reduce_partials(br ? a.ext1 : a.ext0, 2LL * C, br ? a.ext_rows1 : a.ext_rows0, C, c, lane, s1, s2);
+      else
+        warp_reduce_partials(a.partial + br * 2 * C, block_stride, gridDim.x, C, c, lane, s1, s2);
       if (lane == 0) {
         const double m = s1 / double(P);
         double var = s2 / double(P) - m * m;
@@ -458,7 +471,7 @@ __global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) 
       }
     }
   }
-  grid_barrier(a.counters, 2 * gridDim.x);
+  grid_barrier(a.counters, barrier_target);
   grid_barrier_release(a.counters);
   // ---- phase 2: normalise the rows this block reduced (L2 hits)
   const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
@@ -1026,7 +1039,8 @@ static int fused_geometry(long long P, int C, int& grid, int& rows_per_block) {
 
 extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, float* rstd2_out, float* running_mean,
                                float* running_var, float* running_mean2, float* running_var2, float momentum,
-                               float eps, float* ws, void* stream) {
+                               float eps, float* ws, const float* stats, int stats_rows, const float* stats2,
+                               int stats_rows2, void* stream) {
   FB_REQUIRE(ap && ap->y && ap->mean && ap->rstd && ap->gamma && ap->beta && ap->out_hi && ws,
              "fb_bn_fwd_fused: null pointer");
   FB_REQUIRE(!ap->y2 || (mean2_out && rstd2_out && ap->gamma2 && ap->beta2), "fb_bn_fwd_fused: second branch incomplete");
@@ -1052,6 +1066,13 @@ extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, flo
   a.counters = reinterpret_cast<unsigned int*>(ws);
   a.partial = ws + 4;
   a.rows_per_block = rpb;
+  FB_REQUIRE(!stats || stats_rows > 0, "fb_bn_fwd_fused: stats_rows must be positive");
+  FB_REQUIRE(!stats || !ap->y2 || (stats2 && stats_rows2 > 0),
+             "fb_bn_fwd_fused: epilogue statistics must be given for both branches or for none");
+  a.ext0 = stats;
+  a.ext_rows0 = stats_rows;
+  a.ext1 = stats2;
+  a.ext_rows1 = stats_rows2;
   FB_CUDA(launch_pdl(bn_fwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }

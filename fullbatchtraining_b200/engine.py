@@ -95,7 +95,7 @@ class Unit:
                                      (self.dx_target if self.dx_target is not None else self.x.grad)
                                      if self.needs_dx else None, *self.w[i], eng.partial,
                                      dx_accumulate=self.dx_accumulate, split=eng.split,
-                                     alg_k=27 if self.stem else None) for i in range(2)]
+                                     alg_k=27 if self.stem else None, fuse_stats=eng.fuse_stats) for i in range(2)]
 
 
 class Block:
@@ -131,6 +131,8 @@ class FullBatchEngine:
         self.smoothing = float(label_smoothing)
         self.classes = model.fc.out_features
         self.partial_elems = 0
+        # BatchNorm statistics in the conv epilogue (FB_FUSE_STATS=0: statistics pass inside the BatchNorm kernel)
+        self.fuse_stats = os.environ.get("FB_FUSE_STATS", "1") == "1"
         dev = self.device
 
         # ---- flat parameter buffers, parameters() order
@@ -248,7 +250,8 @@ class FullBatchEngine:
             sec = (second.y, second.mean, second.rstd, ga2, be2, *self._bn_buffers(second.bn_name))
         ops.bn_fwd_fused(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, out.hi, out.lo, self.bn_ws,
                          running=self._bn_buffers(u.bn_name), relu=relu, second=sec, res=res, momentum=BN_MOMENTUM,
-                         eps=BN_EPS)
+                         eps=BN_EPS, stats=u.plans[self._pass].stats,
+                         stats2=second.plans[self._pass].stats if second is not None else None)
 
     def _forward(self, P, G, loss_slot, correct_slot):
         self._pass = 0 if P is self.theta else 1

@@ -31,13 +31,13 @@ class ConvGemmArgs(C.Structure):
     _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("n_phases", i32), ("a_planes", i32), ("b_planes", i32),
                 ("n_taps", i32), ("cblocks", i32), ("taps", Tap * FB_MAX_TAPS), ("tile_w", i32), ("tile_h", i32),
                 ("tile_n", i32), ("grid_h", i32), ("grid_n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
-                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32)]
+                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp)]
 
 
 class Conv3x3Args(C.Structure):
     _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("a_planes", i32), ("b_planes", i32), ("b_k0", (i32 * 3) * 3),
                 ("cblocks", i32), ("w", i32), ("h", i32), ("n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
-                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32)]
+                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp)]
 
 
 class WgradTap(C.Structure):
@@ -73,6 +73,7 @@ _SIGNATURES = {
     "fb_tmap_encode_act4d": ([vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32], i32),
     "fb_tmap_encode_mat2d": ([vp, vp, i32, i32, i64, i32, i32], i32),
     "fb_conv_gemm": ([C.POINTER(ConvGemmArgs), vp], i32),
+    "fb_conv_stats_rows": ([i32, i32], i32),
     "fb_conv3x3": ([C.POINTER(Conv3x3Args), vp], i32),
     "fb_conv_wgrad": ([C.POINTER(WgradArgs), vp], i32),
     "fb_wgrad_finalize": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
@@ -83,7 +84,7 @@ _SIGNATURES = {
     "fb_bn_stats": ([vp, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp], i32),
     "fb_bn_apply": ([C.POINTER(BnApplyArgs), vp], i32),
     "fb_bn_bwd": ([C.POINTER(BnBwdArgs), vp], i32),
-    "fb_bn_fwd_fused": ([C.POINTER(BnApplyArgs), vp, vp, vp, vp, vp, vp, f32, f32, vp, vp], i32),
+    "fb_bn_fwd_fused": ([C.POINTER(BnApplyArgs), vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, i32, vp, i32, vp], i32),
     "fb_bn_bwd_fused": ([C.POINTER(BnBwdArgs), vp], i32),
     "fb_avgpool2_fwd": ([vp, vp, i32, i32, i32, i32, vp, vp, vp], i32),
     "fb_avgpool2_bwd": ([vp, i32, i32, i32, i32, vp, i32, vp], i32),

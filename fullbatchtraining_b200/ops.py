@@ -196,7 +196,7 @@ class Conv2dPlan:
     """
 
     def __init__(self, n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
-                 dx_accumulate=False, split=True, alg_k=None):
+                 dx_accumulate=False, split=True, alg_k=None, fuse_stats=False):
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.n, self.h, self.w, self.cin, self.cout, self.k, self.stride = n, h, w, cin, cout, k, stride
@@ -249,6 +249,18 @@ class Conv2dPlan:
             self.fwd = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, n, cout, y, 0,
                                 (ho * wo * cout, wo * cout, cout), False, n_tile)
         self.fwd.flops = self.alg_flops
+        # BatchNorm statistics fused into the forward epilogue: per-CTA partial rows [rows][2][cout]
+        self.stats = None
+        if fuse_stats:
+            a = self.fwd.args
+            if halo:
+                m_t, n_t = n * (h // (2 * (128 // w))), cout // a.n_tile
+            else:
+                m_t, n_t = m_tiles, cout // a.n_tile
+            rows = L.load().fb_conv_stats_rows(m_t, n_t)
+            buf = torch.zeros(rows, 2, cout, device=y.device)
+            a.stats_out = buf.data_ptr()
+            self.stats = (buf, rows)
 
         # ---- dgrad
         self.dgrads = []
@@ -442,7 +454,7 @@ def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_o
 
 
 def bn_fwd_fused(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, ws, running=None, relu=True, second=None, res=None,
-                 momentum=0.1, eps=1e-5):
+                 momentum=0.1, eps=1e-5, stats=None, stats2=None):
     """Train-mode BatchNorm statistics + normalise (+ second normalised branch / residual) + ReLU in one launch.
     second = (y2, mean2, rstd2, gamma2, beta2, running_mean2, running_var2)."""
     a = L.BnApplyArgs()
@@ -458,8 +470,11 @@ def bn_fwd_fused(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, ws, running=
     planes = 1 + (out_lo is not None)
     per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes
     rm, rv = running if running is not None else (None, None)
+    # stats = (tensor [rows][2][C], rows) produced by the convolution's epilogue (Conv2dPlan.stats)
+    st, st_rows = (stats[0].data_ptr(), stats[1]) if stats is not None else (None, 0)
+    st2, st_rows2 = (stats2[0].data_ptr(), stats2[1]) if stats2 is not None else (None, 0)
     _call("bn_fwd", per_elem * P * Cc, "byte", "fb_bn_fwd_fused", C.byref(a), L.ptr(m2), L.ptr(r2), L.ptr(rm), L.ptr(rv),
-          L.ptr(rm2), L.ptr(rv2), momentum, eps, ws.data_ptr())
+          L.ptr(rm2), L.ptr(rv2), momentum, eps, ws.data_ptr(), st, st_rows, st2, st_rows2)
 
 
 def bn_bwd_fused(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None):

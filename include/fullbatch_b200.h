@@ -75,7 +75,12 @@ typedef struct {
   float* out;                     /* fp32; element (n,h,w,c) at out + n*out_sn + h*out_sh + w*out_sw + c */
   int64_t out_sn, out_sh, out_sw;
   int32_t accumulate; /* 0: overwrite, 1: out += result */
+  /* optional BatchNorm statistics fused into the epilogue: stats_out[row][0|1][n_total] receives per-CTA column sums
+   * and sums of squares of `out`, rows = fb_conv_stats_rows(...); feed them to fb_bn_fwd_fused.  NULL: off. */
+  float* stats_out;
 } fb_conv_gemm_args;
+/* number of partial rows written to stats_out for a problem of m_tiles x (n_total / n_tile) tiles */
+int fb_conv_stats_rows(int m_tiles, int n_tiles);
 int fb_conv_gemm(const fb_conv_gemm_args* args, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution (forward or dgrad) with haloed A boxes: per column shift dw one box of
@@ -94,6 +99,7 @@ typedef struct {
   float* out;
   int64_t out_sn, out_sh, out_sw;
   int32_t accumulate;
+  float* stats_out; /* as in fb_conv_gemm_args; m_tiles = n * h / (256 / w * 2) */
 } fb_conv3x3_args;
 int fb_conv3x3(const fb_conv3x3_args* args, void* stream);
 
@@ -199,7 +205,9 @@ int fb_bn_bwd(const fb_bn_bwd_args* args, void* stream);
  * ws: >= 2*C*1024 floats, the first 16 bytes ZERO on first use (self-resetting barrier counters). */
 int fb_bn_fwd_fused(const fb_bn_apply_args* args, float* mean2_out, float* rstd2_out, float* running_mean,
                     float* running_var, float* running_mean2, float* running_var2, float momentum, float eps, float* ws,
-                    void* stream);
+                    const float* stats, int stats_rows, const float* stats2, int stats_rows2, void* stream);
+/* stats / stats2 (optional): per-CTA column statistics [rows][2][C] written by the producing convolution
+ * (fb_conv_gemm_args.stats_out); when given, the kernel skips its own statistics pass and one grid barrier. */
 int fb_bn_bwd_fused(const fb_bn_bwd_args* args, void* stream);
 
 /* AvgPool2d(2) on bf16 hi/lo planes (downsample 'C', resnets.py:147-152) and its backward (dX = up(dP)/4). */

@@ -487,3 +487,48 @@ def test_stem_im2col_u8_augmentation_matches_torchvision_semantics():
         torch.tensor(std, device=DEV)[None, :, None, None]
     ref0 = F.unfold(x0, 3, padding=1).transpose(1, 2).reshape(n * 1024, 27)
     assert float(((p_hi.float() + p_lo.float())[:, :27] - ref0).abs().max()) < 3e-5 * float(ref0.abs().max())
+
+
+@pytest.mark.parametrize("case", [(4, 32, 32, 64, 64, 3, 1), (3, 16, 16, 64, 256, 3, 1), (2, 32, 32, 64, 128, 3, 2),
+                                  (16, 8, 8, 128, 256, 3, 1), (4, 4, 4, 512, 512, 3, 1), (32, 8, 8, 64, 256, 1, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_forward_fused_statistics(case):
+    """BatchNorm statistics fused into the conv epilogue: per-CTA column sums / sums of squares of the output."""
+    n, h, w, cin, cout, k, stride = case
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(n, cin, h, w, device=DEV, generator=g)
+    wt = torch.randn(cout, cin, k, k, device=DEV, generator=g) * (2.0 / (cout * k * k)) ** 0.5
+    ho, wo = h // stride, w // stride
+    x_hi, x_lo = split(nhwc(x))
+    taps = k * k
+    wf_hi = torch.zeros(cout, taps * cin, device=DEV, dtype=torch.bfloat16)
+    wf_lo = torch.zeros_like(wf_hi)
+    ops.weight_prep(wt, cout, cin, taps, wf_hi, wf_lo)
+    y = torch.empty(n, ho, wo, cout, device=DEV)
+    dy = torch.zeros(n, ho, wo, cout, device=DEV, dtype=torch.bfloat16)
+    partial = torch.empty(ops.Conv2dPlan.partial_elems(n, h, w, cin, cout, k, stride), device=DEV)
+    plan = ops.Conv2dPlan(n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, None, wf_hi, wf_lo, None, None, partial,
+                          fuse_stats=True)
+    plan.forward()
+    buf, rows = plan.stats
+    assert buf.shape[0] == rows >= 1
+    yd = y.double().reshape(-1, cout)
+    s1, s2 = buf[:, 0].double().sum(0), buf[:, 1].double().sum(0)
+    assert rel_err(s1, yd.sum(0)) < 1e-5
+    assert rel_err(s2, (yd * yd).sum(0)) < 1e-5
+    # and the fused BatchNorm consumes them: same result as with its own statistics pass
+    P = n * ho * wo
+    gamma, beta = torch.rand(cout, device=DEV, generator=g) + 0.5, torch.randn(cout, device=DEV, generator=g) * 0.1
+    ws = torch.zeros(2 * cout * 1024, device=DEV)
+    outs = []
+    for stats in (None, plan.stats):
+        mean, rstd = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
+        rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+        hi = torch.empty(P, cout, device=DEV, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        for _ in range(2):
+            rm.zero_(); rv.fill_(1)
+            ops.bn_fwd_fused(y, mean, rstd, gamma, beta, P, cout, hi, lo, ws, running=(rm, rv), stats=stats)
+        outs.append((mean, rstd, rm, rv, hi.double() + lo.double()))
+    for u, v in zip(*outs):
+        assert rel_err(u, v) < 2e-5
