@@ -348,12 +348,16 @@ static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStr
 __device__ long long g_dbg[32];
 
 struct alignas(64) Conv3x3KParams {
-  CUtensorMap a_maps[2];  // [plane]: box = 64 ch x W x (2*TH+2) rows x 1 image
+  // [plane]: imgs == 1: dims (C, W, H, N), box = 64 ch x W x (halves*TH+2) rows x 1 image
+  //          imgs  > 1: dims (C, W, N, H), box = 64 ch x W x imgs images x (H+2) rows (image-interleaved slabs)
+  CUtensorMap a_maps[2];
   CUtensorMap b_maps[2];  // [plane]: box = 64 x N_TILE weight rows
   int b_k0[3][3];         // [dw+1][dh+1] -> first K column of that tap in the weight matrix
   int cblocks;
   int w, h, n;            // feature map and images
-  int th;                 // rows per 128-pixel half
+  int th;                 // slabs per 128-pixel half; a slab = one image row of `imgs` consecutive images
+  int imgs;               // images interleaved in a slab (1: a half is TH rows of one image; >1: a half is imgs whole images)
+  int halves;             // 128-pixel halves per CTA tile (they share every weight tile)
   int n_tiles;
   float* out;
   long long out_sn, out_sh, out_sw;
@@ -391,9 +395,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_stage_bytes = PA * a_box_bytes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kAStages * a_stage_bytes;
+  uint8_t* smem_b = smem + Cfg::kAStages * PA * ((p.imgs == 1) ? 1 : p.halves) * a_box_bytes;
   float* epi_stage = reinterpret_cast<float*>(smem_b + b_stages * Cfg::kBStageBytes);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + b_stages * Cfg::kBStageBytes + kEpiStageBytes);
   uint64_t* a_empty = a_full + Cfg::kAStages;
@@ -428,11 +431,17 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   griddep_wait();
   griddep_launch();
 
-  const int tiles_per_img = p.h / (2 * p.th);
-  const int m_tiles = p.n * tiles_per_img;
+  // imgs == 1: a tile is halves*TH consecutive rows of one image, fetched as ONE haloed box;
+  // imgs  > 1: a half is `imgs` whole images with rows interleaved ([h][img][w]); one haloed box per half
+  const int slab_px = p.imgs * p.w;
+  const int tiles_per_img = (p.imgs == 1) ? p.h / (p.halves * p.th) : 1;
+  const int m_tiles = (p.imgs == 1) ? p.n * tiles_per_img : p.n / (p.halves * p.imgs);
   const int total_tiles = m_tiles * p.n_tiles;
-  const int row_bytes = p.w * 128;          // one image row of one 64-channel block
+  const int boxes = (p.imgs == 1) ? 1 : p.halves;
+  const int row_bytes = slab_px * 128;      // one slab of one 64-channel block
   const int half_bytes = p.th * row_bytes;  // 128 pixels = 16 KiB
+  const int half_stride = (p.imgs == 1) ? half_bytes : a_box_bytes;
+  const int a_stage_bytes = PA * boxes * a_box_bytes;
   const bool dbg = p.debug && blockIdx.x == 0;
   const long long t_start = clock64();
   long long dbg_acc[2] = {0, 0};  // register accumulators (slot parity), flushed once per role
@@ -443,7 +452,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
       int ia = 0, ib = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles;
-        const int n0 = mt / tiles_per_img, h0 = (mt % tiles_per_img) * 2 * p.th;
+        const int n0 = (p.imgs == 1) ? mt / tiles_per_img : mt * p.halves * p.imgs;
+        const int h0 = (p.imgs == 1) ? (mt % tiles_per_img) * p.halves * p.th : 0;
         const int n_tile0 = (tile % p.n_tiles) * N_TILE;
         for (int dwi = 0; dwi < 3; ++dwi) {
           for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -451,9 +461,16 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
             FB_DBG_WAIT(0, mbar_wait(&a_empty[as], ((ia / Cfg::kAStages) & 1) ^ 1, 21));
             mbar_arrive_expect_tx(&a_full[as], a_stage_bytes);
 #pragma unroll
-            for (int pl = 0; pl < PA; ++pl)
-              tma_load_4d(smem_a + as * a_stage_bytes + pl * a_box_bytes, &p.a_maps[pl], &a_full[as], cb * kBlockK,
-                          dwi - 1, h0 - 1, n0);
+            for (int pl = 0; pl < PA; ++pl) {
+              uint8_t* dst = smem_a + as * a_stage_bytes + pl * boxes * a_box_bytes;
+              if (p.imgs == 1) {
+                tma_load_4d(dst, &p.a_maps[pl], &a_full[as], cb * kBlockK, dwi - 1, h0 - 1, n0);
+              } else {
+                for (int b = 0; b < boxes; ++b)
+                  tma_load_4d(dst + b * a_box_bytes, &p.a_maps[pl], &a_full[as], cb * kBlockK, dwi - 1,
+                              n0 + b * p.imgs, -1);
+              }
+            }
             ++ia;
             for (int dhi = 0; dhi < 3; ++dhi) {
               const int bs = ib % b_stages;
@@ -501,14 +518,16 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
               const long long t_issue = dbg ? clock64() : 0;
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
-                const uint32_t a_view = a_base + dhi * row_bytes + half * half_bytes;
+                if (half >= p.halves) break;
+                const uint32_t a_view = a_base + dhi * row_bytes + half * half_stride;
 #pragma unroll
                 for (int c = 0; c < Cfg::kCombos; ++c) {
                   const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
                   const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
 #pragma unroll
                   for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t da = make_smem_desc_sw128(a_view + ap * a_box_bytes + k * 32, 16, 1024);
+                    const uint64_t da =
+                        make_smem_desc_sw128(a_view + ap * boxes * a_box_bytes + k * 32, 16, 1024);
                     const uint64_t db = make_smem_desc_sw128(b_base + bp * Cfg::kBBytes + k * 32, 16, 1024);
                     tc_mma_bf16(tmem_d + half * Cfg::kUmmaN, da, db, idesc, (first && c == 0 && k == 0) ? 0u : 1u);
                   }
@@ -538,7 +557,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int w = r % p.w;
-    const int hr = r / p.w;
+    const int hr = r / slab_px;              // slab (image row) inside the half
+    const int img = (r % slab_px) / p.w;     // image inside the slab
     const bool edbg = dbg && warp == 2 && lane == 0;
     float col_acc[N_TILE / 16];
 #pragma unroll
@@ -546,7 +566,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       const int mt = tile / p.n_tiles;
-      const int n0 = mt / tiles_per_img, h0 = (mt % tiles_per_img) * 2 * p.th;
+      const int n0 = (p.imgs == 1) ? mt / tiles_per_img : mt * p.halves * p.imgs;
+      const int h0 = (p.imgs == 1) ? (mt % tiles_per_img) * p.halves * p.th : 0;
       const int n_tile0 = (tile % p.n_tiles) * N_TILE;
       const int buf = tile_i & 1;
       {
@@ -557,8 +578,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
       const long long t_epi = clock64();
       tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const long long row_off = (long long)n0 * p.out_sn + (long long)(h0 + half * p.th + hr) * p.out_sh +
+      for (int half = 0; half < p.halves; ++half) {
+        const int n_img = (p.imgs == 1) ? n0 : n0 + half * p.imgs + img;
+        const int h_row = (p.imgs == 1) ? h0 + half * p.th + hr : hr;
+        const long long row_off = (long long)n_img * p.out_sn + (long long)h_row * p.out_sh +
                                   (long long)w * p.out_sw + n_tile0;
 #pragma unroll 1
         for (int c = 0; c < N_TILE / 16; ++c) {
@@ -601,8 +624,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
 template <int N_TILE, int PA, int PB>
 static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
   using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
-  const int a_box_bytes = (2 * kp.th + 2) * kp.w * 128;
-  const int a_bytes = Cfg::kAStages * PA * a_box_bytes;
+  const int boxes = (kp.imgs == 1) ? 1 : kp.halves;
+  const int box_rows = (kp.imgs == 1) ? kp.halves * kp.th + 2 : kp.th + 2;
+  const int a_box_bytes = box_rows * kp.imgs * kp.w * 128;
+  const int a_bytes = Cfg::kAStages * PA * boxes * a_box_bytes;
   int b_stages = (kSmemBudget - 1024 - a_bytes) / Cfg::kBStageBytes;  // kSmemBudget already excludes the epilogue patch
   if (b_stages > 8) b_stages = 8;
   if (b_stages < 2) {
@@ -615,7 +640,8 @@ static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
     FB_CUDA(cudaFuncSetAttribute(conv3x3_kernel<N_TILE, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int tiles = kp.n * (kp.h / (2 * kp.th)) * kp.n_tiles;
+  const int m_tiles = (kp.imgs == 1) ? kp.n * (kp.h / (kp.halves * kp.th)) : kp.n / (kp.halves * kp.imgs);
+  const int tiles = m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;
   FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), smem, stream, kp, a_box_bytes, b_stages));
@@ -1085,8 +1111,15 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
 extern "C" int fb_conv3x3(const fb_conv3x3_args* a, void* stream) {
   FB_REQUIRE(a && a->host_a_maps && a->host_b_maps && a->out, "fb_conv3x3: null pointer");
   FB_REQUIRE(a->a_planes >= 1 && a->a_planes <= 2 && a->b_planes >= 1 && a->b_planes <= 2, "fb_conv3x3: bad planes");
-  if (a->w < 8 || a->w > 128 || 128 % a->w != 0 || a->h % (2 * (128 / a->w)) != 0) {
-    set_error("fb_conv3x3: feature map %dx%d not supported by the haloed 256-pixel tiling", a->h, a->w);
+  const int imgs = a->imgs > 0 ? a->imgs : 1;
+  const int halves = a->halves > 0 ? a->halves : 2;
+  FB_REQUIRE(halves == 1 || halves == 2, "fb_conv3x3: halves must be 1 or 2");
+  const bool geom_ok =
+      (imgs == 1) ? (a->w >= 8 && a->w <= 128 && 128 % a->w == 0 && a->h % (halves * (128 / a->w)) == 0)
+                  : (imgs * a->w * a->h == 128 && (imgs * a->w) % 8 == 0 && a->n % (halves * imgs) == 0);
+  if (!geom_ok) {
+    set_error("fb_conv3x3: %d images of %dx%d (imgs %d, halves %d) not supported by the haloed tiling", a->n, a->h,
+              a->w, imgs, halves);
     return FB_ERR_UNSUPPORTED;
   }
   if (!(a->n_tile == 64 || a->n_tile == 128) || a->n_total % a->n_tile != 0) {
@@ -1105,7 +1138,9 @@ extern "C" int fb_conv3x3(const fb_conv3x3_args* a, void* stream) {
   kp.w = a->w;
   kp.h = a->h;
   kp.n = a->n;
-  kp.th = 128 / a->w;
+  kp.th = 128 / (imgs * a->w);
+  kp.imgs = imgs;
+  kp.halves = halves;
   kp.n_tiles = a->n_total / a->n_tile;
   kp.out = a->out;
   kp.out_sn = a->out_sn;

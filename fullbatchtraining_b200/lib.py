@@ -37,7 +37,8 @@ class ConvGemmArgs(C.Structure):
 class Conv3x3Args(C.Structure):
     _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("a_planes", i32), ("b_planes", i32), ("b_k0", (i32 * 3) * 3),
                 ("cblocks", i32), ("w", i32), ("h", i32), ("n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
-                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp)]
+                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp),
+                ("imgs", i32), ("halves", i32)]
 
 
 class WgradTap(C.Structure):

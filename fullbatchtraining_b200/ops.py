@@ -144,23 +144,82 @@ class ConvGemm:
         _call("conv_gemm", self.flops, "flop", "fb_conv_gemm", C.byref(self.args))
 
 
-def halo_eligible(h, w, k, stride):
-    """3x3 / stride-1 convs whose 256-pixel tiles are whole image rows of >= 1024 bytes use the haloed-box kernel."""
-    if os.environ.get("FB_DISABLE_HALO") == "1":
-        return False
-    return k == 3 and stride == 1 and w in (16, 32, 64, 128) and h % (256 // w) == 0
+FABRIC_BYTES_PER_CLK = 43.0  # measured L2 -> SM operand bandwidth per SM
+
+
+def halo_geometry(n, h, w, k, stride, n_total, a_planes=2, b_planes=2):
+    """Tile geometry (imgs, halves, n_tile) of the haloed-box kernel for a 3x3 / stride-1 conv, or None.
+
+    imgs == 1: tiles are whole image rows (>= 1024 bytes per row => w >= 8 with 128 % w == 0).  Small maps
+    (imgs * w * h == 128): a 128-pixel half is `imgs` whole images with interleaved rows.  halves and the N tile are
+    chosen by a cost model: waves of the persistent grid x max(tensor-pipe clocks, L2->SM operand bytes / 43 B/clk)
+    per (tap, 64-channel block)."""
+    if os.environ.get("FB_HALO", "0") != "1" or k != 3 or stride != 1:
+        # opt-in: on B200 the generic per-tap kernel (deeper operand pipeline) is faster on every ResNet shape although
+        # it moves 1.5-2.2x more operand bytes (tools/conv_geom_sweep.py, DESIGN.md 5.2)
+        return None
+    if w in (16, 32, 64, 128) and h % (128 // w) == 0:
+        imgs = 1
+    elif w >= 4 and h * w <= 64 and 128 % (h * w) == 0 and (128 // (h * w) * w) % 8 == 0:
+        imgs = 128 // (h * w)
+    else:
+        return None
+    th = 128 // (imgs * w)
+    best = None
+    for halves in (2, 1):
+        if imgs == 1:
+            if h % (halves * th) != 0:
+                continue
+            m_tiles = n * (h // (halves * th))
+            box_bytes = (halves * th + 2) * w * 128
+        else:
+            if n % (halves * imgs) != 0:
+                continue
+            m_tiles = n // (halves * imgs)
+            box_bytes = halves * (th + 2) * imgs * w * 128
+        for nt in (128, 64):
+            if n_total % nt != 0:
+                continue
+            if nt == 64 and b_planes == 2:
+                mma = a_planes * 64
+            else:
+                combos = 3 if (a_planes == 2 and b_planes == 2) else a_planes * b_planes
+                mma = combos * 64
+            mma *= 4 * halves  # four K=16 steps per 64-channel block, per half
+            fabric = (a_planes * box_bytes / 3.0 + b_planes * nt * 128) / FABRIC_BYTES_PER_CLK
+            a_smem = 2 * a_planes * box_bytes  # two A stages
+            if a_smem + 2 * b_planes * nt * 128 > 210 * 1024:
+                continue
+            waves = -(-(m_tiles * (n_total // nt)) // NUM_SMS)
+            cost = waves * max(mma, fabric)
+            if best is None or cost < best[0]:
+                best = (cost, imgs, halves, nt)
+    return None if best is None else best[1:]
 
 
 class Conv3x3:
-    """One launch of fb_conv3x3 (haloed A boxes, 256-pixel tiles) with frozen arguments."""
+    """One launch of fb_conv3x3 (haloed A boxes; 1 or 2 128-pixel halves per tile) with frozen arguments."""
 
-    def __init__(self, planes_a, planes_b, n, h, w, c_k, n_total, b_k0, out, accumulate):
-        """planes_a: list of NHWC bf16 planes [n,h,w,c_k]; planes_b: list of weight matrices [n_total][9*c_k]."""
-        th = 128 // w
-        n_tile = 128 if n_total % 128 == 0 else 64
+    def __init__(self, planes_a, planes_b, n, h, w, c_k, n_total, b_k0, out, accumulate, geom=None):
+        """planes_a: list of NHWC bf16 planes [n,h,w,c_k]; planes_b: list of weight matrices [n_total][9*c_k];
+        geom = (imgs, halves, n_tile) from halo_geometry."""
+        if geom is None:
+            geom = halo_geometry(n, h, w, 3, 1, n_total, len(planes_a), len(planes_b))
+        if geom is None:
+            raise RuntimeError(f"fb_conv3x3 does not support {n} images of {h}x{w}")
+        imgs, halves, n_tile = geom
+        th = 128 // (imgs * w)
         self.a_maps = MapSet(len(planes_a))
         for i, t in enumerate(planes_a):
-            encode_act(self.a_maps, i, t, n, h, w, c_k, (w, 2 * th + 2, 1))
+            if imgs == 1:
+                encode_act(self.a_maps, i, t, n, h, w, c_k, (w, halves * th + 2, 1))
+            else:
+                # dims (C, W, N, H): the box holds rows -1..h of `imgs` images, image-interleaved per row
+                assert t.dtype == torch.bfloat16 and t.is_contiguous()
+                L.check(L.load().fb_tmap_encode_act4d(self.a_maps.slot(i), t.data_ptr(), c_k, w, n, h, c_k,
+                                                      h * w * c_k, w * c_k, 64, w, imgs, h + 2),
+                        "fb_tmap_encode_act4d")
+                self.a_maps.keep.append(t)
         self.b_maps = MapSet(len(planes_b))
         for i, t in enumerate(planes_b):
             encode_mat(self.b_maps, i, t, 9 * c_k, n_total, n_tile)
@@ -173,6 +232,8 @@ class Conv3x3:
         a.cblocks = c_k // 64
         a.w, a.h, a.n = w, h, n
         a.n_total, a.n_tile = n_total, n_tile
+        a.imgs, a.halves = imgs, halves
+        self.m_tiles = n * (h // (halves * th)) if imgs == 1 else n // (halves * imgs)
         self.out = out
         a.out = out.data_ptr()
         a.out_sn, a.out_sh, a.out_sw = h * w * n_total, w * n_total, n_total
@@ -182,7 +243,6 @@ class Conv3x3:
 
     def __call__(self):
         _call("conv_gemm", self.flops, "flop", "fb_conv3x3", C.byref(self.args))
-
 
 
 class Conv2dPlan:
@@ -240,11 +300,12 @@ class Conv2dPlan:
             for kw in range(k):
                 phase, dh, dw = tap_geom(kh, kw)
                 ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
-        halo = halo_eligible(h, w, k, stride)
+        halo = halo_geometry(n, h, w, k, stride, cout, planes, wplanes)
         if halo:
             # b_k0[dw+1][dh+1]: forward tap (kh, kw) reads input pixel (h + kh - 1, w + kw - 1)
             fk0 = [[(dhi * 3 + dwi) * cin for dhi in range(3)] for dwi in range(3)]
-            self.fwd = Conv3x3([x_hi, x_lo][:planes], [wf_hi, wf_lo][:wplanes], n, h, w, cin, cout, fk0, y, False)
+            self.fwd = Conv3x3([x_hi, x_lo][:planes], [wf_hi, wf_lo][:wplanes], n, h, w, cin, cout, fk0, y, False,
+                               halo)
         else:
             self.fwd = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, n, cout, y, 0,
                                 (ho * wo * cout, wo * cout, cout), False, n_tile)
@@ -254,7 +315,7 @@ class Conv2dPlan:
         if fuse_stats:
             a = self.fwd.args
             if halo:
-                m_t, n_t = n * (h // (2 * (128 // w))), cout // a.n_tile
+                m_t, n_t = self.fwd.m_tiles, cout // a.n_tile
             else:
                 m_t, n_t = m_tiles, cout // a.n_tile
             rows = L.load().fb_conv_stats_rows(m_t, n_t)
@@ -272,10 +333,12 @@ class Conv2dPlan:
             ds = MapSet(wplanes)
             for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
                 encode_mat(ds, pl, t, taps * cout, cin, n_tile_d)
-            if halo:
+            halo_d = halo_geometry(n, h, w, k, stride, cin, 1, wplanes)
+            if halo_d:
                 # dgrad tap (kh, kw) reads dY pixel (h + 1 - kh, w + 1 - kw): dh = 1 - kh, dw = 1 - kw
                 dk0 = [[((2 - dhi) * 3 + (2 - dwi)) * cout for dhi in range(3)] for dwi in range(3)]
-                self.dgrads.append(Conv3x3([dy], [wd_hi, wd_lo][:wplanes], n, h, w, cout, cin, dk0, dx, dx_accumulate))
+                self.dgrads.append(Conv3x3([dy], [wd_hi, wd_lo][:wplanes], n, h, w, cout, cin, dk0, dx, dx_accumulate,
+                                           halo_d))
                 self.dgrads[-1].flops = self.alg_flops
             elif stride == 1:
                 dtaps = []

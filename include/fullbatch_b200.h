@@ -99,7 +99,14 @@ typedef struct {
   float* out;
   int64_t out_sn, out_sh, out_sw;
   int32_t accumulate;
-  float* stats_out; /* as in fb_conv_gemm_args; m_tiles = n * h / (256 / w * 2) */
+  float* stats_out; /* as in fb_conv_gemm_args; rows = fb_conv_stats_rows(m_tiles, n_total / n_tile) */
+  /* Tile geometry (0 = default).  imgs == 1: a tile is halves * (128 / w) consecutive rows of one image
+   * (m_tiles = n * h / (halves * 128 / w)), a_maps dims (C, W, H, N), box (64, w, halves*128/w + 2, 1).
+   * imgs > 1 (imgs * w * h == 128, small maps): a 128-pixel half is `imgs` whole images whose rows are interleaved
+   * in shared memory ([h][img][w]) so that the three row shifts stay 1024-byte aligned views;
+   * m_tiles = n / (halves * imgs), a_maps dims (C, W, N, H), box (64, w, imgs, h + 2). */
+  int32_t imgs;   /* default 1 */
+  int32_t halves; /* 128-pixel halves per CTA tile sharing each weight tile: 1 or 2 (default 2) */
 } fb_conv3x3_args;
 int fb_conv3x3(const fb_conv3x3_args* args, void* stream);
 

@@ -217,3 +217,53 @@ def test_grad_reg_variants_match_oracle(name, extra):
         assert rel(eng.pre, O.flat(ref64["pre_grads"])) < RATIO_RAW * FLOOR_RAW * 2
     nbt = [b for k, b in model.named_buffers() if k.endswith("num_batches_tracked")][0]
     assert int(nbt) == int(buf64["stem.1.num_batches_tracked"])  # 2 or 3 passes per microbatch (+1 for the pre-pass)
+
+
+def test_stock_pytorch_gpu_baseline_is_recorded():
+    """SURVEY.md 8d "the real kernel to beat": the torch-op restatement of the path (cuDNN / cuBLAS convolutions and
+    autograd, exactly what the reference executes on a GPU) timed on the same B200 in fp32 and with TF32 convolutions,
+    next to the engine on the same microbatches.  Written to gpurun_out/stock_pytorch.json; the assertion only guards
+    against the engine being slower than the library path it replaces."""
+    depth, mb, n = 18, 128, 128 * 6
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+
+    def stock(tf32):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        p = {k: v.to(DEV).clone() for k, v in params.items()}
+        b = {k: v.to(DEV).clone() for k, v in buffers.items()}
+        O.full_batch_step(depth, p, b, X[:2 * mb], Y[:2 * mb], mb, **HYP)  # warm-up, cuDNN autotune
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        O.full_batch_step(depth, p, b, X, Y, mb, **HYP)
+        e1.record()
+        torch.cuda.synchronize()
+        return n / (e0.elapsed_time(e1) * 1e-3)
+
+    try:
+        fp32, tf32 = stock(False), stock(True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = False
+    eng = FullBatchEngine(model, mb, precision="split", device=DEV)
+    Xf = X.float().contiguous()
+    for _ in range(2):
+        eng.begin_step(n // mb)
+        eng.accumulate_resident(Xf, Y, HYP["lr"], HYP["block_strength"], HYP["eps"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.begin_step(n // mb)
+    eng.accumulate_resident(Xf, Y, HYP["lr"], HYP["block_strength"], HYP["eps"])
+    e1.record()
+    torch.cuda.synchronize()
+    ours = n / (e0.elapsed_time(e1) * 1e-3)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "stock_pytorch.json"), "w") as f:
+        json.dump(dict(workload=f"ResNet-{depth} mb {mb}, {n} images, one full-batch grad-reg step", unit="images/s",
+                       stock_pytorch_fp32=fp32, stock_pytorch_tf32=tf32, engine_split=ours,
+                       torch=torch.__version__), f, indent=1)
+    assert ours > fp32, (ours, fp32)

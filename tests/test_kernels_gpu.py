@@ -71,19 +71,22 @@ CONV_CASES = [
     (32, 8, 8, 64, 256, 1, 1),      # bottleneck 1x1 expansion, N tile 256
     (2, 32, 32, 128, 64, 3, 1),     # haloed-box kernel, 2 channel blocks
     (3, 16, 16, 64, 256, 3, 1),     # haloed-box kernel, 2 N tiles, odd image count
+    (8, 8, 8, 256, 256, 3, 1),      # haloed-box kernel on 8x8 maps: two interleaved images per 128-pixel half
+    (6, 8, 8, 128, 64, 3, 1),       # 8x8, image count only divisible by 2: single-half tiles
+    (32, 4, 4, 128, 128, 3, 1),     # 4x4 maps: eight interleaved images per half
 ]
 
 
 @pytest.fixture(params=["halo", "generic"], autouse=True)
 def conv_path(request, monkeypatch):
-    """3x3/stride-1 convs on 16x16 and 32x32 maps run through the haloed-box kernel by default; the generic per-tap
-    kernel must stay correct for the same shapes (it serves every other shape)."""
-    if request.param == "generic":
+    """3x3/stride-1 convs run through the generic per-tap kernel by default; the haloed-box kernel (FB_HALO=1) must stay
+    correct for the same shapes."""
+    if request.param == "halo":
         if "conv" not in request.node.name:
             pytest.skip("only conv tests depend on the conv path")
-        monkeypatch.setenv("FB_DISABLE_HALO", "1")
+        monkeypatch.setenv("FB_HALO", "1")
     else:
-        monkeypatch.delenv("FB_DISABLE_HALO", raising=False)
+        monkeypatch.delenv("FB_HALO", raising=False)
     return request.param
 
 
@@ -119,6 +122,41 @@ def test_conv_dgrad(case, use_split):
     ref = nhwc(torch.nn.grad.conv2d_input((n, cin, h, w), wr, gy, stride, (k - 1) // 2))
     assert torch.isfinite(c["dx"]).all()
     assert rel_err(c["dx"], ref) < 3e-5
+
+
+@pytest.mark.parametrize("geom", [(8, 8, 8, 2, 2, 64), (8, 8, 8, 2, 1, 64), (8, 8, 8, 2, 2, 128), (8, 8, 8, 2, 1, 128),
+                                  (16, 4, 4, 8, 1, 64), (16, 4, 4, 8, 2, 64), (16, 4, 4, 8, 2, 128),
+                                  (4, 16, 16, 1, 1, 128), (4, 16, 16, 1, 2, 64), (2, 32, 32, 1, 1, 64)],
+                         ids=lambda g: "x".join(map(str, g)))
+@pytest.mark.parametrize("planes", [2, 1], ids=["split", "bf16"])
+def test_conv3x3_tile_geometries(geom, planes, conv_path):
+    """Every (imgs, halves, n_tile) geometry of fb_conv3x3, forced explicitly (the cost model picks one per layer)."""
+    if conv_path == "generic":
+        pytest.skip("geometry test drives fb_conv3x3 directly")
+    n, h, w, imgs, halves, n_tile = geom
+    if planes == 2 and (imgs, halves, n_tile) == (2, 2, 128):
+        pytest.skip("two split 8x8 halves plus 128-wide split weight tiles exceed 227 KB of shared memory")
+    cin, cout = 128, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, cin, h, w, device=DEV, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (cout * 9)) ** 0.5
+    x_hi, x_lo = split(nhwc(x))
+    wf_hi = torch.zeros(cout, 9 * cin, device=DEV, dtype=torch.bfloat16)
+    wf_lo = torch.zeros_like(wf_hi)
+    ops.weight_prep(wt, cout, cin, 9, wf_hi, wf_lo)
+    y = torch.full((n, h, w, cout), float("nan"), device=DEV)
+    fk0 = [[(dhi * 3 + dwi) * cin for dhi in range(3)] for dwi in range(3)]
+    conv = ops.Conv3x3([x_hi, x_lo][:planes], [wf_hi, wf_lo][:planes], n, h, w, cin, cout, fk0, y, False,
+                       (imgs, halves, n_tile))
+    conv()
+    torch.cuda.synchronize()
+    if planes == 2:
+        xr, wr = x.double(), wt.double()
+    else:
+        xr, wr = x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double()
+    ref = nhwc(F.conv2d(xr, wr, None, 1, 1))
+    assert torch.isfinite(y).all()
+    assert rel_err(y, ref) < 3e-5
 
 
 def test_conv_dgrad_accumulate():
@@ -490,7 +528,8 @@ def test_stem_im2col_u8_augmentation_matches_torchvision_semantics():
 
 
 @pytest.mark.parametrize("case", [(4, 32, 32, 64, 64, 3, 1), (3, 16, 16, 64, 256, 3, 1), (2, 32, 32, 64, 128, 3, 2),
-                                  (16, 8, 8, 128, 256, 3, 1), (4, 4, 4, 512, 512, 3, 1), (32, 8, 8, 64, 256, 1, 1)],
+                                  (16, 8, 8, 128, 256, 3, 1), (4, 4, 4, 512, 512, 3, 1), (32, 8, 8, 64, 256, 1, 1),
+                                  (16, 4, 4, 256, 512, 3, 1)],
                          ids=lambda c: "x".join(map(str, c)))
 def test_conv_forward_fused_statistics(case):
     """BatchNorm statistics fused into the conv epilogue: per-CTA column sums / sums of squares of the output."""
