@@ -157,6 +157,28 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// Same instruction with the two 64-bit shared-memory descriptors given as 32-bit halves: the high word (SBO, version,
+// swizzle mode) is a compile-time constant and the low word (start address >> 4 | LBO << 16) advances by plain adds, so
+// an unrolled issue block compiles to back-to-back UTCHMMA with uniform-register operands.
+__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// low / high words of a SWIZZLE_128B shared-memory matrix descriptor (see make_smem_desc_sw128)
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation (bit layout: cute/arch/mma_sm100_desc.hpp
 // InstrDescriptor): c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1, a_major[15], b_major[16],
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.  major: 0 = K-major, 1 = MN-major.

@@ -99,6 +99,9 @@ struct alignas(64) ConvGemmKParams {
   int accumulate;
   float* stats;  // optional [gridDim.x / n_tiles][2][n_total]: per-CTA column sums / sums of squares of the output
   int n_total;
+  // development switch (env FB_CONV_EXPERIMENT, results are WRONG when set): 1 = epilogue without global stores,
+  // 2 = epilogue only hands the accumulator back, 4 = producer stops fetching after the first ring fill
+  int experiment;
 };
 
 constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
@@ -171,7 +174,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, and the producer / MMA roles below run
+  // warp-converged with ONE elected lane issuing, so that their operands live in uniform registers and the unrolled
+  // tcgen05.mma block compiles to back-to-back UTCHMMA (a `lane == 0` branch costs ~13 instructions per MMA and made
+  // the single issuing thread, not the tensor pipe, the bottleneck)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_wait();    // everything above overlapped the predecessor's tail
   griddep_launch();
 
@@ -197,63 +204,100 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n0, h0;
-        tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-        const int n_tile0 = (tile % p.n_tiles) * N_TILE;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const fb_tap tap = p.taps[t];
-          for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, 1);
+    // ---------------- TMA producer ----------------
+    int s = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n0, h0;
+      tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+      for (int t = 0; t < p.n_taps; ++t) {
+        const fb_tap tap = p.taps[t];
+        for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+          mbar_wait(&empty_bar[s], phase ^ 1, 1);
+          if (elect_one()) {
             uint8_t* st = smem + s * Cfg::kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            if ((p.experiment & 4) && it >= STAGES) {
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
 #pragma unroll
-            for (int pl = 0; pl < PA; ++pl)
-              tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
-                          h0 + tap.dh, n0);
+              for (int pl = 0; pl < PA; ++pl)
+                tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
+                            h0 + tap.dh, n0);
 #pragma unroll
-            for (int pl = 0; pl < PB; ++pl)
-              tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
-                          tap.b_k0 + cb * kBlockK, n_tile0);
+              for (int pl = 0; pl < PB; ++pl)
+                tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
+                            tap.b_k0 + cb * kBlockK, n_tile0);
+            }
+          }
+          __syncwarp();
+          if (++s == STAGES) {
+            s = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
-      int it = 0, tile_i = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
-        const int buf = tile_i & 1;
-        mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
+    // ---------------- MMA issuer ----------------
+    // tcgen05.mma issue is (nearly) blocking: the tensor pipe queues only ~1 instruction, so every instruction the
+    // issuing thread executes between two MMAs is dead time for the pipe unless it fits into the ~64 clocks the previous
+    // MMA runs (tools/probes/mma_issue.cu: 120-170 idle clocks per stage for wait + elect + commit).  The loop is
+    // therefore software-pipelined: the wait for the NEXT stage sits between the last two MMAs of the current one.
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
+    constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+    constexpr int kLastC = Cfg::kCombos - 1, kLastK = kBlockK / 16 - 1;
+    const uint32_t smem0 = smem_u32(smem);
+    int s = 0;
+    uint32_t phase = 0;
+    int tile_i = 0;
+    bool prewaited = false;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int buf = tile_i & 1;
+      const bool last_tile = tile + (int)gridDim.x >= total_tiles;
+      mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
+      for (int ki = 0; ki < k_iters; ++ki) {
+        if (!prewaited) mbar_wait(&full_bar[s], phase, 2);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
-        for (int ki = 0; ki < k_iters; ++ki, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1, 2);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t b_base = a_base + PA * kATileBytes;
+        const uint32_t a_lo = smem_desc_lo(smem0 + s * Cfg::kStageBytes, 16);
+        const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
+        // combo c: stacked = A plane c against [B_hi;B_lo]; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
+        if (elect_one()) {
 #pragma unroll
           for (int c = 0; c < Cfg::kCombos; ++c) {
-            // stacked: combo c = A plane c against [B_hi;B_lo]; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
             const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
             const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t da = make_smem_desc_sw128(a_base + ap * kATileBytes + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(b_base + bp * Cfg::kBBytes + k * 32, 16, 1024);
-              tc_mma_bf16(tmem_d, da, db, idesc, (ki | c | k) != 0);
-            }
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (!(c == kLastC && k == kLastK))
+                tc_mma_bf16_lohi(tmem_d, a_lo + ((ap * kATileBytes + k * 32) >> 4),
+                                 b_lo + ((bp * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi, idesc, (ki | c | k) != 0);
           }
-          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&acc_full[buf]);
+        __syncwarp();
+        int s2 = s + 1;
+        uint32_t phase2 = phase;
+        if (s2 == STAGES) {
+          s2 = 0;
+          phase2 ^= 1;
+        }
+        prewaited = (ki + 1 < k_iters) || !last_tile;
+        if (prewaited) mbar_wait(&full_bar[s2], phase2, 2);
+        if (elect_one()) {
+          constexpr int ap = Cfg::kStack ? kLastC : ((PA == 2) ? 1 : 0);
+          constexpr int bp = Cfg::kStack ? 0 : ((PB == 2 && kLastC == 1) ? 1 : 0);
+          tc_mma_bf16_lohi(tmem_d, a_lo + ((ap * kATileBytes + kLastK * 32) >> 4),
+                           b_lo + ((bp * Cfg::kBBytes + kLastK * 32) >> 4), desc_hi, desc_hi, idesc, 1u);
+          tc_commit(&empty_bar[s]);
+          if (ki == k_iters - 1) tc_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        s = s2;
+        phase = phase2;
       }
     }
   } else {
@@ -280,6 +324,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < N_TILE / 16; ++c) {
+        if (p.experiment & 2) break;
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kUmmaN + c * 16;
         tmem_ld_32x16(taddr, v);
@@ -292,7 +337,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         } else {
           tmem_ld_wait();
         }
-        warp_store_rows16(stage, v, p.out, row_off, valid, c * 16, p.accumulate != 0, lane,
+        warp_store_rows16(stage, v, p.out, row_off, valid && !(p.experiment & 1), c * 16, p.accumulate != 0, lane,
                           p.stats ? &col_acc[c] : nullptr);
       }
       tc_fence_before();
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform roles, see conv_gemm_kernel
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kAStages; ++s) {
@@ -427,7 +472,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_wait();
   griddep_launch();
 
@@ -448,17 +493,18 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   long long dbg_issue = 0, dbg_acc_empty = 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int ia = 0, ib = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int n0 = (p.imgs == 1) ? mt / tiles_per_img : mt * p.halves * p.imgs;
-        const int h0 = (p.imgs == 1) ? (mt % tiles_per_img) * p.halves * p.th : 0;
-        const int n_tile0 = (tile % p.n_tiles) * N_TILE;
-        for (int dwi = 0; dwi < 3; ++dwi) {
-          for (int cb = 0; cb < p.cblocks; ++cb) {
-            const int as = ia % Cfg::kAStages;
-            FB_DBG_WAIT(0, mbar_wait(&a_empty[as], ((ia / Cfg::kAStages) & 1) ^ 1, 21));
+    // ---------------- TMA producer (warp-converged, one elected lane issues) ----------------
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int n0 = (p.imgs == 1) ? mt / tiles_per_img : mt * p.halves * p.imgs;
+      const int h0 = (p.imgs == 1) ? (mt % tiles_per_img) * p.halves * p.th : 0;
+      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          FB_DBG_WAIT(0, mbar_wait(&a_empty[as], aphase ^ 1, 21));
+          if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[as], a_stage_bytes);
 #pragma unroll
             for (int pl = 0; pl < PA; ++pl) {
@@ -471,87 +517,106 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
                               n0 + b * p.imgs, -1);
               }
             }
-            ++ia;
-            for (int dhi = 0; dhi < 3; ++dhi) {
-              const int bs = ib % b_stages;
-              FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 22));
+          }
+          __syncwarp();
+          if (++as == Cfg::kAStages) {
+            as = 0;
+            aphase ^= 1;
+          }
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], bphase ^ 1, 22));
+            if (elect_one()) {
               mbar_arrive_expect_tx(&b_full[bs], Cfg::kBStageBytes);
 #pragma unroll
               for (int pl = 0; pl < PB; ++pl)
                 tma_load_2d(smem_b + bs * Cfg::kBStageBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &b_full[bs],
                             p.b_k0[dwi][dhi] + cb * kBlockK, n_tile0);
-              ++ib;
+            }
+            __syncwarp();
+            if (++bs == b_stages) {
+              bs = 0;
+              bphase ^= 1;
             }
           }
         }
       }
-      if (dbg) {
-        g_dbg[0] += dbg_acc[0];
-        g_dbg[1] += dbg_acc[1];
-        g_dbg[10] += clock64() - t_start;
-      }
+    }
+    if (dbg && lane == 0) {
+      g_dbg[0] += dbg_acc[0];
+      g_dbg[1] += dbg_acc[1];
+      g_dbg[10] += clock64() - t_start;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
-      int ia = 0, ib = 0, tile_i = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
-        const int buf = tile_i & 1;
-        {
-          const long long _t = clock64();
-          mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 24);
-          dbg_acc_empty += clock64() - _t;
-        }
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 2 * Cfg::kUmmaN;
-        bool first = true;
-        for (int dwi = 0; dwi < 3; ++dwi) {
-          for (int cb = 0; cb < p.cblocks; ++cb) {
-            const int as = ia % Cfg::kAStages;
-            FB_DBG_WAIT(2, mbar_wait(&a_full[as], (ia / Cfg::kAStages) & 1, 23));
-            const uint32_t a_base = smem_u32(smem_a + as * a_stage_bytes);
-            for (int dhi = 0; dhi < 3; ++dhi) {
-              const int bs = ib % b_stages;
-              FB_DBG_WAIT(3, mbar_wait(&b_full[bs], (ib / b_stages) & 1, 25));
-              tc_fence_after();
-              const uint32_t b_base = smem_u32(smem_b + bs * Cfg::kBStageBytes);
-              const long long t_issue = dbg ? clock64() : 0;
+    // ---------------- MMA issuer (warp-converged, one elected lane issues) ----------------
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
+    constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+    const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
+    int as = 0, bs = 0, tile_i = 0;
+    uint32_t aphase = 0, bphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int buf = tile_i & 1;
+      {
+        const long long _t = clock64();
+        mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 24);
+        dbg_acc_empty += clock64() - _t;
+      }
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * 2 * Cfg::kUmmaN;
+      bool first = true;
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          FB_DBG_WAIT(2, mbar_wait(&a_full[as], aphase, 23));
+          const uint32_t a_base = smem_a0 + as * a_stage_bytes;
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            FB_DBG_WAIT(3, mbar_wait(&b_full[bs], bphase, 25));
+            tc_fence_after();
+            const long long t_issue = dbg ? clock64() : 0;
+            if (elect_one()) {
+              const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * Cfg::kBStageBytes, 16);
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
                 if (half >= p.halves) break;
-                const uint32_t a_view = a_base + dhi * row_bytes + half * half_stride;
+                const uint32_t a_lo = smem_desc_lo(a_base + dhi * row_bytes + half * half_stride, 16);
 #pragma unroll
                 for (int c = 0; c < Cfg::kCombos; ++c) {
                   const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
                   const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
+                  const uint32_t a_pl = a_lo + ((ap * boxes * a_box_bytes) >> 4);
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t da =
-                        make_smem_desc_sw128(a_view + ap * boxes * a_box_bytes + k * 32, 16, 1024);
-                    const uint64_t db = make_smem_desc_sw128(b_base + bp * Cfg::kBBytes + k * 32, 16, 1024);
-                    tc_mma_bf16(tmem_d + half * Cfg::kUmmaN, da, db, idesc, (first && c == 0 && k == 0) ? 0u : 1u);
-                  }
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    tc_mma_bf16_lohi(tmem_d + half * Cfg::kUmmaN, a_pl + ((k * 32) >> 4),
+                                     b_lo + ((bp * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi, idesc,
+                                     (first && c == 0 && k == 0) ? 0u : 1u);
                 }
               }
-              first = false;
               tc_commit(&b_empty[bs]);
-              if (dbg) dbg_issue += clock64() - t_issue;
-              ++ib;
+              if (dhi == 2) {
+                tc_commit(&a_empty[as]);
+                if (dwi == 2 && cb == p.cblocks - 1) tc_commit(&acc_full[buf]);
+              }
             }
-            tc_commit(&a_empty[as]);
-            ++ia;
+            __syncwarp();
+            first = false;
+            if (dbg) dbg_issue += clock64() - t_issue;
+            if (++bs == b_stages) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+          if (++as == Cfg::kAStages) {
+            as = 0;
+            aphase ^= 1;
           }
         }
-        tc_commit(&acc_full[buf]);
       }
-      if (dbg) {
-        g_dbg[2] += dbg_acc[0];
-        g_dbg[3] += dbg_acc[1];
-        g_dbg[4] += dbg_acc_empty;
-        g_dbg[5] += clock64() - t_start;  // MMA role total
-        g_dbg[9] += tile_i;
-        g_dbg[11] += dbg_issue;
-      }
+    }
+    if (dbg && lane == 0) {
+      g_dbg[2] += dbg_acc[0];
+      g_dbg[3] += dbg_acc[1];
+      g_dbg[4] += dbg_acc_empty;
+      g_dbg[5] += clock64() - t_start;  // MMA role total
+      g_dbg[9] += tile_i;
+      g_dbg[11] += dbg_issue;
     }
   } else {
     const int q = warp & 3;
@@ -692,7 +757,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   uint64_t* accum_bar = b_empty + kWgBStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform roles, see conv_gemm_kernel
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgAStages; ++s) {
@@ -710,7 +775,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_wait();
   griddep_launch();
 
@@ -729,75 +794,97 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   long long dbg_acc[2] = {0, 0}, dbg_issue = 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int ia = 0, ib = 0;
-      for (int pb = pb0; pb < pb1; ++pb) {
-        int n0, h0;
-        tile_origin(pb, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-        const int as = ia % kWgAStages;
-        FB_DBG_WAIT(0, mbar_wait(&a_empty[as], ((ia / kWgAStages) & 1) ^ 1, 11));
+    // ---------------- TMA producer (warp-converged, one elected lane issues) ----------------
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    for (int pb = pb0; pb < pb1; ++pb) {
+      int n0, h0;
+      tile_origin(pb, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+      FB_DBG_WAIT(0, mbar_wait(&a_empty[as], aphase ^ 1, 11));
+      if (elect_one()) {
         uint8_t* sa = smem_a + as * kWgABytes;
         mbar_arrive_expect_tx(&a_full[as], two_chunks ? kWgABytes : kATileBytes);
         tma_load_4d(sa, &p.dy_map, &a_full[as], co0, 0, h0, n0);
         if (two_chunks) tma_load_4d(sa + kATileBytes, &p.dy_map, &a_full[as], co0 + 64, 0, h0, n0);
-        ++ia;
-        for (int j = 0; j < n_slots; ++j, ++ib) {
-          const int s = slot0 + j;
-          const fb_wgrad_tap tap = p.taps[s % p.n_taps];
-          const int cb = s / p.n_taps;
-          const int bs = ib % b_stages;
-          FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], ((ib / b_stages) & 1) ^ 1, 12));
+      }
+      __syncwarp();
+      if (++as == kWgAStages) {
+        as = 0;
+        aphase ^= 1;
+      }
+      for (int j = 0; j < n_slots; ++j) {
+        const int s = slot0 + j;
+        const fb_wgrad_tap tap = p.taps[s % p.n_taps];
+        const int cb = s / p.n_taps;
+        FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], bphase ^ 1, 12));
+        if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[bs], p.planes * kWgBBytes);
           for (int pl = 0; pl < p.planes; ++pl)
             tma_load_4d(smem_b + (bs * p.planes + pl) * kWgBBytes, &p.x_maps[tap.phase * p.planes + pl], &b_full[bs],
                         cb * kBlockK, tap.dw, h0 + tap.dh, n0);
         }
-      }
-      if (dbg) {
-        g_dbg[0] += dbg_acc[0];
-        g_dbg[1] += dbg_acc[1];
-        g_dbg[10] += clock64() - t_start;
+        __syncwarp();
+        if (++bs == b_stages) {
+          bs = 0;
+          bphase ^= 1;
+        }
       }
     }
+    if (dbg && lane == 0) {
+      g_dbg[0] += dbg_acc[0];
+      g_dbg[1] += dbg_acc[1];
+      g_dbg[10] += clock64() - t_start;
+    }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // both operands MN-major; the hi and lo X tiles of a stage are adjacent, so ONE instruction with N = 64*planes
-      // computes dY^T*[X_hi, X_lo] into two 64-column halves that the epilogue adds (an SS-mode MMA re-reads its
-      // 128x16 A tile per instruction, N = 64 would run the tensor pipe at half rate)
-      const uint32_t idesc = make_idesc_bf16(128, 64 * p.planes, 1, 1);
-      int ia = 0, ib = 0;
-      for (int pb = pb0; pb < pb1; ++pb) {
-        const int as = ia % kWgAStages;
-        FB_DBG_WAIT(0, mbar_wait(&a_full[as], (ia / kWgAStages) & 1, 13));
-        const uint32_t a_base = smem_u32(smem_a + as * kWgABytes);
-        for (int j = 0; j < n_slots; ++j, ++ib) {
-          const int bs = ib % b_stages;
-          FB_DBG_WAIT(1, mbar_wait(&b_full[bs], (ib / b_stages) & 1, 14));
-          tc_fence_after();
-          const long long t_issue = dbg ? clock64() : 0;
-          const uint32_t b_base = smem_u32(smem_b + bs * p.planes * kWgBBytes);
+    // ---------------- MMA issuer (warp-converged, one elected lane issues) ----------------
+    // both operands MN-major; the hi and lo X tiles of a stage are adjacent, so ONE instruction with N = 64*planes
+    // computes dY^T*[X_hi, X_lo] into two 64-column halves that the epilogue adds (an SS-mode MMA re-reads its
+    // 128x16 A tile per instruction, N = 64 would run the tensor pipe at half rate)
+    const uint32_t idesc = make_idesc_bf16(128, 64 * p.planes, 1, 1);
+    constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+    const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    for (int pb = pb0; pb < pb1; ++pb) {
+      FB_DBG_WAIT(0, mbar_wait(&a_full[as], aphase, 13));
+      // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO), groups of 8
+      // pixel rows are 1024 bytes apart (SBO)
+      const uint32_t a_lo = smem_desc_lo(smem_a0 + as * kWgABytes, kATileBytes);
+      for (int j = 0; j < n_slots; ++j) {
+        FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
+        tc_fence_after();
+        const long long t_issue = dbg ? clock64() : 0;
+        if (elect_one()) {
+          const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
+          const uint32_t tmem_d = tmem_base + j * 64 * p.planes;
 #pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k) {
-            // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO),
-            // groups of 8 pixel rows are 1024 bytes apart (SBO)
-            const uint64_t da = make_smem_desc_sw128(a_base + k * 2048, kATileBytes, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_base + k * 2048, kATileBytes, 1024);
-            tc_mma_bf16(tmem_base + j * 64 * p.planes, da, db, idesc, (pb != pb0 || k != 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kTileM / 16; ++k)
+            tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
+                             (pb != pb0 || k != 0) ? 1u : 0u);
           tc_commit(&b_empty[bs]);
-          if (dbg) dbg_issue += clock64() - t_issue;
+          if (j == n_slots - 1) {
+            tc_commit(&a_empty[as]);
+            if (pb == pb1 - 1) tc_commit(accum_bar);
+          }
         }
-        tc_commit(&a_empty[as]);
-        ++ia;
+        __syncwarp();
+        if (dbg) dbg_issue += clock64() - t_issue;
+        if (++bs == b_stages) {
+          bs = 0;
+          bphase ^= 1;
+        }
       }
-      tc_commit(accum_bar);
-      if (dbg) {
-        g_dbg[2] += dbg_acc[0];
-        g_dbg[3] += dbg_acc[1];
-        g_dbg[5] += clock64() - t_start;
-        g_dbg[9] += pb1 - pb0;
-        g_dbg[11] += dbg_issue;
+      if (++as == kWgAStages) {
+        as = 0;
+        aphase ^= 1;
       }
+    }
+    if (dbg && lane == 0) {
+      g_dbg[2] += dbg_acc[0];
+      g_dbg[3] += dbg_acc[1];
+      g_dbg[5] += clock64() - t_start;
+      g_dbg[9] += pb1 - pb0;
+      g_dbg[11] += dbg_issue;
     }
   } else {
     const int q = warp & 3;
@@ -1099,6 +1186,10 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.accumulate = a->accumulate;
   kp.stats = a->stats_out;
   kp.n_total = a->n_total;
+  {
+    const char* e = getenv("FB_CONV_EXPERIMENT");  // read per call: development only
+    kp.experiment = e ? atoi(e) : 0;
+  }
   FB_REQUIRE(!a->stats_out || !a->accumulate, "fb_conv_gemm: column statistics need accumulate == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a->n_tile) {

@@ -134,8 +134,8 @@ def test_conv3x3_tile_geometries(geom, planes, conv_path):
     if conv_path == "generic":
         pytest.skip("geometry test drives fb_conv3x3 directly")
     n, h, w, imgs, halves, n_tile = geom
-    if planes == 2 and (imgs, halves, n_tile) == (2, 2, 128):
-        pytest.skip("two split 8x8 halves plus 128-wide split weight tiles exceed 227 KB of shared memory")
+    if planes == 2 and (imgs, halves, n_tile) in ((2, 2, 128), (8, 2, 64), (8, 2, 128)):
+        pytest.skip("two split halo boxes per stage plus the weight ring exceed 227 KB of shared memory")
     cin, cout = 128, 128
     g = torch.Generator(device="cuda").manual_seed(3)
     x = torch.randn(n, cin, h, w, device=DEV, generator=g)
