@@ -231,28 +231,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // instruction writes 8 rows x 64 contiguous bytes (16 full sectors).  row_off / valid describe THIS lane's row.
 constexpr int kEpiPitch = 20;                       // floats per staged row
 constexpr int kEpiWarpFloats = 32 * kEpiPitch;      // 2560 B per warp
-// If `stat` is given, the staged patch also yields per-column statistics of the 32 rows for the BatchNorm that follows
-// the convolution: lanes 0-15 add the column sums, lanes 16-31 the column sums of squares (column = lane & 15).
+// If `do_stat` is set, the values the lane moves anyway (rows i*8 + lane/4, columns
+// col0 + 4*(lane%4) .. +3) are added to per-lane column statistics for the BatchNorm that follows the convolution:
+// stat[0..3] += x, stat[4..7] += x*x.  The lanes are combined once per kernel (flush_column_stats), in a fixed order.
 __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
-                                                  bool valid, int col0, bool accumulate, int lane,
-                                                  float* stat = nullptr) {
+                                                  bool valid, int col0, bool accumulate, int lane, float (&stat)[8],
+                                                  bool do_stat) {
   float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                           __uint_as_float(v[4 * j + 3]));
   __syncwarp();
-  if (stat) {
-    const int col = lane & 15;
-    const bool sq = lane >= 16;
-    float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const float x = stage[r * kEpiPitch + col];
-      s += sq ? x * x : x;
-    }
-    *stat += s;
-  }
   const int sub = lane >> 2;
   const int c4 = (lane & 3) * 4;
   float4* d[4];
@@ -271,10 +261,20 @@ __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (
   for (int i = 0; i < 4; ++i) {
     const int row = i * 8 + sub;
     float4 o = *reinterpret_cast<const float4*>(stage + row * kEpiPitch + c4);
+    if (do_stat) {
+      stat[0] += o.x; stat[1] += o.y; stat[2] += o.z; stat[3] += o.w;
+      stat[4] += o.x * o.x; stat[5] += o.y * o.y; stat[6] += o.z * o.z; stat[7] += o.w * o.w;
+    }
     o.x += e[i].x; o.y += e[i].y; o.z += e[i].z; o.w += e[i].w;
     if (ok[i]) *d[i] = o;
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
+                                                  bool valid, int col0, bool accumulate, int lane) {
+  float unused[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  warp_store_rows16(stage, v, base, row_off, valid, col0, accumulate, lane, unused, false);
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -121,23 +121,33 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
   }
 }
 
-// Flush of the per-warp column statistics collected by the epilogue (BatchNorm statistics fused into the producing
-// convolution): the four epilogue warps combine through the staging patch and write one partial row
-// stats[row][0 = sum | 1 = sum of squares][channel].  acc[c] of lane l belongs to column c*16 + (l & 15).
+// Flush of the per-lane column statistics collected by the epilogue (BatchNorm statistics fused into the producing
+// convolution).  acc[c][0..3] / acc[c][4..7] of lane l are the sums / sums of squares of columns
+// c*16 + 4*(l%4) .. +3 over the rows the lane stored (rows = lane/4 mod 8).  Fixed order: shuffle tree over the 8 row
+// groups, then the four epilogue warps through the staging patch; one partial row stats[row][0 = sum | 1 = sq][channel].
 template <int N_TILE>
-__device__ __forceinline__ void flush_column_stats(float* epi_stage, const float (&acc)[N_TILE / 16], int q, int lane,
+__device__ __forceinline__ void flush_column_stats(float* epi_stage, float (&acc)[N_TILE / 16][8], int q, int lane,
                                                    float* stats, int row, int n_total, int n_tile0) {
-  float* sm = epi_stage + q * kEpiWarpFloats;  // [chunk][lane], N_TILE/16 * 32 <= 512 floats per warp
+  static_assert(2 * N_TILE <= kEpiWarpFloats, "staging patch too small for the statistics");
+  float* sm = epi_stage + q * kEpiWarpFloats;  // [0 = sum | 1 = sq][N_TILE] of this warp
 #pragma unroll
-  for (int c = 0; c < N_TILE / 16; ++c) sm[c * 32 + lane] = acc[c];
+  for (int c = 0; c < N_TILE / 16; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[c][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) sm[(j >> 2) * N_TILE + c * 16 + lane * 4 + (j & 3)] = v;
+    }
+  }
   asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
   const int t = q * 32 + lane;
   for (int idx = t; idx < 2 * N_TILE; idx += 128) {
     const int which = idx / N_TILE, col = idx % N_TILE;
-    const int off = (col / 16) * 32 + (col % 16) + 16 * which;
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) v += epi_stage[w * kEpiWarpFloats + off];
+    for (int w = 0; w < 4; ++w) v += epi_stage[w * kEpiWarpFloats + idx];
     stats[((long long)row * 2 + which) * n_total + n_tile0 + col] = v;
   }
 }
@@ -150,19 +160,21 @@ struct ConvGemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 + 256;
   // An SS-mode tcgen05.mma re-reads its 128x16 A tile from shared memory (~64 clocks) whatever N is, so N = 64
-  // instructions run the tensor pipe at half rate.  With split weights and a 64-wide tile the hi and lo B tiles are
-  // adjacent in the stage: ONE N = 128 instruction computes A*[B_hi;B_lo]^T into two 64-column halves that the epilogue
-  // adds ("stacked" mode; it also picks up the tiny lo*lo term).
-  static constexpr bool kStack = (PB == 2 && N_TILE == 64);
-  static constexpr int kUmmaN = kStack ? 128 : N_TILE;
+  // instructions run the tensor pipe at half rate, and the pipe queues only ~2 instructions, so short instructions
+  // expose the issue overhead between pipeline stages.  With split weights the hi and lo B tiles are adjacent in the
+  // stage: ONE instruction with N = 2*N_TILE computes A*[B_hi;B_lo]^T into two N_TILE-column halves that the epilogue
+  // adds ("stacked" mode).  64-wide tiles: both A planes are stacked (N = 128, picks up the tiny lo*lo term);
+  // 128-wide tiles: A_hi is stacked (N = 256) and A_lo multiplies B_hi only (N = 128).
+  static constexpr bool kStack = (PB == 2 && N_TILE <= 128);
+  static constexpr int kUmmaN = kStack ? 2 * N_TILE : N_TILE;
   static constexpr int kTmemCols = 2 * kUmmaN;
-  // operand-plane combinations accumulated into one tile: x*w ~= xh*wh + xh*wl + xl*wh (the lo*lo term is dropped)
+  // instructions per K = 16 step: stacked -> one per A plane; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
   static constexpr int kCombos = kStack ? PA : ((PA == 2 && PB == 2) ? 3 : (PA * PB));
   static_assert(kStages >= 2, "stage does not fit twice into shared memory");
 };
 
 template <int N_TILE, int PA, int PB>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
+__global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
   using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +184,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* turn_bar = acc_empty + 2;       // [2] issue-order token of the two MMA warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_bar + 2);
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, and the producer / MMA roles below run
   // warp-converged with ONE elected lane issuing, so that their operands live in uniform registers and the unrolled
@@ -181,6 +194,12 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
+#pragma unroll
+    for (int pl = 0; pl < PA; ++pl) tma_prefetch_desc(&p.a_maps[p.taps[0].phase * PA + pl]);
+#pragma unroll
+    for (int pl = 0; pl < PB; ++pl) tma_prefetch_desc(&p.b_maps[pl]);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -189,6 +208,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&turn_bar[b], 1);
     }
     fence_barrier_init();
   }
@@ -240,64 +260,70 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    // tcgen05.mma issue is (nearly) blocking: the tensor pipe queues only ~1 instruction, so every instruction the
-    // issuing thread executes between two MMAs is dead time for the pipe unless it fits into the ~64 clocks the previous
-    // MMA runs (tools/probes/mma_issue.cu: 120-170 idle clocks per stage for wait + elect + commit).  The loop is
-    // therefore software-pipelined: the wait for the NEXT stage sits between the last two MMAs of the current one.
-    constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
+  } else if (warp == 1 || warp == 6) {
+    // ---------------- MMA issuers: TWO warps alternate pipeline stages ----------------
+    // A tcgen05.mma blocks its issuing thread until the tensor pipe has taken it, and nothing that thread executes
+    // between two MMAs overlaps with them (tools/probes/mma_issue.cu: every instruction between two MMAs adds its full
+    // latency; one issuing warp reaches 79-98 clk per M128xN128xK16 MMA with 8-4 MMAs per stage, two alternating warps
+    // 64.0 = the pipe's rate).  So the per-stage work (barrier wait, elect, descriptor setup, commit) of one warp runs
+    // while the other warp's MMAs execute; a turn token (mbarrier) keeps the issue order = accumulation order fixed.
+    // The pipe completes MMAs in issue order, so the commit of the issuer of a tile's last stage covers the whole tile.
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
-    constexpr int kLastC = Cfg::kCombos - 1, kLastK = kBlockK / 16 - 1;
+    constexpr int kC = Cfg::kCombos;
+    //   stacked, PA == 2: c0 = A_lo, c1 = A_hi (both against [B_hi;B_lo]); for 128-wide tiles A_lo only needs B_hi, so
+    //     it runs at N = N_TILE except in the first K block of a tile, where it must initialise both halves
+    //   not stacked: (a1,b0) first if PA == 2, then (a0,b0), then (a0,b1) if PB == 2
+    constexpr bool kNarrowLo = Cfg::kStack && N_TILE == 128 && PA == 2;
+    auto ap_of = [](int c) { return (PA == 2 && c == 0) ? 1 : 0; };
+    auto bp_of = [](int c) { return (!Cfg::kStack && PB == 2 && c == kC - 1) ? 1 : 0; };
+    constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
+    constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+    const int me = (warp == 1) ? 0 : 1;
     const uint32_t smem0 = smem_u32(smem);
-    int s = 0;
-    uint32_t phase = 0;
-    int tile_i = 0;
-    bool prewaited = false;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_stages = my_tiles * k_iters;
+    int s = me % STAGES;
+    uint32_t phase = (me / STAGES) & 1, tphase = 0;
+    int ki = me, tile_i = 0;
+    while (ki >= k_iters) {
+      ki -= k_iters;
+      ++tile_i;
+    }
+    for (int it = me; it < total_stages; it += 2) {
       const int buf = tile_i & 1;
-      const bool last_tile = tile + (int)gridDim.x >= total_tiles;
-      mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
-      tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
-      for (int ki = 0; ki < k_iters; ++ki) {
-        if (!prewaited) mbar_wait(&full_bar[s], phase, 2);
-        tc_fence_after();
-        const uint32_t a_lo = smem_desc_lo(smem0 + s * Cfg::kStageBytes, 16);
-        const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
-        // combo c: stacked = A plane c against [B_hi;B_lo]; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
-        if (elect_one()) {
+      if (ki == 0) mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
+      mbar_wait(&full_bar[s], phase, 2);
+      const uint32_t a_lo = smem_desc_lo(smem0 + s * Cfg::kStageBytes, 16);
+      const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
+      if (it > 0) {
+        mbar_wait(&turn_bar[me], tphase, 5);  // the other warp has issued the previous stage
+        tphase ^= 1;
+      }
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int c = 0; c < Cfg::kCombos; ++c) {
-            const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
-            const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
+        for (int c = 0; c < kC; ++c) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              if (!(c == kLastC && k == kLastK))
-                tc_mma_bf16_lohi(tmem_d, a_lo + ((ap * kATileBytes + k * 32) >> 4),
-                                 b_lo + ((bp * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi, idesc, (ki | c | k) != 0);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            tc_mma_bf16_lohi(tmem_d, a_lo + ((ap_of(c) * kATileBytes + k * 32) >> 4),
+                             b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi,
+                             (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full, (ki | c | k) != 0);
         }
-        __syncwarp();
-        int s2 = s + 1;
-        uint32_t phase2 = phase;
-        if (s2 == STAGES) {
-          s2 = 0;
-          phase2 ^= 1;
-        }
-        prewaited = (ki + 1 < k_iters) || !last_tile;
-        if (prewaited) mbar_wait(&full_bar[s2], phase2, 2);
-        if (elect_one()) {
-          constexpr int ap = Cfg::kStack ? kLastC : ((PA == 2) ? 1 : 0);
-          constexpr int bp = Cfg::kStack ? 0 : ((PB == 2 && kLastC == 1) ? 1 : 0);
-          tc_mma_bf16_lohi(tmem_d, a_lo + ((ap * kATileBytes + kLastK * 32) >> 4),
-                           b_lo + ((bp * Cfg::kBBytes + kLastK * 32) >> 4), desc_hi, desc_hi, idesc, 1u);
-          tc_commit(&empty_bar[s]);
-          if (ki == k_iters - 1) tc_commit(&acc_full[buf]);
-        }
-        __syncwarp();
-        s = s2;
-        phase = phase2;
+        mbar_arrive(&turn_bar[me ^ 1]);
+        tc_commit(&empty_bar[s]);
+        if (ki == k_iters - 1) tc_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+      s += 2;
+      if (s >= STAGES) {
+        s -= STAGES;
+        phase ^= 1;
+      }
+      ki += 2;
+      while (ki >= k_iters) {
+        ki -= k_iters;
+        ++tile_i;
       }
     }
   } else {
@@ -308,9 +334,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     const int h = (r / p.tile_w) % p.tile_h;
     const int n = r / (p.tile_w * p.tile_h);
     float* stage = epi_stage + q * kEpiWarpFloats;
-    float col_acc[N_TILE / 16];
+    float col_acc[N_TILE / 16][8];
 #pragma unroll
-    for (int c = 0; c < N_TILE / 16; ++c) col_acc[c] = 0.f;
+    for (int c = 0; c < N_TILE / 16; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) col_acc[c][j] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       int n0, h0;
@@ -322,15 +350,15 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       const int buf = tile_i & 1;
       mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < N_TILE / 16; ++c) {
+#pragma unroll
+      for (int c = 0; c < N_TILE / 16; ++c) {  // unrolled: col_acc must stay in registers
         if (p.experiment & 2) break;
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kUmmaN + c * 16;
         tmem_ld_32x16(taddr, v);
         if (Cfg::kStack) {
           uint32_t v2[16];
-          tmem_ld_32x16(taddr + 64, v2);
+          tmem_ld_32x16(taddr + N_TILE, v2);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
@@ -338,7 +366,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
           tmem_ld_wait();
         }
         warp_store_rows16(stage, v, p.out, row_off, valid && !(p.experiment & 1), c * 16, p.accumulate != 0, lane,
-                          p.stats ? &col_acc[c] : nullptr);
+                          col_acc[c], p.stats != nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -366,7 +394,7 @@ static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
   const int tiles = kp.m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;  // one N tile per CTA (see flush_column_stats)
-  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, kp));
+  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(224), Cfg::kSmemBytes, stream, kp));
   return 0;
 }
 
@@ -435,7 +463,7 @@ struct Conv3x3Cfg {
 };
 
 template <int N_TILE, int PA, int PB>
-__global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__ Conv3x3KParams p, int a_box_bytes,
+__global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__ Conv3x3KParams p, int a_box_bytes,
                                                          int b_stages) {
   using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
   extern __shared__ uint8_t smem_raw[];
@@ -449,7 +477,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
   uint64_t* b_empty = b_full + 8;
   uint64_t* acc_full = b_empty + 8;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* turn_bar = acc_empty + 2;  // [2] issue-order token of the two MMA warps (see conv_gemm_kernel)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform roles, see conv_gemm_kernel
   const int lane = threadIdx.x & 31;
@@ -465,6 +494,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 4);
+      mbar_init(&turn_bar[b], 1);
     }
     fence_barrier_init();
   }
@@ -546,76 +576,73 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
       g_dbg[1] += dbg_acc[1];
       g_dbg[10] += clock64() - t_start;
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (warp-converged, one elected lane issues) ----------------
+  } else if (warp == 1 || warp == 6) {
+    // ---------------- MMA issuers: two warps alternate tap stages (see conv_gemm_kernel) ----------------
     constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
-    int as = 0, bs = 0, tile_i = 0;
-    uint32_t aphase = 0, bphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+    const int me = (warp == 1) ? 0 : 1;
+    const int spt = 9 * p.cblocks;  // tap stages per tile
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_stages = my_tiles * spt;
+    uint32_t tphase = 0;
+    for (int it = me; it < total_stages; it += 2) {
+      // the index arithmetic below is off the critical path: the other warp's MMAs are running meanwhile
+      const int tile_i = it / spt, r = it % spt;
+      const int dhi = r % 3;
+      const int g = it / 3;  // (tile, dw, channel block) group = one A stage
+      const int as = g % Cfg::kAStages;
+      const uint32_t aphase = (g / Cfg::kAStages) & 1;
+      const int bs = it % b_stages;
+      const uint32_t bphase = (it / b_stages) & 1;
       const int buf = tile_i & 1;
-      {
+      if (r == 0) {
         const long long _t = clock64();
         mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 24);
         dbg_acc_empty += clock64() - _t;
       }
-      tc_fence_after();
+      FB_DBG_WAIT(2, mbar_wait(&a_full[as], aphase, 23));
+      FB_DBG_WAIT(3, mbar_wait(&b_full[bs], bphase, 25));
       const uint32_t tmem_d = tmem_base + buf * 2 * Cfg::kUmmaN;
-      bool first = true;
-      for (int dwi = 0; dwi < 3; ++dwi) {
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          FB_DBG_WAIT(2, mbar_wait(&a_full[as], aphase, 23));
-          const uint32_t a_base = smem_a0 + as * a_stage_bytes;
-          for (int dhi = 0; dhi < 3; ++dhi) {
-            FB_DBG_WAIT(3, mbar_wait(&b_full[bs], bphase, 25));
-            tc_fence_after();
-            const long long t_issue = dbg ? clock64() : 0;
-            if (elect_one()) {
-              const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * Cfg::kBStageBytes, 16);
+      const uint32_t a_base = smem_a0 + as * a_stage_bytes + dhi * row_bytes;
+      const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * Cfg::kBStageBytes, 16);
+      if (it > 0) {
+        mbar_wait(&turn_bar[me], tphase, 27);
+        tphase ^= 1;
+      }
+      tc_fence_after();
+      const long long t_issue = dbg ? clock64() : 0;
+      if (elect_one()) {
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                if (half >= p.halves) break;
-                const uint32_t a_lo = smem_desc_lo(a_base + dhi * row_bytes + half * half_stride, 16);
+        for (int half = 0; half < 2; ++half) {
+          if (half >= p.halves) break;
+          const uint32_t a_lo = smem_desc_lo(a_base + half * half_stride, 16);
 #pragma unroll
-                for (int c = 0; c < Cfg::kCombos; ++c) {
-                  const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
-                  const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
-                  const uint32_t a_pl = a_lo + ((ap * boxes * a_box_bytes) >> 4);
+          for (int c = 0; c < Cfg::kCombos; ++c) {
+            const int ap = Cfg::kStack ? c : ((PA == 2 && c == Cfg::kCombos - 1) ? 1 : 0);
+            const int bp = Cfg::kStack ? 0 : ((PB == 2 && c == 1) ? 1 : 0);
+            const uint32_t a_pl = a_lo + ((ap * boxes * a_box_bytes) >> 4);
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
-                    tc_mma_bf16_lohi(tmem_d + half * Cfg::kUmmaN, a_pl + ((k * 32) >> 4),
-                                     b_lo + ((bp * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi, idesc,
-                                     (first && c == 0 && k == 0) ? 0u : 1u);
-                }
-              }
-              tc_commit(&b_empty[bs]);
-              if (dhi == 2) {
-                tc_commit(&a_empty[as]);
-                if (dwi == 2 && cb == p.cblocks - 1) tc_commit(&acc_full[buf]);
-              }
-            }
-            __syncwarp();
-            first = false;
-            if (dbg) dbg_issue += clock64() - t_issue;
-            if (++bs == b_stages) {
-              bs = 0;
-              bphase ^= 1;
-            }
-          }
-          if (++as == Cfg::kAStages) {
-            as = 0;
-            aphase ^= 1;
+            for (int k = 0; k < kBlockK / 16; ++k)
+              tc_mma_bf16_lohi(tmem_d + half * Cfg::kUmmaN, a_pl + ((k * 32) >> 4),
+                               b_lo + ((bp * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi, idesc,
+                               (r == 0 && c == 0 && k == 0) ? 0u : 1u);
           }
         }
+        mbar_arrive(&turn_bar[me ^ 1]);
+        tc_commit(&b_empty[bs]);
+        if (dhi == 2) tc_commit(&a_empty[as]);        // in-order pipe: covers the other warp's taps of this box
+        if (r == spt - 1) tc_commit(&acc_full[buf]);
       }
+      __syncwarp();
+      if (dbg) dbg_issue += clock64() - t_issue;
     }
-    if (dbg && lane == 0) {
+    if (dbg && lane == 0 && me == 0) {
       g_dbg[2] += dbg_acc[0];
       g_dbg[3] += dbg_acc[1];
       g_dbg[4] += dbg_acc_empty;
       g_dbg[5] += clock64() - t_start;  // MMA role total
-      g_dbg[9] += tile_i;
+      g_dbg[9] += my_tiles;
       g_dbg[11] += dbg_issue;
     }
   } else {
@@ -625,9 +652,11 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
     const int hr = r / slab_px;              // slab (image row) inside the half
     const int img = (r % slab_px) / p.w;     // image inside the slab
     const bool edbg = dbg && warp == 2 && lane == 0;
-    float col_acc[N_TILE / 16];
+    float col_acc[N_TILE / 16][8];
 #pragma unroll
-    for (int c = 0; c < N_TILE / 16; ++c) col_acc[c] = 0.f;
+    for (int c = 0; c < N_TILE / 16; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) col_acc[c][j] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       const int mt = tile / p.n_tiles;
@@ -648,8 +677,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
         const int h_row = (p.imgs == 1) ? h0 + half * p.th + hr : hr;
         const long long row_off = (long long)n_img * p.out_sn + (long long)h_row * p.out_sh +
                                   (long long)w * p.out_sw + n_tile0;
-#pragma unroll 1
-        for (int c = 0; c < N_TILE / 16; ++c) {
+#pragma unroll
+        for (int c = 0; c < N_TILE / 16; ++c) {  // unrolled: col_acc must stay in registers
           uint32_t v[16];
           const uint32_t taddr =
               tmem_base + (uint32_t(q * 32) << 16) + buf * 2 * Cfg::kUmmaN + half * Cfg::kUmmaN + c * 16;
@@ -664,7 +693,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_kernel(const __grid_constant__
             tmem_ld_wait();
           }
           warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane,
-                            p.stats ? &col_acc[c] : nullptr);
+                            col_acc[c], p.stats != nullptr);
         }
       }
       tc_fence_before();
@@ -709,7 +738,7 @@ static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
   const int tiles = m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;
-  FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(192), smem, stream, kp, a_box_bytes, b_stages));
+  FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(224), smem, stream, kp, a_box_bytes, b_stages));
   return 0;
 }
 
@@ -744,7 +773,7 @@ constexpr int kWgABytes = 2 * kATileBytes;  // two 64-channel chunks of dY: [chu
 constexpr int kWgBBytes = kATileBytes;      // [128 pixels][64 ci]
 constexpr int kWgTmemCols = 512;
 
-__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+__global__ void __launch_bounds__(224, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -755,7 +784,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   uint64_t* b_full = a_empty + kWgAStages;
   uint64_t* b_empty = b_full + kWgBStages;
   uint64_t* accum_bar = b_empty + kWgBStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* turn_bar = accum_bar + 1;  // [2] issue-order token of the two MMA warps (see conv_gemm_kernel)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform roles, see conv_gemm_kernel
   const int lane = threadIdx.x & 31;
@@ -769,6 +799,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       mbar_init(&b_empty[s], 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(&turn_bar[0], 1);
+    mbar_init(&turn_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kWgTmemCols);
@@ -835,51 +867,62 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       g_dbg[1] += dbg_acc[1];
       g_dbg[10] += clock64() - t_start;
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (warp-converged, one elected lane issues) ----------------
+  } else if (warp == 1 || warp == 6) {
+    // ---------------- MMA issuers: two warps alternate (pixel block, slot) stages, see conv_gemm_kernel ------------
     // both operands MN-major; the hi and lo X tiles of a stage are adjacent, so ONE instruction with N = 64*planes
     // computes dY^T*[X_hi, X_lo] into two 64-column halves that the epilogue adds (an SS-mode MMA re-reads its
     // 128x16 A tile per instruction, N = 64 would run the tensor pipe at half rate)
     const uint32_t idesc = make_idesc_bf16(128, 64 * p.planes, 1, 1);
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
-    int as = 0, bs = 0;
-    uint32_t aphase = 0, bphase = 0;
-    for (int pb = pb0; pb < pb1; ++pb) {
-      FB_DBG_WAIT(0, mbar_wait(&a_full[as], aphase, 13));
+    const int me = (warp == 1) ? 0 : 1;
+    const int total_stages = (pb1 - pb0) * n_slots;
+    int bs = me % b_stages;
+    uint32_t bphase = (me / b_stages) & 1, tphase = 0;
+    int j = me, pbi = 0;  // slot inside the pixel block, pixel block index relative to pb0
+    while (j >= n_slots) {
+      j -= n_slots;
+      ++pbi;
+    }
+    for (int it = me; it < total_stages; it += 2) {
+      const int as = pbi % kWgAStages;
+      FB_DBG_WAIT(0, mbar_wait(&a_full[as], (pbi / kWgAStages) & 1, 13));
+      FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
       // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO), groups of 8
       // pixel rows are 1024 bytes apart (SBO)
       const uint32_t a_lo = smem_desc_lo(smem_a0 + as * kWgABytes, kATileBytes);
-      for (int j = 0; j < n_slots; ++j) {
-        FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
-        tc_fence_after();
-        const long long t_issue = dbg ? clock64() : 0;
-        if (elect_one()) {
-          const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
-          const uint32_t tmem_d = tmem_base + j * 64 * p.planes;
-#pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k)
-            tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
-                             (pb != pb0 || k != 0) ? 1u : 0u);
-          tc_commit(&b_empty[bs]);
-          if (j == n_slots - 1) {
-            tc_commit(&a_empty[as]);
-            if (pb == pb1 - 1) tc_commit(accum_bar);
-          }
-        }
-        __syncwarp();
-        if (dbg) dbg_issue += clock64() - t_issue;
-        if (++bs == b_stages) {
-          bs = 0;
-          bphase ^= 1;
-        }
+      const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
+      const uint32_t tmem_d = tmem_base + j * 64 * p.planes;
+      if (it > 0) {
+        mbar_wait(&turn_bar[me], tphase, 16);
+        tphase ^= 1;
       }
-      if (++as == kWgAStages) {
-        as = 0;
-        aphase ^= 1;
+      tc_fence_after();
+      const long long t_issue = dbg ? clock64() : 0;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kTileM / 16; ++k)
+          tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
+                           (pbi != 0 || k != 0) ? 1u : 0u);
+        mbar_arrive(&turn_bar[me ^ 1]);
+        tc_commit(&b_empty[bs]);
+        if (j == n_slots - 1) tc_commit(&a_empty[as]);   // in-order pipe: covers the other warp's slots too
+        if (it == total_stages - 1) tc_commit(accum_bar);
+      }
+      __syncwarp();
+      if (dbg) dbg_issue += clock64() - t_issue;
+      bs += 2;
+      while (bs >= b_stages) {
+        bs -= b_stages;
+        bphase ^= 1;
+      }
+      j += 2;
+      while (j >= n_slots) {
+        j -= n_slots;
+        ++pbi;
       }
     }
-    if (dbg && lane == 0) {
+    if (dbg && lane == 0 && me == 0) {
       g_dbg[2] += dbg_acc[0];
       g_dbg[3] += dbg_acc[1];
       g_dbg[5] += clock64() - t_start;
@@ -1303,7 +1346,7 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
     FB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  FB_CUDA(launch_pdl(wgrad_kernel, grid, dim3(192), smem, static_cast<cudaStream_t>(stream), kp));
+  FB_CUDA(launch_pdl(wgrad_kernel, grid, dim3(224), smem, static_cast<cudaStream_t>(stream), kp));
   return 0;
 }
 

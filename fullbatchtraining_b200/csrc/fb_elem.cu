@@ -554,12 +554,15 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) 
   }
   grid_barrier(a.counters, 2 * gridDim.x);
   grid_barrier_release(a.counters);
+  // the rows are walked BACKWARDS: phase 1 read them front to back, so the tail of this block's slice is what L2 still
+  // holds when the whole tensor set (up to 117 MB on the 32x32 stage) does not fit
   const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
   const bool invariant = (256 * 8) % C == 0;
-  long long i = e0 + threadIdx.x;
+  const long long first = e0 + threadIdx.x;
+  long long i = first < e1 ? first + ((e1 - 1 - first) / 256) * 256 : e1;
   BnBwdCoef p;
-  if (i < e1 && invariant) p.load(bw, a.coef, int((i * 8) % C));
-  for (; i < e1; i += 256) {
+  if (first < e1 && invariant) p.load(bw, a.coef, int((first * 8) % C));
+  for (; first < e1 && i >= first; i -= 256) {
     const long long off = i * 8;
     if (!invariant) p.load(bw, a.coef, int(off % C));
     float d[8], y[8], o[8];

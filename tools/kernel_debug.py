@@ -56,7 +56,13 @@ def run(n, h, w, cin, cout, split, what):
         print(f"    {name:22s} {v / reps:12.0f} cycles/launch")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("FB_HALO") == "1":
+    run(128, 32, 32, 64, 64, True, "fwd")
+    run(128, 32, 32, 64, 64, True, "dgrad")
+    run(128, 16, 16, 128, 128, True, "fwd")
+    run(128, 32, 32, 64, 64, True, "wgrad")
+    run(128, 16, 16, 128, 128, True, "wgrad")
+elif __name__ == "__main__":
     for shape in [(128, 32, 32, 64, 64), (128, 16, 16, 128, 128), (128, 8, 8, 256, 256), (128, 4, 4, 512, 512)]:
         run(*shape, True, "wgrad")
     run(128, 8, 8, 256, 256, True, "fwd")

@@ -36,6 +36,18 @@ __global__ void __launch_bounds__(512, 2) k_bn_like(float* p) {
   if (p && threadIdx.x == 0 && blockIdx.x == 1000000) p[0] = s[1];
 }
 
+// PDL variants: griddepcontrol.launch_dependents early, griddepcontrol.wait before touching memory
+__global__ void __launch_bounds__(512, 2) k_bn_like_pdl(float* p, int spin) {
+  __shared__ float s[2048];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  s[threadIdx.x] = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  while (clock64() - t0 < spin) {}
+  if (p && threadIdx.x == 0 && blockIdx.x == 1000000) p[0] = s[1];
+}
+
 template <class F>
 float time_us(F f, int reps) {
   cudaEvent_t e0, e1;
@@ -97,6 +109,31 @@ int main() {
     float us = time_us([&](int) { cudaGraphLaunch(ge, st); }, 50) / 100;
     cudaStreamSynchronize(st);
     printf("graph of 100 alternating nodes, bn carve-out %s: %.2f us/node\n", variant ? "100" : "default", us);
+  }
+  // programmatic dependent launch inside a graph: 100 kernels of ~5 us each, with and without the attribute
+  for (int pdl = 0; pdl < 2; ++pdl) {
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal);
+    for (int i = 0; i < 100; ++i) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(296);
+      cfg.blockDim = dim3(512);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl ? 1 : 0;
+      cudaLaunchKernelEx(&cfg, k_bn_like_pdl, (float*)nullptr, 10000);
+    }
+    cudaStreamEndCapture(st, &g);
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    float us = time_us([&](int) { cudaGraphLaunch(ge, st); }, 50) / 100;
+    cudaStreamSynchronize(st);
+    printf("graph of 100 x ~5us kernels, PDL %d: %.2f us/node (instantiate: %s)\n", pdl, us, cudaGetErrorString(e));
   }
   printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
