@@ -107,7 +107,15 @@ struct alignas(64) ConvGemmKParams {
 constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
 constexpr int kBlockK = 64;                        // bf16 elements per K block == one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KiB
-constexpr int kEpiStageBytes = 4 * kEpiWarpFloats * 4;     // 4 epilogue warps x 32 x 20 floats
+// Warp roles of the tensor-core kernels (352 threads): 0 = TMA producer, 1 and 6 = MMA issuers, 2-5 and 7-10 = epilogue.
+// A warp may only read the TMEM lanes 32*(warp%4)..+31, so each lane quarter has TWO epilogue warps (groups 0 and 1)
+// that take alternate 16-column chunks: the accumulator drain, which is fully exposed for the last tile of a CTA, is
+// twice as fast.
+constexpr int kThreads = 352;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytes = kEpiWarps * kEpiWarpFloats * 4;  // 8 epilogue warps x 32 x 20 floats
+__device__ __forceinline__ bool is_epilogue_warp(int warp) { return (warp >= 2 && warp <= 5) || warp >= 7; }
+__device__ __forceinline__ int epilogue_group(int warp) { return warp >= 7 ? 1 : 0; }
 constexpr int kSmemBudget = 227 * 1024 - 2048 - kEpiStageBytes;
 
 __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, int grid_h, int& n0, int& h0) {
@@ -126,28 +134,32 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
 // c*16 + 4*(l%4) .. +3 over the rows the lane stored (rows = lane/4 mod 8).  Fixed order: shuffle tree over the 8 row
 // groups, then the four epilogue warps through the staging patch; one partial row stats[row][0 = sum | 1 = sq][channel].
 template <int N_TILE>
-__device__ __forceinline__ void flush_column_stats(float* epi_stage, float (&acc)[N_TILE / 16][8], int q, int lane,
+__device__ __forceinline__ void flush_column_stats(float* epi_stage, float (&acc)[N_TILE / 32][8], int q, int eg, int lane,
                                                    float* stats, int row, int n_total, int n_tile0) {
   static_assert(2 * N_TILE <= kEpiWarpFloats, "staging patch too small for the statistics");
-  float* sm = epi_stage + q * kEpiWarpFloats;  // [0 = sum | 1 = sq][N_TILE] of this warp
+  float* sm = epi_stage + (eg * 4 + q) * kEpiWarpFloats;  // [0 = sum | 1 = sq][N_TILE] of this warp
 #pragma unroll
-  for (int c = 0; c < N_TILE / 16; ++c) {
+  for (int cc = 0; cc < N_TILE / 32; ++cc) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = acc[c][j];
+      float v = acc[cc][j];
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 4) sm[(j >> 2) * N_TILE + c * 16 + lane * 4 + (j & 3)] = v;
+      if (lane < 4) {
+        const int col = lane * 4 + (j & 3);
+        sm[(j >> 2) * N_TILE + (2 * cc + eg) * 16 + col] = v;        // this warp's chunk
+        sm[(j >> 2) * N_TILE + (2 * cc + (eg ^ 1)) * 16 + col] = 0.f;  // the other group's chunk
+      }
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-  const int t = q * 32 + lane;
-  for (int idx = t; idx < 2 * N_TILE; idx += 128) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+  const int t = (eg * 4 + q) * 32 + lane;
+  for (int idx = t; idx < 2 * N_TILE; idx += 256) {
     const int which = idx / N_TILE, col = idx % N_TILE;
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) v += epi_stage[w * kEpiWarpFloats + idx];
+    for (int w = 0; w < kEpiWarps; ++w) v += epi_stage[w * kEpiWarpFloats + idx];
     stats[((long long)row * 2 + which) * n_total + n_tile0 + col] = v;
   }
 }
@@ -174,7 +186,7 @@ struct ConvGemmCfg {
 };
 
 template <int N_TILE, int PA, int PB>
-__global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
   using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], kEpiWarps);  // one arrival per epilogue warp
       mbar_init(&turn_bar[b], 1);
     }
     fence_barrier_init();
@@ -326,19 +338,20 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant
         ++tile_i;
       }
     }
-  } else {
+  } else if (is_epilogue_warp(warp)) {
     // ---------------- epilogue: TMEM -> registers -> smem transpose -> coalesced global stores (fp32 NHWC) ----------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int eg = epilogue_group(warp);  // 16-column chunks c with c % 2 == eg
     const int r = q * 32 + lane;
     const int w = r % p.tile_w;
     const int h = (r / p.tile_w) % p.tile_h;
     const int n = r / (p.tile_w * p.tile_h);
-    float* stage = epi_stage + q * kEpiWarpFloats;
-    float col_acc[N_TILE / 16][8];
+    float* stage = epi_stage + (eg * 4 + q) * kEpiWarpFloats;
+    float col_acc[N_TILE / 32][8];
 #pragma unroll
-    for (int c = 0; c < N_TILE / 16; ++c)
+    for (int cc = 0; cc < N_TILE / 32; ++cc)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) col_acc[c][j] = 0.f;
+      for (int j = 0; j < 8; ++j) col_acc[cc][j] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       int n0, h0;
@@ -351,8 +364,9 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant
       mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < N_TILE / 16; ++c) {  // unrolled: col_acc must stay in registers
+      for (int cc = 0; cc < N_TILE / 32; ++cc) {  // unrolled: col_acc must stay in registers
         if (p.experiment & 2) break;
+        const int c = 2 * cc + eg;
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kUmmaN + c * 16;
         tmem_ld_32x16(taddr, v);
@@ -366,7 +380,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant
           tmem_ld_wait();
         }
         warp_store_rows16(stage, v, p.out, row_off, valid && !(p.experiment & 1), c * 16, p.accumulate != 0, lane,
-                          col_acc[c], p.stats != nullptr);
+                          col_acc[cc], p.stats != nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -374,7 +388,7 @@ __global__ void __launch_bounds__(224, 1) conv_gemm_kernel(const __grid_constant
     }
     // host guarantees gridDim.x % n_tiles == 0 when stats are requested: this CTA only saw one N tile
     if (p.stats)
-      flush_column_stats<N_TILE>(epi_stage, col_acc, q, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
+      flush_column_stats<N_TILE>(epi_stage, col_acc, q, eg, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
                                  (blockIdx.x % p.n_tiles) * N_TILE);
   }
   tc_fence_before();
@@ -394,7 +408,7 @@ static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
   const int tiles = kp.m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;  // one N tile per CTA (see flush_column_stats)
-  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(224), Cfg::kSmemBytes, stream, kp));
+  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
   return 0;
 }
 
@@ -463,7 +477,7 @@ struct Conv3x3Cfg {
 };
 
 template <int N_TILE, int PA, int PB>
-__global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__ Conv3x3KParams p, int a_box_bytes,
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_constant__ Conv3x3KParams p, int a_box_bytes,
                                                          int b_stages) {
   using Cfg = Conv3x3Cfg<N_TILE, PA, PB>;
   extern __shared__ uint8_t smem_raw[];
@@ -493,7 +507,7 @@ __global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], kEpiWarps);
       mbar_init(&turn_bar[b], 1);
     }
     fence_barrier_init();
@@ -645,18 +659,20 @@ __global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__
       g_dbg[9] += my_tiles;
       g_dbg[11] += dbg_issue;
     }
-  } else {
+  } else if (is_epilogue_warp(warp)) {
     const int q = warp & 3;
+    const int eg = epilogue_group(warp);  // 16-column chunks c with c % 2 == eg
     const int r = q * 32 + lane;
     const int w = r % p.w;
     const int hr = r / slab_px;              // slab (image row) inside the half
     const int img = (r % slab_px) / p.w;     // image inside the slab
     const bool edbg = dbg && warp == 2 && lane == 0;
-    float col_acc[N_TILE / 16][8];
+    float* stage = epi_stage + (eg * 4 + q) * kEpiWarpFloats;
+    float col_acc[N_TILE / 32][8];
 #pragma unroll
-    for (int c = 0; c < N_TILE / 16; ++c)
+    for (int cc = 0; cc < N_TILE / 32; ++cc)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) col_acc[c][j] = 0.f;
+      for (int j = 0; j < 8; ++j) col_acc[cc][j] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       const int mt = tile / p.n_tiles;
@@ -678,7 +694,8 @@ __global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__
         const long long row_off = (long long)n_img * p.out_sn + (long long)h_row * p.out_sh +
                                   (long long)w * p.out_sw + n_tile0;
 #pragma unroll
-        for (int c = 0; c < N_TILE / 16; ++c) {  // unrolled: col_acc must stay in registers
+        for (int cc = 0; cc < N_TILE / 32; ++cc) {  // unrolled: col_acc must stay in registers
+          const int c = 2 * cc + eg;
           uint32_t v[16];
           const uint32_t taddr =
               tmem_base + (uint32_t(q * 32) << 16) + buf * 2 * Cfg::kUmmaN + half * Cfg::kUmmaN + c * 16;
@@ -692,8 +709,8 @@ __global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__
           } else {
             tmem_ld_wait();
           }
-          warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane,
-                            col_acc[c], p.stats != nullptr);
+          warp_store_rows16(stage, v, p.out, row_off, true, c * 16, p.accumulate != 0, lane, col_acc[cc],
+                            p.stats != nullptr);
         }
       }
       tc_fence_before();
@@ -707,7 +724,7 @@ __global__ void __launch_bounds__(224, 1) conv3x3_kernel(const __grid_constant__
       g_dbg[8] += clock64() - t_start;
     }
     if (p.stats)
-      flush_column_stats<N_TILE>(epi_stage, col_acc, q, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
+      flush_column_stats<N_TILE>(epi_stage, col_acc, q, eg, lane, p.stats, blockIdx.x / p.n_tiles, p.n_total,
                                  (blockIdx.x % p.n_tiles) * N_TILE);
   }
   tc_fence_before();
@@ -738,7 +755,7 @@ static int launch_conv3x3(const Conv3x3KParams& kp, cudaStream_t stream) {
   const int tiles = m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;
-  FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(224), smem, stream, kp, a_box_bytes, b_stages));
+  FB_CUDA(launch_pdl(conv3x3_kernel<N_TILE, PA, PB>, dim3(grid), dim3(kThreads), smem, stream, kp, a_box_bytes, b_stages));
   return 0;
 }
 
@@ -773,7 +790,7 @@ constexpr int kWgABytes = 2 * kATileBytes;  // two 64-channel chunks of dY: [chu
 constexpr int kWgBBytes = kATileBytes;      // [128 pixels][64 ci]
 constexpr int kWgTmemCols = 512;
 
-__global__ void __launch_bounds__(224, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -929,8 +946,9 @@ __global__ void __launch_bounds__(224, 1) wgrad_kernel(const __grid_constant__ W
       g_dbg[9] += pb1 - pb0;
       g_dbg[11] += dbg_issue;
     }
-  } else {
+  } else if (is_epilogue_warp(warp)) {
     const int q = warp & 3;
+    const int eg = epilogue_group(warp);  // 16-column chunks c with c % 2 == eg
     const int co = co0 + q * 32 + lane;
     const bool valid = co < p.cout;
     const long long row_off = ((long long)split * p.cout + co) * k_total;
@@ -944,7 +962,7 @@ __global__ void __launch_bounds__(224, 1) wgrad_kernel(const __grid_constant__ W
       const int tap = s % p.n_taps;
       const int cb = s / p.n_taps;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = eg; c < 4; c += 2) {
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + j * 64 * p.planes + c * 16;
         tmem_ld_32x16(taddr, v);
@@ -957,7 +975,7 @@ __global__ void __launch_bounds__(224, 1) wgrad_kernel(const __grid_constant__ W
         } else {
           tmem_ld_wait();
         }
-        warp_store_rows16(epi_stage + q * kEpiWarpFloats, v, p.partial, row_off, valid,
+        warp_store_rows16(epi_stage + (eg * 4 + q) * kEpiWarpFloats, v, p.partial, row_off, valid,
                           tap * p.cin + cb * kBlockK + c * 16, false, lane);
       }
     }
@@ -1346,7 +1364,7 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
     FB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  FB_CUDA(launch_pdl(wgrad_kernel, grid, dim3(224), smem, static_cast<cudaStream_t>(stream), kp));
+  FB_CUDA(launch_pdl(wgrad_kernel, grid, dim3(kThreads), smem, static_cast<cudaStream_t>(stream), kp));
   return 0;
 }
 
