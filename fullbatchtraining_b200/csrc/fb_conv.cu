@@ -107,10 +107,15 @@ struct alignas(64) ConvGemmKParams {
 constexpr int kTileM = 128;                        // pixels per CTA tile == UMMA M
 constexpr int kBlockK = 64;                        // bf16 elements per K block == one 128-byte swizzle row
 constexpr int kATileBytes = kTileM * kBlockK * 2;  // 16 KiB
-// Warp roles of the tensor-core kernels (352 threads): 0 = TMA producer, 1 and 6 = MMA issuers, 2-5 and 7-10 = epilogue.
+// Warp roles of the tensor-core kernels (352 threads): 0 = TMA producer, 1 (and 6 if kMmaIssuers == 2) = MMA issuer,
+// 2-5 and 7-10 = epilogue.
 // A warp may only read the TMEM lanes 32*(warp%4)..+31, so each lane quarter has TWO epilogue warps (groups 0 and 1)
 // that take alternate 16-column chunks: the accumulator drain, which is fully exposed for the last tile of a CTA, is
 // twice as fast.
+// kMmaIssuers = 2 lets warps 1 and 6 issue alternate pipeline stages (a turn token orders the ISSUE; the probe reaches
+// the pipe's 64 clk / MMA that way), but the tensor pipe does not retire MMAs of different warps in a fixed order: the
+// fp32 accumulation order then varies from run to run (seen as non-bit-identical gradients), so the default is ONE issuer.
+constexpr int kMmaIssuers = 1;
 constexpr int kThreads = 352;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytes = kEpiWarps * kEpiWarpFloats * 4;  // 8 epilogue warps x 32 x 20 floats
@@ -273,13 +278,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1 || warp == 6) {
-    // ---------------- MMA issuers: TWO warps alternate pipeline stages ----------------
+    // ---------------- MMA issuer(s) ----------------
     // A tcgen05.mma blocks its issuing thread until the tensor pipe has taken it, and nothing that thread executes
     // between two MMAs overlaps with them (tools/probes/mma_issue.cu: every instruction between two MMAs adds its full
     // latency; one issuing warp reaches 79-98 clk per M128xN128xK16 MMA with 8-4 MMAs per stage, two alternating warps
-    // 64.0 = the pipe's rate).  So the per-stage work (barrier wait, elect, descriptor setup, commit) of one warp runs
-    // while the other warp's MMAs execute; a turn token (mbarrier) keeps the issue order = accumulation order fixed.
-    // The pipe completes MMAs in issue order, so the commit of the issuer of a tile's last stage covers the whole tile.
+    // 64.0 = the pipe's rate).  The role therefore runs warp-converged with an elected lane, so that the descriptors
+    // live in uniform registers and the unrolled block is back-to-back UTCHMMA.  With kMmaIssuers == 2 warps 1 and 6
+    // alternate stages behind a turn token; that is NOT the default because the accumulation order is then no longer
+    // reproducible (see kMmaIssuers).
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     constexpr int kC = Cfg::kCombos;
     //   stacked, PA == 2: c0 = A_lo, c1 = A_hi (both against [B_hi;B_lo]); for 128-wide tiles A_lo only needs B_hi, so
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int me = (warp == 1) ? 0 : 1;
     const uint32_t smem0 = smem_u32(smem);
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_stages = my_tiles * k_iters;
+    const int total_stages = (me < kMmaIssuers) ? my_tiles * k_iters : 0;
     int s = me % STAGES;
     uint32_t phase = (me / STAGES) & 1, tphase = 0;
     int ki = me, tile_i = 0;
@@ -301,14 +307,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ki -= k_iters;
       ++tile_i;
     }
-    for (int it = me; it < total_stages; it += 2) {
+    for (int it = me; it < total_stages; it += kMmaIssuers) {
       const int buf = tile_i & 1;
       const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
       if (ki == 0) mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
       mbar_wait(&full_bar[s], phase, 2);
       const uint32_t a_lo = smem_desc_lo(smem0 + s * Cfg::kStageBytes, 16);
       const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
-      if (it > 0) {
+      if (kMmaIssuers == 2 && it > 0) {
         mbar_wait(&turn_bar[me], tphase, 5);  // the other warp has issued the previous stage
         tphase ^= 1;
       }
@@ -322,17 +328,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                              b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi,
                              (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full, (ki | c | k) != 0);
         }
-        mbar_arrive(&turn_bar[me ^ 1]);
+        if (kMmaIssuers == 2) mbar_arrive(&turn_bar[me ^ 1]);
         tc_commit(&empty_bar[s]);
         if (ki == k_iters - 1) tc_commit(&acc_full[buf]);
       }
       __syncwarp();
-      s += 2;
+      s += kMmaIssuers;
       if (s >= STAGES) {
         s -= STAGES;
         phase ^= 1;
       }
-      ki += 2;
+      ki += kMmaIssuers;
       while (ki >= k_iters) {
         ki -= k_iters;
         ++tile_i;
@@ -591,16 +597,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       g_dbg[10] += clock64() - t_start;
     }
   } else if (warp == 1 || warp == 6) {
-    // ---------------- MMA issuers: two warps alternate tap stages (see conv_gemm_kernel) ----------------
+    // ---------------- MMA issuer(s): one elected lane per warp, see conv_gemm_kernel and kMmaIssuers ----------------
     constexpr uint32_t idesc = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
     const int me = (warp == 1) ? 0 : 1;
     const int spt = 9 * p.cblocks;  // tap stages per tile
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_stages = my_tiles * spt;
+    const int total_stages = (me < kMmaIssuers) ? my_tiles * spt : 0;
     uint32_t tphase = 0;
-    for (int it = me; it < total_stages; it += 2) {
+    for (int it = me; it < total_stages; it += kMmaIssuers) {
       // the index arithmetic below is off the critical path: the other warp's MMAs are running meanwhile
       const int tile_i = it / spt, r = it % spt;
       const int dhi = r % 3;
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
       const uint32_t tmem_d = tmem_base + buf * 2 * Cfg::kUmmaN;
       const uint32_t a_base = smem_a0 + as * a_stage_bytes + dhi * row_bytes;
       const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * Cfg::kBStageBytes, 16);
-      if (it > 0) {
+      if (kMmaIssuers == 2 && it > 0) {
         mbar_wait(&turn_bar[me], tphase, 27);
         tphase ^= 1;
       }
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
                                (r == 0 && c == 0 && k == 0) ? 0u : 1u);
           }
         }
-        mbar_arrive(&turn_bar[me ^ 1]);
+        if (kMmaIssuers == 2) mbar_arrive(&turn_bar[me ^ 1]);
         tc_commit(&b_empty[bs]);
         if (dhi == 2) tc_commit(&a_empty[as]);        // in-order pipe: covers the other warp's taps of this box
         if (r == spt - 1) tc_commit(&acc_full[buf]);
@@ -885,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       g_dbg[10] += clock64() - t_start;
     }
   } else if (warp == 1 || warp == 6) {
-    // ---------------- MMA issuers: two warps alternate (pixel block, slot) stages, see conv_gemm_kernel ------------
+    // ---------------- MMA issuer(s): one elected lane per warp, see conv_gemm_kernel and kMmaIssuers ------------
     // both operands MN-major; the hi and lo X tiles of a stage are adjacent, so ONE instruction with N = 64*planes
     // computes dY^T*[X_hi, X_lo] into two 64-column halves that the epilogue adds (an SS-mode MMA re-reads its
     // 128x16 A tile per instruction, N = 64 would run the tensor pipe at half rate)
@@ -893,7 +899,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
     const int me = (warp == 1) ? 0 : 1;
-    const int total_stages = (pb1 - pb0) * n_slots;
+    const int total_stages = (me < kMmaIssuers) ? (pb1 - pb0) * n_slots : 0;
+    const int all_stages = (pb1 - pb0) * n_slots;
     int bs = me % b_stages;
     uint32_t bphase = (me / b_stages) & 1, tphase = 0;
     int j = me, pbi = 0;  // slot inside the pixel block, pixel block index relative to pb0
@@ -901,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       j -= n_slots;
       ++pbi;
     }
-    for (int it = me; it < total_stages; it += 2) {
+    for (int it = me; it < total_stages; it += kMmaIssuers) {
       const int as = pbi % kWgAStages;
       FB_DBG_WAIT(0, mbar_wait(&a_full[as], (pbi / kWgAStages) & 1, 13));
       FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
@@ -910,7 +917,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const uint32_t a_lo = smem_desc_lo(smem_a0 + as * kWgABytes, kATileBytes);
       const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
       const uint32_t tmem_d = tmem_base + j * 64 * p.planes;
-      if (it > 0) {
+      if (kMmaIssuers == 2 && it > 0) {
         mbar_wait(&turn_bar[me], tphase, 16);
         tphase ^= 1;
       }
@@ -921,19 +928,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         for (int k = 0; k < kTileM / 16; ++k)
           tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
                            (pbi != 0 || k != 0) ? 1u : 0u);
-        mbar_arrive(&turn_bar[me ^ 1]);
+        if (kMmaIssuers == 2) mbar_arrive(&turn_bar[me ^ 1]);
         tc_commit(&b_empty[bs]);
-        if (j == n_slots - 1) tc_commit(&a_empty[as]);   // in-order pipe: covers the other warp's slots too
-        if (it == total_stages - 1) tc_commit(accum_bar);
+        if (j == n_slots - 1) tc_commit(&a_empty[as]);
+        if (it == all_stages - 1) tc_commit(accum_bar);
       }
       __syncwarp();
       if (dbg) dbg_issue += clock64() - t_issue;
-      bs += 2;
+      bs += kMmaIssuers;
       while (bs >= b_stages) {
         bs -= b_stages;
         bphase ^= 1;
       }
-      j += 2;
+      j += kMmaIssuers;
       while (j >= n_slots) {
         j -= n_slots;
         ++pbi;
