@@ -94,6 +94,11 @@ struct alignas(64) ConvGemmKParams {
   int tile_w, tile_h, tile_n;
   int grid_h, grid_n;
   int m_tiles, n_tiles;
+  // tap groups: tile t belongs to group t / (m_tiles * n_tiles); group g accumulates taps [tap0, tap0 + n_taps) and
+  // writes at out + out_off (the four output phases of a stride-2 dgrad in one launch); n_groups == 1: all taps
+  int n_groups;
+  int group_tap0[4], group_taps[4];
+  long long group_off[4];
   float* out;
   long long out_sn, out_sh, out_sw;
   int accumulate;
@@ -237,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   griddep_wait();    // everything above overlapped the predecessor's tail
   griddep_launch();
 
-  const int k_iters = p.n_taps * p.cblocks;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int group_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.n_groups * group_tiles;
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -246,10 +251,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int grp = tile / group_tiles, gt = tile % group_tiles;
       int n0, h0;
-      tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
-      for (int t = 0; t < p.n_taps; ++t) {
+      tile_origin(gt / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+      const int n_tile0 = (gt % p.n_tiles) * N_TILE;
+      for (int t = p.group_tap0[grp]; t < p.group_tap0[grp] + p.group_taps[grp]; ++t) {
         const fb_tap tap = p.taps[t];
         for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
           mbar_wait(&empty_bar[s], phase ^ 1, 1);
@@ -298,14 +304,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, N_TILE, 0, 0);
     const int me = (warp == 1) ? 0 : 1;
     const uint32_t smem0 = smem_u32(smem);
+    // K iterations of this CTA's tile_i-th tile (tap groups have different tap counts)
+    auto k_iters_of = [&](int ti) {
+      return p.group_taps[(int(blockIdx.x) + ti * int(gridDim.x)) / group_tiles] * p.cblocks;
+    };
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_stages = (me < kMmaIssuers) ? my_tiles * k_iters : 0;
+    int total_stages = 0;
+    if (me < kMmaIssuers)
+      for (int ti = 0; ti < my_tiles; ++ti) total_stages += k_iters_of(ti);
     int s = me % STAGES;
     uint32_t phase = (me / STAGES) & 1, tphase = 0;
     int ki = me, tile_i = 0;
-    while (ki >= k_iters) {
+    int k_iters = my_tiles > 0 ? k_iters_of(0) : 1;
+    while (ki >= k_iters && tile_i + 1 < my_tiles) {
       ki -= k_iters;
-      ++tile_i;
+      k_iters = k_iters_of(++tile_i);
     }
     for (int it = me; it < total_stages; it += kMmaIssuers) {
       const int buf = tile_i & 1;
@@ -339,9 +352,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         phase ^= 1;
       }
       ki += kMmaIssuers;
-      while (ki >= k_iters) {
+      while (ki >= k_iters && tile_i + 1 < my_tiles) {
         ki -= k_iters;
-        ++tile_i;
+        k_iters = k_iters_of(++tile_i);
       }
     }
   } else if (is_epilogue_warp(warp)) {
@@ -360,12 +373,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int j = 0; j < 8; ++j) col_acc[cc][j] = 0.f;
     int tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int grp = tile / group_tiles, gt = tile % group_tiles;
       int n0, h0;
-      tile_origin(tile / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-      const int n_tile0 = (tile % p.n_tiles) * N_TILE;
+      tile_origin(gt / p.n_tiles, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+      const int n_tile0 = (gt % p.n_tiles) * N_TILE;
       const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
-      const long long row_off =
-          (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw + n_tile0;
+      const long long row_off = p.group_off[grp] + (long long)(n0 + n) * p.out_sn + (long long)(h0 + h) * p.out_sh +
+                                (long long)w * p.out_sw + n_tile0;
       const int buf = tile_i & 1;
       mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
       tc_fence_after();
@@ -411,7 +425,7 @@ static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
                                  Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int tiles = kp.n_groups * kp.m_tiles * kp.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (kp.stats) grid = (grid / kp.n_tiles) * kp.n_tiles;  // one N tile per CTA (see flush_column_stats)
   FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
@@ -1254,6 +1268,23 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.accumulate = a->accumulate;
   kp.stats = a->stats_out;
   kp.n_total = a->n_total;
+  FB_REQUIRE(a->n_groups >= 0 && a->n_groups <= 4, "fb_conv_gemm: n_groups must be in 0..4");
+  FB_REQUIRE(a->n_groups <= 1 || !a->stats_out, "fb_conv_gemm: tap groups cannot be combined with stats_out");
+  kp.n_groups = a->n_groups > 0 ? a->n_groups : 1;
+  for (int g = 0; g < 4; ++g) {
+    kp.group_tap0[g] = 0;
+    kp.group_taps[g] = a->n_taps;
+    kp.group_off[g] = 0;
+  }
+  if (a->n_groups > 0)
+    for (int g = 0; g < a->n_groups; ++g) {
+      FB_REQUIRE(a->groups[g].tap0 >= 0 && a->groups[g].n_taps >= 1 &&
+                     a->groups[g].tap0 + a->groups[g].n_taps <= a->n_taps,
+                 "fb_conv_gemm: tap group %d out of range", g);
+      kp.group_tap0[g] = a->groups[g].tap0;
+      kp.group_taps[g] = a->groups[g].n_taps;
+      kp.group_off[g] = a->groups[g].out_off;
+    }
   {
     const char* e = getenv("FB_CONV_EXPERIMENT");  // read per call: development only
     kp.experiment = e ? atoi(e) : 0;

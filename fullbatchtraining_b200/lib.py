@@ -27,11 +27,16 @@ class Tap(C.Structure):
     _fields_ = [("phase", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("pad", C.c_int8), ("b_k0", i32)]
 
 
+class TapGroup(C.Structure):
+    _fields_ = [("tap0", i32), ("n_taps", i32), ("out_off", i64)]
+
+
 class ConvGemmArgs(C.Structure):
     _fields_ = [("host_a_maps", vp), ("host_b_maps", vp), ("n_phases", i32), ("a_planes", i32), ("b_planes", i32),
                 ("n_taps", i32), ("cblocks", i32), ("taps", Tap * FB_MAX_TAPS), ("tile_w", i32), ("tile_h", i32),
                 ("tile_n", i32), ("grid_h", i32), ("grid_n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
-                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp)]
+                ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp),
+                ("n_groups", i32), ("groups", TapGroup * 4)]
 
 
 class Conv3x3Args(C.Structure):

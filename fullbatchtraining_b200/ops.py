@@ -120,7 +120,9 @@ class ConvGemm:
     """One launch of fb_conv_gemm with frozen arguments (descriptors are encoded once)."""
 
     def __init__(self, a_maps, b_maps, n_phases, a_planes, b_planes, taps, cblocks, tile, grid_h, grid_n, n_total, out,
-                 out_off, out_strides, accumulate, n_tile):
+                 out_off, out_strides, accumulate, n_tile, groups=None):
+        """groups: optional [(tap0, n_taps, out_off_elements)] -- tap groups that run over the same pixel grid and
+        write to different offsets (the four output phases of a stride-2 dgrad in one launch)."""
         self.a_maps, self.b_maps = a_maps, b_maps
         args = L.ConvGemmArgs()
         args.host_a_maps, args.host_b_maps = a_maps.addr, b_maps.addr
@@ -137,6 +139,12 @@ class ConvGemm:
         args.out = out.data_ptr() + out_off * 4
         args.out_sn, args.out_sh, args.out_sw = out_strides
         args.accumulate = int(accumulate)
+        if groups:
+            if len(groups) > 4:
+                raise RuntimeError("at most 4 tap groups")
+            args.n_groups = len(groups)
+            for i, (tap0, n_taps, off) in enumerate(groups):
+                args.groups[i] = L.TapGroup(tap0, n_taps, off)
         self.args = args
         self.flops = 0.0  # algorithmic FLOPs of this launch (set by Conv2dPlan)
 
@@ -328,7 +336,8 @@ class Conv2dPlan:
         if dx is not None:
             dys = MapSet(1)
             encode_act(dys, 0, dy, n, ho, wo, cout, tile)
-            m_tiles_d = m_tiles
+            grouped = stride == 2 and os.environ.get("FB_S2_DGRAD_GROUPS", "1") == "1"
+            m_tiles_d = m_tiles * (4 if grouped else 1)  # the four output phases of a stride-2 dgrad share one launch
             n_tile_d = choose_n_tile(m_tiles_d, cin, 1, wplanes)
             ds = MapSet(wplanes)
             for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
@@ -354,16 +363,26 @@ class Conv2dPlan:
                 def taps_for(par):
                     return [(1, 0)] if par == 0 else [(0, 1), (2, 0)]  # (k index, shift in the dY grid)
 
+                # one launch: four tap groups = the four output phases (1 + 2 + 2 + 4 taps)
+                dtaps, groups = [], []
                 for ph in range(2):
                     for pw in range(2):
-                        dtaps = []
+                        tap0 = len(dtaps)
                         for kh, dh in taps_for(ph):
                             for kw, dw in taps_for(pw):
                                 dtaps.append((0, dh, dw, (kh * 3 + kw) * cout))
-                        self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, n, cin, dx,
-                                                    (ph * w + pw) * cin, (h * w * cin, 2 * w * cin, 2 * cin),
-                                                    dx_accumulate, n_tile_d))
-                        self.dgrads[-1].flops = self.alg_flops * len(dtaps) / 9.0
+                        groups.append((tap0, len(dtaps) - tap0, (ph * w + pw) * cin))
+                if grouped:
+                    self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, n, cin, dx, 0,
+                                                (h * w * cin, 2 * w * cin, 2 * cin), dx_accumulate, n_tile_d,
+                                                groups=groups))
+                    self.dgrads[-1].flops = self.alg_flops
+                else:
+                    for tap0, cnt, off in groups:
+                        self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps[tap0:tap0 + cnt], cb_out, tile, ho, n,
+                                                    cin, dx, off, (h * w * cin, 2 * w * cin, 2 * cin), dx_accumulate,
+                                                    n_tile_d))
+                        self.dgrads[-1].flops = self.alg_flops * cnt / 9.0
             self.dy_maps_d = dys
 
         # ---- wgrad

@@ -78,6 +78,14 @@ typedef struct {
   /* optional BatchNorm statistics fused into the epilogue: stats_out[row][0|1][n_total] receives per-CTA column sums
    * and sums of squares of `out`, rows = fb_conv_stats_rows(...); feed them to fb_bn_fwd_fused.  NULL: off. */
   float* stats_out;
+  /* optional tap groups (0 = one group of all n_taps): group g covers taps [tap0, tap0 + n_taps) and writes to
+   * out + out_off; every group runs over the same pixel grid.  One launch then serves the four output phases of a
+   * stride-2 dgrad (1 + 2 + 2 + 4 taps).  Not combinable with stats_out. */
+  int32_t n_groups;
+  struct {
+    int32_t tap0, n_taps;
+    int64_t out_off;
+  } groups[4];
 } fb_conv_gemm_args;
 /* number of partial rows written to stats_out for a problem of m_tiles x (n_total / n_tile) tiles */
 int fb_conv_stats_rows(int m_tiles, int n_tiles);
