@@ -8,6 +8,8 @@
 // (fullbatch/models/resnets.py:71,207-230,296-316), AvgPool2d (resnets.py:149), AdaptiveAvgPool2d + Linear
 // (resnets.py:106-107), LabelSmoothCrossEntropyLoss (fullbatch/models/modules.py:96-101), accuracy count
 // (fullbatch/training/training.py:80) and their autograd backward.
+#include <cooperative_groups.h>
+
 #include "../../include/fullbatch_b200.h"
 #include "fb_common.cuh"
 
@@ -591,6 +593,239 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Small feature maps (8x8, 4x4, ...: the whole [P][C] problem is a few MB): variant WITHOUT grid barriers, opt-in (see
+// sliced_geometry for the measurements).  The tensor is cut into channel SLICES of `sw` channels; a slice is owned by
+// `cs` CTAs that split the rows.
+//   forward  (statistics come from the conv epilogue): no synchronisation at all -- every CTA reduces the partial rows
+//            of its own slice redundantly (fixed order), the CTA of row group 0 publishes mean / rstd / running stats;
+//   backward: the cs CTAs of a slice form a thread-block CLUSTER and combine their column sums through distributed
+//            shared memory (fixed rank order -> deterministic) between two hardware cluster barriers.
+// Thread layout: TX = sw/4 threads per row (one float4 each), TY = 256/TX rows per iteration.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSliceMax = 32;   // channels per slice (sw in {8, 16, 32})
+constexpr int kSliceCtas = 8;   // CTAs (= cluster size in the backward kernel) per slice
+
+__device__ __forceinline__ void store4_split(bf16* hi, bf16* lo, long long off, const float4 v) {
+  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  __nv_bfloat162 hh[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
+  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(hh);
+  if (lo) {
+    __nv_bfloat162 ll[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
+    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(ll);
+  }
+}
+__device__ __forceinline__ float4 load4_bf16(const bf16* p) {
+  const uint2 m = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_sliced_kernel(BnFusedFwdArgs a, int sw, int rows_per_cta) {
+  griddep_wait();
+  __shared__ float s_mu[2][kSliceMax], s_scale[2][kSliceMax], s_shift[2][kSliceMax];
+  const fb_bn_apply_args& ap = a.ap;
+  const int C = ap.C;
+  const long long P = ap.P;
+  const int branches = ap.y2 ? 2 : 1;
+  const int c_base = blockIdx.y * sw;
+  {  // per-CTA finalize of this slice from the conv epilogue's partial rows: one warp per (branch, channel)
+    const int lane = threadIdx.x & 31;
+    for (int item = threadIdx.x >> 5; item < branches * sw; item += 8) {
+      const int br = item / sw, cl = item % sw, c = c_base + cl;
+      double s1, s2;
+      warp_reduce_partials(br ? a.ext1 : a.ext0, 2LL * C, br ? a.ext_rows1 : a.ext_rows0, C, c, lane, s1, s2);
+      if (lane == 0) {
+        const double m = s1 / double(P);
+        double var = s2 / double(P) - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float mean = float(m), rstd = float(1.0 / sqrt(var + double(a.eps)));
+        const float ga = (br ? ap.gamma2 : ap.gamma)[c], be = (br ? ap.beta2 : ap.beta)[c];
+        s_mu[br][cl] = mean;
+        s_scale[br][cl] = rstd * ga;
+        s_shift[br][cl] = be;
+        if (blockIdx.x == 0) {
+          (br ? a.mean2 : a.mean)[c] = mean;
+          (br ? a.rstd2 : a.rstd)[c] = rstd;
+          float* rm = br ? a.running_mean2 : a.running_mean;
+          float* rv = br ? a.running_var2 : a.running_var;
+          if (rm) {
+            const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
+            rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * mean;
+            rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * float(unbiased);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int TX = sw / 4, TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int cl = tx * 4, c = c_base + cl;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(P, r0 + rows_per_cta);
+  float mu[2][4], sc[2][4], sh[2][4];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mu[b][j] = s_mu[b][cl + j];
+      sc[b][j] = s_scale[b][cl + j];
+      sh[b][j] = s_shift[b][cl + j];
+    }
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += TY) {
+    const long long off = r * C + c;
+    const float4 y = *reinterpret_cast<const float4*>(ap.y + off);
+    float4 o = make_float4((y.x - mu[0][0]) * sc[0][0] + sh[0][0], (y.y - mu[0][1]) * sc[0][1] + sh[0][1],
+                           (y.z - mu[0][2]) * sc[0][2] + sh[0][2], (y.w - mu[0][3]) * sc[0][3] + sh[0][3]);
+    if (ap.y2) {
+      const float4 z = *reinterpret_cast<const float4*>(ap.y2 + off);
+      o.x += (z.x - mu[1][0]) * sc[1][0] + sh[1][0];
+      o.y += (z.y - mu[1][1]) * sc[1][1] + sh[1][1];
+      o.z += (z.z - mu[1][2]) * sc[1][2] + sh[1][2];
+      o.w += (z.w - mu[1][3]) * sc[1][3] + sh[1][3];
+    }
+    if (ap.res_hi) {
+      float4 rh = load4_bf16(static_cast<const bf16*>(ap.res_hi) + off);
+      if (ap.res_lo) {
+        const float4 rl = load4_bf16(static_cast<const bf16*>(ap.res_lo) + off);
+        rh.x += rl.x; rh.y += rl.y; rh.z += rl.z; rh.w += rl.w;
+      }
+      o.x += rh.x; o.y += rh.y; o.z += rh.z; o.w += rh.w;
+    }
+    if (ap.relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    store4_split(static_cast<bf16*>(ap.out_hi), static_cast<bf16*>(ap.out_lo), off, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_cluster_kernel(BnFusedBwdArgs a, int sw, int rows_per_cta) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  griddep_wait();
+  __shared__ float4 red[2][256];
+  __shared__ float part[2][kSliceMax];  // this CTA's column sums, read by the other CTAs of the cluster
+  __shared__ float coef[2][kSliceMax];
+  const fb_bn_bwd_args& bw = a.bw;
+  const int C = bw.C;
+  const long long P = bw.P;
+  const unsigned rank = cluster.block_rank(), cs = cluster.num_blocks();
+  const int c_base = blockIdx.y * sw;
+  const int TX = sw / 4, TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int cl = tx * 4, c = c_base + cl;
+  const long long r0 = (long long)rank * rows_per_cta;
+  const long long r1 = min(P, r0 + rows_per_cta);
+  const float4 mu = *reinterpret_cast<const float4*>(bw.mean + c);
+  const float4 rs = *reinterpret_cast<const float4*>(bw.rstd + c);
+  const bf16* mask = static_cast<const bf16*>(bw.mask_hi);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += TY) {
+    const long long off = r * C + c;
+    const float4 v = *reinterpret_cast<const float4*>(bw.y + off);
+    float4 d = *reinterpret_cast<const float4*>(bw.dA + off);
+    if (bw.dA2) {
+      const float4 d2 = *reinterpret_cast<const float4*>(bw.dA2 + off);
+      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+    }
+    if (mask) {
+      const float4 m = load4_bf16(mask + off);
+      d.x = m.x > 0.f ? d.x : 0.f;
+      d.y = m.y > 0.f ? d.y : 0.f;
+      d.z = m.z > 0.f ? d.z : 0.f;
+      d.w = m.w > 0.f ? d.w : 0.f;
+    }
+    s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+    s2.x += d.x * (v.x - mu.x) * rs.x;
+    s2.y += d.y * (v.y - mu.y) * rs.y;
+    s2.z += d.z * (v.z - mu.z) * rs.z;
+    s2.w += d.w * (v.w - mu.w) * rs.w;
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < TY; ++j) {
+      const float4 p1 = red[0][j * TX + tx], p2 = red[1][j * TX + tx];
+      s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
+      s2.x += p2.x; s2.y += p2.y; s2.z += p2.z; s2.w += p2.w;
+    }
+    *reinterpret_cast<float4*>(&part[0][cl]) = s1;
+    *reinterpret_cast<float4*>(&part[1][cl]) = s2;
+  }
+  cluster.sync();
+  if (threadIdx.x < sw) {  // every CTA sums the cluster's partials in rank order: identical totals everywhere
+    double t1 = 0.0, t2 = 0.0;
+    for (unsigned k = 0; k < cs; ++k) {
+      const float* rp = cluster.map_shared_rank(&part[0][0], k);
+      t1 += rp[threadIdx.x];
+      t2 += rp[kSliceMax + threadIdx.x];
+    }
+    coef[0][threadIdx.x] = float(t1 / double(P));
+    coef[1][threadIdx.x] = float(t2 / double(P));
+    if (rank == 0) {
+      bw.dbeta[c_base + threadIdx.x] = float(t1);
+      bw.dgamma[c_base + threadIdx.x] = float(t2);
+    }
+  }
+  cluster.sync();  // all remote reads of `part` are done (no CTA may exit before), coef visible to the block
+  const float4 ga = *reinterpret_cast<const float4*>(bw.gamma + c);
+  const float4 grs = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+  const float4 c1 = *reinterpret_cast<const float4*>(&coef[0][cl]);
+  const float4 c2 = *reinterpret_cast<const float4*>(&coef[1][cl]);
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += TY) {
+    const long long off = r * C + c;
+    const float4 v = *reinterpret_cast<const float4*>(bw.y + off);
+    float4 d = *reinterpret_cast<const float4*>(bw.dA + off);
+    if (bw.dA2) {
+      const float4 d2 = *reinterpret_cast<const float4*>(bw.dA2 + off);
+      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+    }
+    if (mask) {
+      const float4 m = load4_bf16(mask + off);
+      d.x = m.x > 0.f ? d.x : 0.f;
+      d.y = m.y > 0.f ? d.y : 0.f;
+      d.z = m.z > 0.f ? d.z : 0.f;
+      d.w = m.w > 0.f ? d.w : 0.f;
+    }
+    float4 o;
+    o.x = grs.x * (d.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
+    o.y = grs.y * (d.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
+    o.z = grs.z * (d.z - c1.z - (v.z - mu.z) * rs.z * c2.z);
+    o.w = grs.w * (d.w - c1.w - (v.w - mu.w) * rs.w * c2.w);
+    __nv_bfloat162 ob[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
+    *reinterpret_cast<uint2*>(static_cast<bf16*>(bw.dy_bf16) + off) = *reinterpret_cast<uint2*>(ob);
+    if (bw.dz_out) *reinterpret_cast<float4*>(bw.dz_out + off) = d;
+  }
+}
+
+// slice width / rows per CTA of the small-map kernels, or false if the problem should use the grid-barrier kernels
+static bool sliced_geometry(long long P, int C, int& sw, int& rows_per_cta) {
+  // opt-in (FB_BN_SLICED_MAX = largest P*C in elements): measured on B200 (tools/bn_timing.py) the cluster kernel wins
+  // only with L2-warm operands and 128-byte slice rows (4x4 maps: 9.2 vs 12.9 us); in the step Y and the ReLU mask
+  // come from HBM and the two variants are within 1 us, narrower slices (64 / 32-byte rows) are 1.3-2.4x slower.
+  const char* e = getenv("FB_BN_SLICED_MAX");
+  const long long max_elems = e ? atoll(e) : 0;
+  if (P * C > max_elems || C % 8 != 0) return false;
+  sw = C < kSliceMax ? C : kSliceMax;
+  while (sw > 8 && C % sw != 0) sw /= 2;
+  if (C % sw != 0) return false;
+  const int TY = 256 / (sw / 4);
+  long long rows = (P + kSliceCtas - 1) / kSliceCtas;
+  rows = (rows + TY - 1) / TY * TY;
+  rows_per_cta = int(rows);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // AvgPool2d(2)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int n, int h, int w,
@@ -1076,6 +1311,12 @@ extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, flo
   a.ext_rows0 = stats_rows;
   a.ext1 = stats2;
   a.ext_rows1 = stats_rows2;
+  int sw, rows_per_cta;
+  if (stats && sliced_geometry(ap->P, ap->C, sw, rows_per_cta)) {
+    FB_CUDA(launch_pdl(bn_fwd_sliced_kernel, dim3(kSliceCtas, ap->C / sw), dim3(256), 0,
+                       static_cast<cudaStream_t>(stream), a, sw, rows_per_cta));
+    return 0;
+  }
   FB_CUDA(launch_pdl(bn_fwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }
@@ -1096,6 +1337,29 @@ extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
   a.partial = bw->ws + 4;
   a.coef = a.partial + (long long)2 * bw->C * 2 * kNumSMs;
   a.rows_per_block = rpb;
+  int sw, rows_per_cta;
+  if (sliced_geometry(bw->P, bw->C, sw, rows_per_cta)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kSliceCtas, bw->C / sw);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSliceCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int n_attr = 1;
+    if (pdl_enabled()) {
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      n_attr = 2;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    FB_CUDA(cudaLaunchKernelEx(&cfg, bn_bwd_cluster_kernel, a, sw, rows_per_cta));
+    return 0;
+  }
   FB_CUDA(launch_pdl(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }

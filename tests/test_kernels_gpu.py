@@ -2,6 +2,8 @@
 seeded inputs.  Tolerances are stated per test: the split (hi+lo bf16) tensor-core path carries ~16 mantissa bits per
 operand, so products are exact to ~2^-16 relative and results are checked at 3e-5 of the output scale; the plain-bf16
 path is checked against torch run on bf16-rounded operands (products then exact in fp32)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -430,8 +432,16 @@ def test_bn_bwd_second_addend():
 
 @pytest.mark.parametrize("P,Cc,variant", [(131072, 64, "residual"), (32768, 128, "dual"), (2048, 512, "plain"),
                                           (512, 2048, "plain"), (1000, 128, "residual"), (8192, 256, "dual")])
-def test_bn_fused_kernels_match_unfused(P, Cc, variant):
-    """fb_bn_fwd_fused / fb_bn_bwd_fused (one persistent launch, grid barriers) against the three-launch kernels."""
+@pytest.mark.parametrize("sliced", [False, True], ids=["barrier", "cluster"])
+def test_bn_fused_kernels_match_unfused(P, Cc, variant, sliced, monkeypatch):
+    """fb_bn_fwd_fused / fb_bn_bwd_fused (one persistent launch, grid barriers; or the opt-in small-map variant with a
+    thread-block cluster + distributed shared memory, FB_BN_SLICED_MAX) against the three-launch kernels."""
+    if sliced:
+        if P * Cc > 4500000:
+            pytest.skip("small-map variant")
+        monkeypatch.setenv("FB_BN_SLICED_MAX", "4500000")
+    else:
+        monkeypatch.delenv("FB_BN_SLICED_MAX", raising=False)
     g = torch.Generator(device="cuda").manual_seed(P + Cc)
     y = torch.randn(P, Cc, device=DEV, generator=g) * 1.5 + 0.3
     y2 = torch.randn(P, Cc, device=DEV, generator=g)
@@ -560,7 +570,10 @@ def test_conv_forward_fused_statistics(case):
     gamma, beta = torch.rand(cout, device=DEV, generator=g) + 0.5, torch.randn(cout, device=DEV, generator=g) * 0.1
     ws = torch.zeros(2 * cout * 1024, device=DEV)
     outs = []
-    for stats in (None, plan.stats):
+    for stats in (None, plan.stats, "sliced"):
+        if stats == "sliced":  # the barrier-free forward variant consumes the same epilogue statistics
+            os.environ["FB_BN_SLICED_MAX"] = "4500000"
+            stats = plan.stats
         mean, rstd = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
         rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
         hi = torch.empty(P, cout, device=DEV, dtype=torch.bfloat16)
@@ -569,5 +582,7 @@ def test_conv_forward_fused_statistics(case):
             rm.zero_(); rv.fill_(1)
             ops.bn_fwd_fused(y, mean, rstd, gamma, beta, P, cout, hi, lo, ws, running=(rm, rv), stats=stats)
         outs.append((mean, rstd, rm, rv, hi.double() + lo.double()))
-    for u, v in zip(*outs):
-        assert rel_err(u, v) < 2e-5
+    os.environ.pop("FB_BN_SLICED_MAX", None)
+    for other in outs[1:]:
+        for u, v in zip(outs[0], other):
+            assert rel_err(u, v) < 2e-5
