@@ -281,6 +281,62 @@ class FullBatchEngine:
                          self.labels_mb, self.classes, self.smoothing, self.head_ws, self.scal, loss_slot, correct_slot,
                          self._view(G, "fc.weight"), self._view(G, "fc.bias"), a.grad)
 
+    @torch.no_grad()
+    def forward_eval(self, x):
+        """Eval-mode forward of `x` [n <= microbatch, 3, 32, 32] fp32 on the CUDA kernels (training.py:343-388 calls
+        model(inputs) in eval mode): BatchNorm uses the running statistics (fb_bn_apply), nothing is written to the
+        model's buffers or gradients.  Returns the logits [n, classes] (the final 512->10 linear on the pooled features
+        runs in torch: the caller needs logits, not the loss, for the test_time_flips softmax sum)."""
+        n = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (3, 32, 32) and n <= self.mb
+        if not hasattr(self, "_eval_x"):
+            self._eval_x = torch.zeros(self.mb, 3, 32, 32, device=self.device)
+            self._eval_y = torch.zeros(self.mb, dtype=torch.int64, device=self.device)
+        self._eval_x.zero_()
+        self._eval_x[:n].copy_(x)  # a short last batch is zero padded: eval-mode BN is per sample
+        P = self.theta
+        self._pass = 0
+        self.wprep[0](P)
+        ops.stem_im2col(self._eval_x, self._eval_y, None, None, 0, self.mb, self.patches.hi, self.patches.lo,
+                        self.labels_mb)
+
+        def bn_eval(u, out, second=None, res=None):
+            def stat(v):
+                rm, rv = self._bn_buffers(v.bn_name)
+                ga, be = self._bn_params(v, P)
+                return rm, torch.rsqrt(rv + BN_EPS), ga, be
+            rm, rs, ga, be = stat(u)
+            sec = None
+            if second is not None:
+                rm2, rs2, ga2, be2 = stat(second)
+                sec = (second.y, rm2, rs2, ga2, be2)
+            ops.bn_apply(u.y, rm, rs, ga, be, u.P, u.cout, out.hi, out.lo, relu=True, second=sec, res=res)
+
+        u = self.stem
+        u.plans[0].forward()
+        bn_eval(u, u.out)
+        for blk in self.blocks:
+            last = len(blk.units) - 1
+            for i, u in enumerate(blk.units):
+                u.plans[0].forward()
+                if i < last:
+                    bn_eval(u, u.out)
+            u = blk.units[last]
+            if blk.ds is not None:
+                d = blk.ds
+                if blk.pooled is not None:
+                    xin = blk.x
+                    ops.avgpool2_fwd(xin.hi, xin.lo, xin.n, xin.h, xin.w, xin.c, blk.pooled.hi, blk.pooled.lo)
+                d.plans[0].forward()
+                bn_eval(u, blk.out, second=d)
+            else:
+                bn_eval(u, blk.out, res=(blk.x.hi, blk.x.lo))
+        a = self.last
+        pooled = (a.hi.float() + (a.lo.float() if a.lo is not None else 0.0)).view(a.n, a.h * a.w, a.c).mean(dim=1)
+        logits = torch.addmm(self._view(P, "fc.bias").view(-1), pooled,
+                             self._view(P, "fc.weight").view(self.classes, a.c).t())
+        return logits[:n]
+
     def _unit_backward(self, u, P, G, act, dz_out=None):
         """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
         ga, _ = self._bn_params(u, P)

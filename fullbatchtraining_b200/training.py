@@ -331,7 +331,8 @@ class Trainer:
         step = self.step_count
         if validate and self.validloader is not None and (step % cfg.impl.validate_every_nth_step == 0
                                                           or step == cfg.hyp.steps or cfg.dryrun or step == 1):
-            evaluate(self.model, self.validloader, self.stats, self.setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun)
+            evaluate(self.model, self.validloader, self.stats, self.setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun,
+                     engine=self.engine if getattr(cfg.impl, "kernel_evaluate", True) else None)
         if self.rank == 0:
             log.info(status_message(self.optimizer, self.stats, step))
             if self.checkpoint_file is not None and ((step - 1) % cfg.impl.checkpoint.save_every_nth_step == 0
@@ -353,7 +354,8 @@ def train(model, trainloader, validloader, setup, cfg):
         if n_full > 0 and min(trainer.stats["train_acc"][-n_full:]) == 1:
             log.info("Terminating training after fitting all datapoints.")
             if validloader is not None:
-                evaluate(model, validloader, trainer.stats, setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun)
+                evaluate(model, validloader, trainer.stats, setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun,
+                         engine=trainer.engine if getattr(cfg.impl, "kernel_evaluate", True) else None)
             break
         if cfg.dryrun:
             break
@@ -383,10 +385,18 @@ def measure_implementation_noise(model, trainloader, validloader, setup, cfg):
 
 
 @torch.no_grad()
-def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False):
-    """training.py:343-388: eval-mode forward over the validation loader (plain PyTorch; not on the hot path)."""
+def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False, engine=None):
+    """training.py:343-388: eval-mode forward over the validation loader.  With `engine` (the trainer's
+    FullBatchEngine) the forward runs on the CUDA kernels (engine.forward_eval, in chunks of the microbatch size);
+    without it through the torch modules, exactly as the reference."""
     loss_fn = torch.nn.CrossEntropyLoss()
     model.eval()
+    if engine is not None:
+        def forward(x):
+            return torch.cat([engine.forward_eval(x[i:i + engine.mb].contiguous())
+                              for i in range(0, x.shape[0], engine.mb)])
+    else:
+        forward = model
     device = torch.device(setup["device"])
     if cfg_impl.setup.dist and torch.distributed.is_available() and torch.distributed.is_initialized():
         # training.py:347-357: ranks see different microbatches, so BN running statistics are averaged first
@@ -407,9 +417,9 @@ def evaluate(model, dataloader, stats, setup, cfg_impl, cfg_hyp, dryrun=False):
         labels = labels.to(device=device, dtype=torch.long)
         datapoints += labels.shape[0]
         if cfg_hyp.test_time_flips:  # training.py:370-373
-            outputs = model(inputs).softmax(dim=1) + model(torch.flip(inputs, [3])).softmax(dim=1)
+            outputs = forward(inputs).softmax(dim=1) + forward(torch.flip(inputs, [3])).softmax(dim=1)
         else:
-            outputs = model(inputs)
+            outputs = forward(inputs)
         step_loss += loss_fn(outputs, labels).item() * labels.shape[0]
         step_preds += (outputs.argmax(dim=-1) == labels).float().sum().item()
         if dryrun:

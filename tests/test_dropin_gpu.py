@@ -288,3 +288,30 @@ def test_measure_floating_point_accuracy_reports_zero_drift():
     rep = measure_implementation_noise(fresh(), HostBlockLoader(X, Y, mb), None, dict(device=DEV, dtype=torch.float32),
                                        _cfg(mb))
     assert rep["grad_l2"] > 0 and rep["diff_linf"] == 0.0 and rep["diff_l2"] == 0.0
+
+
+@pytest.mark.parametrize("flips", [False, True], ids=["plain", "test_time_flips"])
+def test_evaluate_on_kernels_matches_torch_eval(flips):
+    """training.py:343-388 (`evaluate`): the kernel path (engine.forward_eval: convs on the tensor cores, eval-mode
+    BatchNorm from the running statistics) against the same function through the torch modules, after one training
+    step has moved the running statistics; 300 validation images = two microbatches + a zero-padded remainder."""
+    from fullbatchtraining_b200.training import evaluate
+
+    mb, n = 128, 256
+    X, Y = O.synthetic_cifar(n)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(X, Y), batch_size=mb, shuffle=False)
+    Xv, Yv = O.synthetic_cifar(300, seed=77)
+    valid = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(Xv, Yv), batch_size=150, shuffle=False)
+    setup = dict(device=DEV, dtype=torch.float32)
+    cfg = _cfg(mb, **{"hyp.test_time_flips": flips})
+    trainer = Trainer(fresh(), loader, valid, setup, cfg)
+    trainer.step(validate=False)
+    ref = evaluate(trainer.model, valid, None, setup, cfg.impl, cfg.hyp)
+    got = evaluate(trainer.model, valid, None, setup, cfg.impl, cfg.hyp, engine=trainer.engine)
+    assert got["valid_loss"][0] == pytest.approx(ref["valid_loss"][0], rel=2e-4)
+    assert abs(got["valid_acc"][0] - ref["valid_acc"][0]) <= 1.0 / 300 + 1e-9
+    # evaluation must not disturb training state: parameters, BN buffers
+    before = [b.clone() for b in trainer.model.buffers()]
+    evaluate(trainer.model, valid, None, setup, cfg.impl, cfg.hyp, engine=trainer.engine)
+    for a, b in zip(before, trainer.model.buffers()):
+        assert torch.equal(a, b)
