@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1 || warp == 6) {
-    // ---------------- MMA issuer(s) ----------------
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     // A tcgen05.mma blocks its issuing thread until the tensor pipe has taken it, and nothing that thread executes
     // between two MMAs overlaps with them (tools/probes/mma_issue.cu: every instruction between two MMAs adds its full
     // latency; one issuing warp reaches 79-98 clk per M128xN128xK16 MMA with 8-4 MMAs per stage, two alternating warps
@@ -302,59 +302,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     auto bp_of = [](int c) { return (!Cfg::kStack && PB == 2 && c == kC - 1) ? 1 : 0; };
     constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
     constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, N_TILE, 0, 0);
-    const int me = (warp == 1) ? 0 : 1;
     const uint32_t smem0 = smem_u32(smem);
-    // K iterations of this CTA's tile_i-th tile (tap groups have different tap counts)
-    auto k_iters_of = [&](int ti) {
-      return p.group_taps[(int(blockIdx.x) + ti * int(gridDim.x)) / group_tiles] * p.cblocks;
+    // Single issuer (kMmaIssuers == 1, see above): everything the issuing warp executes between two MMAs is dead time
+    // for the tensor pipe (~270 clocks per barrier wait + elect + descriptor set-up + commit round), so TWO pipeline
+    // stages are waited for and issued per round whenever the tile has another stage left.
+    static_assert(kMmaIssuers == 1, "conv_gemm_kernel issues from one warp; the two-issuer variant lives in the probes");
+    (void)turn_bar;
+    auto issue_stage = [&](uint32_t tmem_d, int st, int ki) {
+      const uint32_t a_lo = smem_desc_lo(smem0 + st * Cfg::kStageBytes, 16);
+      const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          tc_mma_bf16_lohi(tmem_d, a_lo + ((ap_of(c) * kATileBytes + k * 32) >> 4),
+                           b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi,
+                           (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full, (ki | c | k) != 0);
+      }
+      tc_commit(&empty_bar[st]);
     };
-    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    int total_stages = 0;
-    if (me < kMmaIssuers)
-      for (int ti = 0; ti < my_tiles; ++ti) total_stages += k_iters_of(ti);
-    int s = me % STAGES;
-    uint32_t phase = (me / STAGES) & 1, tphase = 0;
-    int ki = me, tile_i = 0;
-    int k_iters = my_tiles > 0 ? k_iters_of(0) : 1;
-    while (ki >= k_iters && tile_i + 1 < my_tiles) {
-      ki -= k_iters;
-      k_iters = k_iters_of(++tile_i);
-    }
-    for (int it = me; it < total_stages; it += kMmaIssuers) {
+    int s = 0;
+    uint32_t phase = 0;
+    int tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int k_iters = p.group_taps[tile / group_tiles] * p.cblocks;
       const int buf = tile_i & 1;
       const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
-      if (ki == 0) mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
-      mbar_wait(&full_bar[s], phase, 2);
-      const uint32_t a_lo = smem_desc_lo(smem0 + s * Cfg::kStageBytes, 16);
-      const uint32_t b_lo = a_lo + ((PA * kATileBytes) >> 4);
-      if (kMmaIssuers == 2 && it > 0) {
-        mbar_wait(&turn_bar[me], tphase, 5);  // the other warp has issued the previous stage
-        tphase ^= 1;
-      }
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int c = 0; c < kC; ++c) {
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            tc_mma_bf16_lohi(tmem_d, a_lo + ((ap_of(c) * kATileBytes + k * 32) >> 4),
-                             b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi,
-                             (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full, (ki | c | k) != 0);
+      mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
+      for (int ki = 0; ki < k_iters; ki += 2) {
+        const bool pair = ki + 1 < k_iters;
+        int s1 = s + 1;
+        uint32_t phase1 = phase;
+        if (s1 == STAGES) {
+          s1 = 0;
+          phase1 ^= 1;
         }
-        if (kMmaIssuers == 2) mbar_arrive(&turn_bar[me ^ 1]);
-        tc_commit(&empty_bar[s]);
-        if (ki == k_iters - 1) tc_commit(&acc_full[buf]);
-      }
-      __syncwarp();
-      s += kMmaIssuers;
-      if (s >= STAGES) {
-        s -= STAGES;
-        phase ^= 1;
-      }
-      ki += kMmaIssuers;
-      while (ki >= k_iters && tile_i + 1 < my_tiles) {
-        ki -= k_iters;
-        k_iters = k_iters_of(++tile_i);
+        mbar_wait(&full_bar[s], phase, 2);
+        if (pair) mbar_wait(&full_bar[s1], phase1, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_stage(tmem_d, s, ki);
+          if (pair) issue_stage(tmem_d, s1, ki + 1);
+          if (ki + 2 >= k_iters) tc_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (pair) {
+          s = s1 + 1;
+          phase = phase1;
+          if (s == STAGES) {
+            s = 0;
+            phase ^= 1;
+          }
+        } else {
+          s = s1;
+          phase = phase1;
+        }
       }
     }
   } else if (is_epilogue_warp(warp)) {
@@ -802,6 +804,7 @@ struct alignas(64) WgradKParams {
   int splits, n_pixblocks;
   float* partial;
   int debug;
+  int halo;  // 1: a B stage is ONE haloed X box per plane ((tile_h + 2) rows) shared by the CTA's three dh taps
 };
 
 constexpr int kWgAStages = 2;
@@ -813,10 +816,14 @@ constexpr int kWgTmemCols = 512;
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // operand region = dY ring (2 stages of one or two 64-channel chunks) followed by the X ring, which takes the rest
+  constexpr int kWgOperandBytes = kWgAStages * kWgABytes + kWgBStages * kWgBBytes;
+  const int a_stage_bytes = (p.cout > 64) ? kWgABytes : kATileBytes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kWgAStages * kWgABytes;
-  float* epi_stage = reinterpret_cast<float*>(smem_b + kWgBStages * kWgBBytes);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kWgBBytes + kEpiStageBytes);
+  uint8_t* smem_b = smem + kWgAStages * a_stage_bytes;
+  const int b_region_bytes = kWgOperandBytes - kWgAStages * a_stage_bytes;
+  float* epi_stage = reinterpret_cast<float*>(smem + kWgOperandBytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kWgOperandBytes + kEpiStageBytes);
   uint64_t* a_empty = a_full + kWgAStages;
   uint64_t* b_full = a_empty + kWgAStages;
   uint64_t* b_empty = b_full + kWgBStages;
@@ -853,7 +860,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int n_slots_total = p.n_taps * p.cblocks;
   const int n_slots = min(p.slots_per_cta, n_slots_total - slot0);
   const int split = blockIdx.z;
-  const int b_stages = kWgBStages / p.planes;
+  const int halo_box_bytes = (p.tile_h + 2) * p.tile_w * 128;  // haloed X box of one plane
+  const int halo_row_bytes = p.tile_w * 128;                   // one image row = one dh shift
+  int b_stages = b_region_bytes / (p.planes * (p.halo ? halo_box_bytes : kWgBBytes));
+  b_stages = b_stages > kWgBStages ? kWgBStages : b_stages;  // the barrier arrays hold kWgBStages entries
   const int pb0 = int((long long)split * p.n_pixblocks / p.splits);
   const int pb1 = int((long long)(split + 1) * p.n_pixblocks / p.splits);
   const bool two_chunks = (co0 + 64) < p.cout;
@@ -871,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       tile_origin(pb, p.tile_h, p.tile_n, p.grid_h, n0, h0);
       FB_DBG_WAIT(0, mbar_wait(&a_empty[as], aphase ^ 1, 11));
       if (elect_one()) {
-        uint8_t* sa = smem_a + as * kWgABytes;
+        uint8_t* sa = smem_a + as * a_stage_bytes;
         mbar_arrive_expect_tx(&a_full[as], two_chunks ? kWgABytes : kATileBytes);
         tma_load_4d(sa, &p.dy_map, &a_full[as], co0, 0, h0, n0);
         if (two_chunks) tma_load_4d(sa + kATileBytes, &p.dy_map, &a_full[as], co0 + 64, 0, h0, n0);
@@ -880,6 +890,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       if (++as == kWgAStages) {
         as = 0;
         aphase ^= 1;
+      }
+      if (p.halo) {  // one haloed box per plane serves the three dh taps of this CTA
+        const fb_wgrad_tap tap = p.taps[slot0 % p.n_taps];
+        const int cb = slot0 / p.n_taps;
+        FB_DBG_WAIT(1, mbar_wait(&b_empty[bs], bphase ^ 1, 12));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[bs], p.planes * halo_box_bytes);
+          for (int pl = 0; pl < p.planes; ++pl)
+            tma_load_4d(smem_b + (bs * p.planes + pl) * halo_box_bytes, &p.x_maps[pl], &b_full[bs], cb * kBlockK, tap.dw,
+                        h0 - 1, n0);
+        }
+        __syncwarp();
+        if (++bs == b_stages) {
+          bs = 0;
+          bphase ^= 1;
+        }
+        continue;
       }
       for (int j = 0; j < n_slots; ++j) {
         const int s = slot0 + j;
@@ -927,9 +954,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       FB_DBG_WAIT(0, mbar_wait(&a_full[as], (pbi / kWgAStages) & 1, 13));
       FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
       // K = 16 pixels = 16 rows of 128 bytes; MN chunks of 64 channels are kATileBytes apart (LBO), groups of 8
-      // pixel rows are 1024 bytes apart (SBO)
-      const uint32_t a_lo = smem_desc_lo(smem_a0 + as * kWgABytes, kATileBytes);
-      const uint32_t b_lo = smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
+      // pixel rows are 1024 bytes apart (SBO).  Halo mode: slot j is the view shifted by j rows of the stage's box and
+      // the hi / lo planes are one box apart.
+      const uint32_t a_lo = smem_desc_lo(smem_a0 + as * a_stage_bytes, kATileBytes);
+      const uint32_t b_lo = p.halo ? smem_desc_lo(smem_b0 + bs * p.planes * halo_box_bytes + j * halo_row_bytes,
+                                                  halo_box_bytes)
+                                   : smem_desc_lo(smem_b0 + bs * p.planes * kWgBBytes, kATileBytes);
       const uint32_t tmem_d = tmem_base + j * 64 * p.planes;
       if (kMmaIssuers == 2 && it > 0) {
         mbar_wait(&turn_bar[me], tphase, 16);
@@ -943,13 +973,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
                            (pbi != 0 || k != 0) ? 1u : 0u);
         if (kMmaIssuers == 2) mbar_arrive(&turn_bar[me ^ 1]);
-        tc_commit(&b_empty[bs]);
+        if (!p.halo || j == n_slots - 1) tc_commit(&b_empty[bs]);
         if (j == n_slots - 1) tc_commit(&a_empty[as]);
         if (it == all_stages - 1) tc_commit(accum_bar);
       }
       __syncwarp();
       if (dbg) dbg_issue += clock64() - t_issue;
-      bs += kMmaIssuers;
+      if (!p.halo) {
+        bs += kMmaIssuers;
+      } else if (j == n_slots - 1) {  // halo mode (single issuer): the B stage advances once per pixel block
+        bs += 1;
+      }
       while (bs >= b_stages) {
         bs -= b_stages;
         bphase ^= 1;
@@ -980,7 +1014,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     tc_fence_after();
     for (int j = 0; j < n_slots; ++j) {
       const int s = slot0 + j;
-      const int tap = s % p.n_taps;
+      const int tap = p.taps[s % p.n_taps].k_index;  // filter position = column block of the partial matrix
       const int cb = s / p.n_taps;
 #pragma unroll 1
       for (int c = eg; c < 4; c += 2) {
@@ -1387,6 +1421,20 @@ extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
   kp.splits = a->splits;
   kp.n_pixblocks = n_pixblocks;
   kp.partial = a->partial;
+  kp.halo = a->halo ? 1 : 0;
+  if (a->halo) {
+    FB_REQUIRE(kMmaIssuers == 1, "fb_conv_wgrad: halo mode needs the single-issuer build");
+    FB_REQUIRE(a->n_taps == 9 && a->slots_per_cta == 3 && a->tile_n == 1 && (a->tile_w * 128) % 1024 == 0,
+               "fb_conv_wgrad: halo mode needs 9 taps, 3 slots per CTA and whole-row tiles of >= 1024 bytes");
+    for (int t = 0; t < 9; t += 3)
+      FB_REQUIRE(a->taps[t].dw == a->taps[t + 1].dw && a->taps[t].dw == a->taps[t + 2].dw && a->taps[t].dh == -1 &&
+                     a->taps[t + 1].dh == 0 && a->taps[t + 2].dh == 1 && a->taps[t].phase == 0,
+                 "fb_conv_wgrad: halo mode needs taps in triples (dh = -1, 0, 1) that share dw");
+    FB_REQUIRE(a->planes * (a->tile_h + 2) * a->tile_w * 128 * 2 <= kWgBStages * kWgBBytes,
+               "fb_conv_wgrad: two haloed stages do not fit");
+  }
+  for (int t = 0; t < a->n_taps; ++t)
+    FB_REQUIRE(a->taps[t].k_index >= 0 && a->taps[t].k_index < a->n_taps, "fb_conv_wgrad: tap %d has a bad k_index", t);
   {
     static const bool debug = [] {
       const char* e = getenv("FB_KERNEL_DEBUG");

@@ -47,14 +47,14 @@ class Conv3x3Args(C.Structure):
 
 
 class WgradTap(C.Structure):
-    _fields_ = [("phase", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("pad", C.c_int8)]
+    _fields_ = [("phase", C.c_int8), ("dh", C.c_int8), ("dw", C.c_int8), ("k_index", C.c_int8)]
 
 
 class WgradArgs(C.Structure):
     _fields_ = [("host_dy_map", vp), ("host_x_maps", vp), ("n_x_maps", i32), ("planes", i32), ("n_taps", i32),
                 ("cblocks", i32), ("taps", WgradTap * FB_MAX_WGRAD_TAPS), ("slots_per_cta", i32), ("cout", i32),
                 ("cin", i32), ("tile_w", i32), ("tile_h", i32), ("tile_n", i32), ("grid_h", i32), ("grid_n", i32),
-                ("splits", i32), ("partial", vp)]
+                ("splits", i32), ("partial", vp), ("halo", i32)]
 
 
 class WprepEntry(C.Structure):

@@ -390,18 +390,35 @@ class Conv2dPlan:
         dym = MapSet(1)
         encode_act(dym, 0, dy, n, ho, wo, cout, tile)
         self.dy_map_w = dym
-        wa.host_dy_map, wa.host_x_maps = dym.addr, xs.addr
-        wa.n_x_maps, wa.planes = xs.n, planes
-        wa.n_taps, wa.cblocks = taps, cb_in
-        for kh in range(k):
-            for kw in range(k):
-                phase, dh, dw = tap_geom(kh, kw)
-                wa.taps[kh * k + kw] = L.WgradTap(phase, dh, dw, 0)
         n_slots = taps * cb_in
-        spc = self._slots_per_cta(n_slots, planes)
         co_tiles = -(-cout // 128)
-        groups = -(-n_slots // spc)
         n_pixblocks = m_tiles
+        halo_w = self._wgrad_halo(k, stride, tile, planes)
+        if halo_w:
+            # taps in triples that share dw: per pixel block ONE haloed X box (tile_h + 2 rows) serves dh = -1, 0, +1
+            hx = MapSet(planes)
+            for pl, t in enumerate((x_hi, x_lo)[:planes]):
+                encode_act(hx, pl, t, n, h, w, cin, (tile[0], tile[1] + 2, 1))
+            self.x_maps_halo = hx
+            wa.host_x_maps, wa.n_x_maps = hx.addr, hx.n
+            i = 0
+            for dwi in (-1, 0, 1):
+                for dhi in (-1, 0, 1):
+                    wa.taps[i] = L.WgradTap(0, dhi, dwi, (dhi + 1) * 3 + (dwi + 1))
+                    i += 1
+            spc = 3
+            wa.halo = 1
+        else:
+            wa.host_x_maps, wa.n_x_maps = xs.addr, xs.n
+            for kh in range(k):
+                for kw in range(k):
+                    phase, dh, dw = tap_geom(kh, kw)
+                    wa.taps[kh * k + kw] = L.WgradTap(phase, dh, dw, kh * k + kw)
+            spc = self._slots_per_cta(n_slots, planes)
+        wa.host_dy_map = dym.addr
+        wa.planes = planes
+        wa.n_taps, wa.cblocks = taps, cb_in
+        groups = -(-n_slots // spc)
         splits = max(1, min(n_pixblocks, NUM_SMS // (co_tiles * groups)))
         wa.slots_per_cta = spc
         wa.cout, wa.cin = cout, cin
@@ -415,6 +432,14 @@ class Conv2dPlan:
         wa.partial = partial.data_ptr()
         self.wargs = wa
         self.splits = splits
+
+    @staticmethod
+    def _wgrad_halo(k, stride, tile, planes):
+        """Haloed X boxes for wgrad: 3x3 / stride 1 on maps whose 128-pixel tiles are whole rows of one image with
+        1024-byte-aligned rows, two stages of `planes` boxes within the 128 KB X ring (fb_wgrad_args.halo)."""
+        if os.environ.get("FB_WGRAD_HALO", "1") != "1" or k != 3 or stride != 1 or tile[2] != 1:
+            return False
+        return (tile[0] * 128) % 1024 == 0 and planes * (tile[1] + 2) * tile[0] * 128 * 2 <= 128 * 1024
 
     @staticmethod
     def _slots_per_cta(n_slots, planes):
@@ -437,6 +462,8 @@ class Conv2dPlan:
             spc = Conv2dPlan._slots_per_cta(n_slots, pl)
             splits = max(1, min(m_tiles, NUM_SMS // ((-(-cout // 128)) * (-(-n_slots // spc)))))
             worst = max(worst, splits)
+            if k == 3 and stride == 1 and tile[2] == 1:  # haloed variant: 3 slots per CTA
+                worst = max(worst, max(1, min(m_tiles, NUM_SMS // ((-(-cout // 128)) * (-(-n_slots // 3))))))
         return worst * cout * taps * cin
 
     def forward(self):

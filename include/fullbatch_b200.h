@@ -119,7 +119,8 @@ typedef struct {
 int fb_conv3x3(const fb_conv3x3_args* args, void* stream);
 
 typedef struct {
-  int8_t phase, dh, dw, pad;
+  int8_t phase, dh, dw;
+  int8_t k_index; /* filter position this tap's gradient belongs to: partial column block k_index*cin (kh*k + kw) */
 } fb_wgrad_tap;
 
 /* Weight gradient: partial[split][co][tap*cin + ci] = sum_{pixels of split} dY[pixel, co] * X[pixel + tap shift, ci]
@@ -136,6 +137,11 @@ typedef struct {
   int32_t grid_h, grid_n; /* dY pixel grid */
   int32_t splits;         /* split-K over 128-pixel blocks */
   float* partial;         /* [splits][cout][n_taps*cin] fp32 */
+  /* halo != 0 (3x3 / stride 1, tile_n == 1, tile_w * 128 B a multiple of 1024): taps are ordered in triples that share
+   * dw (dh = -1, 0, +1), slots_per_cta == 3, and the X maps have boxes of tile_h + 2 rows: per pixel block and triple
+   * ONE haloed X box is fetched and the three row shifts are aligned views of it (a third less operand traffic for a
+   * kernel that is bound by it). */
+  int32_t halo;
 } fb_wgrad_args;
 int fb_conv_wgrad(const fb_wgrad_args* args, void* stream);
 

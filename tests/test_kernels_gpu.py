@@ -82,13 +82,15 @@ CONV_CASES = [
 @pytest.fixture(params=["halo", "generic"], autouse=True)
 def conv_path(request, monkeypatch):
     """3x3/stride-1 convs run through the generic per-tap kernel by default; the haloed-box kernel (FB_HALO=1) must stay
-    correct for the same shapes."""
+    correct for the same shapes.  The same switch selects the haloed (default) / per-tap wgrad variant."""
     if request.param == "halo":
         if "conv" not in request.node.name:
             pytest.skip("only conv tests depend on the conv path")
         monkeypatch.setenv("FB_HALO", "1")
+        monkeypatch.setenv("FB_WGRAD_HALO", "1")
     else:
         monkeypatch.delenv("FB_HALO", raising=False)
+        monkeypatch.setenv("FB_WGRAD_HALO", "0")
     return request.param
 
 
