@@ -104,6 +104,10 @@ struct alignas(64) ConvGemmKParams {
   int accumulate;
   float* stats;  // optional [gridDim.x / n_tiles][2][n_total]: per-CTA column sums / sums of squares of the output
   int n_total;
+  // BatchNorm-backward statistics instead (fb_conv_gemm_args.bwd_y): sums of d*m and d*m*xhat of the stored gradient d
+  const float* bwd_y;
+  const __nv_bfloat16* bwd_mask;
+  const float *bwd_mean, *bwd_rstd;
   // development switch (env FB_CONV_EXPERIMENT, results are WRONG when set): 1 = epilogue without global stores,
   // 2 = epilogue only hands the accumulator back, 4 = producer stops fetching after the first ring fill
   int experiment;
@@ -401,8 +405,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         } else {
           tmem_ld_wait();
         }
+        EpiBwd bwd;
+        int stat_mode = p.stats ? kEpiStatFwd : kEpiStatNone;
+        if (p.bwd_y) {
+          stat_mode = kEpiStatBwd;
+          bwd.y = p.bwd_y;
+          bwd.mask = p.bwd_mask;
+          const int col = n_tile0 + c * 16 + (lane & 3) * 4;
+          const float4 mu = *reinterpret_cast<const float4*>(p.bwd_mean + col);
+          const float4 rs = *reinterpret_cast<const float4*>(p.bwd_rstd + col);
+          bwd.mu[0] = mu.x; bwd.mu[1] = mu.y; bwd.mu[2] = mu.z; bwd.mu[3] = mu.w;
+          bwd.rs[0] = rs.x; bwd.rs[1] = rs.y; bwd.rs[2] = rs.z; bwd.rs[3] = rs.w;
+        }
         warp_store_rows16(stage, v, p.out, row_off, valid && !(p.experiment & 1), c * 16, p.accumulate != 0, lane,
-                          col_acc[cc], p.stats != nullptr);
+                          col_acc[cc], stat_mode, bwd);
       }
       tc_fence_before();
       __syncwarp();
@@ -1302,6 +1318,12 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.accumulate = a->accumulate;
   kp.stats = a->stats_out;
   kp.n_total = a->n_total;
+  kp.bwd_y = a->bwd_y;
+  kp.bwd_mask = static_cast<const __nv_bfloat16*>(a->bwd_mask);
+  kp.bwd_mean = a->bwd_mean;
+  kp.bwd_rstd = a->bwd_rstd;
+  FB_REQUIRE(!a->bwd_y || (a->stats_out && a->bwd_mean && a->bwd_rstd && a->n_groups <= 1),
+             "fb_conv_gemm: bwd_y needs stats_out, bwd_mean, bwd_rstd and a single tap group");
   FB_REQUIRE(a->n_groups >= 0 && a->n_groups <= 4, "fb_conv_gemm: n_groups must be in 0..4");
   FB_REQUIRE(a->n_groups <= 1 || !a->stats_out, "fb_conv_gemm: tap groups cannot be combined with stats_out");
   kp.n_groups = a->n_groups > 0 ? a->n_groups : 1;

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) 
 }
 
 struct BnFusedBwdArgs {
-  fb_bn_bwd_args bw;       // dA, dA2, mask, y, mean, rstd, gamma, P, C, ws, dgamma, dbeta, dy, dz_out
+  fb_bn_bwd_args bw;       // dA, dA2, mask, y, mean, rstd, gamma, P, C, ws, dgamma, dbeta, dy, dz_out, (stats, stats_rows)
   float* partial;          // [grid][2][C]
   float* coef;             // [2][C]
   unsigned int* counters;  // [2]
@@ -538,14 +538,23 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) 
   const long long r0 = (long long)blockIdx.x * a.rows_per_block;
   const long long r1 = min(P, r0 + a.rows_per_block);
   const long long block_stride = 2LL * C;
-  block_column_sums<true>(bw.y, bw.dA, bw.dA2, static_cast<const bf16*>(bw.mask_hi), bw.mean, bw.rstd, r0, r1, C,
-                          a.partial + blockIdx.x * block_stride, red);
-  grid_barrier(a.counters, gridDim.x);
+  // statistics already reduced per CTA by the dgrad that produced dA (fb_conv_gemm_args.bwd_y): no first pass, one barrier
+  const bool external = bw.stats != nullptr;
+  unsigned int barrier_target = gridDim.x;
+  if (!external) {
+    block_column_sums<true>(bw.y, bw.dA, bw.dA2, static_cast<const bf16*>(bw.mask_hi), bw.mean, bw.rstd, r0, r1, C,
+                            a.partial + blockIdx.x * block_stride, red);
+    grid_barrier(a.counters, gridDim.x);
+    barrier_target = 2 * gridDim.x;
+  }
   {
     const int lane = threadIdx.x & 31;
     for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < C; c += gridDim.x * 8) {
       double s1, s2;
-      warp_reduce_partials(a.partial, block_stride, gridDim.x, C, c, lane, s1, s2);
+      if (external)
+        warp_reduce_partials(bw.stats, 2LL * C, bw.stats_rows, C, c, lane, s1, s2);
+      else
+        warp_reduce_partials(a.partial, block_stride, gridDim.x, C, c, lane, s1, s2);
       if (lane == 0) {
         bw.dbeta[c] = float(s1);
         bw.dgamma[c] = float(s2);
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) 
       }
     }
   }
-  grid_barrier(a.counters, 2 * gridDim.x);
+  grid_barrier(a.counters, barrier_target);
   grid_barrier_release(a.counters);
   // the rows are walked BACKWARDS: phase 1 read them front to back, so the tail of this block's slice is what L2 still
   // holds when the whole tensor set (up to 117 MB on the 32x32 stage) does not fit
@@ -1326,6 +1335,8 @@ extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
                  bw->dy_bf16,
              "fb_bn_bwd_fused: null pointer");
   FB_REQUIRE(!bw->dz_accumulate, "fb_bn_bwd_fused: dz_accumulate is not supported");
+  FB_REQUIRE(!bw->stats || (bw->stats_rows > 0 && !bw->dA2),
+             "fb_bn_bwd_fused: epilogue statistics need stats_rows > 0 and a single gradient addend");
   int grid, rpb;
   if (fused_geometry(bw->P, bw->C, grid, rpb)) {
     set_error("fb_bn_bwd_fused: unsupported channel count %d", bw->C);

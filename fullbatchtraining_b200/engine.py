@@ -89,13 +89,23 @@ class Unit:
         self.dx_accumulate, self.needs_dx = dx_accumulate, needs_dx
         self.dx_target = dx_target  # fp32 buffer receiving the input gradient (default: x.grad)
         self.plans = None
+        # unit whose BatchNorm(+ReLU) output is this unit's input and has no other consumer (conv1 -> conv2 inside a
+        # block): this unit's dgrad epilogue then reduces that BatchNorm's backward statistics
+        self.bn_producer = None
 
     def finish(self, eng):
         self.plans = [ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
                                      (self.dx_target if self.dx_target is not None else self.x.grad)
                                      if self.needs_dx else None, *self.w[i], eng.partial,
                                      dx_accumulate=self.dx_accumulate, split=eng.split,
-                                     alg_k=27 if self.stem else None, fuse_stats=eng.fuse_stats) for i in range(2)]
+                                     alg_k=27 if self.stem else None, fuse_stats=eng.fuse_stats,
+                                     dgrad_bn=self._dgrad_bn(eng)) for i in range(2)]
+
+    def _dgrad_bn(self, eng):
+        v = self.bn_producer
+        if v is None or not eng.fuse_bwd_stats or self.dx_target is not None or self.dx_accumulate:
+            return None
+        return v.y, v.out.hi, v.mean, v.rstd
 
 
 class Block:
@@ -133,6 +143,10 @@ class FullBatchEngine:
         self.partial_elems = 0
         # BatchNorm statistics in the conv epilogue (FB_FUSE_STATS=0: statistics pass inside the BatchNorm kernel)
         self.fuse_stats = os.environ.get("FB_FUSE_STATS", "1") == "1"
+        # BatchNorm-backward statistics from the epilogue of the dgrad that produces the BatchNorm's upstream gradient
+        # (conv2 -> bn1 of every block).  Opt-in: measured -1.5 % on B200 -- the epilogue has to pull the BatchNorm's
+        # pre-activation and ReLU mask from HBM, which costs the tensor-core kernel more than the skipped pass saves.
+        self.fuse_bwd_stats = os.environ.get("FB_FUSE_BWD_STATS", "0") == "1"
         dev = self.device
 
         # ---- flat parameter buffers, parameters() order
@@ -187,6 +201,9 @@ class FullBatchEngine:
                     k, st = conv.kernel_size[0], conv.stride[0]
                     u = Unit(self, f"{pre}.{cn}", f"{pre}.{bnn}", x, conv.out_channels, k, st)
                     u.out = Act(x.n, u.ho, u.wo, conv.out_channels, self.split, dev)
+                    if i > 0:
+                        u.bn_producer = blk.units[i - 1]
+                        blk.units[i - 1].bn_consumer = u
                     blk.units.append(u)
                     x = u.out
                     max_c = max(max_c, conv.out_channels)
@@ -340,9 +357,11 @@ class FullBatchEngine:
     def _unit_backward(self, u, P, G, act, dz_out=None):
         """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
         ga, _ = self._bn_params(u, P)
+        consumer = getattr(u, "bn_consumer", None)  # the unit whose dgrad produced act.grad and its statistics
+        stats = consumer.plans[self._pass].dgrad_stats if (consumer is not None and act.grad2 is None) else None
         ops.bn_bwd_fused(act.grad, act.hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
                          self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out,
-                         dA2=act.grad2)
+                         dA2=act.grad2, stats=stats)
         gw = self._view(G, u.conv_name + ".weight")
         plan = u.plans[self._pass]
         # wgrad (+ its split-K reduction) only feeds the flat gradient: it runs on a side stream, concurrently with the

@@ -36,7 +36,8 @@ class ConvGemmArgs(C.Structure):
                 ("n_taps", i32), ("cblocks", i32), ("taps", Tap * FB_MAX_TAPS), ("tile_w", i32), ("tile_h", i32),
                 ("tile_n", i32), ("grid_h", i32), ("grid_n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("stats_out", vp),
-                ("n_groups", i32), ("groups", TapGroup * 4)]
+                ("n_groups", i32), ("groups", TapGroup * 4), ("bwd_y", vp), ("bwd_mask", vp), ("bwd_mean", vp),
+                ("bwd_rstd", vp)]
 
 
 class Conv3x3Args(C.Structure):
@@ -70,7 +71,8 @@ class BnApplyArgs(C.Structure):
 
 class BnBwdArgs(C.Structure):
     _fields_ = [("dA", vp), ("dA2", vp), ("mask_hi", vp), ("y", vp), ("mean", vp), ("rstd", vp), ("gamma", vp), ("P", i64), ("C", i32),
-                ("ws", vp), ("dgamma", vp), ("dbeta", vp), ("dy_bf16", vp), ("dz_out", vp), ("dz_accumulate", i32)]
+                ("ws", vp), ("dgamma", vp), ("dbeta", vp), ("dy_bf16", vp), ("dz_out", vp), ("dz_accumulate", i32),
+                ("stats", vp), ("stats_rows", i32)]
 
 
 _SIGNATURES = {

@@ -264,7 +264,7 @@ class Conv2dPlan:
     """
 
     def __init__(self, n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
-                 dx_accumulate=False, split=True, alg_k=None, fuse_stats=False):
+                 dx_accumulate=False, split=True, alg_k=None, fuse_stats=False, dgrad_bn=None):
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.n, self.h, self.w, self.cin, self.cout, self.k, self.stride = n, h, w, cin, cout, k, stride
@@ -331,8 +331,10 @@ class Conv2dPlan:
             a.stats_out = buf.data_ptr()
             self.stats = (buf, rows)
 
-        # ---- dgrad
+        # ---- dgrad.  dgrad_bn = (y, mask_hi, mean, rstd) of the BatchNorm(+ReLU) whose upstream gradient is `dx` and has
+        # no other producer: the dgrad epilogue then also reduces that BatchNorm's backward statistics (dgrad_stats).
         self.dgrads = []
+        self.dgrad_stats = None
         if dx is not None:
             dys = MapSet(1)
             encode_act(dys, 0, dy, n, ho, wo, cout, tile)
@@ -358,6 +360,16 @@ class Conv2dPlan:
                 self.dgrads.append(ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, n, cin, dx, 0,
                                             (h * w * cin, w * cin, cin), dx_accumulate, n_tile_d))
                 self.dgrads[-1].flops = self.alg_flops
+                if dgrad_bn is not None and not dx_accumulate:
+                    by, bmask, bmean, brstd = dgrad_bn
+                    a = self.dgrads[-1].args
+                    rows = L.load().fb_conv_stats_rows(m_tiles_d, cin // n_tile_d)
+                    buf = torch.zeros(rows, 2, cin, device=dx.device)
+                    a.stats_out = buf.data_ptr()
+                    a.bwd_y, a.bwd_mask = by.data_ptr(), L.ptr(bmask)
+                    a.bwd_mean, a.bwd_rstd = bmean.data_ptr(), brstd.data_ptr()
+                    self.dgrad_stats = (buf, rows)
+                    self._dgrad_bn_keep = dgrad_bn
             else:
                 # stride 2: output pixel (2i+ph, 2j+pw) gathers taps kh with (ph + 1 - kh) even: ho = i + (ph+1-kh)/2
                 def taps_for(par):
@@ -586,13 +598,16 @@ def bn_fwd_fused(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, ws, running=
           L.ptr(rm2), L.ptr(rv2), momentum, eps, ws.data_ptr(), st, st_rows, st2, st_rows2)
 
 
-def bn_bwd_fused(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None):
+def bn_bwd_fused(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None, stats=None):
+    """stats = (buffer, rows): partial sums written by the dgrad that produced dA (Conv2dPlan.dgrad_stats)."""
     a = L.BnBwdArgs()
     a.dA, a.dA2, a.mask_hi, a.y, a.mean, a.rstd, a.gamma = dA.data_ptr(), L.ptr(dA2), L.ptr(mask_hi), y.data_ptr(), \
         mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
     a.P, a.C, a.ws = P, Cc, ws.data_ptr()
     a.dgamma, a.dbeta, a.dy_bf16 = dgamma.data_ptr(), dbeta.data_ptr(), dy.data_ptr()
     a.dz_out, a.dz_accumulate = L.ptr(dz_out), 0
+    if stats is not None:
+        a.stats, a.stats_rows = stats[0].data_ptr(), stats[1]
     per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0) + \
         (4.0 if dA2 is not None else 0.0)
     _call("bn_bwd", per_elem * P * Cc, "byte", "fb_bn_bwd_fused", C.byref(a))

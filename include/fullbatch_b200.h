@@ -86,6 +86,15 @@ typedef struct {
     int32_t tap0, n_taps;
     int64_t out_off;
   } groups[4];
+  /* optional BatchNorm-BACKWARD statistics of the stored tensor (a dgrad whose output is the upstream gradient dA of a
+   * BatchNorm + ReLU): with bwd_y != NULL, stats_out receives per-CTA sums of dA*m and dA*m*xhat instead, where
+   * m = (bwd_mask > 0) (bf16 post-activation plane, may be NULL) and xhat = (bwd_y - bwd_mean) * bwd_rstd; bwd_y and
+   * bwd_mask have the layout of `out`.  Feed them to fb_bn_bwd_fused (fb_bn_bwd_args.stats): its first pass over
+   * dA / y / mask and one grid barrier disappear.  Requires a single producer of dA (accumulate == 0, one tap group). */
+  const float* bwd_y;
+  const void* bwd_mask;
+  const float* bwd_mean;
+  const float* bwd_rstd;
 } fb_conv_gemm_args;
 /* number of partial rows written to stats_out for a problem of m_tiles x (n_total / n_tile) tiles */
 int fb_conv_stats_rows(int m_tiles, int n_tiles);
@@ -217,6 +226,10 @@ typedef struct {
   void* dy_bf16;
   float* dz_out;
   int32_t dz_accumulate;
+  /* fb_bn_bwd_fused only: per-CTA partial sums [stats_rows][2][C] of dA*m and dA*m*xhat written by the dgrad that
+   * produced dA (fb_conv_gemm_args.bwd_y); NULL: the kernel reduces them itself. */
+  const float* stats;
+  int32_t stats_rows;
 } fb_bn_bwd_args;
 int fb_bn_bwd(const fb_bn_bwd_args* args, void* stream);
 

@@ -588,3 +588,54 @@ def test_conv_forward_fused_statistics(case):
     for other in outs[1:]:
         for u, v in zip(outs[0], other):
             assert rel_err(u, v) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(4, 32, 32, 64, 64, 3, 1), (8, 16, 16, 128, 128, 3, 1), (16, 8, 8, 256, 128, 1, 1),
+                                  (16, 4, 4, 512, 512, 3, 1)], ids=lambda c: "x".join(map(str, c)))
+def test_dgrad_epilogue_bn_backward_statistics(case, conv_path):
+    """BatchNorm-backward statistics fused into the dgrad epilogue (fb_conv_gemm_args.bwd_y): sums of dA*m and
+    dA*m*xhat of the stored gradient, and fb_bn_bwd_fused consuming them gives what its own first pass gives."""
+    if conv_path == "halo":
+        pytest.skip("the haloed kernel has no backward-statistics epilogue")
+    n, h, w, cin, cout, k, stride = case
+    g = torch.Generator(device="cuda").manual_seed(5)
+    wt = torch.randn(cout, cin, k, k, device=DEV, generator=g) * (2.0 / (cout * k * k)) ** 0.5
+    gy = torch.randn(n, cout, h, w, device=DEV, generator=g) * 1e-2
+    x_hi, x_lo = split(torch.randn(n, h, w, cin, device=DEV, generator=g))
+    taps = k * k
+    wf_hi = torch.zeros(cout, taps * cin, device=DEV, dtype=torch.bfloat16)
+    wf_lo, wd_hi = torch.zeros_like(wf_hi), torch.zeros(cin, taps * cout, device=DEV, dtype=torch.bfloat16)
+    wd_lo = torch.zeros_like(wd_hi)
+    ops.weight_prep(wt, cout, cin, taps, wf_hi, wf_lo, wd_hi, wd_lo)
+    y = torch.empty(n, h, w, cout, device=DEV)
+    dy = nhwc(gy).to(torch.bfloat16)
+    dx = torch.full((n, h, w, cin), float("nan"), device=DEV)
+    # the BatchNorm(+ReLU) that produced the conv input: its pre-activation, output plane, mean, rstd
+    P = n * h * w
+    by = torch.randn(P, cin, device=DEV, generator=g) * 1.3 + 0.2
+    bmean, bvar = by.mean(0), by.var(0, unbiased=False)
+    brstd = torch.rsqrt(bvar + 1e-5)
+    gamma = torch.rand(cin, device=DEV, generator=g) + 0.5
+    act = torch.relu((by - bmean) * brstd * gamma + 0.1 * torch.randn(cin, device=DEV, generator=g))
+    mask_hi = act.to(torch.bfloat16)
+    partial = torch.empty(ops.Conv2dPlan.partial_elems(n, h, w, cin, cout, k, stride), device=DEV)
+    plan = ops.Conv2dPlan(n, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wf_hi, wf_lo, wd_hi, wd_lo, partial,
+                          dgrad_bn=(by, mask_hi, bmean, brstd))
+    assert plan.dgrad_stats is not None
+    plan.dgrad()
+    buf, rows = plan.dgrad_stats
+    d = dx.double().reshape(P, cin)
+    m = (mask_hi.double() > 0).double()
+    xhat = (by.double() - bmean.double()) * brstd.double()
+    s1, s2 = buf[:, 0].double().sum(0), buf[:, 1].double().sum(0)
+    assert rel_err(s1, (d * m).sum(0)) < 1e-5
+    assert rel_err(s2, (d * m * xhat).sum(0)) < 1e-5
+    ws = torch.zeros(2 * cin * 1024, device=DEV)
+    outs = []
+    for stats in (None, plan.dgrad_stats):
+        dg, db = torch.empty(cin, device=DEV), torch.empty(cin, device=DEV)
+        dyo = torch.empty(P, cin, device=DEV, dtype=torch.bfloat16)
+        ops.bn_bwd_fused(dx, mask_hi, by, bmean, brstd, gamma, P, cin, ws, dg, db, dyo, stats=stats)
+        outs.append((dg, db, dyo.double()))
+    for u, v in zip(*outs):
+        assert rel_err(u, v) < 2e-4
