@@ -1342,7 +1342,12 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
       kp.group_off[g] = a->groups[g].out_off;
     }
   {
-    const char* e = getenv("FB_CONV_EXPERIMENT");  // read per call: development only
+    // development only (tools/conv_experiments.py): honoured only together with FB_KERNEL_DEBUG=1, read per call
+    static const bool dev = [] {
+      const char* d = getenv("FB_KERNEL_DEBUG");
+      return d && d[0] == '1';
+    }();
+    const char* e = dev ? getenv("FB_CONV_EXPERIMENT") : nullptr;
     kp.experiment = e ? atoi(e) : 0;
   }
   FB_REQUIRE(!a->stats_out || !a->accumulate, "fb_conv_gemm: column statistics need accumulate == 0");

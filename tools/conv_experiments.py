@@ -3,6 +3,7 @@ kernel switched off through FB_CONV_EXPERIMENT (1 = no global stores, 2 = no epi
 import os
 import sys
 
+os.environ["FB_KERNEL_DEBUG"] = "1"  # the experiment switch is only honoured in debug mode
 sys.path.insert(0, ".")
 import torch  # noqa: E402
 
