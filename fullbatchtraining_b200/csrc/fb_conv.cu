@@ -4,12 +4,14 @@
 //                      A = NHWC activation boxes fetched by 4-D TMA with a per-tap spatial shift (halo / padding comes
 //                      from TMA out-of-bounds zero fill), B = weight rows, both K-major SWIZZLE_128B tiles, fp32
 //                      accumulation in double-buffered TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-//                      Serves conv forward, dgrad (stride 1 and the 4 phases of stride 2), 1x1 convs and the
-//                      im2col'ed stem.  A pipeline stage holds the hi and lo bf16 planes of both operands; the
-//                      hi*hi + hi*lo + lo*hi products are three MMA groups on the same stage.
+//                      Serves conv forward, dgrad (stride 1; the 4 phases of stride 2 as tap groups of one launch), 1x1
+//                      convs and the im2col'ed stem.  A pipeline stage holds the hi and lo bf16 planes of both
+//                      operands; hi*hi + hi*lo + lo*hi are "stacked" instructions on the same stage (ConvGemmCfg).
+//                      352 threads: TMA producer warp, MMA issuer warp (warp-converged, elected lane), 8 epilogue warps.
+//   conv3x3_kernel   : opt-in haloed-box variant for 3x3 / stride 1 (row shifts are aligned views of one box).
 //   wgrad_kernel     : partial[co, (tap,ci)] = sum_pixels dY[pixel, co] * X[pixel + tap, ci]; both operands are
 //                      MN-major (the channel dimension is contiguous in NHWC), split-K over 128-pixel blocks,
-//                      up to 8 (tap, ci-block) accumulators of 64 TMEM columns per CTA.
+//                      up to 8 (tap, ci-block) accumulators of 64 TMEM columns per CTA; haloed X boxes on 32x32 / 16x16.
 //
 // Reference call sites replaced: torch.nn.Conv2d forward (fullbatch/models/resnets.py:69-73,206-210,285-291) and its
 // autograd backward (fullbatch/training/training.py:82, fullbatch/models/modules.py:230).
@@ -84,7 +86,7 @@ static int encode(void* blob, const void* base, int rank, const cuuint64_t* dims
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// conv_gemm_kernel: persistent, warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), double-buffered TMEM
+// conv_gemm_kernel: persistent, warp-specialised (TMA producer / MMA issuer / 8 epilogue warps), double-buffered TMEM
 // ---------------------------------------------------------------------------------------------------------------
 struct alignas(64) ConvGemmKParams {
   CUtensorMap a_maps[FB_MAX_A_MAPS];
@@ -146,7 +148,7 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
 // Flush of the per-lane column statistics collected by the epilogue (BatchNorm statistics fused into the producing
 // convolution).  acc[c][0..3] / acc[c][4..7] of lane l are the sums / sums of squares of columns
 // c*16 + 4*(l%4) .. +3 over the rows the lane stored (rows = lane/4 mod 8).  Fixed order: shuffle tree over the 8 row
-// groups, then the four epilogue warps through the staging patch; one partial row stats[row][0 = sum | 1 = sq][channel].
+// groups, then the eight epilogue warps through the staging patch; one partial row stats[row][0 = sum | 1 = sq][channel].
 template <int N_TILE>
 __device__ __forceinline__ void flush_column_stats(float* epi_stage, float (&acc)[N_TILE / 32][8], int q, int eg, int lane,
                                                    float* stats, int row, int n_total, int n_tile0) {
