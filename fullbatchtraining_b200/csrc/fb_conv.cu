@@ -967,7 +967,40 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       j -= n_slots;
       ++pbi;
     }
-    for (int it = me; it < total_stages; it += kMmaIssuers) {
+    if (p.halo && me == 0) {
+      // halo mode: the three dh slots of a pixel block share ONE X stage -> one wait / elect / commit round per pixel
+      // block (24 MMAs) instead of three (the issuing warp's per-round work is dead time for the tensor pipe)
+      for (int pb = 0; pb < pb1 - pb0; ++pb) {
+        const int as = pb % kWgAStages;
+        FB_DBG_WAIT(0, mbar_wait(&a_full[as], (pb / kWgAStages) & 1, 13));
+        FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
+        const uint32_t a_lo = smem_desc_lo(smem_a0 + as * a_stage_bytes, kATileBytes);
+        const uint32_t b0_lo = smem_desc_lo(smem_b0 + bs * p.planes * halo_box_bytes, halo_box_bytes);
+        tc_fence_after();
+        const long long t_issue = dbg ? clock64() : 0;
+        if (elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            const uint32_t b_lo = b0_lo + ((jj * halo_row_bytes) >> 4);
+            const uint32_t tmem_d = tmem_base + jj * 64 * p.planes;
+#pragma unroll
+            for (int k = 0; k < kTileM / 16; ++k)
+              tc_mma_bf16_lohi(tmem_d, a_lo + ((k * 2048) >> 4), b_lo + ((k * 2048) >> 4), desc_hi, desc_hi, idesc,
+                               (pb != 0 || k != 0) ? 1u : 0u);
+          }
+          tc_commit(&b_empty[bs]);
+          tc_commit(&a_empty[as]);
+          if (pb == pb1 - pb0 - 1) tc_commit(accum_bar);
+        }
+        __syncwarp();
+        if (dbg) dbg_issue += clock64() - t_issue;
+        if (++bs == b_stages) {
+          bs = 0;
+          bphase ^= 1;
+        }
+      }
+    }
+    for (int it = me; it < (p.halo ? 0 : total_stages); it += kMmaIssuers) {
       const int as = pbi % kWgAStages;
       FB_DBG_WAIT(0, mbar_wait(&a_full[as], (pbi / kWgAStages) & 1, 13));
       FB_DBG_WAIT(1, mbar_wait(&b_full[bs], bphase, 14));
