@@ -231,21 +231,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // instruction writes 8 rows x 64 contiguous bytes (16 full sectors).  row_off / valid describe THIS lane's row.
 constexpr int kEpiPitch = 20;                       // floats per staged row
 constexpr int kEpiWarpFloats = 32 * kEpiPitch;      // 2560 B per warp
-// Column statistics collected while storing (stat[0..3] / stat[4..7] of a lane belong to columns
-// col0 + 4*(lane%4) .. +3 of the rows it stores; the lanes are combined once per kernel, flush_column_stats):
-//   kEpiStatFwd: sum x, sum x^2            -> the BatchNorm FORWARD that consumes the stored conv output;
-//   kEpiStatBwd: sum d*m, sum d*m*xhat     -> the BatchNorm BACKWARD whose upstream gradient d is being stored:
-//                m = ReLU mask of that BatchNorm's output, xhat = (y - mean)*rstd of its input y (same layout as d).
-constexpr int kEpiStatNone = 0, kEpiStatFwd = 1, kEpiStatBwd = 2;
-struct EpiBwd {
-  const float* y;
-  const __nv_bfloat16* mask;  // may be nullptr (no ReLU)
-  float mu[4], rs[4];          // mean / rstd of this lane's four columns
-};
-
+// With do_stat the column sums / sums of squares of the stored values are collected on the way (stat[0..3] / stat[4..7]
+// of a lane belong to columns col0 + 4*(lane%4) .. +3 of the rows it stores; the lanes are combined per super-tile,
+// flush_column_stats): the statistics of the BatchNorm that consumes the stored conv output.
 __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
                                                   bool valid, int col0, bool accumulate, int lane, float (&stat)[8],
-                                                  int stat_mode, const EpiBwd& bwd) {
+                                                  bool do_stat) {
   float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -255,8 +246,7 @@ __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (
   const int sub = lane >> 2;
   const int c4 = (lane & 3) * 4;
   long long eoff[4];
-  float4 e[4], yv[4];
-  uint2 mv[4];
+  float4 e[4];
   bool ok[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // all global loads first: independent requests in flight
@@ -266,34 +256,14 @@ __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (
     eoff[i] = off + col0 + c4;
     e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (accumulate && ok[i]) e[i] = *reinterpret_cast<const float4*>(base + eoff[i]);
-    if (stat_mode == kEpiStatBwd) {
-      yv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      mv[i] = make_uint2(0x3f803f80u, 0x3f803f80u);  // bf16 1.0: mask open
-      if (ok[i]) {
-        yv[i] = *reinterpret_cast<const float4*>(bwd.y + eoff[i]);
-        if (bwd.mask) mv[i] = *reinterpret_cast<const uint2*>(bwd.mask + eoff[i]);
-      }
-    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = i * 8 + sub;
     float4 o = *reinterpret_cast<const float4*>(stage + row * kEpiPitch + c4);
-    if (stat_mode == kEpiStatFwd) {
+    if (do_stat) {  // rows of out-of-range images are exact zeros (TMA zero fill): they do not disturb the sums
       stat[0] += o.x; stat[1] += o.y; stat[2] += o.z; stat[3] += o.w;
       stat[4] += o.x * o.x; stat[5] += o.y * o.y; stat[6] += o.z * o.z; stat[7] += o.w * o.w;
-    } else if (stat_mode == kEpiStatBwd) {
-      if (ok[i]) {
-        const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mv[i].x));
-        const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mv[i].y));
-        const float dx = m01.x > 0.f ? o.x : 0.f, dy = m01.y > 0.f ? o.y : 0.f;
-        const float dz = m23.x > 0.f ? o.z : 0.f, dw = m23.y > 0.f ? o.w : 0.f;
-        stat[0] += dx; stat[1] += dy; stat[2] += dz; stat[3] += dw;
-        stat[4] += dx * (yv[i].x - bwd.mu[0]) * bwd.rs[0];
-        stat[5] += dy * (yv[i].y - bwd.mu[1]) * bwd.rs[1];
-        stat[6] += dz * (yv[i].z - bwd.mu[2]) * bwd.rs[2];
-        stat[7] += dw * (yv[i].w - bwd.mu[3]) * bwd.rs[3];
-      }
     }
     o.x += e[i].x; o.y += e[i].y; o.z += e[i].z; o.w += e[i].w;
     if (ok[i]) *reinterpret_cast<float4*>(base + eoff[i]) = o;
@@ -302,18 +272,9 @@ __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (
 }
 
 __device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
-                                                  bool valid, int col0, bool accumulate, int lane, float (&stat)[8],
-                                                  bool do_stat) {
-  EpiBwd none = {};
-  warp_store_rows16(stage, v, base, row_off, valid, col0, accumulate, lane, stat, do_stat ? kEpiStatFwd : kEpiStatNone,
-                    none);
-}
-
-__device__ __forceinline__ void warp_store_rows16(float* stage, const uint32_t (&v)[16], float* base, long long row_off,
                                                   bool valid, int col0, bool accumulate, int lane) {
   float unused[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  EpiBwd none = {};
-  warp_store_rows16(stage, v, base, row_off, valid, col0, accumulate, lane, unused, kEpiStatNone, none);
+  warp_store_rows16(stage, v, base, row_off, valid, col0, accumulate, lane, unused, false);
 }
 
 __device__ __forceinline__ bool elect_one() {

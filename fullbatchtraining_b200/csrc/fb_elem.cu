@@ -1,15 +1,15 @@
-// Bandwidth-bound layer kernels of the full-batch step (sm_100a): BatchNorm (train mode) statistics / apply / backward
-// fused with ReLU and the residual add, AvgPool2d(2), stem im2col, and the pooled-linear-cross-entropy head.
-// All of them are coalesced, 16-byte vectorised streaming kernels; reductions are two-stage and deterministic
-// (fixed partition, fixed summation order), so repeated runs are bit-identical
-// (cf. measure_floating_point_accuracy.py / fullbatch/training/training.py:429-600).
+// Bandwidth-bound layer kernels of the full-batch step (sm_100a): BatchNorm (train mode) apply / backward fused with
+// ReLU and the residual add, AvgPool2d(2), stem im2col, the pooled-linear-cross-entropy head and the running-stat EMA.
+// All of them are coalesced, 16-byte vectorised streaming kernels over `ng` microbatch groups per launch; reductions
+// are two-stage and deterministic (fixed partition that only depends on ONE group's problem, fixed summation order), so
+// repeated runs are bit-identical (cf. measure_floating_point_accuracy.py / fullbatch/training/training.py:429-600) and
+// results do not depend on how many groups share a launch.  No kernel spins on a grid-wide barrier: cross-block
+// reductions finish in the last block to arrive (atomic ticket), the apply pass is a separate launch.
 //
 // Reference call sites replaced: torch.nn.BatchNorm2d / ReLU(inplace) / `out += identity`
 // (fullbatch/models/resnets.py:71,207-230,296-316), AvgPool2d (resnets.py:149), AdaptiveAvgPool2d + Linear
 // (resnets.py:106-107), LabelSmoothCrossEntropyLoss (fullbatch/models/modules.py:96-101), accuracy count
 // (fullbatch/training/training.py:80) and their autograd backward.
-#include <cooperative_groups.h>
-
 #include "../../include/fullbatch_b200.h"
 #include "fb_common.cuh"
 
@@ -63,24 +63,18 @@ __device__ __forceinline__ void store8_bf16(bf16* dst, long long off, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-channel column reductions over a [P][C] fp32 matrix: shared skeleton for BN statistics and BN backward.
-// Block = 256 threads = TX float4-columns x TY rows; grid = (chunks, column slabs) -> partial[chunk][2][C].
-// The LAST block to finish (atomic ticket) reduces the partials in a fixed order and finalises, so the whole reduction
-// is one launch and still deterministic.
+// Stand-alone BatchNorm statistics over a [P][C] fp32 matrix (fb_bn_stats): block = 256 threads = TX float4-columns x
+// TY rows; grid = (chunks, column slabs) -> partial[chunk][2][C]; a second launch reduces the chunks in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------
 struct BnFinalize {
   long long P;
   int chunks;
-  // forward (statistics)
   float *mean_out, *rstd_out, *running_mean, *running_var;
   float momentum, eps;
-  // backward
-  float *coef, *dgamma, *dbeta;
 };
 
-// Second stage: block = 8 channels x 32 lanes; lane l sums chunks l, l+32, ... (independent loads in flight), lanes
-// are combined by a fixed shuffle tree -> deterministic.
-template <bool BWD>
+// block = 8 channels x 32 lanes; lane l sums chunks l, l+32, ... (independent loads in flight), lanes are combined by
+// a fixed shuffle tree -> deterministic.
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int C, BnFinalize f) {
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -95,30 +89,19 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
   if (lane != 0 || c >= C) return;
-  if (!BWD) {
-    const double m = s1 / double(f.P);
-    double var = s2 / double(f.P) - m * m;
-    var = var < 0.0 ? 0.0 : var;
-    f.mean_out[c] = float(m);
-    f.rstd_out[c] = float(1.0 / sqrt(var + double(f.eps)));
-    if (f.running_mean) {
-      const double unbiased = f.P > 1 ? var * double(f.P) / double(f.P - 1) : var;
-      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(m);
-      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
-    }
-  } else {
-    f.dbeta[c] = float(s1);
-    f.dgamma[c] = float(s2);
-    f.coef[c] = float(s1 / double(f.P));
-    f.coef[C + c] = float(s2 / double(f.P));
+  const double m = s1 / double(f.P);
+  double var = s2 / double(f.P) - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  f.mean_out[c] = float(m);
+  f.rstd_out[c] = float(1.0 / sqrt(var + double(f.eps)));
+  if (f.running_mean) {
+    const double unbiased = f.P > 1 ? var * double(f.P) / double(f.P - 1) : var;
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(m);
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
   }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ y, const float* __restrict__ dA,
-                                                        const float* __restrict__ dA2,
-                                                        const bf16* __restrict__ mask, const float* __restrict__ mean,
-                                                        const float* __restrict__ rstd, long long P, int C, int TX,
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ y, long long P, int C, int TX,
                                                         int rows_per_chunk, float* __restrict__ partial) {
   __shared__ float4 red[2][256];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
@@ -126,38 +109,11 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(P, r0 + rows_per_chunk);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  float4 mu = s1, rs = s1;
-  if (BWD) {
-    mu = *reinterpret_cast<const float4*>(mean + c);
-    rs = *reinterpret_cast<const float4*>(rstd + c);
-  }
 #pragma unroll 8
   for (long long r = r0 + ty; r < r1; r += TY) {
     const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
-    if (!BWD) {
-      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-      s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
-    } else {
-      float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
-      if (dA2) {
-        const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
-        d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
-      }
-      if (mask) {
-        const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
-        const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
-        const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
-        d.x = m01.x > 0.f ? d.x : 0.f;
-        d.y = m01.y > 0.f ? d.y : 0.f;
-        d.z = m23.x > 0.f ? d.z : 0.f;
-        d.w = m23.y > 0.f ? d.w : 0.f;
-      }
-      s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-      s2.x += d.x * (v.x - mu.x) * rs.x;
-      s2.y += d.y * (v.y - mu.y) * rs.y;
-      s2.z += d.z * (v.z - mu.z) * rs.z;
-      s2.w += d.w * (v.w - mu.w) * rs.w;
-    }
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
   }
   red[0][threadIdx.x] = s1;
   red[1][threadIdx.x] = s2;
@@ -175,10 +131,10 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// BN apply (+ second normalised branch, + residual, + ReLU) -> bf16 hi/lo
+// BN apply (+ second normalised branch, + residual, + ReLU) -> bf16 hi/lo, grid = (blocks, groups)
 // ---------------------------------------------------------------------------------------------------------------
-// Per-thread channel parameters are loop invariant: the grid stride (gridDim.x * 2048 elements) is a multiple of C for
-// every channel count of the ResNet family (C | 2048), so they are loaded once per thread.
+// Per-thread channel parameters are loop invariant when the grid stride (gridDim.x * 2048 elements) is a multiple of C
+// (every channel count of the ResNet family divides 2048), so they are loaded once per thread.
 struct BnAffine {
   float mu[8], scale[8], shift[8];
   __device__ __forceinline__ void load(const float* mean, const float* rstd, const float* gamma, const float* beta,
@@ -194,22 +150,36 @@ struct BnAffine {
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
+  griddep_wait();
+  griddep_launch();
+  const int g = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const long long total8 = a.P * a.C / 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool invariant = (stride * 8) % a.C == 0;
+  const long long gbase = (long long)g * a.P * a.C;
+  const float* mean = a.mean + (long long)g * a.C;
+  const float* rstd = a.rstd + (long long)g * a.C;
+  const float* gamma = a.gamma + (long long)g * a.param_gstride;
+  const float* beta = a.beta + (long long)g * a.param_gstride;
+  const float* mean2 = a.y2 ? a.mean2 + (long long)g * a.C : nullptr;
+  const float* rstd2 = a.y2 ? a.rstd2 + (long long)g * a.C : nullptr;
+  const float* gamma2 = a.y2 ? a.gamma2 + (long long)g * a.param_gstride : nullptr;
+  const float* beta2 = a.y2 ? a.beta2 + (long long)g * a.param_gstride : nullptr;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   BnAffine p1, p2;
   if (i < total8) {
-    const int c = int((i * 8) % a.C);
-    p1.load(a.mean, a.rstd, a.gamma, a.beta, c);
-    if (a.y2) p2.load(a.mean2, a.rstd2, a.gamma2, a.beta2, c);
+    const long long e = a.reverse ? total8 - 1 - i : i;
+    const int c = int((e * 8) % a.C);
+    p1.load(mean, rstd, gamma, beta, c);
+    if (a.y2) p2.load(mean2, rstd2, gamma2, beta2, c);
   }
   for (; i < total8; i += stride) {
-    const long long off = i * 8;
+    const long long e = a.reverse ? total8 - 1 - i : i;
+    const long long off = gbase + e * 8;
     if (!invariant) {
-      const int c = int(off % a.C);
-      p1.load(a.mean, a.rstd, a.gamma, a.beta, c);
-      if (a.y2) p2.load(a.mean2, a.rstd2, a.gamma2, a.beta2, c);
+      const int c = int((e * 8) % a.C);
+      p1.load(mean, rstd, gamma, beta, c);
+      if (a.y2) p2.load(mean2, rstd2, gamma2, beta2, c);
     }
     float y[8], o[8];
     load8(a.y + off, y);
@@ -241,32 +211,176 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// BN backward apply: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) -> bf16; optional dz (fp32) output
+// BN backward: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) -> bf16; optional dz (fp32) output.
+//   launch 1 (bn_bwd_reduce_kernel, grid = chunks x column slabs x groups): per-chunk column sums of dz and dz*xhat;
+//            the LAST block of a group (atomic ticket) sums the chunks in a fixed order -> dgamma, dbeta, coef;
+//   launch 2 (bn_bwd_apply_kernel, grid = blocks x groups): streaming apply.
+// The reduce walks the tensors in the opposite direction of the apply, so that the apply starts on what the reduce
+// touched last (L2), and the pair starts where the producer of dA ended when `reverse` says so.
 // ---------------------------------------------------------------------------------------------------------------
+struct BnBwdGeom {
+  int TX, slabs, chunks, rows_per_chunk;
+};
+
+struct BnBwdK {
+  fb_bn_bwd_args a;
+  BnBwdGeom geo;
+  float* partial;          // [ng][chunks][2][C]
+  float* coef;             // [ng][2][C]
+  unsigned int* tickets;   // [ng]
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdK k) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float4 red[2][256];
+  __shared__ unsigned int s_last;
+  const fb_bn_bwd_args& a = k.a;
+  const int C = a.C;
+  const long long P = a.P;
+  const int g = blockIdx.z;
+  const int TX = k.geo.TX, TY = 256 / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int chunk = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int c = (blockIdx.y * TX + tx) * 4;
+  const long long gbase = (long long)g * P * C;
+  const float* y = a.y + gbase;
+  const float* dA = a.dA + gbase;
+  const float* dA2 = a.dA2 ? a.dA2 + gbase : nullptr;
+  const bf16* mask = a.mask_hi ? static_cast<const bf16*>(a.mask_hi) + gbase : nullptr;
+  const long long r0 = (long long)chunk * k.geo.rows_per_chunk;
+  const long long r1 = min(P, r0 + k.geo.rows_per_chunk);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const float4 mu = *reinterpret_cast<const float4*>(a.mean + (long long)g * C + c);
+  const float4 rs = *reinterpret_cast<const float4*>(a.rstd + (long long)g * C + c);
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += TY) {
+    const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
+    float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
+    if (dA2) {
+      const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
+      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+    }
+    if (mask) {
+      const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
+      const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
+      const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
+      d.x = m01.x > 0.f ? d.x : 0.f;
+      d.y = m01.y > 0.f ? d.y : 0.f;
+      d.z = m23.x > 0.f ? d.z : 0.f;
+      d.w = m23.y > 0.f ? d.w : 0.f;
+    }
+    s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+    s2.x += d.x * (v.x - mu.x) * rs.x;
+    s2.y += d.y * (v.y - mu.y) * rs.y;
+    s2.z += d.z * (v.z - mu.z) * rs.z;
+    s2.w += d.w * (v.w - mu.w) * rs.w;
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  __syncthreads();
+  float* part_g = k.partial + (long long)g * k.geo.chunks * 2 * C;
+  if (ty == 0) {
+    for (int j = 1; j < TY; ++j) {
+      const float4 p1 = red[0][j * TX + tx], p2 = red[1][j * TX + tx];
+      s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
+      s2.x += p2.x; s2.y += p2.y; s2.z += p2.z; s2.w += p2.w;
+    }
+    float* dst = part_g + (long long)chunk * 2 * C;
+    *reinterpret_cast<float4*>(dst + c) = s1;
+    *reinterpret_cast<float4*>(dst + C + c) = s2;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int prev = atomicAdd(k.tickets + g, 1u);
+    const bool last = prev == total - 1;
+    if (last) k.tickets[g] = 0u;  // every block of this group has arrived: ready for the next launch
+    __threadfence();
+    s_last = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block of the group: sum the chunks (row slices in parallel, then the slices in order)
+  double* scratch = reinterpret_cast<double*>(&red[0][0]);  // [256][4] doubles = sizeof(red)
+  const int n_items = C / 2;                                 // (sum | dot) x float4 column
+  const int per = n_items < 256 ? n_items : 256;
+  const int S = 256 / per;
+  const int t = threadIdx.x;
+  for (int base = 0; base < n_items; base += per) {
+    const int item = base + t % per, slice = t / per;
+    const int which = item / (C / 4), c4 = item % (C / 4);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (slice < S && item < n_items) {
+      const float* src = part_g + (long long)which * C + c4 * 4;
+#pragma unroll 4
+      for (int ch = slice; ch < k.geo.chunks; ch += S) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)ch * 2 * C));
+        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+      }
+    }
+    __syncthreads();
+    scratch[t * 4 + 0] = a0; scratch[t * 4 + 1] = a1; scratch[t * 4 + 2] = a2; scratch[t * 4 + 3] = a3;
+    __syncthreads();
+    if (t < per && item < n_items) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += scratch[(s * per + t) * 4 + j];
+      float* coef = k.coef + (long long)g * 2 * C;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = c4 * 4 + j;
+        if (which == 0) {
+          a.dbeta[(long long)g * a.grad_gstride + ch] = float(v[j]);
+          coef[ch] = float(v[j] / double(P));
+        } else {
+          a.dgamma[(long long)g * a.grad_gstride + ch] = float(v[j]);
+          coef[C + ch] = float(v[j] / double(P));
+        }
+      }
+    }
+  }
+}
+
 struct BnBwdCoef {
   float mu[8], rs[8], grs[8], c1[8], c2[8];
-  __device__ __forceinline__ void load(const fb_bn_bwd_args& a, const float* coef, int c) {
+  __device__ __forceinline__ void load(const float* mean, const float* rstd, const float* gamma, const float* coef,
+                                       int C, int c) {
     float ga[8];
-    load8(a.mean + c, mu);
-    load8(a.rstd + c, rs);
-    load8(a.gamma + c, ga);
+    load8(mean + c, mu);
+    load8(rstd + c, rs);
+    load8(gamma + c, ga);
     load8(coef + c, c1);
-    load8(coef + a.C + c, c2);
+    load8(coef + C + c, c2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) grs[j] = ga[j] * rs[j];
   }
 };
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, const float* __restrict__ coef) {
-  const long long total8 = a.P * a.C / 8;
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdK k) {
+  griddep_wait();
+  griddep_launch();
+  const fb_bn_bwd_args& a = k.a;
+  const int g = blockIdx.y;
+  const int C = a.C;
+  const long long total8 = a.P * C / 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const bool invariant = (stride * 8) % a.C == 0;
+  const bool invariant = (stride * 8) % C == 0;
+  const bool backwards = !a.reverse;  // opposite direction of the reduce pass
+  const long long gbase = (long long)g * a.P * C;
+  const float* mean = a.mean + (long long)g * C;
+  const float* rstd = a.rstd + (long long)g * C;
+  const float* gamma = a.gamma + (long long)g * a.param_gstride;
+  const float* coef = k.coef + (long long)g * 2 * C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   BnBwdCoef p;
-  if (i < total8) p.load(a, coef, int((i * 8) % a.C));
+  if (i < total8) p.load(mean, rstd, gamma, coef, C, int(((backwards ? total8 - 1 - i : i) * 8) % C));
   for (; i < total8; i += stride) {
-    const long long off = i * 8;
-    if (!invariant) p.load(a, coef, int(off % a.C));
+    const long long e = backwards ? total8 - 1 - i : i;
+    const long long off = gbase + e * 8;
+    if (!invariant) p.load(mean, rstd, gamma, coef, C, int((e * 8) % C));
     float d[8], y[8], o[8];
     load8(a.dA + off, d);
     if (a.dA2) {
@@ -288,550 +402,35 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(fb_bn_bwd_args a, con
       o[j] = p.grs[j] * (d[j] - p.c1[j] - xhat * p.c2[j]);
     }
     store8_bf16(static_cast<bf16*>(a.dy_bf16), off, o);
-    if (a.dz_out) {
-      if (a.dz_accumulate) {
-        float e[8];
-        load8(a.dz_out + off, e);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] += e[j];
-      }
-      store8(a.dz_out + off, d);
-    }
+    if (a.dz_out) store8(a.dz_out + off, d);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused BatchNorm kernels: statistics -> finalize -> apply in ONE persistent launch with two grid-wide barriers.
-// All blocks are co-resident (grid <= 2 per SM, checked on the host), so a spin barrier on a global counter is safe; it
-// is bounded and traps instead of hanging.  Every block applies to the same rows it reduced, so the second pass over
-// Y / dA / mask is served by L2 (the largest ResNet-18 tensors are 33 MB, L2 is 126 MB) instead of HBM, and the two
-// extra launches per BatchNorm disappear.
+// Running-stat EMA of every BatchNorm layer, in the reference's order (group = microbatch, pass 1 then the FD passes)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const long long t0 = clock64();
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
-      if (clock64() - t0 > 4000000000LL) {
-        printf("[fb] grid barrier timeout: block %d target %u have %u\n", blockIdx.x, target, *counter);
-        __trap();
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-// after the last barrier: the last block to leave resets the counters for the next launch
-__device__ __forceinline__ void grid_barrier_release(unsigned int* counters) {
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(counters + 1, 1u);
-    if (prev == gridDim.x - 1) {
-      counters[0] = 0u;
-      counters[1] = 0u;
-      __threadfence();
-    }
-  }
-}
-
-struct BnFusedFwdArgs {
-  fb_bn_apply_args ap;           // y, gamma, beta, (y2, gamma2, beta2), residual, relu, P, C, outputs; mean/rstd = outputs
-  float *mean, *rstd, *mean2, *rstd2;
-  float *running_mean, *running_var, *running_mean2, *running_var2;
-  float momentum, eps;
-  float* partial;                // [grid][2 branches][2][C]
-  unsigned int* counters;        // [2], zero on entry
-  int rows_per_block;
-  // statistics already reduced per CTA by the producing convolution's epilogue (fb_conv_gemm / fb_conv3x3 stats_out):
-  // [ext_rows][2][C] per branch; when given, phase 1 and the first barrier are skipped
-  const float *ext0, *ext1;
-  int ext_rows0, ext_rows1;
-};
-
-// column sums of one branch over rows [r0, r1): partial[2][C] of this block
-template <bool BWD>
-__device__ __forceinline__ void block_column_sums(const float* __restrict__ y, const float* __restrict__ dA,
-                                                  const float* __restrict__ dA2, const bf16* __restrict__ mask,
-                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                  long long r0, long long r1, int C, float* __restrict__ out,
-                                                  float4 (*red)[256]) {
-  const int c4 = C / 4;
-  const int TX = c4 < 256 ? c4 : 256;
-  const int TY = 256 / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  for (int slab = 0; slab < c4 / TX; ++slab) {
-    const int c = (slab * TX + tx) * 4;
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, mu = s1, rs = s1;
-    if (BWD) {
-      mu = *reinterpret_cast<const float4*>(mean + c);
-      rs = *reinterpret_cast<const float4*>(rstd + c);
-    }
-#pragma unroll 4
-    for (long long r = r0 + ty; r < r1; r += TY) {
-      const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
-      if (!BWD) {
-        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-        s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
-      } else {
-        float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
-        if (dA2) {
-          const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
-          d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
-        }
-        if (mask) {
-          const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
-          const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
-          const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
-          d.x = m01.x > 0.f ? d.x : 0.f;
-          d.y = m01.y > 0.f ? d.y : 0.f;
-          d.z = m23.x > 0.f ? d.z : 0.f;
-          d.w = m23.y > 0.f ? d.w : 0.f;
-        }
-        s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-        s2.x += d.x * (v.x - mu.x) * rs.x;
-        s2.y += d.y * (v.y - mu.y) * rs.y;
-        s2.z += d.z * (v.z - mu.z) * rs.z;
-        s2.w += d.w * (v.w - mu.w) * rs.w;
-      }
-    }
-    __syncthreads();
-    red[0][threadIdx.x] = s1;
-    red[1][threadIdx.x] = s2;
-    __syncthreads();
-    if (ty == 0) {
-      for (int j = 1; j < TY; ++j) {
-        const float4 a = red[0][j * TX + tx], b = red[1][j * TX + tx];
-        s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
-        s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
-      }
-      *reinterpret_cast<float4*>(out + c) = s1;
-      *reinterpret_cast<float4*>(out + C + c) = s2;
-    }
-  }
-}
-
-// fixed-order reduction of the per-block partials of channel c by one warp (lane = block index mod 32)
-__device__ __forceinline__ void warp_reduce_partials(const float* __restrict__ partial, long long block_stride, int nblk,
-                                                     int C, int c, int lane, double& s1, double& s2) {
-  s1 = 0.0;
-  s2 = 0.0;
-#pragma unroll 4
-  for (int k = lane; k < nblk; k += 32) {
-    s1 += __ldcg(partial + (long long)k * block_stride + c);
-    s2 += __ldcg(partial + (long long)k * block_stride + C + c);
-  }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-}
-
-__global__ void __launch_bounds__(256, 2) bn_fwd_fused_kernel(BnFusedFwdArgs a) {
+__global__ void __launch_bounds__(256) bn_ema_multi_kernel(const fb_bn_ema_entry* __restrict__ table, int n,
+                                                           int total_channels, int n_passes, int ng, float momentum) {
   griddep_wait();
-  __shared__ float4 red[2][256];
-  const fb_bn_apply_args& ap = a.ap;
-  const int C = ap.C;
-  const long long P = ap.P;
-  const int branches = ap.y2 ? 2 : 1;
-  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
-  const long long r1 = min(P, r0 + a.rows_per_block);
-  const long long block_stride = (long long)branches * 2 * C;
-  float* mine = a.partial + blockIdx.x * block_stride;
-  const bool external = a.ext0 != nullptr;
-  unsigned int barrier_target = gridDim.x;
-  if (!external) {
-    // ---- phase 1: per-block column sums
-    block_column_sums<false>(ap.y, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine, red);
-    if (ap.y2)
-      block_column_sums<false>(ap.y2, nullptr, nullptr, nullptr, nullptr, nullptr, r0, r1, C, mine + 2 * C, red);
-    grid_barrier(a.counters, gridDim.x);
-    barrier_target = 2 * gridDim.x;
+  griddep_launch();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_channels) return;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {  // last entry with c_start <= t
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].c_start <= t) lo = mid; else hi = mid - 1;
   }
-  // ---- finalize: one warp per channel, spread over the blocks
-  {
-    const int lane = threadIdx.x & 31;
-    const int total = branches * C;
-    for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += gridDim.x * 8) {
-      const int br = item / C, c = item % C;
-      double s1, s2;
-      if (external)
-        warp_reduce_partials(br ? a.ext1 : a.ext0, 2LL * C, br ? a.ext_rows1 : a.ext_rows0, C, c, lane, s1, s2);
-      else
-        warp_reduce_partials(a.partial + br * 2 * C, block_stride, gridDim.x, C, c, lane, s1, s2);
-      if (lane == 0) {
-        const double m = s1 / double(P);
-        double var = s2 / double(P) - m * m;
-        var = var < 0.0 ? 0.0 : var;
-        (br ? a.mean2 : a.mean)[c] = float(m);
-        (br ? a.rstd2 : a.rstd)[c] = float(1.0 / sqrt(var + double(a.eps)));
-        float* rm = br ? a.running_mean2 : a.running_mean;
-        float* rv = br ? a.running_var2 : a.running_var;
-        if (rm) {
-          const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
-          rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * float(m);
-          rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * float(unbiased);
-        }
-      }
+  const fb_bn_ema_entry e = table[lo];
+  const int c = t - e.c_start;
+  float rm = e.running_mean[c], rv = e.running_var[c];
+  for (int g = 0; g < ng; ++g)
+    for (int p = 0; p < n_passes; ++p) {
+      const float* b = e.batch + (long long)p * e.pass_stride + (long long)g * 2 * e.C;
+      rm = (1.f - momentum) * rm + momentum * b[c];
+      rv = (1.f - momentum) * rv + momentum * b[e.C + c];
     }
-  }
-  grid_barrier(a.counters, barrier_target);
-  grid_barrier_release(a.counters);
-  // ---- phase 2: normalise the rows this block reduced (L2 hits)
-  const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
-  const bool invariant = (256 * 8) % C == 0;
-  long long i = e0 + threadIdx.x;
-  BnAffine p1, p2;
-  if (i < e1 && invariant) {
-    const int c = int((i * 8) % C);
-    p1.load(a.mean, a.rstd, ap.gamma, ap.beta, c);
-    if (ap.y2) p2.load(a.mean2, a.rstd2, ap.gamma2, ap.beta2, c);
-  }
-  for (; i < e1; i += 256) {
-    const long long off = i * 8;
-    if (!invariant) {
-      const int c = int(off % C);
-      p1.load(a.mean, a.rstd, ap.gamma, ap.beta, c);
-      if (ap.y2) p2.load(a.mean2, a.rstd2, ap.gamma2, ap.beta2, c);
-    }
-    float y[8], o[8];
-    load8(ap.y + off, y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (y[j] - p1.mu[j]) * p1.scale[j] + p1.shift[j];
-    if (ap.y2) {
-      load8(ap.y2 + off, y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (y[j] - p2.mu[j]) * p2.scale[j] + p2.shift[j];
-    }
-    if (ap.res_hi) {
-      float rh[8];
-      load8_bf16(static_cast<const bf16*>(ap.res_hi) + off, rh);
-      if (ap.res_lo) {
-        float rl[8];
-        load8_bf16(static_cast<const bf16*>(ap.res_lo) + off, rl);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rh[j] += rl[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += rh[j];
-    }
-    if (ap.relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-    }
-    store8_split(static_cast<bf16*>(ap.out_hi), static_cast<bf16*>(ap.out_lo), off, o);
-  }
-}
-
-struct BnFusedBwdArgs {
-  fb_bn_bwd_args bw;       // dA, dA2, mask, y, mean, rstd, gamma, P, C, ws, dgamma, dbeta, dy, dz_out, (stats, stats_rows)
-  float* partial;          // [grid][2][C]
-  float* coef;             // [2][C]
-  unsigned int* counters;  // [2]
-  int rows_per_block;
-};
-
-__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnFusedBwdArgs a) {
-  griddep_wait();
-  __shared__ float4 red[2][256];
-  const fb_bn_bwd_args& bw = a.bw;
-  const int C = bw.C;
-  const long long P = bw.P;
-  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
-  const long long r1 = min(P, r0 + a.rows_per_block);
-  const long long block_stride = 2LL * C;
-  // statistics already reduced per CTA by the dgrad that produced dA (fb_conv_gemm_args.bwd_y): no first pass, one barrier
-  const bool external = bw.stats != nullptr;
-  unsigned int barrier_target = gridDim.x;
-  if (!external) {
-    block_column_sums<true>(bw.y, bw.dA, bw.dA2, static_cast<const bf16*>(bw.mask_hi), bw.mean, bw.rstd, r0, r1, C,
-                            a.partial + blockIdx.x * block_stride, red);
-    grid_barrier(a.counters, gridDim.x);
-    barrier_target = 2 * gridDim.x;
-  }
-  {
-    const int lane = threadIdx.x & 31;
-    for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < C; c += gridDim.x * 8) {
-      double s1, s2;
-      if (external)
-        warp_reduce_partials(bw.stats, 2LL * C, bw.stats_rows, C, c, lane, s1, s2);
-      else
-        warp_reduce_partials(a.partial, block_stride, gridDim.x, C, c, lane, s1, s2);
-      if (lane == 0) {
-        bw.dbeta[c] = float(s1);
-        bw.dgamma[c] = float(s2);
-        a.coef[c] = float(s1 / double(P));
-        a.coef[C + c] = float(s2 / double(P));
-      }
-    }
-  }
-  grid_barrier(a.counters, barrier_target);
-  grid_barrier_release(a.counters);
-  // the rows are walked BACKWARDS: phase 1 read them front to back, so the tail of this block's slice is what L2 still
-  // holds when the whole tensor set (up to 117 MB on the 32x32 stage) does not fit
-  const long long e0 = r0 * C / 8, e1 = r1 * C / 8;
-  const bool invariant = (256 * 8) % C == 0;
-  const long long first = e0 + threadIdx.x;
-  long long i = first < e1 ? first + ((e1 - 1 - first) / 256) * 256 : e1;
-  BnBwdCoef p;
-  if (first < e1 && invariant) p.load(bw, a.coef, int((first * 8) % C));
-  for (; first < e1 && i >= first; i -= 256) {
-    const long long off = i * 8;
-    if (!invariant) p.load(bw, a.coef, int(off % C));
-    float d[8], y[8], o[8];
-    load8(bw.dA + off, d);
-    if (bw.dA2) {
-      float d2[8];
-      load8(bw.dA2 + off, d2);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] += d2[j];
-    }
-    if (bw.mask_hi) {
-      float m[8];
-      load8_bf16(static_cast<const bf16*>(bw.mask_hi) + off, m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
-    }
-    load8(bw.y + off, y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (y[j] - p.mu[j]) * p.rs[j];
-      o[j] = p.grs[j] * (d[j] - p.c1[j] - xhat * p.c2[j]);
-    }
-    store8_bf16(static_cast<bf16*>(bw.dy_bf16), off, o);
-    if (bw.dz_out) store8(bw.dz_out + off, d);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Small feature maps (8x8, 4x4, ...: the whole [P][C] problem is a few MB): variant WITHOUT grid barriers, opt-in (see
-// sliced_geometry for the measurements).  The tensor is cut into channel SLICES of `sw` channels; a slice is owned by
-// `cs` CTAs that split the rows.
-//   forward  (statistics come from the conv epilogue): no synchronisation at all -- every CTA reduces the partial rows
-//            of its own slice redundantly (fixed order), the CTA of row group 0 publishes mean / rstd / running stats;
-//   backward: the cs CTAs of a slice form a thread-block CLUSTER and combine their column sums through distributed
-//            shared memory (fixed rank order -> deterministic) between two hardware cluster barriers.
-// Thread layout: TX = sw/4 threads per row (one float4 each), TY = 256/TX rows per iteration.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kSliceMax = 32;   // channels per slice (sw in {8, 16, 32})
-constexpr int kSliceCtas = 8;   // CTAs (= cluster size in the backward kernel) per slice
-
-__device__ __forceinline__ void store4_split(bf16* hi, bf16* lo, long long off, const float4 v) {
-  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-  split_bf16(v.x, h0, l0);
-  split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2);
-  split_bf16(v.w, h3, l3);
-  __nv_bfloat162 hh[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
-  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(hh);
-  if (lo) {
-    __nv_bfloat162 ll[2] = {__halves2bfloat162(l0, l1), __halves2bfloat162(l2, l3)};
-    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(ll);
-  }
-}
-__device__ __forceinline__ float4 load4_bf16(const bf16* p) {
-  const uint2 m = *reinterpret_cast<const uint2*>(p);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-__global__ void __launch_bounds__(256) bn_fwd_sliced_kernel(BnFusedFwdArgs a, int sw, int rows_per_cta) {
-  griddep_wait();
-  __shared__ float s_mu[2][kSliceMax], s_scale[2][kSliceMax], s_shift[2][kSliceMax];
-  const fb_bn_apply_args& ap = a.ap;
-  const int C = ap.C;
-  const long long P = ap.P;
-  const int branches = ap.y2 ? 2 : 1;
-  const int c_base = blockIdx.y * sw;
-  {  // per-CTA finalize of this slice from the conv epilogue's partial rows: one warp per (branch, channel)
-    const int lane = threadIdx.x & 31;
-    for (int item = threadIdx.x >> 5; item < branches * sw; item += 8) {
-      const int br = item / sw, cl = item % sw, c = c_base + cl;
-      double s1, s2;
-      warp_reduce_partials(br ? a.ext1 : a.ext0, 2LL * C, br ? a.ext_rows1 : a.ext_rows0, C, c, lane, s1, s2);
-      if (lane == 0) {
-        const double m = s1 / double(P);
-        double var = s2 / double(P) - m * m;
-        var = var < 0.0 ? 0.0 : var;
-        const float mean = float(m), rstd = float(1.0 / sqrt(var + double(a.eps)));
-        const float ga = (br ? ap.gamma2 : ap.gamma)[c], be = (br ? ap.beta2 : ap.beta)[c];
-        s_mu[br][cl] = mean;
-        s_scale[br][cl] = rstd * ga;
-        s_shift[br][cl] = be;
-        if (blockIdx.x == 0) {
-          (br ? a.mean2 : a.mean)[c] = mean;
-          (br ? a.rstd2 : a.rstd)[c] = rstd;
-          float* rm = br ? a.running_mean2 : a.running_mean;
-          float* rv = br ? a.running_var2 : a.running_var;
-          if (rm) {
-            const double unbiased = P > 1 ? var * double(P) / double(P - 1) : var;
-            rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * mean;
-            rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * float(unbiased);
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const int TX = sw / 4, TY = 256 / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int cl = tx * 4, c = c_base + cl;
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
-  const long long r1 = min(P, r0 + rows_per_cta);
-  float mu[2][4], sc[2][4], sh[2][4];
-#pragma unroll
-  for (int b = 0; b < 2; ++b)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mu[b][j] = s_mu[b][cl + j];
-      sc[b][j] = s_scale[b][cl + j];
-      sh[b][j] = s_shift[b][cl + j];
-    }
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += TY) {
-    const long long off = r * C + c;
-    const float4 y = *reinterpret_cast<const float4*>(ap.y + off);
-    float4 o = make_float4((y.x - mu[0][0]) * sc[0][0] + sh[0][0], (y.y - mu[0][1]) * sc[0][1] + sh[0][1],
-                           (y.z - mu[0][2]) * sc[0][2] + sh[0][2], (y.w - mu[0][3]) * sc[0][3] + sh[0][3]);
-    if (ap.y2) {
-      const float4 z = *reinterpret_cast<const float4*>(ap.y2 + off);
-      o.x += (z.x - mu[1][0]) * sc[1][0] + sh[1][0];
-      o.y += (z.y - mu[1][1]) * sc[1][1] + sh[1][1];
-      o.z += (z.z - mu[1][2]) * sc[1][2] + sh[1][2];
-      o.w += (z.w - mu[1][3]) * sc[1][3] + sh[1][3];
-    }
-    if (ap.res_hi) {
-      float4 rh = load4_bf16(static_cast<const bf16*>(ap.res_hi) + off);
-      if (ap.res_lo) {
-        const float4 rl = load4_bf16(static_cast<const bf16*>(ap.res_lo) + off);
-        rh.x += rl.x; rh.y += rl.y; rh.z += rl.z; rh.w += rl.w;
-      }
-      o.x += rh.x; o.y += rh.y; o.z += rh.z; o.w += rh.w;
-    }
-    if (ap.relu) {
-      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-    }
-    store4_split(static_cast<bf16*>(ap.out_hi), static_cast<bf16*>(ap.out_lo), off, o);
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_cluster_kernel(BnFusedBwdArgs a, int sw, int rows_per_cta) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  griddep_wait();
-  __shared__ float4 red[2][256];
-  __shared__ float part[2][kSliceMax];  // this CTA's column sums, read by the other CTAs of the cluster
-  __shared__ float coef[2][kSliceMax];
-  const fb_bn_bwd_args& bw = a.bw;
-  const int C = bw.C;
-  const long long P = bw.P;
-  const unsigned rank = cluster.block_rank(), cs = cluster.num_blocks();
-  const int c_base = blockIdx.y * sw;
-  const int TX = sw / 4, TY = 256 / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int cl = tx * 4, c = c_base + cl;
-  const long long r0 = (long long)rank * rows_per_cta;
-  const long long r1 = min(P, r0 + rows_per_cta);
-  const float4 mu = *reinterpret_cast<const float4*>(bw.mean + c);
-  const float4 rs = *reinterpret_cast<const float4*>(bw.rstd + c);
-  const bf16* mask = static_cast<const bf16*>(bw.mask_hi);
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += TY) {
-    const long long off = r * C + c;
-    const float4 v = *reinterpret_cast<const float4*>(bw.y + off);
-    float4 d = *reinterpret_cast<const float4*>(bw.dA + off);
-    if (bw.dA2) {
-      const float4 d2 = *reinterpret_cast<const float4*>(bw.dA2 + off);
-      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
-    }
-    if (mask) {
-      const float4 m = load4_bf16(mask + off);
-      d.x = m.x > 0.f ? d.x : 0.f;
-      d.y = m.y > 0.f ? d.y : 0.f;
-      d.z = m.z > 0.f ? d.z : 0.f;
-      d.w = m.w > 0.f ? d.w : 0.f;
-    }
-    s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-    s2.x += d.x * (v.x - mu.x) * rs.x;
-    s2.y += d.y * (v.y - mu.y) * rs.y;
-    s2.z += d.z * (v.z - mu.z) * rs.z;
-    s2.w += d.w * (v.w - mu.w) * rs.w;
-  }
-  red[0][threadIdx.x] = s1;
-  red[1][threadIdx.x] = s2;
-  __syncthreads();
-  if (ty == 0) {
-    for (int j = 1; j < TY; ++j) {
-      const float4 p1 = red[0][j * TX + tx], p2 = red[1][j * TX + tx];
-      s1.x += p1.x; s1.y += p1.y; s1.z += p1.z; s1.w += p1.w;
-      s2.x += p2.x; s2.y += p2.y; s2.z += p2.z; s2.w += p2.w;
-    }
-    *reinterpret_cast<float4*>(&part[0][cl]) = s1;
-    *reinterpret_cast<float4*>(&part[1][cl]) = s2;
-  }
-  cluster.sync();
-  if (threadIdx.x < sw) {  // every CTA sums the cluster's partials in rank order: identical totals everywhere
-    double t1 = 0.0, t2 = 0.0;
-    for (unsigned k = 0; k < cs; ++k) {
-      const float* rp = cluster.map_shared_rank(&part[0][0], k);
-      t1 += rp[threadIdx.x];
-      t2 += rp[kSliceMax + threadIdx.x];
-    }
-    coef[0][threadIdx.x] = float(t1 / double(P));
-    coef[1][threadIdx.x] = float(t2 / double(P));
-    if (rank == 0) {
-      bw.dbeta[c_base + threadIdx.x] = float(t1);
-      bw.dgamma[c_base + threadIdx.x] = float(t2);
-    }
-  }
-  cluster.sync();  // all remote reads of `part` are done (no CTA may exit before), coef visible to the block
-  const float4 ga = *reinterpret_cast<const float4*>(bw.gamma + c);
-  const float4 grs = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
-  const float4 c1 = *reinterpret_cast<const float4*>(&coef[0][cl]);
-  const float4 c2 = *reinterpret_cast<const float4*>(&coef[1][cl]);
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += TY) {
-    const long long off = r * C + c;
-    const float4 v = *reinterpret_cast<const float4*>(bw.y + off);
-    float4 d = *reinterpret_cast<const float4*>(bw.dA + off);
-    if (bw.dA2) {
-      const float4 d2 = *reinterpret_cast<const float4*>(bw.dA2 + off);
-      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
-    }
-    if (mask) {
-      const float4 m = load4_bf16(mask + off);
-      d.x = m.x > 0.f ? d.x : 0.f;
-      d.y = m.y > 0.f ? d.y : 0.f;
-      d.z = m.z > 0.f ? d.z : 0.f;
-      d.w = m.w > 0.f ? d.w : 0.f;
-    }
-    float4 o;
-    o.x = grs.x * (d.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
-    o.y = grs.y * (d.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
-    o.z = grs.z * (d.z - c1.z - (v.z - mu.z) * rs.z * c2.z);
-    o.w = grs.w * (d.w - c1.w - (v.w - mu.w) * rs.w * c2.w);
-    __nv_bfloat162 ob[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
-    *reinterpret_cast<uint2*>(static_cast<bf16*>(bw.dy_bf16) + off) = *reinterpret_cast<uint2*>(ob);
-    if (bw.dz_out) *reinterpret_cast<float4*>(bw.dz_out + off) = d;
-  }
-}
-
-// slice width / rows per CTA of the small-map kernels, or false if the problem should use the grid-barrier kernels
-static bool sliced_geometry(long long P, int C, int& sw, int& rows_per_cta) {
-  // opt-in (FB_BN_SLICED_MAX = largest P*C in elements): measured on B200 (tools/bn_timing.py) the cluster kernel wins
-  // only with L2-warm operands and 128-byte slice rows (4x4 maps: 9.2 vs 12.9 us); in the step Y and the ReLU mask
-  // come from HBM and the two variants are within 1 us, narrower slices (64 / 32-byte rows) are 1.3-2.4x slower.
-  const char* e = getenv("FB_BN_SLICED_MAX");
-  const long long max_elems = e ? atoll(e) : 0;
-  if (P * C > max_elems || C % 8 != 0) return false;
-  sw = C < kSliceMax ? C : kSliceMax;
-  while (sw > 8 && C % sw != 0) sw /= 2;
-  if (C % sw != 0) return false;
-  const int TY = 256 / (sw / 4);
-  long long rows = (P + kSliceCtas - 1) / kSliceCtas;
-  rows = (rows + TY - 1) / TY * TY;
-  rows_per_cta = int(rows);
-  return true;
+  e.running_mean[c] = rm;
+  e.running_var[c] = rv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -905,11 +504,11 @@ __global__ void avgpool2_bwd_kernel(const float* __restrict__ dP, int n, int h, 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void stem_im2col_kernel(const float* __restrict__ x, const long long* __restrict__ labels,
                                    const long long* __restrict__ perm, const int* __restrict__ first_dev,
-                                   long long first, int n, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
-                                   long long* __restrict__ labels_out) {
+                                   long long first, int cursor_stride, int n, bf16* __restrict__ p_hi,
+                                   bf16* __restrict__ p_lo, long long* __restrict__ labels_out) {
   griddep_wait();
   griddep_launch();
-  if (first_dev) first += (long long)(*first_dev) * n;
+  if (first_dev) first += (long long)(*first_dev) * cursor_stride;
   const long long total = (long long)n * 1024 * 8;  // 8 groups of 8 columns per pixel
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -949,12 +548,12 @@ struct AugNorm {
 
 __global__ void stem_im2col_u8aug_kernel(const uint8_t* __restrict__ x, const long long* __restrict__ labels,
                                          const long long* __restrict__ perm, const int* __restrict__ first_dev,
-                                         long long first, int n, const char4* __restrict__ aug, AugNorm nrm,
-                                         bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
+                                         long long first, int cursor_stride, int n, const char4* __restrict__ aug,
+                                         AugNorm nrm, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo,
                                          long long* __restrict__ labels_out) {
   griddep_wait();
   griddep_launch();
-  if (first_dev) first += (long long)(*first_dev) * n;
+  if (first_dev) first += (long long)(*first_dev) * cursor_stride;
   const long long total = (long long)n * 1024 * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -989,14 +588,14 @@ __global__ void stem_im2col_u8aug_kernel(const uint8_t* __restrict__ x, const lo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// head: global average pool -> linear -> label-smoothed cross entropy (+accuracy) and backward
+// head: global average pool -> linear -> label-smoothed cross entropy (+accuracy) and backward, ng groups of n images
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxClasses = 16;
 
-// grid = n, block = 128
+// grid = ng*n, block = 128
 __global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo,
-                                                       int n, int hw, int c, const float* __restrict__ fc_w,
-                                                       const float* __restrict__ fc_b,
+                                                       int n, int hw, int c, const float* __restrict__ fc_w_base,
+                                                       const float* __restrict__ fc_b_base, long long param_gstride,
                                                        const long long* __restrict__ labels, int classes,
                                                        float smoothing, float* __restrict__ pooled,
                                                        float* __restrict__ dlogits, float* __restrict__ loss_n,
@@ -1006,6 +605,9 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ 
   extern __shared__ float sp[];  // c floats + classes logits
   float* logits = sp + c;
   const int img = blockIdx.x;
+  const int g = img / n;
+  const float* fc_w = fc_w_base + (long long)g * param_gstride;
+  const float* fc_b = fc_b_base + (long long)g * param_gstride;
   const float inv = 1.f / float(hw);
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.f;
@@ -1046,48 +648,55 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const bf16* __restrict__ 
       loss -= wk * logp;
       // d/dz_k of -sum_j w_j logp_j = softmax_k * sum_j w_j - w_k; mean over the microbatch -> / n
       const float wsum = w_on + w_off * float(classes - 1);
-      dlogits[img * kMaxClasses + k] = (expf(logp) * wsum - wk) / float(n);
+      dlogits[(long long)img * kMaxClasses + k] = (expf(logp) * wsum - wk) / float(n);
     }
     loss_n[img] = loss;
     correct_n[img] = (arg == label) ? 1.f : 0.f;
   }
 }
 
-// grid = (c/128, n): dA[n][p][ch] = (sum_k dlogits[n][k] * W[k][ch]) / hw
+// grid = (c/128, ng*n): dA[img][p][ch] = (sum_k dlogits[img][k] * W_g[k][ch]) / hw
 __global__ void __launch_bounds__(128) head_bwd_act_kernel(const float* __restrict__ dlogits,
-                                                           const float* __restrict__ fc_w, int hw, int c, int classes,
+                                                           const float* __restrict__ fc_w_base,
+                                                           long long param_gstride, int n, int hw, int c, int classes,
                                                            float* __restrict__ dA) {
   griddep_wait();
   griddep_launch();
   const int ch = blockIdx.x * 128 + threadIdx.x;
   const int img = blockIdx.y;
   if (ch >= c) return;
+  const float* fc_w = fc_w_base + (long long)(img / n) * param_gstride;
   float s = 0.f;
-  for (int k = 0; k < classes; ++k) s += dlogits[img * kMaxClasses + k] * fc_w[(long long)k * c + ch];
+  for (int k = 0; k < classes; ++k) s += dlogits[(long long)img * kMaxClasses + k] * fc_w[(long long)k * c + ch];
   s /= float(hw);
   for (int p = 0; p < hw; ++p) dA[((long long)img * hw + p) * c + ch] = s;
 }
 
-// grid = c/32 (+ block 0 also reduces bias grad, loss, accuracy); block = 32 channels x 8 sample lanes
+// grid = (c/32, ng) (block x == 0 also reduces bias grad, loss, accuracy of its group); block = 32 channels x 8 sample lanes
 __global__ void __launch_bounds__(256) head_bwd_param_kernel(const float* __restrict__ dlogits,
                                                              const float* __restrict__ pooled,
                                                              const float* __restrict__ loss_n,
                                                              const float* __restrict__ correct_n, int n, int c,
-                                                             int classes, float* __restrict__ d_fcw,
-                                                             float* __restrict__ d_fcb, float* __restrict__ scal,
-                                                             int loss_slot, int correct_slot) {
+                                                             int classes, float* __restrict__ d_fcw_base,
+                                                             float* __restrict__ d_fcb_base, long long grad_gstride,
+                                                             float* __restrict__ scal, int loss_base,
+                                                             int correct_base) {
   griddep_wait();
   griddep_launch();
   __shared__ float red[8][kMaxClasses][33];
+  const int g = blockIdx.y;
+  const int i0 = g * n;
+  float* d_fcw = d_fcw_base + (long long)g * grad_gstride;
+  float* d_fcb = d_fcb_base + (long long)g * grad_gstride;
   const int cl = threadIdx.x & 31, lane_n = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
   float acc[kMaxClasses];
 #pragma unroll
   for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
   if (ch < c) {
-    for (int i = lane_n; i < n; i += 8) {
+    for (int i = i0 + lane_n; i < i0 + n; i += 8) {
       const float pv = pooled[(long long)i * c + ch];
-      const float4* dl = reinterpret_cast<const float4*>(dlogits + i * kMaxClasses);
+      const float4* dl = reinterpret_cast<const float4*>(dlogits + (long long)i * kMaxClasses);
 #pragma unroll
       for (int q = 0; q < kMaxClasses / 4; ++q) {
         const float4 d = dl[q];
@@ -1114,16 +723,16 @@ __global__ void __launch_bounds__(256) head_bwd_param_kernel(const float* __rest
   if (blockIdx.x == 0) {
     if (threadIdx.x < classes) {
       float sum = 0.f;
-      for (int i = 0; i < n; ++i) sum += dlogits[i * kMaxClasses + threadIdx.x];
+      for (int i = i0; i < i0 + n; ++i) sum += dlogits[(long long)i * kMaxClasses + threadIdx.x];
       d_fcb[threadIdx.x] = sum;
     } else if (threadIdx.x == 32) {
       double sum = 0.0;
-      for (int i = 0; i < n; ++i) sum += loss_n[i];
-      scal[loss_slot] += float(sum / double(n));
+      for (int i = i0; i < i0 + n; ++i) sum += loss_n[i];
+      scal[loss_base + g] = float(sum / double(n));
     } else if (threadIdx.x == 64) {
       float sum = 0.f;
-      for (int i = 0; i < n; ++i) sum += correct_n[i];
-      scal[correct_slot] += sum;
+      for (int i = i0; i < i0 + n; ++i) sum += correct_n[i];
+      scal[correct_base + g] = sum;
     }
   }
 }
@@ -1140,6 +749,27 @@ static int reduce_geometry(long long P, int C, int& TX, int& slabs, int& chunks,
   chunks = int(want < kMaxChunks ? want : kMaxChunks);
   rows_per_chunk = int((P + chunks - 1) / chunks);
   chunks = int((P + rows_per_chunk - 1) / rows_per_chunk);
+  return 0;
+}
+
+// BN backward: ~2 blocks per SM over all groups of the launch policy; the partition only depends on (P, C, policy)
+static int bwd_geometry(long long P, int C, int policy_groups, BnBwdGeom& geo) {
+  if (C % 8 != 0) return FB_ERR_UNSUPPORTED;
+  const int c4 = C / 4;
+  geo.TX = c4 < 256 ? c4 : 256;
+  if (256 % geo.TX != 0 || c4 % geo.TX != 0) return FB_ERR_UNSUPPORTED;
+  geo.slabs = c4 / geo.TX;
+  const int TY = 256 / geo.TX;
+  if (policy_groups < 1) policy_groups = 1;
+  long long target = (2LL * kNumSMs) / ((long long)policy_groups * geo.slabs);
+  if (target < 1) target = 1;
+  long long most = P / (TY * 4);  // >= 4 rows per thread
+  if (most < 1) most = 1;
+  long long chunks = target < most ? target : most;
+  long long rpc = (P + chunks - 1) / chunks;
+  rpc = (rpc + TY - 1) / TY * TY;
+  geo.rows_per_chunk = int(rpc);
+  geo.chunks = int((P + rpc - 1) / rpc);
   return 0;
 }
 
@@ -1171,9 +801,8 @@ extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* m
   fin.running_var = running_var;
   fin.momentum = momentum;
   fin.eps = eps;
-  bn_reduce_kernel<false><<<dim3(chunks, slabs), 256, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, P, C, TX,
-                                                               rpc, ws);
-  bn_finalize_kernel<false><<<(C + 7) / 8, 256, 0, st>>>(ws, C, fin);
+  bn_reduce_kernel<<<dim3(chunks, slabs), 256, 0, st>>>(y, P, C, TX, rpc, ws);
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(ws, C, fin);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1181,33 +810,49 @@ extern "C" int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* m
 extern "C" int fb_bn_apply(const fb_bn_apply_args* a, void* stream) {
   FB_REQUIRE(a && a->y && a->mean && a->rstd && a->gamma && a->beta && a->out_hi, "fb_bn_apply: null pointer");
   FB_REQUIRE(a->C % 8 == 0 && a->P > 0, "fb_bn_apply: C must be a multiple of 8");
-  bn_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
-  FB_CUDA(cudaGetLastError());
+  FB_REQUIRE(!a->y2 || (a->mean2 && a->rstd2 && a->gamma2 && a->beta2), "fb_bn_apply: second branch incomplete");
+  fb_bn_apply_args k = *a;
+  if (k.ng <= 0) k.ng = 1;
+  FB_REQUIRE(k.ng <= FB_MAX_GROUPS, "fb_bn_apply: at most %d groups", FB_MAX_GROUPS);
+  // grid.x: a multiple of C/8-thread periods keeps the per-thread channel parameters loop invariant (C | 2048)
+  FB_CUDA(launch_pdl(bn_apply_kernel, dim3(stream_grid(k.P * k.C / 8), k.ng), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), k));
   return 0;
+}
+
+extern "C" int fb_bn_bwd_chunks(int64_t P, int C, int policy_groups) {
+  BnBwdGeom geo;
+  if (bwd_geometry(P, C, policy_groups, geo)) return -1;
+  return geo.chunks;
 }
 
 extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   FB_REQUIRE(a && a->dA && a->y && a->mean && a->rstd && a->gamma && a->ws && a->dgamma && a->dbeta && a->dy_bf16,
              "fb_bn_bwd: null pointer");
   FB_REQUIRE(a->C % 8 == 0 && a->P > 0, "fb_bn_bwd: C must be a multiple of 8");
-  int TX, slabs, chunks, rpc;
-  if (reduce_geometry(a->P, a->C, TX, slabs, chunks, rpc)) {
+  BnBwdK k;
+  k.a = *a;
+  if (k.a.ng <= 0) k.a.ng = 1;
+  FB_REQUIRE(k.a.ng <= FB_MAX_GROUPS, "fb_bn_bwd: at most %d groups", FB_MAX_GROUPS);
+  if (bwd_geometry(a->P, a->C, a->policy_groups > 0 ? a->policy_groups : k.a.ng, k.geo)) {
     set_error("fb_bn_bwd: unsupported channel count %d", a->C);
     return FB_ERR_UNSUPPORTED;
   }
+  k.tickets = reinterpret_cast<unsigned int*>(a->ws);
+  k.partial = a->ws + 16;
+  k.coef = k.partial + (long long)k.a.ng * k.geo.chunks * 2 * a->C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* coef = a->ws + (long long)2 * a->C * kMaxChunks;
-  BnFinalize fin = {};
-  fin.P = a->P;
-  fin.chunks = chunks;
-  fin.coef = coef;
-  fin.dgamma = a->dgamma;
-  fin.dbeta = a->dbeta;
-  bn_reduce_kernel<true><<<dim3(chunks, slabs), 256, 0, st>>>(a->y, a->dA, a->dA2, static_cast<const bf16*>(a->mask_hi),
-                                                              a->mean, a->rstd, a->P, a->C, TX, rpc, a->ws);
-  bn_finalize_kernel<true><<<(a->C + 7) / 8, 256, 0, st>>>(a->ws, a->C, fin);
-  bn_bwd_apply_kernel<<<stream_grid(a->P * a->C / 8), 256, 0, st>>>(*a, coef);
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(launch_pdl(bn_bwd_reduce_kernel, dim3(k.geo.chunks, k.geo.slabs, k.a.ng), dim3(256), 0, st, k));
+  FB_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(stream_grid(a->P * a->C / 8), k.a.ng), dim3(256), 0, st, k));
+  return 0;
+}
+
+extern "C" int fb_bn_ema_multi(const fb_bn_ema_entry* table_dev, int n_entries, int total_channels, int n_passes, int ng,
+                               float momentum, void* stream) {
+  FB_REQUIRE(table_dev && n_entries > 0 && total_channels > 0 && n_passes >= 1 && ng >= 1 && ng <= FB_MAX_GROUPS,
+             "fb_bn_ema_multi: bad arguments");
+  FB_CUDA(launch_pdl(bn_ema_multi_kernel, dim3((total_channels + 255) / 256), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), table_dev, n_entries, total_channels, n_passes, ng, momentum));
   return 0;
 }
 
@@ -1228,157 +873,22 @@ extern "C" int fb_avgpool2_bwd(const float* dP, int n, int h, int w, int c, floa
 }
 
 extern "C" int fb_stem_im2col(const float* x, const int64_t* labels, const int64_t* perm, const int32_t* first_dev,
-                              int64_t first, int n, void* patches_hi, void* patches_lo, int64_t* labels_out,
-                              void* stream) {
+                              int64_t first, int cursor_stride, int n, void* patches_hi, void* patches_lo,
+                              int64_t* labels_out, void* stream) {
   FB_REQUIRE(x && patches_hi && n > 0, "fb_stem_im2col: bad arguments");
   FB_REQUIRE(!labels_out || labels, "fb_stem_im2col: labels_out needs labels");
   FB_CUDA(launch_pdl(stem_im2col_kernel, dim3(stream_grid((long long)n * 1024 * 8)), dim3(256), 0,
                      static_cast<cudaStream_t>(stream), x, reinterpret_cast<const long long*>(labels),
-                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, n,
+                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, cursor_stride, n,
                      static_cast<bf16*>(patches_hi), static_cast<bf16*>(patches_lo),
                      reinterpret_cast<long long*>(labels_out)));
   return 0;
 }
 
-extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw, int c, const float* fc_w,
-                               const float* fc_b, const int64_t* labels, int classes, float smoothing, float* ws,
-                               float* scal, int loss_slot, int correct_slot, float* d_fcw, float* d_fcb, float* dA,
-                               void* stream) {
-  FB_REQUIRE(a_hi && fc_w && fc_b && labels && ws && scal && d_fcw && d_fcb && dA, "fb_head_fwd_bwd: null pointer");
-  if (classes > kMaxClasses || classes < 2) {
-    set_error("fb_head_fwd_bwd: classes %d not supported (max %d)", classes, kMaxClasses);
-    return FB_ERR_UNSUPPORTED;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* pooled = ws;
-  float* dlogits = pooled + (long long)n * c;
-  float* loss_n = dlogits + (long long)n * kMaxClasses;
-  float* correct_n = loss_n + n;
-  FB_CUDA(launch_pdl(head_fwd_kernel, dim3(n), dim3(128), (c + kMaxClasses) * sizeof(float), st,
-                     static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
-                     reinterpret_cast<const long long*>(labels), classes, smoothing, pooled, dlogits, loss_n, correct_n));
-  FB_CUDA(launch_pdl(head_bwd_act_kernel, dim3((c + 127) / 128, n), dim3(128), 0, st, (const float*)dlogits, fc_w, hw, c,
-                     classes, dA));
-  FB_CUDA(launch_pdl(head_bwd_param_kernel, dim3((c + 31) / 32), dim3(256), 0, st, (const float*)dlogits,
-                     (const float*)pooled, (const float*)loss_n, (const float*)correct_n, n, c, classes, d_fcw, d_fcb, scal,
-                     loss_slot, correct_slot));
-  return 0;
-}
-
-static int fused_geometry(long long P, int C, int& grid, int& rows_per_block) {
-  if (C % 8 != 0) return FB_ERR_UNSUPPORTED;
-  const int c4 = C / 4;
-  const int TX = c4 < 256 ? c4 : 256;
-  if (256 % TX != 0 || c4 % TX != 0) return FB_ERR_UNSUPPORTED;
-  const int TY = 256 / TX;
-  // every block must own whole groups of TY rows and an element range that keeps the channel offset thread-invariant:
-  // rows_per_block is a multiple of lcm(TY, 2048 / C)
-  int unit = TY;
-  const int inv = (2048 % C == 0) ? 2048 / C : 1;
-  if (inv > unit) unit = inv;
-  long long units = (P + unit - 1) / unit;
-  long long g = units < 2 * kNumSMs ? units : 2 * kNumSMs;
-  long long upb = (units + g - 1) / g;
-  rows_per_block = int(upb * unit);
-  grid = int((P + rows_per_block - 1) / rows_per_block);
-  return 0;
-}
-
-extern "C" int fb_bn_fwd_fused(const fb_bn_apply_args* ap, float* mean2_out, float* rstd2_out, float* running_mean,
-                               float* running_var, float* running_mean2, float* running_var2, float momentum,
-                               float eps, float* ws, const float* stats, int stats_rows, const float* stats2,
-                               int stats_rows2, void* stream) {
-  FB_REQUIRE(ap && ap->y && ap->mean && ap->rstd && ap->gamma && ap->beta && ap->out_hi && ws,
-             "fb_bn_fwd_fused: null pointer");
-  FB_REQUIRE(!ap->y2 || (mean2_out && rstd2_out && ap->gamma2 && ap->beta2), "fb_bn_fwd_fused: second branch incomplete");
-  int grid, rpb;
-  if (fused_geometry(ap->P, ap->C, grid, rpb)) {
-    set_error("fb_bn_fwd_fused: unsupported channel count %d", ap->C);
-    return FB_ERR_UNSUPPORTED;
-  }
-  BnFusedFwdArgs a;
-  a.ap = *ap;
-  a.mean = const_cast<float*>(ap->mean);
-  a.rstd = const_cast<float*>(ap->rstd);
-  a.mean2 = mean2_out;
-  a.rstd2 = rstd2_out;
-  a.ap.mean2 = mean2_out;
-  a.ap.rstd2 = rstd2_out;
-  a.running_mean = running_mean;
-  a.running_var = running_var;
-  a.running_mean2 = running_mean2;
-  a.running_var2 = running_var2;
-  a.momentum = momentum;
-  a.eps = eps;
-  a.counters = reinterpret_cast<unsigned int*>(ws);
-  a.partial = ws + 4;
-  a.rows_per_block = rpb;
-  FB_REQUIRE(!stats || stats_rows > 0, "fb_bn_fwd_fused: stats_rows must be positive");
-  FB_REQUIRE(!stats || !ap->y2 || (stats2 && stats_rows2 > 0),
-             "fb_bn_fwd_fused: epilogue statistics must be given for both branches or for none");
-  a.ext0 = stats;
-  a.ext_rows0 = stats_rows;
-  a.ext1 = stats2;
-  a.ext_rows1 = stats_rows2;
-  int sw, rows_per_cta;
-  if (stats && sliced_geometry(ap->P, ap->C, sw, rows_per_cta)) {
-    FB_CUDA(launch_pdl(bn_fwd_sliced_kernel, dim3(kSliceCtas, ap->C / sw), dim3(256), 0,
-                       static_cast<cudaStream_t>(stream), a, sw, rows_per_cta));
-    return 0;
-  }
-  FB_CUDA(launch_pdl(bn_fwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
-  return 0;
-}
-
-extern "C" int fb_bn_bwd_fused(const fb_bn_bwd_args* bw, void* stream) {
-  FB_REQUIRE(bw && bw->dA && bw->y && bw->mean && bw->rstd && bw->gamma && bw->ws && bw->dgamma && bw->dbeta &&
-                 bw->dy_bf16,
-             "fb_bn_bwd_fused: null pointer");
-  FB_REQUIRE(!bw->dz_accumulate, "fb_bn_bwd_fused: dz_accumulate is not supported");
-  FB_REQUIRE(!bw->stats || (bw->stats_rows > 0 && !bw->dA2),
-             "fb_bn_bwd_fused: epilogue statistics need stats_rows > 0 and a single gradient addend");
-  int grid, rpb;
-  if (fused_geometry(bw->P, bw->C, grid, rpb)) {
-    set_error("fb_bn_bwd_fused: unsupported channel count %d", bw->C);
-    return FB_ERR_UNSUPPORTED;
-  }
-  BnFusedBwdArgs a;
-  a.bw = *bw;
-  a.counters = reinterpret_cast<unsigned int*>(bw->ws);
-  a.partial = bw->ws + 4;
-  a.coef = a.partial + (long long)2 * bw->C * 2 * kNumSMs;
-  a.rows_per_block = rpb;
-  int sw, rows_per_cta;
-  if (sliced_geometry(bw->P, bw->C, sw, rows_per_cta)) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kSliceCtas, bw->C / sw);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kSliceCtas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    int n_attr = 1;
-    if (pdl_enabled()) {
-      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[1].val.programmaticStreamSerializationAllowed = 1;
-      n_attr = 2;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n_attr;
-    FB_CUDA(cudaLaunchKernelEx(&cfg, bn_bwd_cluster_kernel, a, sw, rows_per_cta));
-    return 0;
-  }
-  FB_CUDA(launch_pdl(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
-  return 0;
-}
-
 extern "C" int fb_stem_im2col_u8aug(const uint8_t* x_hwc, const int64_t* labels, const int64_t* perm,
-                                    const int32_t* first_dev, int64_t first, int n, const int8_t* aug,
-                                    const float* mean3, const float* std3, void* patches_hi, void* patches_lo,
-                                    int64_t* labels_out, void* stream) {
+                                    const int32_t* first_dev, int64_t first, int cursor_stride, int n,
+                                    const int8_t* aug, const float* mean3, const float* std3, void* patches_hi,
+                                    void* patches_lo, int64_t* labels_out, void* stream) {
   FB_REQUIRE(x_hwc && patches_hi && mean3 && std3 && n > 0, "fb_stem_im2col_u8aug: bad arguments");
   FB_REQUIRE(!labels_out || labels, "fb_stem_im2col_u8aug: labels_out needs labels");
   AugNorm nrm;
@@ -1388,8 +898,37 @@ extern "C" int fb_stem_im2col_u8aug(const uint8_t* x_hwc, const int64_t* labels,
   }
   FB_CUDA(launch_pdl(stem_im2col_u8aug_kernel, dim3(stream_grid((long long)n * 1024 * 8)), dim3(256), 0,
                      static_cast<cudaStream_t>(stream), x_hwc, reinterpret_cast<const long long*>(labels),
-                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, n,
+                     reinterpret_cast<const long long*>(perm), first_dev, (long long)first, cursor_stride, n,
                      reinterpret_cast<const char4*>(aug), nrm, static_cast<bf16*>(patches_hi),
                      static_cast<bf16*>(patches_lo), reinterpret_cast<long long*>(labels_out)));
+  return 0;
+}
+
+extern "C" int fb_head_fwd_bwd(const void* a_hi, const void* a_lo, int n, int hw, int c, const float* fc_w,
+                               const float* fc_b, const int64_t* labels, int classes, float smoothing, float* ws,
+                               float* scal, int loss_base, int correct_base, float* d_fcw, float* d_fcb, float* dA,
+                               int ng, int64_t param_gstride, int64_t grad_gstride, void* stream) {
+  FB_REQUIRE(a_hi && fc_w && fc_b && labels && ws && scal && d_fcw && d_fcb && dA, "fb_head_fwd_bwd: null pointer");
+  if (classes > kMaxClasses || classes < 2) {
+    set_error("fb_head_fwd_bwd: classes %d not supported (max %d)", classes, kMaxClasses);
+    return FB_ERR_UNSUPPORTED;
+  }
+  if (ng <= 0) ng = 1;
+  FB_REQUIRE(ng <= FB_MAX_GROUPS, "fb_head_fwd_bwd: at most %d groups", FB_MAX_GROUPS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nt = (long long)ng * n;
+  float* pooled = ws;
+  float* dlogits = pooled + nt * c;
+  float* loss_n = dlogits + nt * kMaxClasses;
+  float* correct_n = loss_n + nt;
+  FB_CUDA(launch_pdl(head_fwd_kernel, dim3((unsigned)nt), dim3(128), (c + kMaxClasses) * sizeof(float), st,
+                     static_cast<const bf16*>(a_hi), static_cast<const bf16*>(a_lo), n, hw, c, fc_w, fc_b,
+                     (long long)param_gstride, reinterpret_cast<const long long*>(labels), classes, smoothing, pooled,
+                     dlogits, loss_n, correct_n));
+  FB_CUDA(launch_pdl(head_bwd_act_kernel, dim3((c + 127) / 128, (unsigned)nt), dim3(128), 0, st, (const float*)dlogits,
+                     fc_w, (long long)param_gstride, n, hw, c, classes, dA));
+  FB_CUDA(launch_pdl(head_bwd_param_kernel, dim3((c + 31) / 32, ng), dim3(256), 0, st, (const float*)dlogits,
+                     (const float*)pooled, (const float*)loss_n, (const float*)correct_n, n, c, classes, d_fcw, d_fcb,
+                     (long long)grad_gstride, scal, loss_base, correct_base));
   return 0;
 }

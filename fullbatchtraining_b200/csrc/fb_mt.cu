@@ -1,12 +1,15 @@
 // Flat-buffer ("multi-tensor") kernels of the full-batch step (sm_100a).
 //
 // All parameters / gradients live in persistent flat fp32 buffers in model.parameters() order (the order of
-// fullbatch/training/utils.py:34), so every list-of-tensors `torch._foreach_*` sweep of the reference becomes one
-// vectorised, coalesced pass:
-//   fb_flat_sqnorm   : sum g^2                         (training.py:162, modules.py:223: 62 pow/sum kernels + stack)
-//   fb_fd_perturb    : eps_n, theta' = theta + eps_n*bs*g   (modules.py:215-226: clone + mul + add_)
-//   fb_fd_combine    : g += cf*(g2-g)/eps_n ; avg += (g-avg)/k   (modules.py:232-240 + training.py:45-47,165-168)
+// fullbatch/training/utils.py:34), one gradient buffer per microbatch group of a launch, so every list-of-tensors
+// `torch._foreach_*` sweep of the reference becomes one vectorised, coalesced pass over `ng` groups:
+//   fb_flat_sqnorm    : sum g^2 per group, eps_n per group      (training.py:162, modules.py:223: 62 pow/sum kernels)
+//   fb_perturb_ranges : theta' = theta + eps_n*v for the non-conv parameters (modules.py:215-226; conv weights are
+//                       perturbed inside fb_weight_prep_multi, theta' is never materialised for them)
+//   fb_fd_combine     : g += cf*(g2-g)/eps_n ; avg += (g-avg)/k, groups in loader order  (modules.py:232-240 +
+//                       training.py:45-47,165-168)
 // eps_n and the norms stay on the device (the reference syncs the host once per microbatch through alpha=eps_n).
+// Conv weight gradients are in the kernels' native [co][tap][ci] layout; fb_flat_relayout converts at the boundary.
 #include "../../include/fullbatch_b200.h"
 #include "fb_common.cuh"
 
@@ -14,21 +17,34 @@ namespace fb {
 
 constexpr int kSqBlocks = 1024;
 
-__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ x, long long n,
-                                                             double* __restrict__ partial) {
+// grid = (kSqBlocks, ng)
+__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ x, long long x_gstride,
+                                                             const float* __restrict__ y, float a, float b,
+                                                             long long n, double* __restrict__ partial) {
   griddep_wait();
   griddep_launch();
   __shared__ double red[8];
+  const int g = blockIdx.y;
+  const float* xg = x + (long long)g * x_gstride;
   float acc = 0.f;
-  const long long n4 = n / 4;
-  const float4* x4 = reinterpret_cast<const float4*>(x);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = x4[i];
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
-    const float v = x[n4 * 4 + threadIdx.x];
-    acc += v * v;
+  if (!y && a == 1.f) {
+    const long long n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(xg);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = x4[i];
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
+      const float v = xg[n4 * 4 + threadIdx.x];
+      acc += v * v;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float v = a * xg[i] + (y ? b * y[i] : 0.f);
+      acc += v * v;
+    }
   }
   double d = warp_sum(double(acc));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
@@ -36,89 +52,201 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += red[i];
-    partial[blockIdx.x] = s;
+    partial[(long long)g * gridDim.x + blockIdx.x] = s;
   }
 }
 
+// grid = ng
 __global__ void __launch_bounds__(256) sqnorm_final_kernel(const double* __restrict__ partial, int nblocks,
-                                                           float* __restrict__ scal, int slot,
+                                                           float* __restrict__ scal, int slot_base,
                                                            float* __restrict__ norms_out,
-                                                           const int* __restrict__ cursor) {
+                                                           const int* __restrict__ cursor, int eps_mode, float bs,
+                                                           float eps, int eps_base) {
   griddep_wait();
   griddep_launch();
   __shared__ double red[8];
+  const int g = blockIdx.x;
   double d = 0.0;
-  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) d += partial[i];
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) d += partial[(long long)g * nblocks + i];
   d = warp_sum(d);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += red[i];
-    scal[slot] = float(s);
-    if (norms_out) norms_out[cursor ? *cursor : 0] = float(s);
+    const float n2 = float(s);
+    scal[slot_base + g] = n2;
+    if (norms_out) norms_out[(cursor ? *cursor : 0) + g] = n2;
+    if (eps_mode == 1) scal[eps_base + g] = eps / sqrtf(bs * bs * n2);  // modules.py:223 with v = bs*g
+    if (eps_mode == 2) scal[eps_base + g] = eps / sqrtf(n2);
   }
 }
 
-__global__ void __launch_bounds__(256) fd_perturb_kernel(const float* __restrict__ theta, const float* __restrict__ g,
-                                                         long long n, float bs, float eps, float* __restrict__ scal,
-                                                         int sq_slot, int eps_slot, float* __restrict__ theta_p) {
+// grid = (blocks, ng); thread -> element of the concatenated ranges (binary search over the first-thread column)
+__global__ void __launch_bounds__(256) perturb_ranges_kernel(const float* __restrict__ theta,
+                                                             const float* __restrict__ grad, long long grad_gstride,
+                                                             const float* __restrict__ pre,
+                                                             const long long* __restrict__ ranges, int n_ranges,
+                                                             long long total, float bs, float acc, float scale,
+                                                             const float* __restrict__ scal, int eps_base,
+                                                             float* __restrict__ theta_p, long long theta_p_gstride) {
   griddep_wait();
   griddep_launch();
-  const float n2 = scal[sq_slot];
-  // modules.py:223: eps / sqrt(sum (bs*g)^2)
-  const float eps_n = eps / sqrtf(bs * bs * n2);
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal[eps_slot] = eps_n;
-  const long long n4 = n / 4;
-  const float4* t4 = reinterpret_cast<const float4*>(theta);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  float4* o4 = reinterpret_cast<float4*>(theta_p);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 t = t4[i], v = g4[i];
-    o4[i] = make_float4(t.x + eps_n * (bs * v.x), t.y + eps_n * (bs * v.y), t.z + eps_n * (bs * v.z),
-                        t.w + eps_n * (bs * v.w));
-  }
-  if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
-    const long long i = n4 * 4 + threadIdx.x;
-    theta_p[i] = theta[i] + eps_n * (bs * g[i]);
+  const int g = blockIdx.y;
+  const float step = scale * scal[eps_base + g];
+  const float* gg = grad + (long long)g * grad_gstride;
+  float* out = theta_p + (long long)g * theta_p_gstride;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_ranges - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (ranges[3 * mid + 2] <= t) lo = mid; else hi = mid - 1;
+    }
+    const long long i = ranges[3 * lo] + (t - ranges[3 * lo + 2]);
+    float v = bs * gg[i];
+    if (pre && acc != 0.f) v += acc * pre[i];
+    out[i] = theta[i] + step * v;
   }
 }
 
-template <bool REG>
-__global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ g, const float* __restrict__ g2,
-                                                         float* __restrict__ avg, long long n,
-                                                         const float* __restrict__ scal, int eps_slot, float cf,
-                                                         int cf_slot, const int* __restrict__ cursor, int count0,
-                                                         int write_g) {
+__global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ grad, const float* __restrict__ g_plus,
+                                                         const float* __restrict__ g_minus, long long gstride,
+                                                         float* __restrict__ avg, long long n, int ng,
+                                                         const float* __restrict__ scal, int eps_base, int cf_slot,
+                                                         const int* __restrict__ cursor, int write_g) {
   griddep_wait();
   griddep_launch();
-  const float eps_n = REG ? scal[eps_slot] : 1.f;
-  if (REG && cf_slot >= 0) cf = scal[cf_slot];
-  const int count = count0 + (cursor ? *cursor : 0) + 1;
-  const float inv = float(1.0 / double(count));
+  const float cf = scal[cf_slot];
+  const int count0 = cursor ? *cursor : 0;
+  float eps_n[FB_MAX_GROUPS], inv[FB_MAX_GROUPS];
+#pragma unroll
+  for (int g = 0; g < FB_MAX_GROUPS; ++g) {
+    eps_n[g] = g < ng ? scal[eps_base + g] : 1.f;
+    inv[g] = float(1.0 / double(count0 + g + 1));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float gr = g[i];
-    if (REG) {
-      const float h = (g2[i] - gr) / eps_n;  // modules.py:232-234
-      gr = gr + cf * h;                       // modules.py:240
-      if (write_g) g[i] = gr;
+    float a = avg ? avg[i] : 0.f;
+#pragma unroll
+    for (int g = 0; g < FB_MAX_GROUPS; ++g) {
+      if (g >= ng) break;
+      const long long o = (long long)g * gstride + i;
+      float gr = grad[o];
+      const float base = g_minus ? g_minus[o] : gr;
+      const float h = (g_plus[o] - base) / eps_n[g];  // modules.py:232-234 / :292-293
+      gr = gr + cf * h;                               // modules.py:240 / :299
+      if (write_g) grad[o] = gr;
+      a = a + (gr - a) * inv[g];                      // training.py:45-47
     }
-    if (avg) {
-      const float a = avg[i];
-      avg[i] = a + (gr - a) * inv;  // training.py:45-47
-    }
+    if (avg) avg[i] = a;
   }
 }
 
-__global__ void cursor_add_kernel(int* cursor, int delta) {
+__global__ void __launch_bounds__(256) mean_accumulate_kernel(float* __restrict__ grad, long long gstride,
+                                                              float* __restrict__ avg, long long n, int ng,
+                                                              const int* __restrict__ cursor, float* __restrict__ scal,
+                                                              int norm_base, float clip, int clipped_slot) {
   griddep_wait();
   griddep_launch();
-  *cursor += delta;
+  const int count0 = cursor ? *cursor : 0;
+  float coef[FB_MAX_GROUPS], inv[FB_MAX_GROUPS];
+  bool clipped[FB_MAX_GROUPS];
+  int n_clipped = 0;
+#pragma unroll
+  for (int g = 0; g < FB_MAX_GROUPS; ++g) {
+    coef[g] = 1.f;
+    clipped[g] = false;
+    inv[g] = float(1.0 / double(count0 + g + 1));
+    if (g < ng && clip > 0.f) {
+      const float norm = sqrtf(scal[norm_base + g]);
+      if (norm > clip) {  // training/utils.py:4-19
+        coef[g] = clip / (norm + 1e-6f);
+        clipped[g] = true;
+        ++n_clipped;
+      }
+    }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = avg[i];
+#pragma unroll
+    for (int g = 0; g < FB_MAX_GROUPS; ++g) {
+      if (g >= ng) break;
+      const long long o = (long long)g * gstride + i;
+      const float gr = grad[o] * coef[g];
+      if (clipped[g]) grad[o] = gr;  // the reference scales the microbatch gradient in place
+      a = a + (gr - a) * inv[g];
+    }
+    avg[i] = a;
+  }
+  if (n_clipped && blockIdx.x == 0 && threadIdx.x == 0) scal[clipped_slot] += float(n_clipped);
+}
+
+__global__ void group_finish_kernel(int* cursor, int ng, float* scal, int loss_slot, int correct_slot, int loss_base,
+                                    int correct_base) {
+  griddep_wait();
+  griddep_launch();
+  float loss = scal[loss_slot], correct = scal[correct_slot];
+  for (int g = 0; g < ng; ++g) {  // training.py:172-173, loader order
+    loss += scal[loss_base + g];
+    correct += scal[correct_base + g];
+  }
+  scal[loss_slot] = loss;
+  scal[correct_slot] = correct;
+  *cursor += ng;
 }
 
 __global__ void __launch_bounds__(256) flat_scale_kernel(float* __restrict__ x, long long n, float alpha) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] *= alpha;
+}
+
+// One block per (3x3 conv, co): [ci][tap] <-> [tap][ci] through shared memory; a leading grid-stride copy moves
+// everything else.  table: (offset, cout, cin, taps, first block) per conv.
+__global__ void __launch_bounds__(256) flat_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            long long n, const long long* __restrict__ table,
+                                                            int n_entries, int conv_blocks, int to_native) {
+  extern __shared__ float tile[];
+  if ((int)blockIdx.x >= conv_blocks) {  // the remaining blocks copy everything that is not a permuted conv weight
+    const long long nb = gridDim.x - conv_blocks;
+    for (long long i = (long long)(blockIdx.x - conv_blocks) * blockDim.x + threadIdx.x; i < n; i += nb * blockDim.x) {
+      // elements of a permuted conv are written by that conv's own blocks
+      int lo = 0, hi = n_entries - 1;
+      bool in_conv = false;
+      if (n_entries > 0 && i >= table[0]) {
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (table[5 * mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        in_conv = i < table[5 * lo] + table[5 * lo + 1] * table[5 * lo + 2] * table[5 * lo + 3];
+      }
+      if (!in_conv) dst[i] = src[i];
+    }
+    return;
+  }
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[5 * mid + 4] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const long long off = table[5 * lo];
+  const int cin = int(table[5 * lo + 2]), taps = int(table[5 * lo + 3]);
+  const int co = int(blockIdx.x - table[5 * lo + 4]);
+  const long long base = off + (long long)co * cin * taps;
+  const int len = cin * taps;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) tile[i] = src[base + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    // to_native: dst[tap][ci] = src[ci][tap]; else dst[ci][tap] = src[tap][ci]
+    int s;
+    if (to_native) {
+      const int tap = i / cin, ci = i % cin;
+      s = ci * taps + tap;
+    } else {
+      const int ci = i / taps, tap = i % taps;
+      s = tap * cin + ci;
+    }
+    dst[base + i] = tile[s];
+  }
 }
 
 static int flat_grid(long long n) {
@@ -131,54 +259,78 @@ static int flat_grid(long long n) {
 
 using namespace fb;
 
-extern "C" int fb_flat_sqnorm(const float* x, int64_t n, double* ws, float* scal, int slot, float* norms_out,
-                              const int32_t* cursor, void* stream) {
-  FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm: bad arguments");
-  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fb_flat_sqnorm: x must be 16-byte aligned");
+extern "C" int fb_flat_sqnorm(const float* x, int64_t x_gstride, const float* y, float a, float b, int64_t n, int ng,
+                              double* ws, float* scal, int slot_base, float* norms_out, const int32_t* cursor,
+                              int eps_mode, float bs, float eps, int eps_base, void* stream) {
+  FB_REQUIRE(x && ws && scal && n > 0 && ng >= 1 && ng <= FB_MAX_GROUPS, "fb_flat_sqnorm: bad arguments");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && x_gstride % 4 == 0,
+             "fb_flat_sqnorm: x and its group stride must be 16-byte aligned");
+  FB_REQUIRE(eps_mode >= 0 && eps_mode <= 2, "fb_flat_sqnorm: eps_mode must be 0, 1 or 2");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  FB_CUDA(launch_pdl(sqnorm_partial_kernel, dim3(kSqBlocks), dim3(256), 0, st, x, (long long)n, ws));
-  FB_CUDA(launch_pdl(sqnorm_final_kernel, dim3(1), dim3(256), 0, st, (const double*)ws, kSqBlocks, scal, slot, norms_out,
-                     (const int*)cursor));
+  FB_CUDA(launch_pdl(sqnorm_partial_kernel, dim3(kSqBlocks, ng), dim3(256), 0, st, x, (long long)x_gstride, y, a, b,
+                     (long long)n, ws));
+  FB_CUDA(launch_pdl(sqnorm_final_kernel, dim3(ng), dim3(256), 0, st, (const double*)ws, kSqBlocks, scal, slot_base,
+                     norms_out, (const int*)cursor, eps_mode, bs, eps, eps_base));
   return 0;
 }
 
-extern "C" int fb_fd_perturb(const float* theta, const float* g, int64_t n, float block_strength, float eps, float* scal,
-                             int sq_slot, int eps_slot, float* theta_p, void* stream) {
-  FB_REQUIRE(theta && g && scal && theta_p && n > 0, "fb_fd_perturb: bad arguments");
-  FB_REQUIRE(((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) |
-               reinterpret_cast<uintptr_t>(theta_p)) & 15) == 0,
-             "fb_fd_perturb: buffers must be 16-byte aligned");
-  FB_CUDA(launch_pdl(fd_perturb_kernel, dim3(flat_grid(n / 4 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), theta,
-                     g, (long long)n, block_strength, eps, scal, sq_slot, eps_slot, theta_p));
+extern "C" int fb_perturb_ranges(const float* theta, const float* grad, int64_t grad_gstride, const float* pre,
+                                 const int64_t* ranges_dev, int n_ranges, int64_t total, float bs, float acc,
+                                 float scale, const float* scal, int eps_base, float* theta_p, int64_t theta_p_gstride,
+                                 int ng, void* stream) {
+  FB_REQUIRE(theta && grad && ranges_dev && scal && theta_p && n_ranges > 0 && total > 0 && ng >= 1 &&
+                 ng <= FB_MAX_GROUPS,
+             "fb_perturb_ranges: bad arguments");
+  FB_CUDA(launch_pdl(perturb_ranges_kernel, dim3(flat_grid(total), ng), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                     theta, grad, (long long)grad_gstride, pre, reinterpret_cast<const long long*>(ranges_dev), n_ranges,
+                     (long long)total, bs, acc, scale, scal, eps_base, theta_p, (long long)theta_p_gstride));
   return 0;
 }
 
-extern "C" int fb_fd_combine(float* g, const float* g2, float* avg, int64_t n, const float* scal, int eps_slot, float cf,
-                             int cf_slot, const int32_t* cursor, int32_t count0, int write_g, void* stream) {
-  FB_REQUIRE(g && g2 && scal && n > 0, "fb_fd_combine: bad arguments");
-  FB_CUDA(launch_pdl(fd_combine_kernel<true>, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g, g2,
-                     avg, (long long)n, scal, eps_slot, cf, cf_slot, (const int*)cursor, (int)count0, write_g));
+extern "C" int fb_fd_combine(float* grad, const float* g_plus, const float* g_minus, int64_t gstride, float* avg,
+                             int64_t n, int ng, const float* scal, int eps_base, int cf_slot, const int32_t* cursor,
+                             int write_g, void* stream) {
+  FB_REQUIRE(grad && g_plus && scal && n > 0 && ng >= 1 && ng <= FB_MAX_GROUPS && cf_slot >= 0,
+             "fb_fd_combine: bad arguments");
+  FB_CUDA(launch_pdl(fd_combine_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), grad,
+                     g_plus, g_minus, (long long)gstride, avg, (long long)n, ng, scal, eps_base, cf_slot,
+                     (const int*)cursor, write_g));
   return 0;
 }
 
-extern "C" int fb_mean_accumulate(const float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0,
-                                  void* stream) {
-  FB_REQUIRE(g && avg && n > 0, "fb_mean_accumulate: bad arguments");
-  FB_CUDA(launch_pdl(fd_combine_kernel<false>, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                     const_cast<float*>(g), (const float*)nullptr, avg, (long long)n, (const float*)nullptr, 0, 0.f, -1,
-                     (const int*)cursor, (int)count0, 0));
+extern "C" int fb_mean_accumulate(float* grad, int64_t gstride, float* avg, int64_t n, int ng, const int32_t* cursor,
+                                  float* scal, int norm_base, float clip, int clipped_slot, void* stream) {
+  FB_REQUIRE(grad && avg && n > 0 && ng >= 1 && ng <= FB_MAX_GROUPS, "fb_mean_accumulate: bad arguments");
+  FB_REQUIRE(clip <= 0.f || scal, "fb_mean_accumulate: clipping needs scal");
+  FB_CUDA(launch_pdl(mean_accumulate_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), grad,
+                     (long long)gstride, avg, (long long)n, ng, (const int*)cursor, scal, norm_base, clip,
+                     clipped_slot));
   return 0;
 }
 
-extern "C" int fb_cursor_add(int32_t* cursor, int32_t delta, void* stream) {
-  FB_REQUIRE(cursor, "fb_cursor_add: null pointer");
-  FB_CUDA(launch_pdl(cursor_add_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), (int*)cursor, (int)delta));
+extern "C" int fb_group_finish(int32_t* cursor, int ng, float* scal, int loss_slot, int correct_slot, int loss_base,
+                               int correct_base, void* stream) {
+  FB_REQUIRE(cursor && scal && ng >= 1 && ng <= FB_MAX_GROUPS, "fb_group_finish: bad arguments");
+  FB_CUDA(launch_pdl(group_finish_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), (int*)cursor, ng, scal,
+                     loss_slot, correct_slot, loss_base, correct_base));
   return 0;
 }
 
 extern "C" int fb_flat_scale(float* x, int64_t n, float alpha, void* stream) {
   FB_REQUIRE(x && n > 0, "fb_flat_scale: bad arguments");
   flat_scale_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, alpha);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_flat_relayout(const float* src, float* dst, int64_t n, const int64_t* table_dev, int n_entries,
+                                int total_blocks, int to_native, void* stream) {
+  FB_REQUIRE(src && dst && src != dst && n > 0 && (n_entries == 0 || table_dev) && total_blocks >= 0,
+             "fb_flat_relayout: bad arguments");
+  const int copy_blocks = flat_grid(n);
+  const size_t smem = size_t(512) * 9 * sizeof(float);  // cin <= 512 for 3x3 convs of the ResNet family
+  flat_relayout_kernel<<<total_blocks + copy_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      src, dst, (long long)n, reinterpret_cast<const long long*>(table_dev), n_entries, total_blocks, to_native);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -191,6 +343,7 @@ extern "C" int fb_flat_scale(float* x, int64_t n, float alpha, void* stream) {
 //   d = g * coef + wd * theta ; buf = first ? d : momentum * buf + (1 - dampening) * d ; d = nesterov ? d + momentum*buf
 //   : buf ; theta -= lr * d            (torch/optim/sgd.py, _single_tensor_sgd, same operation order)
 // ---------------------------------------------------------------------------------------------------------------
+namespace fb {
 __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ theta, float* __restrict__ g,
                                                        float* __restrict__ buf, long long n,
                                                        const float* __restrict__ scal, int norm_slot, float clip,
@@ -227,6 +380,7 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ theta
     partial[blockIdx.x] = tot;
   }
 }
+}  // namespace fb
 
 extern "C" int fb_sgd_step(float* theta, float* grad, float* momentum_buf, int64_t n, float* scal, int norm_slot,
                            float clip, float lr, float momentum, float dampening, float weight_decay, int nesterov,
@@ -237,129 +391,7 @@ extern "C" int fb_sgd_step(float* theta, float* grad, float* momentum_buf, int64
   const int blocks = flat_grid(n) < kSqBlocks ? flat_grid(n) : kSqBlocks;
   sgd_step_kernel<<<blocks, 256, 0, st>>>(theta, grad, momentum_buf, n, scal, norm_slot, clip, lr, momentum, dampening,
                                           weight_decay, nesterov, first_step, write_clipped_grad, ws);
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, blocks, scal, param_norm_slot, nullptr, nullptr);
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, blocks, scal, param_norm_slot, nullptr, nullptr, 0, 0.f, 0.f, 0);
   FB_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Generalised variants for the rest of the hyp.grad_reg surface:
-//   acc_strength  : v = bs*g + acc*pre_grads                       (modules.py:217-221, training.py:128-142)
-//   central diffs : theta +- 0.5*eps_n*v, vhp = (g+ - g-)/eps_n    (modules.py:266-300)
-//   batch_clip    : per-microbatch L2 clip before the running mean (training/utils.py:4-19, training.py:166-168)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sqnorm_axpby_partial_kernel(const float* __restrict__ x,
-                                                                   const float* __restrict__ y, float a, float b,
-                                                                   long long n, double* __restrict__ partial) {
-  __shared__ double red[8];
-  griddep_wait();
-  griddep_launch();
-  float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = a * x[i] + (y ? b * y[i] : 0.f);
-    acc += v * v;
-  }
-  double d = warp_sum(double(acc));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < 8; ++i) s += red[i];
-    partial[blockIdx.x] = s;
-  }
-}
-
-__global__ void __launch_bounds__(256) fd_perturb_ex_kernel(const float* __restrict__ theta, const float* __restrict__ g,
-                                                            const float* __restrict__ pre, long long n, float bs,
-                                                            float acc, float eps, float scale, float* __restrict__ scal,
-                                                            int vsq_slot, int eps_slot, float* __restrict__ theta_p) {
-  griddep_wait();
-  griddep_launch();
-  const float eps_n = eps / sqrtf(scal[vsq_slot]);  // scal[vsq_slot] = sum v^2
-  if (blockIdx.x == 0 && threadIdx.x == 0) scal[eps_slot] = eps_n;
-  const float step = scale * eps_n;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = bs * g[i] + (pre ? acc * pre[i] : 0.f);
-    theta_p[i] = theta[i] + step * v;
-  }
-}
-
-__global__ void __launch_bounds__(256) fd_combine_ex_kernel(float* __restrict__ g, const float* __restrict__ g_plus,
-                                                            const float* __restrict__ g_minus, float* __restrict__ avg,
-                                                            long long n, const float* __restrict__ scal, int eps_slot,
-                                                            float cf, int cf_slot, const int* __restrict__ cursor,
-                                                            int count0, int write_g) {
-  griddep_wait();
-  griddep_launch();
-  const float eps_n = scal[eps_slot];
-  if (cf_slot >= 0) cf = scal[cf_slot];
-  const int count = count0 + (cursor ? *cursor : 0) + 1;
-  const float inv = float(1.0 / double(count));
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float h = (g_plus[i] - g_minus[i]) / eps_n;  // modules.py:292-293
-    const float gr = g[i] + cf * h;                    // modules.py:299
-    if (write_g) g[i] = gr;
-    if (avg) {
-      const float a = avg[i];
-      avg[i] = a + (gr - a) * inv;
-    }
-  }
-}
-
-// avg += (coef*g - avg)/count with coef = clip/(norm+1e-6) if norm > clip (norm = sqrt(scal[norm_slot]));
-// scal[clipped_slot] += 1 when the microbatch was clipped; g is scaled in place like the reference does.
-__global__ void __launch_bounds__(256) mean_accumulate_clip_kernel(float* __restrict__ g, float* __restrict__ avg,
-                                                                   long long n, const int* __restrict__ cursor,
-                                                                   int count0, float* __restrict__ scal, int norm_slot,
-                                                                   float clip, int clipped_slot) {
-  griddep_wait();
-  griddep_launch();
-  const float norm = sqrtf(scal[norm_slot]);
-  const bool clipped = norm > clip;
-  const float coef = clipped ? clip / (norm + 1e-6f) : 1.f;
-  const int count = count0 + (cursor ? *cursor : 0) + 1;
-  const float inv = float(1.0 / double(count));
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gr = g[i] * coef;
-    if (clipped) g[i] = gr;
-    const float a = avg[i];
-    avg[i] = a + (gr - a) * inv;
-  }
-  if (clipped && blockIdx.x == 0 && threadIdx.x == 0) scal[clipped_slot] += 1.f;
-}
-
-extern "C" int fb_flat_sqnorm_axpby(const float* x, const float* y, float a, float b, int64_t n, double* ws, float* scal,
-                                    int slot, void* stream) {
-  FB_REQUIRE(x && ws && scal && n > 0, "fb_flat_sqnorm_axpby: bad arguments");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  FB_CUDA(launch_pdl(sqnorm_axpby_partial_kernel, dim3(kSqBlocks), dim3(256), 0, st, x, y, a, b, (long long)n, ws));
-  FB_CUDA(launch_pdl(sqnorm_final_kernel, dim3(1), dim3(256), 0, st, (const double*)ws, kSqBlocks, scal, slot,
-                     (float*)nullptr, (const int*)nullptr));
-  return 0;
-}
-
-extern "C" int fb_fd_perturb_ex(const float* theta, const float* g, const float* pre, int64_t n, float block_strength,
-                                float acc_strength, float eps, float scale, float* scal, int vsq_slot, int eps_slot,
-                                float* theta_p, void* stream) {
-  FB_REQUIRE(theta && g && scal && theta_p && n > 0, "fb_fd_perturb_ex: bad arguments");
-  FB_CUDA(launch_pdl(fd_perturb_ex_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), theta, g,
-                     pre, (long long)n, block_strength, acc_strength, eps, scale, scal, vsq_slot, eps_slot, theta_p));
-  return 0;
-}
-
-extern "C" int fb_fd_combine_ex(float* g, const float* g_plus, const float* g_minus, float* avg, int64_t n,
-                                const float* scal, int eps_slot, float cf, int cf_slot, const int32_t* cursor,
-                                int32_t count0, int write_g, void* stream) {
-  FB_REQUIRE(g && g_plus && g_minus && scal && n > 0, "fb_fd_combine_ex: bad arguments");
-  FB_CUDA(launch_pdl(fd_combine_ex_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g, g_plus,
-                     g_minus, avg, (long long)n, scal, eps_slot, cf, cf_slot, (const int*)cursor, (int)count0, write_g));
-  return 0;
-}
-
-extern "C" int fb_mean_accumulate_clip(float* g, float* avg, int64_t n, const int32_t* cursor, int32_t count0,
-                                       float* scal, int norm_slot, float clip, int clipped_slot, void* stream) {
-  FB_REQUIRE(g && avg && scal && n > 0 && clip > 0.f, "fb_mean_accumulate_clip: bad arguments");
-  FB_CUDA(launch_pdl(mean_accumulate_clip_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), g,
-                     avg, (long long)n, (const int*)cursor, (int)count0, scal, norm_slot, clip, clipped_slot));
   return 0;
 }

@@ -1,20 +1,32 @@
-"""Whole-microbatch executor of the full-batch gradient-regularised step on one B200.
+"""Executor of the full-batch gradient-regularised step on one B200, G microbatches per launch.
 
 Replaces the device work of ``_accumulate_full_gradient`` (reference fullbatch/training/training.py:121-185) and
-``GradRegularizer._forward_differences`` (fullbatch/models/modules.py:211-241):
+``GradRegularizer._forward_differences`` (fullbatch/models/modules.py:211-241).  The reference walks its microbatches
+one by one; here ONE replay of a captured CUDA graph serves a GROUP LAUNCH of up to G consecutive microbatches ("groups"
+of the C ABI): every kernel of the network takes the group dimension, so a ResNet-18 step over 390 microbatches of 128
+images is 49 replays of ~190 large launches instead of 390 replays of 262 small ones.  Per group launch:
 
-  per microbatch k (a replay of ONE captured CUDA graph, no host synchronisation):
-    im2col of the microbatch (stem)                                              [fb_stem_im2col]
-    pass 1: forward / loss / backward at theta           -> g      (flat fp32)   [tcgen05 convs + layer kernels]
-    n2 = |g|^2 -> grad_norms[k]; eps_n = eps / (bs*sqrt(n2)); theta' = theta + eps_n*bs*g   [fb_flat_sqnorm, fb_fd_perturb]
-    pass 2: forward / loss / backward at theta'          -> g2
-    g_reg = g + (lr/4) (g2 - g)/eps_n ; avg += (g_reg - avg)/(k+1)               [fb_fd_combine]
+    im2col of the ng microbatches (stem)                                          [fb_stem_im2col]
+    pass 1: forward / loss / backward at theta (weights shared by the groups) -> g[0..ng)     [tcgen05 convs + layer kernels]
+    n2_k = |g_k|^2 -> grad_norms[k]; eps_k = eps / (bs*sqrt(n2_k))                [fb_flat_sqnorm]
+    pass 2: forward / backward of microbatch k at ITS point theta + eps_k*bs*g_k -> g2[0..ng)
+            (conv operands of the perturbed points come straight from fb_weight_prep_multi; BatchNorm / fc parameters from
+            fb_perturb_ranges; the weight tile of a GEMM tile is picked by the tile's group)
+    for k in loader order: g_reg = g_k + (lr/4)(g2_k - g_k)/eps_k ; avg += (g_reg - avg)/(k+1)          [fb_fd_combine]
+    BatchNorm running statistics: EMA in the reference's order (p1_k, p2_k, p1_{k+1}, ...)              [fb_bn_ema_multi]
+
+BatchNorm statistics, loss, gradient norm and weight gradient of a microbatch never mix with another microbatch's, and
+every reduction order is a function of one microbatch's problem only: results are bit-identical for every G.
 
 Persistent state (allocated once, kernels never allocate):
-  theta, theta', g, g2, avg : flat fp32 buffers in model.parameters() order (= training/utils.py:34 order);
-                              the model's parameters are re-pointed to views of ``theta`` so optimizers update it in place
-  per conv: bf16 hi/lo GEMM operands of the weights, refreshed from theta / theta' at the start of each pass
-  per layer: fp32 conv output, bf16 hi/lo activation planes, fp32 activation gradient, bf16 output gradient
+  theta                     : flat fp32 parameters in model.parameters() order (= training/utils.py:34 order); the model's
+                              parameters are re-pointed to views of it so optimizers update it in place
+  theta_p, g_n, g2_n        : [G][stride] perturbed non-conv parameters / per-microbatch gradients (conv weights in the
+                              kernels' native [co][tap][ci] layout)
+  avg_n -> avg              : running mean in native layout; converted once per step to `avg` (reference layout, the
+                              storage of param.grad)
+  per conv: bf16 hi/lo GEMM operands of theta (one set) and of the G perturbed points
+  per layer: fp32 conv output, bf16 hi/lo activation planes, fp32 activation gradient, bf16 output gradient, [G*mb] images
 
 theta itself is never modified by the regulariser, so the reference's "restore from a clone" (modules.py:237-238) is
 exact by construction.
@@ -23,11 +35,15 @@ import os
 
 import torch
 
+from . import lib as L
 from . import ops
 from .models import ResNet, ResidualBlock
 
-S_N2, S_EPS, S_LOSS, S_CORRECT, S_LOSS2, S_CORRECT2, S_CF = 0, 1, 2, 3, 4, 5, 6
-S_VSQ, S_CLIPPED, S_REGSQ = 9, 10, 11  # (7, 8 are used by optim.FlatSGD)
+# scal layout: single slots, then arrays of FB_MAX_GROUPS per-group slots
+S_LOSS, S_CORRECT, S_CF, S_CLIPPED = 0, 1, 2, 3
+S_GNORM, S_PNORM = 7, 8  # used by optim.FlatSGD
+S_N2G, S_EPSG, S_LOSSG, S_CORRG, S_LOSS2G, S_CORR2G, S_VSQG, S_REGSQG = (16 * i for i in range(1, 9))
+SCAL_SLOTS = 16 * 9
 
 # hyp.grad_reg.implementation -> device recipe.  `forward-differences-legacy` (modules.py:243-264) perturbs along g
 # instead of bs*g and scales the correction by bs: the same update up to rounding, so it shares the forward recipe.
@@ -35,6 +51,15 @@ IMPLEMENTATIONS = {"finite_diff": "forward", "forward-differences": "forward", "
                    "central-differences": "central"}
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+MAX_PASSES = 3  # train-mode forward passes of one group launch: pass 1 + forward FD (2) or central FD (3)
+
+
+def default_groups(microbatch):
+    """Microbatches per launch: ~1024 images (enough 128-pixel tiles for several waves of 148 SMs on the 4x4 stage)."""
+    env = os.environ.get("FB_GROUPS")
+    if env:
+        return max(1, min(L.FB_MAX_GROUPS, int(env)))
+    return max(1, min(L.FB_MAX_GROUPS, 1024 // max(int(microbatch), 1)))
 
 
 class Act:
@@ -53,59 +78,43 @@ class Act:
         self.grad2 = torch.zeros_like(self.grad)
         return self.grad2
 
-    @property
-    def P(self):
-        return self.n * self.h * self.w
-
 
 class Unit:
     """conv (bias-free) + BatchNorm: buffers, descriptors and parameter offsets."""
 
-    def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, dx_accumulate=False, needs_dx=True, stem=False,
-                 dx_target=None):
-        dev, split = eng.device, eng.split
+    def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, needs_dx=True, stem=False, dx_target=None):
+        dev, split, G = eng.device, eng.split, eng.G
         self.conv_name, self.bn_name, self.x, self.stem = conv_name, bn_name, x, stem
         self.cin, self.cout, self.k, self.stride = x.c, cout, k, stride
         n, h, w = x.n, x.h, x.w
         self.ho, self.wo = h // stride, w // stride
-        self.P = n * self.ho * self.wo
+        self.Pg = eng.mb * self.ho * self.wo  # pixels per group
         self.y = torch.zeros(n, self.ho, self.wo, cout, device=dev)
         self.dy = torch.zeros(n, self.ho, self.wo, cout, device=dev, dtype=torch.bfloat16)
-        self.mean = torch.zeros(cout, device=dev)
-        self.rstd = torch.zeros(cout, device=dev)
+        self.mean = torch.zeros(G, cout, device=dev)
+        self.rstd = torch.zeros(G, cout, device=dev)
+        self.bn_batch = torch.zeros(MAX_PASSES, G, 2, cout, device=dev)  # batch mean / unbiased variance per pass, group
         taps = k * k
         self.taps = taps
         bf = dict(device=dev, dtype=torch.bfloat16)
-        # two sets of bf16 GEMM operands: [0] from theta (refreshed once per step), [1] from theta' (every microbatch)
+        # bf16 GEMM operands: [0] from theta (refreshed once per step), [1] of the G perturbed points (every launch)
         self.w = []
-        for _ in range(2):
-            self.w.append((torch.zeros(cout, taps * x.c, **bf),
-                           torch.zeros(cout, taps * x.c, **bf) if split else None,
-                           torch.zeros(x.c, taps * cout, **bf) if needs_dx else None,
-                           torch.zeros(x.c, taps * cout, **bf) if (needs_dx and split) else None))
-        need = ops.Conv2dPlan.partial_elems(n, h, w, x.c, cout, k, stride)
-        eng.partial_elems = max(eng.partial_elems, need)
-        self.args = (n, h, w, x.c, cout, k, stride)
-        self.dx_accumulate, self.needs_dx = dx_accumulate, needs_dx
-        self.dx_target = dx_target  # fp32 buffer receiving the input gradient (default: x.grad)
-        self.plans = None
-        # unit whose BatchNorm(+ReLU) output is this unit's input and has no other consumer (conv1 -> conv2 inside a
-        # block): this unit's dgrad epilogue then reduces that BatchNorm's backward statistics
-        self.bn_producer = None
+        for rows in (1, G):
+            self.w.append((torch.zeros(rows * cout, taps * x.c, **bf),
+                           torch.zeros(rows * cout, taps * x.c, **bf) if split else None,
+                           torch.zeros(rows * x.c, taps * cout, **bf) if needs_dx else None,
+                           torch.zeros(rows * x.c, taps * cout, **bf) if (needs_dx and split) else None))
+        self.w_offset = eng.offsets[conv_name + ".weight"]
+        self.gamma_off = eng.offsets[bn_name + ".weight"]
+        self.beta_off = eng.offsets[bn_name + ".bias"]
+        dx = (dx_target if dx_target is not None else x.grad) if needs_dx else None
+        self.plan = ops.Conv2dPlan(eng.mb, G, h, w, x.c, cout, k, stride, x.hi, x.lo, self.y, self.dy, dx, self.w,
+                                   self.w_offset, split=split, alg_k=27 if stem else None,
+                                   grad_cols=27 if stem else None, bn=(self.mean, self.rstd, BN_EPS))
+        self.out = None
 
-    def finish(self, eng):
-        self.plans = [ops.Conv2dPlan(*self.args, self.x.hi, self.x.lo, self.y, self.dy,
-                                     (self.dx_target if self.dx_target is not None else self.x.grad)
-                                     if self.needs_dx else None, *self.w[i], eng.partial,
-                                     dx_accumulate=self.dx_accumulate, split=eng.split,
-                                     alg_k=27 if self.stem else None, fuse_stats=eng.fuse_stats,
-                                     dgrad_bn=self._dgrad_bn(eng)) for i in range(2)]
-
-    def _dgrad_bn(self, eng):
-        v = self.bn_producer
-        if v is None or not eng.fuse_bwd_stats or self.dx_target is not None or self.dx_accumulate:
-            return None
-        return v.y, v.out.hi, v.mean, v.rstd
+    def bn_batch_ptr(self, pass_idx):
+        return self.bn_batch.data_ptr() + pass_idx * self.bn_batch.stride(0) * 4
 
 
 class Block:
@@ -123,9 +132,10 @@ class FullBatchEngine:
     precision: "split"  -- activations and weights enter the tensor cores as bf16 hi+lo pairs (3 MMAs forward,
                            2 dgrad, 2 wgrad; ~16 mantissa bits per operand): the parity mode;
                "bf16"   -- plain bf16 operands (1 MMA each): the fast mode, cannot resolve the FD perturbation.
+    groups:    microbatches per launch (1..16; default ~1024 images); a pure performance knob, results do not depend on it.
     """
 
-    def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None):
+    def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None, groups=None):
         if not isinstance(model, ResNet):
             raise RuntimeError("FullBatchEngine needs a model built by fullbatchtraining_b200.construct_model "
                                "(there is no fallback path)")
@@ -136,18 +146,14 @@ class FullBatchEngine:
         self.device = torch.device(device or "cuda")
         self.model = model.to(self.device, torch.float32)
         self.mb = int(microbatch)
+        self.G = int(groups) if groups else default_groups(self.mb)
+        if not 1 <= self.G <= L.FB_MAX_GROUPS:
+            raise ValueError(f"groups must be in 1..{L.FB_MAX_GROUPS}")
         self.split = precision == "split"
         self.precision = precision
         self.smoothing = float(label_smoothing)
         self.classes = model.fc.out_features
-        self.partial_elems = 0
-        # BatchNorm statistics in the conv epilogue (FB_FUSE_STATS=0: statistics pass inside the BatchNorm kernel)
-        self.fuse_stats = os.environ.get("FB_FUSE_STATS", "1") == "1"
-        # BatchNorm-backward statistics from the epilogue of the dgrad that produces the BatchNorm's upstream gradient
-        # (conv2 -> bn1 of every block).  Opt-in: measured -1.5 % on B200 -- the epilogue has to pull the BatchNorm's
-        # pre-activation and ReLU mask from HBM, which costs the tensor-core kernel more than the skipped pass saves.
-        self.fuse_bwd_stats = os.environ.get("FB_FUSE_BWD_STATS", "0") == "1"
-        dev = self.device
+        dev, G = self.device, self.G
 
         # ---- flat parameter buffers, parameters() order
         self.names, self.offsets, self.shapes = [], {}, {}
@@ -158,12 +164,14 @@ class FullBatchEngine:
             self.shapes[name] = tuple(p.shape)
             off += p.numel()
         self.numel = off
-        pad = (-off) % 4
-        self.theta = torch.zeros(off + pad, device=dev)[:off]
-        self.theta_p = torch.zeros(off + pad, device=dev)[:off]
-        self.g = torch.zeros(off + pad, device=dev)[:off]
-        self.g2 = torch.zeros(off + pad, device=dev)[:off]
-        self.avg = torch.zeros(off + pad, device=dev)[:off]
+        self.stride = (off + 63) // 64 * 64  # elements between the flat buffers of consecutive groups
+        self.theta = torch.zeros(self.stride, device=dev)[:off]
+        self.theta_p = torch.zeros(G, self.stride, device=dev)
+        self.g_n = torch.zeros(G, self.stride, device=dev)    # per-microbatch gradients, native layout
+        self.g2_n = torch.zeros(G, self.stride, device=dev)
+        self.avg_n = torch.zeros(self.stride, device=dev)[:off]
+        self.avg = torch.zeros(self.stride, device=dev)[:off]  # running mean in the reference's layout (param.grad)
+        self.g = torch.zeros(self.stride, device=dev)[:off]    # gradient of ONE microbatch in the reference's layout
         with torch.no_grad():
             for name, p in self.model.named_parameters():
                 o = self.offsets[name]
@@ -171,23 +179,22 @@ class FullBatchEngine:
                     raise RuntimeError(f"parameter {name} is not 16-byte aligned in the flat buffer")
                 self.theta[o:o + p.numel()].copy_(p.reshape(-1))
                 p.data = self.theta[o:o + p.numel()].view(p.shape)
-        self.scal = torch.zeros(16, device=dev)
+        self.scal = torch.zeros(SCAL_SLOTS, device=dev)
         self.cursor = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.sq_ws = torch.zeros(1024, device=dev, dtype=torch.float64)
-        self.labels_mb = torch.zeros(self.mb, device=dev, dtype=torch.int64)
+        self.sq_ws = torch.zeros(1024 * G, device=dev, dtype=torch.float64)
+        self.labels_mb = torch.zeros(G * self.mb, device=dev, dtype=torch.int64)
 
         # ---- network plan
-        n = self.mb
+        n = G * self.mb
         self.patches = Act(n, 32, 32, 64, self.split, dev, grad=False)
         stem_conv = self.model.stem[0]
         if stem_conv.in_channels != 3 or stem_conv.out_channels != 64:
             raise RuntimeError("the stem kernel expects 3 input channels and 64 output channels")
-        self.stem = Unit(self, "stem.0", "stem.1", self.patches, 64, 1, 1, False, needs_dx=False, stem=True)
+        self.stem = Unit(self, "stem.0", "stem.1", self.patches, 64, 1, 1, needs_dx=False, stem=True)
         self.a0 = Act(n, 32, 32, 64, self.split, dev)
         self.stem.out = self.a0
         self.blocks = []
         cur = self.a0
-        max_c = 64
         for s, stage in enumerate(self.model.layers):
             for b, mod in enumerate(stage):
                 assert isinstance(mod, ResidualBlock)
@@ -195,18 +202,13 @@ class FullBatchEngine:
                 blk.x = cur
                 pre = f"layers.{s}.{b}"
                 x = cur
-                pairs = mod.conv_bn_pairs()
-                for i, (cn, bnn) in enumerate(pairs):
+                for cn, bnn in mod.conv_bn_pairs():
                     conv = getattr(mod, cn)
                     k, st = conv.kernel_size[0], conv.stride[0]
                     u = Unit(self, f"{pre}.{cn}", f"{pre}.{bnn}", x, conv.out_channels, k, st)
                     u.out = Act(x.n, u.ho, u.wo, conv.out_channels, self.split, dev)
-                    if i > 0:
-                        u.bn_producer = blk.units[i - 1]
-                        blk.units[i - 1].bn_consumer = u
                     blk.units.append(u)
                     x = u.out
-                    max_c = max(max_c, conv.out_channels)
                 cur.add_grad2()  # shortcut-branch gradient of this block's input
                 if mod.downsample is not None:
                     pool, dconv = mod.downsample[0], mod.downsample[1]
@@ -223,25 +225,64 @@ class FullBatchEngine:
                 self.blocks.append(blk)
                 cur = x
         self.last = cur
-        self.partial = torch.zeros(self.partial_elems, device=dev)
-        self.bn_ws = torch.zeros(2 * max_c * 1024, device=dev)
-        self.head_ws = torch.zeros(n * (cur.c + 32), device=dev)
         self.units = [self.stem] + [u for blk in self.blocks for u in (blk.units + ([blk.ds] if blk.ds else []))]
+
+        # ---- workspaces and device tables
+        need = sum(u.plan.partial_elems() for u in self.units)
+        self.partial = torch.zeros(max(need, 4), device=dev)
+        entries, o = [], 0
         for u in self.units:
-            u.finish(self)
+            pe = u.plan.partial_elems()
+            if pe:
+                entries.append(u.plan.bind_partial(self.partial[o:o + pe]))
+                o += pe
+        self.reduce = ops.ReduceTable(entries, dev) if entries else None
+        self.bn_ws = torch.zeros(max(ops.bn_bwd_ws_floats(u.Pg, u.cout, G) for u in self.units), device=dev)
+        self.head_ws = torch.zeros(ops.head_ws_floats(n, cur.c), device=dev)
         self.wprep = []
         for i in range(2):
-            entries = [(self.offsets[u.conv_name + ".weight"], 64 if u.stem else u.cout, 3 if u.stem else u.cin,
-                        9 if u.stem else u.taps, *u.w[i]) for u in self.units]
-            self.wprep.append(ops.WeightPrepTable(entries, dev))
+            ent = [(u.w_offset, 64 if u.stem else u.cout, 3 if u.stem else u.cin, 9 if u.stem else u.taps, *u.w[i])
+                   for u in self.units]
+            self.wprep.append(ops.WeightPrepTable(ent, dev, per_group=(i == 1)))
+        # parameters that are not conv weights (BatchNorm weight / bias, fc): perturbed into theta_p by fb_perturb_ranges
+        conv_w = {u.conv_name + ".weight" for u in self.units}
+        ranges, t0 = [], 0
+        for name in self.names:
+            if name in conv_w:
+                continue
+            cnt = 1
+            for d in self.shapes[name]:
+                cnt *= d
+            if ranges and ranges[-1][0] + ranges[-1][1] == self.offsets[name]:
+                ranges[-1][1] += cnt
+            else:
+                ranges.append([self.offsets[name], cnt, t0])
+            t0 += cnt
+        pos = 0
+        for r in ranges:  # third column: index of the first thread of the range
+            r[2] = pos
+            pos += r[1]
+        self.ranges = torch.tensor(ranges, dtype=torch.int64, device=dev)
+        self.n_ranges, self.ranges_total = len(ranges), pos
+        # 3x3 convs whose native gradient layout [co][tap][ci] differs from OIHW: (offset, cout, cin, taps, first block)
+        table, blk0 = [], 0
+        for u in self.units:
+            if u.taps > 1 and not u.stem:
+                table.append([u.w_offset, u.cout, u.cin, u.taps, blk0])
+                blk0 += u.cout
+        self.relayout_table = torch.tensor(table, dtype=torch.int64, device=dev) if table else None
+        self.relayout_entries, self.relayout_blocks = len(table), blk0
         self._bn_modules = dict(self.model.named_modules())
+        self.ema = ops.BnEmaTable([(self._bn_modules[u.bn_name].running_mean, self._bn_modules[u.bn_name].running_var,
+                                    u.bn_batch, u.bn_batch.stride(0), u.cout) for u in self.units], dev)
         self._graphs = {}
-        # FB_WGRAD_STREAM=0 disables the side stream (everything in one stream)
-        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "1") == "1" else None
+        # FB_WGRAD_STREAM=1: wgrad on a side stream, concurrently with the dgrad -> BatchNorm-backward chain below it
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "0") == "1" else None
         self.grad_norms = None
         self.aug_params, self.aug_mean, self.aug_std = None, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
         self.norm_offset = 0
         self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
+        self.h2d_bytes = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def _view(self, flat, name):
@@ -255,87 +296,138 @@ class FullBatchEngine:
         m = self._bn_modules[bn_name]
         return m.running_mean, m.running_var
 
-    def _bn_params(self, u, P):
-        return self._view(P, u.bn_name + ".weight"), self._view(P, u.bn_name + ".bias")
+    def to_native(self, src, dst):
+        """flat buffer in the reference's order (OIHW conv weights) -> the kernels' native gradient layout"""
+        ops.flat_relayout(src, dst, self.numel, self.relayout_table, self.relayout_entries, self.relayout_blocks, True)
 
-    def _bn_forward(self, u, P, out, relu=True, second=None, res=None):
-        """fused train-mode BatchNorm of unit `u` (statistics, running-stat EMA, normalise, add, ReLU) -> `out` planes"""
-        ga, be = self._bn_params(u, P)
+    def from_native(self, src, dst):
+        ops.flat_relayout(src, dst, self.numel, self.relayout_table, self.relayout_entries, self.relayout_blocks, False)
+
+    # ---- one pass over the network for ng groups -----------------------------------------------------------------
+    def _bn_forward(self, u, ng, P, pstride, out, relu=True, second=None, res=None):
+        """train-mode BatchNorm of unit `u` with the statistics its convolution left in u.mean / u.rstd -> `out`"""
+        base = P.data_ptr()
         sec = None
         if second is not None:
-            ga2, be2 = self._bn_params(second, P)
-            sec = (second.y, second.mean, second.rstd, ga2, be2, *self._bn_buffers(second.bn_name))
-        ops.bn_fwd_fused(u.y, u.mean, u.rstd, ga, be, u.P, u.cout, out.hi, out.lo, self.bn_ws,
-                         running=self._bn_buffers(u.bn_name), relu=relu, second=sec, res=res, momentum=BN_MOMENTUM,
-                         eps=BN_EPS, stats=u.plans[self._pass].stats,
-                         stats2=second.plans[self._pass].stats if second is not None else None)
+            sec = (second.y, second.mean, second.rstd, base + 4 * second.gamma_off, base + 4 * second.beta_off)
+        ops.bn_apply(u.y, u.mean, u.rstd, base + 4 * u.gamma_off, base + 4 * u.beta_off, u.Pg, u.cout, out.hi, out.lo,
+                     relu=relu, second=sec, res=res, ng=ng, param_gstride=pstride)
 
-    def _forward(self, P, G, loss_slot, correct_slot):
-        self._pass = 0 if P is self.theta else 1
-        if self._pass == 1:
-            self.wprep[1](P)  # operands of theta' = theta + eps_n*v; those of theta are refreshed once per step
+    def _forward(self, ng, wset, P, pstride, Gbuf, loss_base, correct_base, pass_idx):
+        """P: flat parameters (theta: pstride 0, shared; theta_p: one row per group); Gbuf: [G][stride] gradients"""
         u = self.stem
-        u.plans[self._pass].forward()
-        self._bn_forward(u, P, u.out)
+        u.plan.forward(ng, wset, u.bn_batch_ptr(pass_idx))
+        self._bn_forward(u, ng, P, pstride, u.out)
         for blk in self.blocks:
             last = len(blk.units) - 1
             for i, u in enumerate(blk.units):
-                u.plans[self._pass].forward()
+                u.plan.forward(ng, wset, u.bn_batch_ptr(pass_idx))
                 if i < last:
-                    self._bn_forward(u, P, u.out)
+                    self._bn_forward(u, ng, P, pstride, u.out)
             u = blk.units[last]
             if blk.ds is not None:
                 d = blk.ds
                 if blk.pooled is not None:
                     x = blk.x
-                    ops.avgpool2_fwd(x.hi, x.lo, x.n, x.h, x.w, x.c, blk.pooled.hi, blk.pooled.lo)
-                d.plans[self._pass].forward()
-                self._bn_forward(u, P, blk.out, second=d)
+                    ops.avgpool2_fwd(x.hi, x.lo, ng * self.mb, x.h, x.w, x.c, blk.pooled.hi, blk.pooled.lo)
+                d.plan.forward(ng, wset, d.bn_batch_ptr(pass_idx))
+                self._bn_forward(u, ng, P, pstride, blk.out, second=d)
             else:
-                self._bn_forward(u, P, blk.out, res=(blk.x.hi, blk.x.lo))
+                self._bn_forward(u, ng, P, pstride, blk.out, res=(blk.x.hi, blk.x.lo))
         a = self.last
-        ops.head_fwd_bwd(a.hi, a.lo, a.n, a.h * a.w, a.c, self._view(P, "fc.weight"), self._view(P, "fc.bias"),
-                         self.labels_mb, self.classes, self.smoothing, self.head_ws, self.scal, loss_slot, correct_slot,
-                         self._view(G, "fc.weight"), self._view(G, "fc.bias"), a.grad)
+        pb, gb = P.data_ptr(), Gbuf.data_ptr()
+        fw, fb = 4 * self.offsets["fc.weight"], 4 * self.offsets["fc.bias"]
+        ops.head_fwd_bwd(a.hi, a.lo, self.mb, a.h * a.w, a.c, pb + fw, pb + fb, self.labels_mb, self.classes,
+                         self.smoothing, self.head_ws, self.scal, loss_base, correct_base, gb + fw, gb + fb, a.grad,
+                         ng=ng, param_gstride=pstride, grad_gstride=self.stride)
+
+    def _unit_backward(self, u, ng, wset, P, pstride, Gbuf, act, dz_out=None):
+        """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
+        pb, gb = P.data_ptr(), Gbuf.data_ptr()
+        ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
+                   gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
+                   param_gstride=pstride, grad_gstride=self.stride)
+        # wgrad only feeds the flat gradient: optionally on a side stream, concurrently with the dgrad ->
+        # BatchNorm-backward chain of the layers below (fork here, join at the end of the backward pass)
+        if self.wgrad_stream is not None:
+            main = torch.cuda.current_stream()
+            self.wgrad_stream.wait_stream(main)
+            with torch.cuda.stream(self.wgrad_stream):
+                u.plan.wgrad(ng, Gbuf, self.stride)
+        else:
+            u.plan.wgrad(ng, Gbuf, self.stride)
+        if not u.stem:
+            u.plan.dgrad(ng, wset)
+
+    def _backward(self, ng, wset, P, pstride, Gbuf):
+        for blk in reversed(self.blocks):
+            out = blk.out
+            last = len(blk.units) - 1
+            if blk.ds is not None:
+                # shortcut branch: its input gradient goes to the block input's second gradient buffer (grad2)
+                d = blk.ds
+                self._unit_backward(d, ng, wset, P, pstride, Gbuf, out)
+                if blk.pooled is not None:
+                    x = blk.x
+                    ops.avgpool2_bwd(blk.pooled.grad, ng * self.mb, x.h, x.w, x.c, x.grad2, accumulate=False)
+                dz_out = None
+            else:
+                dz_out = blk.x.grad2  # identity shortcut: dz of the last BN is the shortcut gradient
+            for i in range(last, -1, -1):
+                u = blk.units[i]
+                if i == last:
+                    self._unit_backward(u, ng, wset, P, pstride, Gbuf, out, dz_out=dz_out)
+                else:
+                    self._unit_backward(u, ng, wset, P, pstride, Gbuf, u.out)
+        self._unit_backward(self.stem, ng, wset, P, pstride, Gbuf, self.a0)
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join
+        if self.reduce is not None:
+            self.reduce(ng, Gbuf, self.stride)  # split-K partials of all layers -> flat gradient, fixed order
 
     @torch.no_grad()
     def forward_eval(self, x):
-        """Eval-mode forward of `x` [n <= microbatch, 3, 32, 32] fp32 on the CUDA kernels (training.py:343-388 calls
+        """Eval-mode forward of `x` [n <= G*microbatch, 3, 32, 32] fp32 on the CUDA kernels (training.py:343-388 calls
         model(inputs) in eval mode): BatchNorm uses the running statistics (fb_bn_apply), nothing is written to the
         model's buffers or gradients.  Returns the logits [n, classes] (the final 512->10 linear on the pooled features
         runs in torch: the caller needs logits, not the loss, for the test_time_flips softmax sum)."""
         n = x.shape[0]
-        assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (3, 32, 32) and n <= self.mb
+        assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (3, 32, 32) and n <= self.G * self.mb
+        ng = -(-n // self.mb)
         if not hasattr(self, "_eval_x"):
-            self._eval_x = torch.zeros(self.mb, 3, 32, 32, device=self.device)
-            self._eval_y = torch.zeros(self.mb, dtype=torch.int64, device=self.device)
-        self._eval_x.zero_()
+            self._eval_x = torch.zeros(self.G * self.mb, 3, 32, 32, device=self.device)
+            self._eval_y = torch.zeros(self.G * self.mb, dtype=torch.int64, device=self.device)
+            self._eval_stat = {}
+        self._eval_x[:ng * self.mb].zero_()
         self._eval_x[:n].copy_(x)  # a short last batch is zero padded: eval-mode BN is per sample
         P = self.theta
-        self._pass = 0
         self.wprep[0](P)
-        ops.stem_im2col(self._eval_x, self._eval_y, None, None, 0, self.mb, self.patches.hi, self.patches.lo,
+        ops.stem_im2col(self._eval_x, self._eval_y, None, None, 0, 0, ng * self.mb, self.patches.hi, self.patches.lo,
                         self.labels_mb)
 
+        def stat(v):
+            rm, rv = self._bn_buffers(v.bn_name)
+            # the same running statistics for every group
+            mean = rm.unsqueeze(0).expand(ng, -1).contiguous()
+            rstd = torch.rsqrt(rv + BN_EPS).unsqueeze(0).expand(ng, -1).contiguous()
+            self._eval_stat[v.bn_name] = (mean, rstd)
+            return mean, rstd, P.data_ptr() + 4 * v.gamma_off, P.data_ptr() + 4 * v.beta_off
+
         def bn_eval(u, out, second=None, res=None):
-            def stat(v):
-                rm, rv = self._bn_buffers(v.bn_name)
-                ga, be = self._bn_params(v, P)
-                return rm, torch.rsqrt(rv + BN_EPS), ga, be
             rm, rs, ga, be = stat(u)
             sec = None
             if second is not None:
                 rm2, rs2, ga2, be2 = stat(second)
                 sec = (second.y, rm2, rs2, ga2, be2)
-            ops.bn_apply(u.y, rm, rs, ga, be, u.P, u.cout, out.hi, out.lo, relu=True, second=sec, res=res)
+            ops.bn_apply(u.y, rm, rs, ga, be, u.Pg, u.cout, out.hi, out.lo, relu=True, second=sec, res=res, ng=ng)
 
         u = self.stem
-        u.plans[0].forward()
+        u.plan.forward(ng, 0, stats=False)
         bn_eval(u, u.out)
         for blk in self.blocks:
             last = len(blk.units) - 1
             for i, u in enumerate(blk.units):
-                u.plans[0].forward()
+                u.plan.forward(ng, 0, stats=False)
                 if i < last:
                     bn_eval(u, u.out)
             u = blk.units[last]
@@ -343,174 +435,134 @@ class FullBatchEngine:
                 d = blk.ds
                 if blk.pooled is not None:
                     xin = blk.x
-                    ops.avgpool2_fwd(xin.hi, xin.lo, xin.n, xin.h, xin.w, xin.c, blk.pooled.hi, blk.pooled.lo)
-                d.plans[0].forward()
+                    ops.avgpool2_fwd(xin.hi, xin.lo, ng * self.mb, xin.h, xin.w, xin.c, blk.pooled.hi, blk.pooled.lo)
+                d.plan.forward(ng, 0, stats=False)
                 bn_eval(u, blk.out, second=d)
             else:
                 bn_eval(u, blk.out, res=(blk.x.hi, blk.x.lo))
         a = self.last
-        pooled = (a.hi.float() + (a.lo.float() if a.lo is not None else 0.0)).view(a.n, a.h * a.w, a.c).mean(dim=1)
+        hi, lo = a.hi[:n], (a.lo[:n] if a.lo is not None else None)
+        pooled = (hi.float() + (lo.float() if lo is not None else 0.0)).view(n, a.h * a.w, a.c).mean(dim=1)
         logits = torch.addmm(self._view(P, "fc.bias").view(-1), pooled,
                              self._view(P, "fc.weight").view(self.classes, a.c).t())
-        return logits[:n]
-
-    def _unit_backward(self, u, P, G, act, dz_out=None):
-        """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
-        ga, _ = self._bn_params(u, P)
-        consumer = getattr(u, "bn_consumer", None)  # the unit whose dgrad produced act.grad and its statistics
-        stats = consumer.plans[self._pass].dgrad_stats if (consumer is not None and act.grad2 is None) else None
-        ops.bn_bwd_fused(act.grad, act.hi, u.y, u.mean, u.rstd, ga, u.P, u.cout, self.bn_ws,
-                         self._view(G, u.bn_name + ".weight"), self._view(G, u.bn_name + ".bias"), u.dy, dz_out=dz_out,
-                         dA2=act.grad2, stats=stats)
-        gw = self._view(G, u.conv_name + ".weight")
-        plan = u.plans[self._pass]
-        # wgrad (+ its split-K reduction) only feeds the flat gradient: it runs on a side stream, concurrently with the
-        # dgrad -> BatchNorm-backward chain of the layers below (fork here, join at the end of the backward pass)
-        if self.wgrad_stream is not None:
-            main = torch.cuda.current_stream()
-            self.wgrad_stream.wait_stream(main)
-            with torch.cuda.stream(self.wgrad_stream):
-                plan.wgrad(gw, cin_real=3, mode=1) if u.stem else plan.wgrad(gw)
-        else:
-            plan.wgrad(gw, cin_real=3, mode=1) if u.stem else plan.wgrad(gw)
-        if not u.stem:
-            plan.dgrad()
-
-    def _backward(self, P, G):
-        for blk in reversed(self.blocks):
-            out = blk.out
-            last = len(blk.units) - 1
-            if blk.ds is not None:
-                # shortcut branch: its input gradient goes to the block input's second gradient buffer (grad2)
-                d = blk.ds
-                self._unit_backward(d, P, G, out)
-                if blk.pooled is not None:
-                    x = blk.x
-                    ops.avgpool2_bwd(blk.pooled.grad, x.n, x.h, x.w, x.c, x.grad2, accumulate=False)
-                dz_out = None
-            else:
-                dz_out = blk.x.grad2  # identity shortcut: dz of the last BN is the shortcut gradient
-            for i in range(last, -1, -1):
-                u = blk.units[i]
-                if i == last:
-                    self._unit_backward(u, P, G, out, dz_out=dz_out)
-                else:
-                    self._unit_backward(u, P, G, u.out)
-        self._unit_backward(self.stem, P, G, self.a0)
-        if self.wgrad_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join: g is complete, activations are free
+        return logits
 
     # ------------------------------------------------------------------------------------------------------------
-    def _microbatch_ops(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g,
-                        mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
-        """mode "full": whole per-microbatch recipe; "raw": pass 1 only (training.py:76-83 + :162);
-        "reg": regulariser only, self.g already holds the raw gradient of this microbatch (modules.py:211-241).
-        impl "forward" | "central" (modules.py:211-241 / :266-300); acc: acc_strength with self.pre as pre_grads;
+    def _group_ops(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate, write_g,
+                   mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
+        """One group launch of ng microbatches.
+        mode "full": whole per-microbatch recipe; "raw": pass 1 only (training.py:76-83 + :162);
+        "reg": regulariser only, self.g_n[0] already holds the raw gradient of the microbatch (modules.py:211-241).
+        impl "forward" | "central" (modules.py:211-241 / :266-300); acc: acc_strength with self.pre_n as pre_grads;
         batch_clip: per-microbatch L2 clip before the running mean (training.py:166-168); target "avg" | "pre"
-        (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into self.pre)."""
-        dst = self.avg if target == "avg" else self.pre
+        (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into self.pre_n)."""
+        dst = self.avg_n if target == "avg" else self.pre_n
+        mb, st, n = self.mb, self.stride, self.numel
+        cur = self.cursor if use_cursor else None
         if x_src.dtype == torch.uint8:  # raw HWC dataset: crop / flip / normalise fused into the im2col
-            ops.stem_im2col_u8aug(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb,
-                                  self.aug_params, self.aug_mean, self.aug_std, self.patches.hi, self.patches.lo,
-                                  self.labels_mb)
+            ops.stem_im2col_u8aug(x_src, labels_src, perm, cur, first, mb, ng * mb, self.aug_params, self.aug_mean,
+                                  self.aug_std, self.patches.hi, self.patches.lo, self.labels_mb)
         else:
-            ops.stem_im2col(x_src, labels_src, perm, self.cursor if use_cursor else None, first, self.mb,
-                            self.patches.hi, self.patches.lo, self.labels_mb)
+            ops.stem_im2col(x_src, labels_src, perm, cur, first, mb, ng * mb, self.patches.hi, self.patches.lo,
+                            self.labels_mb)
+        passes = 0
+        g, g2 = self.g_n, self.g2_n
         if mode != "reg":
-            self._forward(self.theta, self.g, S_LOSS, S_CORRECT)
-            self._backward(self.theta, self.g)
+            self._forward(ng, 0, self.theta, 0, g, S_LOSSG, S_CORRG, passes)
+            self._backward(ng, 0, self.theta, 0, g)
+            passes += 1
         norms = None
         if target == "avg":
             norms = self.grad_norms[self.norm_offset:] if self.norm_offset else self.grad_norms
-        ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_N2, norms, self.cursor)
+        simple = acc == 0
+        # |g_k|^2 -> grad_norms[k] (training.py:162) and, without acc_strength, eps_k = eps / (bs * |g_k|) (modules.py:223)
+        ops.flat_sqnorm(g, n, self.sq_ws, self.scal, S_N2G, ng=ng, gstride=st, norms_out=norms, cursor=self.cursor,
+                        eps_mode=1 if simple else 0, bs=block_strength, eps=eps, eps_base=S_EPSG)
         regularise = (block_strength != 0 or acc != 0) and mode != "raw"
         fused_mean = dst if (accumulate and batch_clip is None) else None
         if regularise:
-            if impl == "forward" and acc == 0:
-                ops.fd_perturb(self.theta, self.g, self.numel, block_strength, eps, self.scal, S_N2, S_EPS, self.theta_p)
-                self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
-                self._backward(self.theta_p, self.g2)
-                ops.fd_combine(self.g, self.g2, fused_mean, self.numel, self.scal, S_EPS, 0.0, self.cursor, 0,
-                               write_g or batch_clip is not None, cf_slot=S_CF)
-            else:
-                pre = self.pre if acc != 0 else None
-                ops.flat_sqnorm_axpby(self.g, pre, block_strength, acc, self.numel, self.sq_ws, self.scal, S_VSQ)
-                if impl == "forward":
-                    ops.fd_perturb_ex(self.theta, self.g, pre, self.numel, block_strength, acc, eps, 1.0, self.scal,
-                                      S_VSQ, S_EPS, self.theta_p)
-                    self._forward(self.theta_p, self.g2, S_LOSS2, S_CORRECT2)
-                    self._backward(self.theta_p, self.g2)
-                    ops.fd_combine(self.g, self.g2, fused_mean, self.numel, self.scal, S_EPS, 0.0, self.cursor, 0,
-                                   write_g or batch_clip is not None, cf_slot=S_CF)
-                else:
-                    for scale, gbuf in ((0.5, self.g2), (-0.5, self._g3())):
-                        ops.fd_perturb_ex(self.theta, self.g, pre, self.numel, block_strength, acc, eps, scale,
-                                          self.scal, S_VSQ, S_EPS, self.theta_p)
-                        self._forward(self.theta_p, gbuf, S_LOSS2, S_CORRECT2)
-                        self._backward(self.theta_p, gbuf)
-                    ops.fd_combine_ex(self.g, self.g2, self._g3(), fused_mean, self.numel, self.scal, S_EPS, 0.0,
-                                      self.cursor, 0, write_g or batch_clip is not None, cf_slot=S_CF)
+            pre = self.pre_n if acc != 0 else None
+            if not simple:  # |bs*g + acc*pre|^2 -> eps_k (modules.py:217-223)
+                ops.flat_sqnorm(g, n, self.sq_ws, self.scal, S_VSQG, ng=ng, gstride=st, y=pre, a=block_strength, b=acc,
+                                eps_mode=2, eps=eps, eps_base=S_EPSG)
+            points = ((1.0, g2),) if impl == "forward" else ((0.5, g2), (-0.5, self._g3()))
+            for scale, gbuf in points:
+                self.wprep[1](self.theta, ng=ng, grad=g, gstride=st, pre=pre, bs=block_strength, acc=acc, scale=scale,
+                              scal=self.scal, eps_base=S_EPSG)
+                ops.perturb_ranges(self.theta, g, st, pre, self.ranges, self.n_ranges, self.ranges_total,
+                                   block_strength, acc, scale, self.scal, S_EPSG, self.theta_p, st, ng)
+                self._forward(ng, 1, self.theta_p, st, gbuf, S_LOSS2G, S_CORR2G, passes)
+                self._backward(ng, 1, self.theta_p, st, gbuf)
+                passes += 1
+            ops.fd_combine(g, g2, None if impl == "forward" else self._g3(), st, fused_mean, n, ng, self.scal, S_EPSG,
+                           S_CF, self.cursor, write_g or batch_clip is not None)
             if accumulate and batch_clip is not None:
-                ops.flat_sqnorm(self.g, self.numel, self.sq_ws, self.scal, S_REGSQ)
-                ops.mean_accumulate_clip(self.g, dst, self.numel, self.cursor, 0, self.scal, S_REGSQ, batch_clip,
-                                         S_CLIPPED)
+                ops.flat_sqnorm(g, n, self.sq_ws, self.scal, S_REGSQG, ng=ng, gstride=st)
+                ops.mean_accumulate(g, st, dst, n, ng, self.cursor, self.scal, S_REGSQG, batch_clip, S_CLIPPED)
         elif accumulate:
-            if batch_clip is not None:
-                ops.mean_accumulate_clip(self.g, dst, self.numel, self.cursor, 0, self.scal, S_N2, batch_clip, S_CLIPPED)
-            else:
-                ops.mean_accumulate(self.g, dst, self.numel, self.cursor, 0)
-        ops.cursor_add(self.cursor, 1)
+            ops.mean_accumulate(g, st, dst, n, ng, self.cursor, self.scal, S_N2G, batch_clip or 0.0, S_CLIPPED)
+        # running statistics: EMA over (microbatch, pass) in the reference's order
+        self.ema(passes, ng, BN_MOMENTUM)
+        if mode != "reg":
+            ops.group_finish(self.cursor, ng, self.scal, S_LOSS, S_CORRECT, S_LOSSG, S_CORRG)
+        return passes
 
     def _g3(self):
-        if not hasattr(self, "g3"):
-            self.g3 = torch.zeros_like(self.g)
-        return self.g3
+        if not hasattr(self, "g3_n"):
+            self.g3_n = torch.zeros_like(self.g_n)
+        return self.g3_n
 
-    def _program(self, x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate=True, write_g=False,
-                 use_graph=True, mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
-        """Returns a callable running one microbatch; captured into a CUDA graph on first use."""
+    def _pre(self):
+        if not hasattr(self, "pre_n"):
+            self.pre_n = torch.zeros(self.stride, device=self.device)[:self.numel]
+            self.pre = torch.zeros(self.stride, device=self.device)[:self.numel]
+        return self.pre_n
+
+    def _program(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate=True,
+                 write_g=False, use_graph=True, mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
+        """Returns a callable running one group launch of ng microbatches; captured into a CUDA graph on first use."""
         if acc != 0 or target == "pre":
-            if not hasattr(self, "pre"):
-                self.pre = torch.zeros_like(self.g)
+            self._pre()
         if impl == "central":
             self._g3()
-        args = (x_src, labels_src, perm, first, use_cursor, block_strength, eps, accumulate, write_g, mode, impl, acc,
+        args = (x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate, write_g, mode, impl, acc,
                 batch_clip, target)
         if not use_graph:
-            return lambda: self._microbatch_ops(*args)
-        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor,
+            return lambda: self._group_ops(*args)
+        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor, ng,
                float(block_strength), float(eps), accumulate, write_g, mode, impl, float(acc), batch_clip, target,
                self.grad_norms.data_ptr(), self.norm_offset,
                None if self.aug_params is None else self.aug_params.data_ptr(), tuple(self.aug_mean), tuple(self.aug_std))
         if key not in self._graphs:
-            state = self._save_state()
+            state = self._save_state(mode)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up launch (sets kernel attributes, loads modules) outside capture
-                self._microbatch_ops(*args)
+                self._group_ops(*args)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            self._restore_state(state)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._microbatch_ops(*args)
-            self._restore_state(state)
+                self._group_ops(*args)
             self._graphs[key] = (graph, (x_src, labels_src, perm))
         return self._graphs[key][0].replay
 
-    def _save_state(self):
+    def _save_state(self, mode):
         bufs = [b.clone() for b in self.model.buffers()]
-        return dict(avg=self.avg.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
-                    norms=self.grad_norms.clone(), g=self.g.clone(),
-                    pre=self.pre.clone() if hasattr(self, "pre") else None)
+        return dict(avg=self.avg_n.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
+                    norms=self.grad_norms.clone(), g=self.g_n[0].clone() if mode == "reg" else None,
+                    pre=self.pre_n.clone() if hasattr(self, "pre_n") else None)
 
     def _restore_state(self, st):
-        self.avg.copy_(st["avg"])
+        self.avg_n.copy_(st["avg"])
         self.scal.copy_(st["scal"])
         self.cursor.copy_(st["cursor"])
         self.grad_norms.copy_(st["norms"])
-        self.g.copy_(st["g"])
+        if st["g"] is not None:
+            self.g_n[0].copy_(st["g"])
         if st["pre"] is not None:
-            self.pre.copy_(st["pre"])
+            self.pre_n.copy_(st["pre"])
         for b, s in zip(self.model.buffers(), st["bufs"]):
             b.copy_(s)
 
@@ -538,22 +590,34 @@ class FullBatchEngine:
         self.scal[S_CF] = lr / 4
 
     def begin_step(self, num_microbatches):
-        if self.grad_norms is None or self.grad_norms.numel() < num_microbatches:
-            self.grad_norms = torch.zeros(max(num_microbatches, 16), device=self.device)
+        if self.grad_norms is None or self.grad_norms.numel() < num_microbatches + self.G:
+            self.grad_norms = torch.zeros(max(num_microbatches, 16) + self.G, device=self.device)
             self._graphs.clear()
         self.grad_norms.zero_()
-        self.avg.zero_()
-        self.scal[S_LOSS:S_CORRECT2 + 1] = 0
+        self.avg_n.zero_()
+        self.scal[S_LOSS:S_CORRECT + 1] = 0
         self.scal[S_CLIPPED] = 0
         self.cursor.zero_()
-        self.wprep[0](self.theta)  # theta is constant during the step: pass-1 operands once, not per microbatch
+        self.wprep[0](self.theta)  # theta is constant during the step: pass-1 operands once, not per launch
+
+    def _run_groups(self, count, make):
+        """count microbatches as full launches of G groups plus one shorter launch"""
+        full, rem = divmod(count, self.G)
+        if full:
+            run = make(self.G)
+            for _ in range(full):
+                run()
+        if rem:
+            make(rem)()
 
     def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
                             num_norms=None, norm_offset=0, implementation="forward-differences", acc_strength=0.0,
-                            batch_clip=None):
+                            batch_clip=None, reduce_pre=None):
         """Full-batch accumulation over `count` consecutive microbatches of a device-resident dataset
-        X [N,3,32,32] fp32, Y [N] int64, starting at sample `first` (optionally through the index tensor `perm`).
-        Returns after enqueueing; results: self.avg (running mean), self.grad_norms[:count], loss/correct sums in scal."""
+        X [N,3,32,32] fp32 (or [N,32,32,3] uint8), Y [N] int64, starting at sample `first` (optionally through the index
+        tensor `perm`).  Returns after enqueueing; results: self.avg (running mean, reference layout),
+        self.grad_norms[:count], loss/correct sums in scal.  reduce_pre: callable applied to the mean raw gradient of
+        the acc_strength pre-pass before it is used (the all-reduce of training.py:139-140)."""
         assert X.is_cuda and X.is_contiguous() and Y.dtype == torch.int64
         if X.dtype == torch.uint8:
             assert tuple(X.shape[1:]) == (32, 32, 3), "uint8 datasets are HWC [N,32,32,3]"
@@ -561,33 +625,38 @@ class FullBatchEngine:
             assert X.dtype == torch.float32 and tuple(X.shape[1:]) == (3, 32, 32)
         n_avail = (perm.numel() if perm is not None else X.shape[0]) - first
         count = n_avail // self.mb if count is None else count
+        if count < 0 or first < 0 or count * self.mb > n_avail:
+            raise ValueError(f"{count} microbatches of {self.mb} from sample {first} exceed the {n_avail + first} samples "
+                             "of the dataset (drop_last?)")
         impl = IMPLEMENTATIONS[implementation]
         self.begin_step(num_norms or count)
         self.norm_offset = int(norm_offset)
         self.set_lr(lr)
         if acc_strength != 0:
-            # training.py:128-142: extra sweep for the mean raw gradient (pre_grads); single GPU only for now
-            self.pre = torch.zeros_like(self.g) if not hasattr(self, "pre") else self.pre.zero_()
-            pre_run = self._program(X, Y, perm, first, True, 0.0, eps, use_graph=use_graph, mode="raw", impl=impl,
-                                    batch_clip=batch_clip, target="pre")
-            for _ in range(count):
-                pre_run()
+            # training.py:128-142: extra sweep for the mean raw gradient (pre_grads)
+            self._pre().zero_()
+            self._run_groups(count, lambda ng: self._program(X, Y, perm, first, True, ng, 0.0, eps, use_graph=use_graph,
+                                                             mode="raw", impl=impl, batch_clip=batch_clip, target="pre"))
+            if reduce_pre is not None:
+                reduce_pre(self.pre_n)
+            self.from_native(self.pre_n, self.pre)
             self.bn_passes += count
-            self.scal[S_LOSS:S_CORRECT2 + 1] = 0
+            self.scal[S_LOSS:S_CORRECT + 1] = 0
             self.scal[S_CLIPPED] = 0
             self.cursor.zero_()
-        run = self._program(X, Y, perm, first, True, block_strength, eps, use_graph=use_graph, impl=impl,
-                            acc=acc_strength, batch_clip=batch_clip)
-        for _ in range(count):
-            run()
+        self._run_groups(count, lambda ng: self._program(X, Y, perm, first, True, ng, block_strength, eps,
+                                                         use_graph=use_graph, impl=impl, acc=acc_strength,
+                                                         batch_clip=batch_clip))
+        self.from_native(self.avg_n, self.avg)
         regularised = block_strength != 0 or acc_strength != 0
         self.bn_passes += count * ((3 if impl == "central" else 2) if regularised else 1)
         return count
 
     def _stages(self):
         if not hasattr(self, "_x_stage"):
-            self._x_stage = [torch.zeros(self.mb, 3, 32, 32, device=self.device) for _ in range(2)]
-            self._y_stage = [torch.zeros(self.mb, device=self.device, dtype=torch.int64) for _ in range(2)]
+            n = self.G * self.mb
+            self._x_stage = [torch.zeros(n, 3, 32, 32, device=self.device) for _ in range(2)]
+            self._y_stage = [torch.zeros(n, device=self.device, dtype=torch.int64) for _ in range(2)]
             self._stage_free = [torch.cuda.Event() for _ in range(2)]
             self._copy_stream = torch.cuda.Stream()
         return self._x_stage, self._y_stage
@@ -595,45 +664,59 @@ class FullBatchEngine:
     def accumulate_stream(self, loader, lr, block_strength, eps, num_microbatches, use_graph=True, norm_offset=0):
         """Full-batch accumulation over blocks (inputs [B,3,32,32], labels [B]) coming from a host-side iterable (the
         reference's DataLoader protocol, training.py:148-152): every block is split into microbatches
-        (torch.chunk, training.py:155-156), copied host->device on a copy stream into one of two staging buffers and
-        consumed by a captured graph, so the copy of microbatch k+1 overlaps the compute of microbatch k."""
+        (torch.chunk, training.py:155-156), copied host->device on a copy stream into one of two staging buffers of G
+        microbatches and consumed by a captured graph, so the copies of launch j+1 overlap the compute of launch j."""
         xs, ys = self._stages()
         self.begin_step(num_microbatches)
         self.norm_offset = int(norm_offset)
         self.set_lr(lr)
-        runs = [self._program(xs[i], ys[i], None, 0, False, block_strength, eps, use_graph=use_graph) for i in range(2)]
         main = torch.cuda.current_stream()
-        k = 0
-        h2d = 0
+        mb = self.mb
+        state = dict(k=0, slot=0, stage=0, h2d=0)
+
+        def flush():
+            i, ng = state["stage"], state["slot"]
+            if ng == 0:
+                return
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+            main.wait_event(ready)
+            self._program(xs[i], ys[i], None, 0, False, ng, block_strength, eps, use_graph=use_graph)()
+            self._stage_free[i].record(main)
+            state["stage"], state["slot"] = i ^ 1, 0
+
         for inputs, labels in loader:
-            chunks = max(labels.shape[0] // self.mb, 1)
+            chunks = max(labels.shape[0] // mb, 1)
             for xc, yc in zip(torch.chunk(inputs, chunks, dim=0), torch.chunk(labels, chunks, dim=0)):
-                if xc.shape[0] != self.mb:
-                    raise RuntimeError(f"microbatch of {xc.shape[0]} samples, engine built for {self.mb} (drop_last?)")
-                i = k & 1
+                if xc.shape[0] != mb:
+                    raise RuntimeError(f"microbatch of {xc.shape[0]} samples, engine built for {mb} (drop_last?)")
+                i, j = state["stage"], state["slot"]
                 with torch.cuda.stream(self._copy_stream):
-                    self._copy_stream.wait_event(self._stage_free[i])
-                    xs[i].copy_(xc, non_blocking=True)
-                    ys[i].copy_(yc, non_blocking=True)
-                    ready = torch.cuda.Event()
-                    ready.record(self._copy_stream)
-                main.wait_event(ready)
-                runs[i]()
-                self._stage_free[i].record(main)
-                h2d += xc.numel() * xc.element_size() + yc.numel() * yc.element_size()
-                k += 1
-        self.bn_passes += k * (2 if block_strength != 0 else 1)
-        self.h2d_bytes = h2d
-        return k
+                    if j == 0:
+                        self._copy_stream.wait_event(self._stage_free[i])
+                    xs[i][j * mb:(j + 1) * mb].copy_(xc, non_blocking=True)
+                    ys[i][j * mb:(j + 1) * mb].copy_(yc, non_blocking=True)
+                state["h2d"] += xc.numel() * xc.element_size() + yc.numel() * yc.element_size()
+                state["k"] += 1
+                state["slot"] = j + 1
+                if state["slot"] == self.G:
+                    flush()
+        flush()
+        self.from_native(self.avg_n, self.avg)
+        self.bn_passes += state["k"] * (2 if block_strength != 0 else 1)
+        self.h2d_bytes = state["h2d"]
+        return state["k"]
 
     # ---- GradRegularizer / _compute_batched_gradient protocol ------------------------------------------------------
     def microbatch_gradient(self, inputs, labels):
-        """training.py:76-83 on the device for one microbatch: fills self.g (raw gradient), returns (loss, correct)."""
+        """training.py:76-83 on the device for one microbatch: fills self.g (raw gradient, reference layout), returns
+        (loss, correct) as device scalars."""
         xs, ys = self._stages()
-        xs[0].copy_(inputs)
-        ys[0].copy_(labels)
+        xs[0][:self.mb].copy_(inputs)
+        ys[0][:self.mb].copy_(labels)
         self.begin_step(1)
-        self._program(xs[0], ys[0], None, 0, False, 0.0, 0.0, accumulate=False, mode="raw")()
+        self._program(xs[0], ys[0], None, 0, False, 1, 0.0, 0.0, accumulate=False, mode="raw")()
+        self.from_native(self.g_n[0, :self.numel], self.g)
         self.bn_passes += 1
         return self.scal[S_LOSS], self.scal[S_CORRECT]
 
@@ -642,24 +725,25 @@ class FullBatchEngine:
         """modules.py:211-300: self.g (raw gradient of this microbatch) <- regularised gradient, in place
         (acc_strength uses self.pre, see load_pre)."""
         xs, ys = self._stages()
-        xs[0].copy_(inputs)
-        ys[0].copy_(labels)
+        xs[0][:self.mb].copy_(inputs)
+        ys[0][:self.mb].copy_(labels)
         if self.grad_norms is None:
             self.begin_step(1)
         self.cursor.zero_()
         self.set_lr(lr)
-        self._pass = 1
         impl = IMPLEMENTATIONS[implementation]
-        self._program(xs[0], ys[0], None, 0, False, block_strength, eps, accumulate=False, write_g=True, mode="reg",
+        self.to_native(self.g, self.g_n[0, :self.numel])
+        self._program(xs[0], ys[0], None, 0, False, 1, block_strength, eps, accumulate=False, write_g=True, mode="reg",
                       impl=impl, acc=acc_strength)()
+        self.from_native(self.g_n[0, :self.numel], self.g)
         self.bn_passes += 2 if impl == "central" else 1
 
     def load_pre(self, pre_grads):
-        """pre_grads (list shaped like model.parameters(), training.py:128-142) -> flat self.pre"""
-        if not hasattr(self, "pre"):
-            self.pre = torch.zeros_like(self.g)
+        """pre_grads (list shaped like model.parameters(), training.py:128-142) -> flat self.pre (+ native copy)"""
+        self._pre()
         for name, t in zip(self.names, pre_grads):
             self._view(self.pre, name).copy_(t.reshape(-1))
+        self.to_native(self.pre, self.pre_n)
 
     def load_grads(self, grads):
         for name, gt in zip(self.names, grads):
@@ -674,6 +758,14 @@ class FullBatchEngine:
                 gt.copy_(v.view(gt.shape))
 
     # ---- multi-GPU: one all-reduce of the flat buffer per full-batch pass (training/utils.py:31-41) -----------------
+    def all_reduce_flat(self, flat, local_count, global_count):
+        """fb_allreduce_flat of SURVEY.md 8b: flat <- sum over ranks of flat * local_count / global_count (the weights
+        make the sum the exact global mean of per-rank running means), one NCCL all-reduce over NVLink."""
+        import torch.distributed as dist
+
+        ops.flat_scale(flat, flat.numel(), float(local_count) / float(global_count))
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
     def all_reduce_mean(self, local_count, global_count):
         """avg holds the running mean over this rank's `local_count` microbatches; after this call every rank holds the
         mean over all `global_count` microbatches (exactly the single-process result up to fp32 summation order).
@@ -681,18 +773,18 @@ class FullBatchEngine:
         deliberately not reproduced."""
         import torch.distributed as dist
 
-        ops.flat_scale(self.avg, self.numel, float(local_count) / float(global_count))
-        dist.all_reduce(self.avg, op=dist.ReduceOp.SUM)
-        pack = torch.cat([self.scal[S_LOSS:S_CORRECT + 1], self.grad_norms])
+        self.all_reduce_flat(self.avg, local_count, global_count)
+        pack = torch.cat([self.scal[S_LOSS:S_CORRECT + 1], self.scal[S_CLIPPED:S_CLIPPED + 1], self.grad_norms])
         dist.all_reduce(pack, op=dist.ReduceOp.SUM)
         self.scal[S_LOSS:S_CORRECT + 1] = pack[:2]
-        self.grad_norms.copy_(pack[2:])
+        self.scal[S_CLIPPED] = pack[2]
+        self.grad_norms.copy_(pack[3:])
 
     def results(self, count):
         """Host read of the step scalars (one synchronisation): mean loss, correct count, grad_norms."""
-        s = self.scal.tolist()
-        return dict(loss=s[S_LOSS] / max(count, 1), correct=s[S_CORRECT], loss_sum=s[S_LOSS],
-                    grad_norms=self.grad_norms[:count].clone(), clipped_batches=int(s[S_CLIPPED]))
+        pack = torch.cat([self.scal[:4], self.grad_norms[:count]]).tolist()
+        return dict(loss=pack[S_LOSS] / max(count, 1), correct=pack[S_CORRECT], loss_sum=pack[S_LOSS],
+                    grad_norms=torch.tensor(pack[4:], dtype=torch.float32), clipped_batches=int(pack[S_CLIPPED]))
 
     def sync_bn_counters(self):
         """num_batches_tracked += number of train-mode passes (2 per microbatch with the regulariser)."""
@@ -703,5 +795,5 @@ class FullBatchEngine:
             self.bn_passes = 0
 
     def grads_list(self, flat):
-        """Views of a flat buffer shaped like model.parameters()."""
+        """Views of a flat buffer (reference layout) shaped like model.parameters()."""
         return [self._view(flat, n).view(self.shapes[n]) for n in self.names]

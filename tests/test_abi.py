@@ -3,6 +3,7 @@ ctypes binding must cover all of them.  No compute call is made here."""
 import ctypes
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -27,11 +28,30 @@ def test_library_exports_every_declared_symbol():
     assert handle.fb_version() >= 100
 
 
-def test_struct_sizes_match_the_header_layout():
-    assert ctypes.sizeof(lib.Tap) == 8
-    assert ctypes.sizeof(lib.WgradTap) == 4
-    assert ctypes.sizeof(lib.WprepEntry) == 80
-    assert ctypes.sizeof(lib.ConvGemmArgs) % 8 == 0
+def test_struct_sizes_match_the_header_layout(tmp_path):
+    """sizeof / last-member offset of every argument struct as gcc lays the header out == the ctypes mirror"""
+    structs = {"fb_tap": (lib.Tap, "b_k0"), "fb_wgrad_tap": (lib.WgradTap, "k_index"),
+               "fb_conv_gemm_args": (lib.ConvGemmArgs, "bn_eps"), "fb_wgrad_args": (lib.WgradArgs, "ng"),
+               "fb_reduce_entry": (lib.ReduceEntry, "vec"), "fb_wprep_entry": (lib.WprepEntry, "wd_gstride"),
+               "fb_bn_apply_args": (lib.BnApplyArgs, "reverse"), "fb_bn_bwd_args": (lib.BnBwdArgs, "reverse"),
+               "fb_bn_ema_entry": (lib.BnEmaEntry, "c_start")}
+    src = tmp_path / "sizes.c"
+    body = "".join(f'  printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last}));\n' for n, (_, last) in structs.items())
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{ROOT}/include/fullbatch_b200.h"\n'
+                   f"int main(void) {{\n{body}  return 0;\n}}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line.strip():
+            continue
+        name, size, off = line.split()
+        cls, last = structs[name]
+        assert ctypes.sizeof(cls) == int(size), name
+        assert getattr(cls, last).offset == int(off), name
+        seen += 1
+    assert seen == len(structs)
 
 
 def test_errors_are_reported_not_thrown():

@@ -24,11 +24,12 @@ def _free_port():
 class _StubEngine:
     """Only the state all_reduce_mean touches."""
     all_reduce_mean = E.FullBatchEngine.all_reduce_mean
+    all_reduce_flat = E.FullBatchEngine.all_reduce_flat
 
     def __init__(self, numel, K):
         self.numel = numel
         self.avg = torch.zeros(numel)
-        self.scal = torch.zeros(16)
+        self.scal = torch.zeros(E.SCAL_SLOTS)
         self.grad_norms = torch.zeros(max(K, 16))
 
 

@@ -81,15 +81,10 @@ def test_full_batch_step_matches_oracle(depth, mb, n):
     e_new, e32 = rel(eng.avg, avg64), rel(avg32, avg64)
     rep = dict(e_new_avg=e_new, e32_avg=e32, cos_avg=cos(eng.avg, avg64), loss=res["loss"], loss64=float(ref64["loss"]),
                grad_norms=res["grad_norms"].tolist(), grad_norms64=ref64["grad_norms"].tolist())
-    # per-microbatch raw / regularised gradient of microbatch 0 (eager, single microbatch programs)
-    eng.begin_step(1)
-    eng.set_lr(HYP["lr"])
-    eng._program(X, Y, None, 0, True, 0.0, HYP["eps"], accumulate=False, use_graph=False)()
+    # per-microbatch raw / regularised gradient of microbatch 0 through the GradRegularizer protocol of the engine
+    eng.microbatch_gradient(X[:mb], Y[:mb])
     raw = eng.g.clone()
-    eng.begin_step(1)
-    eng.set_lr(HYP["lr"])
-    eng._program(X, Y, None, 0, True, HYP["block_strength"], HYP["eps"], accumulate=False, write_g=True,
-                 use_graph=False)()
+    eng.regularize(X[:mb], Y[:mb], HYP["lr"], HYP["block_strength"], HYP["eps"])
     reg = eng.g.clone()
     k64, k32 = ref64["kept"][0], ref32["kept"][0]
     rep.update(e_new_raw=rel(raw, O.flat(k64["raw"])), e32_raw=rel(O.flat(k32["raw"]), O.flat(k64["raw"])),
@@ -134,6 +129,24 @@ def test_running_stats_and_determinism():
         b.copy_(buffers[name].to(DEV))
     eng.accumulate_resident(X, Y, HYP["lr"], HYP["block_strength"], HYP["eps"])
     assert torch.equal(first, eng.avg)
+
+
+def test_result_does_not_depend_on_the_group_count():
+    """G microbatches per launch is a pure performance knob: 1, 2 (with a remainder launch) and 5 groups give the same
+    bits for the accumulated gradient, the gradient norms, the loss and the BatchNorm running statistics."""
+    depth, mb, n = 18, 16, 80
+    outs = []
+    for G in (1, 2, 5):
+        model, params, buffers, X, Y = setup_case(depth, mb, n)
+        eng = FullBatchEngine(model, mb, precision="split", groups=G)
+        K = eng.accumulate_resident(X, Y, 0.8, 0.5, 1e-2)
+        res = eng.results(K)
+        outs.append((eng.avg.clone(), res["grad_norms"].clone(), torch.tensor(res["loss_sum"]),
+                     torch.cat([b.reshape(-1).float() for b in model.buffers()])))
+        assert K == 5
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
 
 
 def test_graph_replay_equals_eager():

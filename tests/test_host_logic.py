@@ -1,7 +1,11 @@
-"""Host-side planning logic that needs no GPU: tile / geometry cost models of fullbatchtraining_b200.ops."""
+"""Host-side planning logic that needs no GPU: tile / geometry policies of fullbatchtraining_b200.ops and the group
+scheduling of the engine.  The policies must depend on ONE microbatch's problem only (never on the number of groups in
+a launch): that is what makes results independent of the group count."""
+import inspect
+
 import pytest
 
-from fullbatchtraining_b200 import ops
+from fullbatchtraining_b200 import engine, ops
 
 
 def test_pixel_tile_covers_128_pixels():
@@ -12,9 +16,19 @@ def test_pixel_tile_covers_128_pixels():
         ops.pixel_tile(24, 24)
 
 
+def test_tiles_per_group_requires_whole_boxes():
+    assert ops.tiles_per_group(128, 32, ops.pixel_tile(32, 32)) == 1024
+    assert ops.tiles_per_group(128, 16, ops.pixel_tile(16, 16)) == 256
+    assert ops.tiles_per_group(128, 8, ops.pixel_tile(8, 8)) == 64
+    assert ops.tiles_per_group(128, 4, ops.pixel_tile(4, 4)) == 16
+    with pytest.raises(RuntimeError):
+        ops.tiles_per_group(12, 4, ops.pixel_tile(4, 4))  # 8 images per box on 4x4 maps
+
+
 def test_choose_n_tile_follows_the_cost_model():
-    # 64-channel stage: only 64 divides; 4x4 stage (16 M tiles): 64-wide stacked tiles fill more SMs than 128-wide ones
+    # 64-channel stage: only 64 divides
     assert ops.choose_n_tile(1024, 64, 2, 2) == 64
+    # 4x4 stage, few M tiles: 64-wide stacked tiles fill more SMs than 128-wide ones
     assert ops.choose_n_tile(16, 512, 2, 2) == 64
     # 8x8 stage: 64 M tiles x 2 N tiles of 128 = one wave
     assert ops.choose_n_tile(64, 256, 2, 2) == 128
@@ -22,33 +36,38 @@ def test_choose_n_tile_follows_the_cost_model():
         assert n % ops.choose_n_tile(m, n) == 0
 
 
-def test_halo_geometry_is_opt_in_and_consistent(monkeypatch):
-    monkeypatch.delenv("FB_HALO", raising=False)
-    assert ops.halo_geometry(128, 32, 32, 3, 1, 64) is None
-    monkeypatch.setenv("FB_HALO", "1")
-    assert ops.halo_geometry(128, 32, 32, 3, 1, 64) == (1, 2, 64)
-    assert ops.halo_geometry(128, 16, 16, 3, 1, 128) == (1, 2, 128)
-    imgs, halves, nt = ops.halo_geometry(128, 8, 8, 3, 1, 256)
-    assert imgs == 2 and 128 % (halves * imgs) == 0 and 256 % nt == 0
-    assert ops.halo_geometry(128, 4, 4, 3, 1, 512)[0] == 8
-    assert ops.halo_geometry(4, 4, 4, 3, 1, 512) is None       # fewer images than one interleaved half
-    assert ops.halo_geometry(128, 32, 32, 1, 1, 64) is None    # 1x1
-    assert ops.halo_geometry(128, 32, 32, 3, 2, 64) is None    # stride 2
-
-
-def test_wgrad_halo_eligibility(monkeypatch):
-    monkeypatch.delenv("FB_WGRAD_HALO", raising=False)
+def test_wgrad_policies():
     assert ops.Conv2dPlan._wgrad_halo(3, 1, (32, 4, 1), 2)
     assert ops.Conv2dPlan._wgrad_halo(3, 1, (16, 8, 1), 2)
     assert not ops.Conv2dPlan._wgrad_halo(3, 1, (8, 8, 2), 2)   # tiles span two images
     assert not ops.Conv2dPlan._wgrad_halo(1, 1, (32, 4, 1), 2)
     assert not ops.Conv2dPlan._wgrad_halo(3, 2, (16, 8, 1), 2)
-    monkeypatch.setenv("FB_WGRAD_HALO", "0")
-    assert not ops.Conv2dPlan._wgrad_halo(3, 1, (32, 4, 1), 2)
+    assert ops.Conv2dPlan._slots_per_cta(9, 2) == 3 and ops.Conv2dPlan._slots_per_cta(72, 2) == 4
+    assert ops.Conv2dPlan._slots_per_cta(2, 2) == 2 and ops.Conv2dPlan._slots_per_cta(16, 1) == 8
+    # split-K: POLICY_GROUPS groups fill one wave; never more splits than pixel blocks; no split on the wide stages
+    s = ops.Conv2dPlan.wgrad_splits(1024, 1, 3)
+    assert 1 <= s <= 1024 and 3 * s * ops.POLICY_GROUPS <= ops.NUM_SMS
+    assert ops.Conv2dPlan.wgrad_splits(16, 4, 18) == 1
+    assert ops.Conv2dPlan.wgrad_splits(2, 1, 1) == 2
+    # the policy has no access to the number of groups of a launch
+    assert "ng" not in inspect.signature(ops.Conv2dPlan.wgrad_splits).parameters
+    assert "ng" not in inspect.signature(ops.choose_n_tile).parameters
 
 
-def test_partial_workspace_bound_covers_every_mode():
-    for case in [(128, 32, 32, 64, 64, 3, 1), (128, 16, 16, 128, 128, 3, 1), (128, 8, 8, 256, 256, 3, 1),
-                 (128, 32, 32, 64, 128, 3, 2), (32, 8, 8, 1024, 256, 1, 1)]:
-        n, h, w, cin, cout, k, stride = case
-        assert ops.Conv2dPlan.partial_elems(*case) >= cout * k * k * cin
+def test_default_groups(monkeypatch):
+    monkeypatch.delenv("FB_GROUPS", raising=False)
+    assert engine.default_groups(128) == 8
+    assert engine.default_groups(32) == 16
+    assert engine.default_groups(2048) == 1
+    monkeypatch.setenv("FB_GROUPS", "3")
+    assert engine.default_groups(128) == 3
+    monkeypatch.setenv("FB_GROUPS", "99")
+    assert engine.default_groups(128) == 16
+
+
+def test_scalar_slots_do_not_overlap():
+    singles = [engine.S_LOSS, engine.S_CORRECT, engine.S_CF, engine.S_CLIPPED, engine.S_GNORM, engine.S_PNORM]
+    assert len(set(singles)) == len(singles) and max(singles) < 16
+    bases = [engine.S_N2G, engine.S_EPSG, engine.S_LOSSG, engine.S_CORRG, engine.S_LOSS2G, engine.S_CORR2G,
+             engine.S_VSQG, engine.S_REGSQG]
+    assert sorted(bases) == list(range(16, 16 * 9, 16)) and engine.SCAL_SLOTS >= max(bases) + 16
