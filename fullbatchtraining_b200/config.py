@@ -43,7 +43,9 @@ _DEFAULT = dict(
               # "bf16" = plain bf16 operands (fast mode)
               precision="split",
               # B200-path switches: keep the dataset in HBM when the loader wraps a TensorDataset; fused clip+SGD sweep
-              resident_dataset=True, fused_optimizer=True, kernel_evaluate=True),
+              resident_dataset=True, fused_optimizer=True, kernel_evaluate=True,
+              # microbatches per kernel launch (None: ~1024 images per launch); results do not depend on it
+              groups=None),
     hyp=dict(template_name="fbgradreg", train_stochastic=False, shuffle=False, steps=3000, sub_batch=128,
              optim=dict(name="Gradient Descent", lr=0.8, momentum=0.9, weight_decay=5e-4, dampening=0.0, nesterov=True,
                         line_search="none"),

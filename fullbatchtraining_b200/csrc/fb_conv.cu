@@ -368,10 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // unrolled block is back-to-back UTCHMMA, and TWO pipeline stages are waited for and issued per round.
     constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
     constexpr int kC = Cfg::kCombos;
-    //   stacked, PA == 2: c0 = A_lo, c1 = A_hi (both against [B_hi;B_lo]); for 128-wide tiles A_lo only needs B_hi, so
-    //     it runs at N = N_TILE except in the first K block of a tile, where it must initialise both halves
+    //   stacked, PA == 2: c0 = A_lo, c1 = A_hi (both against [B_hi;B_lo]); A_lo only needs B_hi, so it runs at
+    //     N = N_TILE except in the first K block of a tile, where it must initialise both halves
     //   not stacked: (a1,b0) first if PA == 2, then (a0,b0), then (a0,b1) if PB == 2
-    constexpr bool kNarrowLo = Cfg::kStack && N_TILE == 128 && PA == 2;
+    constexpr bool kNarrowLo = Cfg::kStack && PA == 2;
     auto ap_of = [](int c) { return (PA == 2 && c == 0) ? 1 : 0; };
     auto bp_of = [](int c) { return (!Cfg::kStack && PB == 2 && c == kC - 1) ? 1 : 0; };
     constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
@@ -529,10 +529,17 @@ static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStr
   return FB_ERR_UNSUPPORTED;
 }
 
+// Super-tile rows per (group, N tile).  At most one row per CTA of a wave (148 / n_tiles); if the group has more M tiles
+// than that, prefer a row count that DIVIDES them (every super-tile then holds the same number of tiles, and the
+// super-tiles of all groups of a launch spread evenly over the persistent CTAs) unless it would idle a quarter of the
+// SMs.  Depends on one group's problem only.
 static int stats_rows(int m_tiles_per_group, int n_tiles) {
   int cap = kNumSMs / (n_tiles > 0 ? n_tiles : 1);
   if (cap < 1) cap = 1;
-  return m_tiles_per_group < cap ? m_tiles_per_group : cap;
+  if (m_tiles_per_group <= cap) return m_tiles_per_group;
+  for (int d = cap; 4 * d >= 3 * cap; --d)
+    if (m_tiles_per_group % d == 0) return d;
+  return cap;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -133,80 +133,84 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // BN apply (+ second normalised branch, + residual, + ReLU) -> bf16 hi/lo, grid = (blocks, groups)
 // ---------------------------------------------------------------------------------------------------------------
-// Per-thread channel parameters are loop invariant when the grid stride (gridDim.x * 2048 elements) is a multiple of C
-// (every channel count of the ResNet family divides 2048), so they are loaded once per thread.
-struct BnAffine {
-  float mu[8], scale[8], shift[8];
-  __device__ __forceinline__ void load(const float* mean, const float* rstd, const float* gamma, const float* beta,
-                                       int c) {
-    float rs[8], ga[8];
-    load8(mean + c, mu);
-    load8(rstd + c, rs);
-    load8(gamma + c, ga);
-    load8(beta + c, shift);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) scale[j] = rs[j] * ga[j];
-  }
+// The per-channel affine parameters (mean, rstd*gamma, beta) of the group live in shared memory; every thread streams
+// items of 8 consecutive channels, TWO items per loop round with all loads issued before the arithmetic, so that
+// ~3 blocks x 256 threads x 128-192 bytes are in flight per SM (the kernel is a pure HBM stream).
+struct BnItem {
+  float y[8], y2[8], r[8];
 };
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(fb_bn_apply_args a) {
+template <bool DUAL, bool RES>
+__device__ __forceinline__ void bn_item_load(const fb_bn_apply_args& a, long long off, BnItem& it) {
+  load8(a.y + off, it.y);
+  if (DUAL) load8(a.y2 + off, it.y2);
+  if (RES) {
+    load8_bf16(static_cast<const bf16*>(a.res_hi) + off, it.r);
+    if (a.res_lo) {
+      float rl[8];
+      load8_bf16(static_cast<const bf16*>(a.res_lo) + off, rl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) it.r[j] += rl[j];
+    }
+  }
+}
+
+template <bool DUAL, bool RES>
+__device__ __forceinline__ void bn_item_store(const fb_bn_apply_args& a, long long off, int c, const float* sp,
+                                              const BnItem& it) {
+  const int C = a.C;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (it.y[j] - sp[c + j]) * sp[C + c + j] + sp[2 * C + c + j];
+  if (DUAL) {
+    const float* sp2 = sp + 3 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += (it.y2[j] - sp2[c + j]) * sp2[C + c + j] + sp2[2 * C + c + j];
+  }
+  if (RES) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += it.r[j];
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  store8_split(static_cast<bf16*>(a.out_hi), static_cast<bf16*>(a.out_lo), off, o);
+}
+
+template <bool DUAL, bool RES>
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const __grid_constant__ fb_bn_apply_args a) {
+  extern __shared__ float sp[];  // [mean | rstd*gamma | beta][C] (x2 with the second branch)
   griddep_wait();
   griddep_launch();
+  // reverse: start with the last elements of the last group = what the producer of y (the convolution) wrote last
   const int g = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-  const long long total8 = a.P * a.C / 8;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const bool invariant = (stride * 8) % a.C == 0;
-  const long long gbase = (long long)g * a.P * a.C;
-  const float* mean = a.mean + (long long)g * a.C;
-  const float* rstd = a.rstd + (long long)g * a.C;
-  const float* gamma = a.gamma + (long long)g * a.param_gstride;
-  const float* beta = a.beta + (long long)g * a.param_gstride;
-  const float* mean2 = a.y2 ? a.mean2 + (long long)g * a.C : nullptr;
-  const float* rstd2 = a.y2 ? a.rstd2 + (long long)g * a.C : nullptr;
-  const float* gamma2 = a.y2 ? a.gamma2 + (long long)g * a.param_gstride : nullptr;
-  const float* beta2 = a.y2 ? a.beta2 + (long long)g * a.param_gstride : nullptr;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  BnAffine p1, p2;
-  if (i < total8) {
-    const long long e = a.reverse ? total8 - 1 - i : i;
-    const int c = int((e * 8) % a.C);
-    p1.load(mean, rstd, gamma, beta, c);
-    if (a.y2) p2.load(mean2, rstd2, gamma2, beta2, c);
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const long long pc = (long long)g * a.param_gstride + c;
+    sp[c] = a.mean[(long long)g * C + c];
+    sp[C + c] = a.rstd[(long long)g * C + c] * a.gamma[pc];
+    sp[2 * C + c] = a.beta[pc];
+    if (DUAL) {
+      sp[3 * C + c] = a.mean2[(long long)g * C + c];
+      sp[4 * C + c] = a.rstd2[(long long)g * C + c] * a.gamma2[pc];
+      sp[5 * C + c] = a.beta2[pc];
+    }
   }
-  for (; i < total8; i += stride) {
-    const long long e = a.reverse ? total8 - 1 - i : i;
-    const long long off = gbase + e * 8;
-    if (!invariant) {
-      const int c = int((e * 8) % a.C);
-      p1.load(mean, rstd, gamma, beta, c);
-      if (a.y2) p2.load(mean2, rstd2, gamma2, beta2, c);
-    }
-    float y[8], o[8];
-    load8(a.y + off, y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (y[j] - p1.mu[j]) * p1.scale[j] + p1.shift[j];
-    if (a.y2) {
-      load8(a.y2 + off, y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (y[j] - p2.mu[j]) * p2.scale[j] + p2.shift[j];
-    }
-    if (a.res_hi) {
-      float rh[8];
-      load8_bf16(static_cast<const bf16*>(a.res_hi) + off, rh);
-      if (a.res_lo) {
-        float rl[8];
-        load8_bf16(static_cast<const bf16*>(a.res_lo) + off, rl);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rh[j] += rl[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += rh[j];
-    }
-    if (a.relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-    }
-    store8_split(static_cast<bf16*>(a.out_hi), static_cast<bf16*>(a.out_lo), off, o);
+  __syncthreads();
+  const long long total8 = a.P * C / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long gbase = (long long)g * a.P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < total8;
+    const long long e1 = a.reverse ? total8 - 1 - i : i;
+    const long long e2 = a.reverse ? total8 - 1 - i2 : i2;
+    BnItem it1, it2;
+    bn_item_load<DUAL, RES>(a, gbase + e1 * 8, it1);
+    if (two) bn_item_load<DUAL, RES>(a, gbase + e2 * 8, it2);
+    bn_item_store<DUAL, RES>(a, gbase + e1 * 8, int((e1 * 8) % C), sp, it1);
+    if (two) bn_item_store<DUAL, RES>(a, gbase + e2 * 8, int((e2 * 8) % C), sp, it2);
   }
 }
 
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdK k) {
   const fb_bn_bwd_args& a = k.a;
   const int C = a.C;
   const long long P = a.P;
-  const int g = blockIdx.z;
+  const int g = a.reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
   const int TX = k.geo.TX, TY = 256 / TX;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int chunk = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
@@ -363,12 +367,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdK k) {
   griddep_wait();
   griddep_launch();
   const fb_bn_bwd_args& a = k.a;
-  const int g = blockIdx.y;
+  const bool backwards = !a.reverse;  // opposite direction of the reduce pass (groups included)
+  const int g = backwards ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int C = a.C;
   const long long total8 = a.P * C / 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool invariant = (stride * 8) % C == 0;
-  const bool backwards = !a.reverse;  // opposite direction of the reduce pass
   const long long gbase = (long long)g * a.P * C;
   const float* mean = a.mean + (long long)g * C;
   const float* rstd = a.rstd + (long long)g * C;
@@ -814,9 +818,18 @@ extern "C" int fb_bn_apply(const fb_bn_apply_args* a, void* stream) {
   fb_bn_apply_args k = *a;
   if (k.ng <= 0) k.ng = 1;
   FB_REQUIRE(k.ng <= FB_MAX_GROUPS, "fb_bn_apply: at most %d groups", FB_MAX_GROUPS);
-  // grid.x: a multiple of C/8-thread periods keeps the per-thread channel parameters loop invariant (C | 2048)
-  FB_CUDA(launch_pdl(bn_apply_kernel, dim3(stream_grid(k.P * k.C / 8), k.ng), dim3(256), 0,
-                     static_cast<cudaStream_t>(stream), k));
+  const size_t smem = size_t(k.y2 ? 6 : 3) * k.C * sizeof(float);
+  FB_REQUIRE(smem <= 48 * 1024, "fb_bn_apply: at most %d channels", k.y2 ? 2048 : 4096);
+  const dim3 grid(stream_grid(k.P * k.C / 16), k.ng);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k.y2) {
+    FB_REQUIRE(!k.res_hi, "fb_bn_apply: a second normalised branch and an identity residual exclude each other");
+    FB_CUDA(launch_pdl(bn_apply_kernel<true, false>, grid, dim3(256), smem, st, k));
+  } else if (k.res_hi) {
+    FB_CUDA(launch_pdl(bn_apply_kernel<false, true>, grid, dim3(256), smem, st, k));
+  } else {
+    FB_CUDA(launch_pdl(bn_apply_kernel<false, false>, grid, dim3(256), smem, st, k));
+  }
   return 0;
 }
 

@@ -110,6 +110,15 @@ __global__ void __launch_bounds__(256) perturb_ranges_kernel(const float* __rest
   }
 }
 
+// The two sweeps below read every group's gradient once and keep the running mean in registers.  Per element the groups
+// are combined in loader order (a sequential chain, as in the reference), but the LOADS of four groups are issued
+// together (16-byte vectors), so enough bytes are in flight to stream at HBM rate.
+constexpr int kGroupChunk = 4;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float& comp(float4& v, int j) { return (&v.x)[j]; }
+
+template <bool MINUS>
 __global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ grad, const float* __restrict__ g_plus,
                                                          const float* __restrict__ g_minus, long long gstride,
                                                          float* __restrict__ avg, long long n, int ng,
@@ -117,26 +126,60 @@ __global__ void __launch_bounds__(256) fd_combine_kernel(float* __restrict__ gra
                                                          const int* __restrict__ cursor, int write_g) {
   griddep_wait();
   griddep_launch();
+  __shared__ float s_eps[FB_MAX_GROUPS], s_inv[FB_MAX_GROUPS];
   const float cf = scal[cf_slot];
-  const int count0 = cursor ? *cursor : 0;
-  float eps_n[FB_MAX_GROUPS], inv[FB_MAX_GROUPS];
-#pragma unroll
-  for (int g = 0; g < FB_MAX_GROUPS; ++g) {
-    eps_n[g] = g < ng ? scal[eps_base + g] : 1.f;
-    inv[g] = float(1.0 / double(count0 + g + 1));
+  if (threadIdx.x < FB_MAX_GROUPS) {
+    const int count0 = cursor ? *cursor : 0;
+    s_eps[threadIdx.x] = (int)threadIdx.x < ng ? scal[eps_base + threadIdx.x] : 1.f;
+    s_inv[threadIdx.x] = float(1.0 / double(count0 + (int)threadIdx.x + 1));
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float a = avg ? avg[i] : 0.f;
+  __syncthreads();
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = avg ? ldg4(avg + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g0 = 0; g0 < ng; g0 += kGroupChunk) {
+      float4 gr[kGroupChunk], gp[kGroupChunk], gm[kGroupChunk];
 #pragma unroll
-    for (int g = 0; g < FB_MAX_GROUPS; ++g) {
-      if (g >= ng) break;
+      for (int j = 0; j < kGroupChunk; ++j) {
+        if (g0 + j < ng) {
+          const long long o = (long long)(g0 + j) * gstride + 4 * i;
+          gr[j] = ldg4(grad + o);
+          gp[j] = ldg4(g_plus + o);
+          if (MINUS) gm[j] = ldg4(g_minus + o);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kGroupChunk; ++j) {
+        if (g0 + j < ng) {
+          const float eps_n = s_eps[g0 + j], inv = s_inv[g0 + j];
+          float4 r;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float g = comp(gr[j], c);
+            const float base = MINUS ? comp(gm[j], c) : g;
+            const float h = (comp(gp[j], c) - base) / eps_n;  // modules.py:232-234 / :292-293
+            const float v = g + cf * h;                        // modules.py:240 / :299
+            comp(r, c) = v;
+            comp(a, c) = comp(a, c) + (v - comp(a, c)) * inv;  // training.py:45-47
+          }
+          if (write_g) *reinterpret_cast<float4*>(grad + (long long)(g0 + j) * gstride + 4 * i) = r;
+        }
+      }
+    }
+    if (avg) *reinterpret_cast<float4*>(avg + 4 * i) = a;
+  }
+  // tail (n % 4 elements)
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - n4 * 4)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    float a = avg ? avg[i] : 0.f;
+    for (int g = 0; g < ng; ++g) {
       const long long o = (long long)g * gstride + i;
       float gr = grad[o];
-      const float base = g_minus ? g_minus[o] : gr;
-      const float h = (g_plus[o] - base) / eps_n[g];  // modules.py:232-234 / :292-293
-      gr = gr + cf * h;                               // modules.py:240 / :299
+      const float base = MINUS ? g_minus[o] : gr;
+      const float h = (g_plus[o] - base) / s_eps[g];
+      gr = gr + cf * h;
       if (write_g) grad[o] = gr;
-      a = a + (gr - a) * inv[g];                      // training.py:45-47
+      a = a + (gr - a) * s_inv[g];
     }
     if (avg) avg[i] = a;
   }
@@ -148,37 +191,67 @@ __global__ void __launch_bounds__(256) mean_accumulate_kernel(float* __restrict_
                                                               int norm_base, float clip, int clipped_slot) {
   griddep_wait();
   griddep_launch();
-  const int count0 = cursor ? *cursor : 0;
-  float coef[FB_MAX_GROUPS], inv[FB_MAX_GROUPS];
-  bool clipped[FB_MAX_GROUPS];
-  int n_clipped = 0;
-#pragma unroll
-  for (int g = 0; g < FB_MAX_GROUPS; ++g) {
-    coef[g] = 1.f;
-    clipped[g] = false;
-    inv[g] = float(1.0 / double(count0 + g + 1));
+  __shared__ float s_coef[FB_MAX_GROUPS], s_inv[FB_MAX_GROUPS];
+  __shared__ int s_clipped[FB_MAX_GROUPS];
+  if (threadIdx.x < FB_MAX_GROUPS) {
+    const int g = threadIdx.x;
+    const int count0 = cursor ? *cursor : 0;
+    float coef = 1.f;
+    int clipped = 0;
     if (g < ng && clip > 0.f) {
       const float norm = sqrtf(scal[norm_base + g]);
       if (norm > clip) {  // training/utils.py:4-19
-        coef[g] = clip / (norm + 1e-6f);
-        clipped[g] = true;
-        ++n_clipped;
+        coef = clip / (norm + 1e-6f);
+        clipped = 1;
       }
     }
+    s_coef[g] = coef;
+    s_clipped[g] = clipped;
+    s_inv[g] = float(1.0 / double(count0 + g + 1));
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float a = avg[i];
+  __syncthreads();
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = ldg4(avg + 4 * i);
+    for (int g0 = 0; g0 < ng; g0 += kGroupChunk) {
+      float4 gr[kGroupChunk];
 #pragma unroll
-    for (int g = 0; g < FB_MAX_GROUPS; ++g) {
-      if (g >= ng) break;
+      for (int j = 0; j < kGroupChunk; ++j)
+        if (g0 + j < ng) gr[j] = ldg4(grad + (long long)(g0 + j) * gstride + 4 * i);
+#pragma unroll
+      for (int j = 0; j < kGroupChunk; ++j) {
+        if (g0 + j < ng) {
+          const float coef = s_coef[g0 + j], inv = s_inv[g0 + j];
+          float4 r;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float v = comp(gr[j], c) * coef;
+            comp(r, c) = v;
+            comp(a, c) = comp(a, c) + (v - comp(a, c)) * inv;
+          }
+          // the reference scales the microbatch gradient in place
+          if (s_clipped[g0 + j]) *reinterpret_cast<float4*>(grad + (long long)(g0 + j) * gstride + 4 * i) = r;
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(avg + 4 * i) = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - n4 * 4)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    float a = avg[i];
+    for (int g = 0; g < ng; ++g) {
       const long long o = (long long)g * gstride + i;
-      const float gr = grad[o] * coef[g];
-      if (clipped[g]) grad[o] = gr;  // the reference scales the microbatch gradient in place
-      a = a + (gr - a) * inv[g];
+      const float v = grad[o] * s_coef[g];
+      if (s_clipped[g]) grad[o] = v;
+      a = a + (v - a) * s_inv[g];
     }
     avg[i] = a;
   }
-  if (n_clipped && blockIdx.x == 0 && threadIdx.x == 0) scal[clipped_slot] += float(n_clipped);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int n_clipped = 0;
+    for (int g = 0; g < ng; ++g) n_clipped += s_clipped[g];
+    if (n_clipped) scal[clipped_slot] += float(n_clipped);
+  }
 }
 
 __global__ void group_finish_kernel(int* cursor, int ng, float* scal, int loss_slot, int correct_slot, int loss_base,
@@ -292,9 +365,17 @@ extern "C" int fb_fd_combine(float* grad, const float* g_plus, const float* g_mi
                              int write_g, void* stream) {
   FB_REQUIRE(grad && g_plus && scal && n > 0 && ng >= 1 && ng <= FB_MAX_GROUPS && cf_slot >= 0,
              "fb_fd_combine: bad arguments");
-  FB_CUDA(launch_pdl(fd_combine_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), grad,
-                     g_plus, g_minus, (long long)gstride, avg, (long long)n, ng, scal, eps_base, cf_slot,
-                     (const int*)cursor, write_g));
+  FB_REQUIRE(((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(g_plus) |
+               reinterpret_cast<uintptr_t>(g_minus) | reinterpret_cast<uintptr_t>(avg)) & 15) == 0 && gstride % 4 == 0,
+             "fb_fd_combine: buffers and the group stride must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(flat_grid(n / 4 + 1));
+  if (g_minus)
+    FB_CUDA(launch_pdl(fd_combine_kernel<true>, grid, dim3(256), 0, st, grad, g_plus, g_minus, (long long)gstride, avg,
+                       (long long)n, ng, scal, eps_base, cf_slot, (const int*)cursor, write_g));
+  else
+    FB_CUDA(launch_pdl(fd_combine_kernel<false>, grid, dim3(256), 0, st, grad, g_plus, g_minus, (long long)gstride, avg,
+                       (long long)n, ng, scal, eps_base, cf_slot, (const int*)cursor, write_g));
   return 0;
 }
 
@@ -302,7 +383,9 @@ extern "C" int fb_mean_accumulate(float* grad, int64_t gstride, float* avg, int6
                                   float* scal, int norm_base, float clip, int clipped_slot, void* stream) {
   FB_REQUIRE(grad && avg && n > 0 && ng >= 1 && ng <= FB_MAX_GROUPS, "fb_mean_accumulate: bad arguments");
   FB_REQUIRE(clip <= 0.f || scal, "fb_mean_accumulate: clipping needs scal");
-  FB_CUDA(launch_pdl(mean_accumulate_kernel, dim3(flat_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), grad,
+  FB_REQUIRE(((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(avg)) & 15) == 0 && gstride % 4 == 0,
+             "fb_mean_accumulate: buffers and the group stride must be 16-byte aligned");
+  FB_CUDA(launch_pdl(mean_accumulate_kernel, dim3(flat_grid(n / 4 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), grad,
                      (long long)gstride, avg, (long long)n, ng, (const int*)cursor, scal, norm_base, clip,
                      clipped_slot));
   return 0;

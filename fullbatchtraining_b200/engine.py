@@ -276,6 +276,7 @@ class FullBatchEngine:
         self.ema = ops.BnEmaTable([(self._bn_modules[u.bn_name].running_mean, self._bn_modules[u.bn_name].running_var,
                                     u.bn_batch, u.bn_batch.stride(0), u.cout) for u in self.units], dev)
         self._graphs = {}
+        self.l2_order = os.environ.get("FB_L2_ORDER", "1") == "1"
         # FB_WGRAD_STREAM=1: wgrad on a side stream, concurrently with the dgrad -> BatchNorm-backward chain below it
         self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "0") == "1" else None
         self.grad_norms = None
@@ -310,8 +311,10 @@ class FullBatchEngine:
         sec = None
         if second is not None:
             sec = (second.y, second.mean, second.rstd, base + 4 * second.gamma_off, base + 4 * second.beta_off)
+        # l2_order: walk back to front = start on what the convolution wrote last (still in L2) and end where the next
+        # convolution starts
         ops.bn_apply(u.y, u.mean, u.rstd, base + 4 * u.gamma_off, base + 4 * u.beta_off, u.Pg, u.cout, out.hi, out.lo,
-                     relu=relu, second=sec, res=res, ng=ng, param_gstride=pstride)
+                     relu=relu, second=sec, res=res, ng=ng, param_gstride=pstride, reverse=self.l2_order)
 
     def _forward(self, ng, wset, P, pstride, Gbuf, loss_base, correct_base, pass_idx):
         """P: flat parameters (theta: pstride 0, shared; theta_p: one row per group); Gbuf: [G][stride] gradients"""
@@ -344,9 +347,14 @@ class FullBatchEngine:
     def _unit_backward(self, u, ng, wset, P, pstride, Gbuf, act, dz_out=None):
         """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
         pb, gb = P.data_ptr(), Gbuf.data_ptr()
+        # l2_order: the reduce pass starts where the producer of the upstream gradient ended, the apply pass walks the
+        # other way, the dgrad starts where the apply ended -- the direction alternates from layer to layer so that each
+        # kernel begins on the ~100 MB its predecessor left in L2
+        rev = self._rev and self.l2_order
+        self._rev = not self._rev
         ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
                    gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
-                   param_gstride=pstride, grad_gstride=self.stride)
+                   param_gstride=pstride, grad_gstride=self.stride, reverse=rev)
         # wgrad only feeds the flat gradient: optionally on a side stream, concurrently with the dgrad ->
         # BatchNorm-backward chain of the layers below (fork here, join at the end of the backward pass)
         if self.wgrad_stream is not None:
@@ -357,9 +365,10 @@ class FullBatchEngine:
         else:
             u.plan.wgrad(ng, Gbuf, self.stride)
         if not u.stem:
-            u.plan.dgrad(ng, wset)
+            u.plan.dgrad(ng, wset, reverse=rev)
 
     def _backward(self, ng, wset, P, pstride, Gbuf):
+        self._rev = True  # the head wrote the first upstream gradient front to back
         for blk in reversed(self.blocks):
             out = blk.out
             last = len(blk.units) - 1

@@ -22,7 +22,7 @@ NUM_SMS = 148
 POLICY_GROUPS = int(os.environ.get("FB_POLICY_GROUPS", "8"))
 
 # Optional per-launch timing for bench.py's roofline: set PROFILE = [] to collect
-# (family, algorithmic work, unit, start event, end event) around every wrapped launch on the current stream.
+# (family, algorithmic work, unit, start event, end event, label) around every wrapped launch on the current stream.
 PROFILE = None
 LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py's gpu_launches claim)
 _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv_wgrad": 1, "fb_reduce_multi": 1,
@@ -33,7 +33,7 @@ _KERNELS_PER_CALL = {"fb_weight_prep_multi": 1, "fb_conv_gemm": 1, "fb_conv_wgra
                      "fb_sgd_step": 2}
 
 
-def _call(family, work, unit, name, *args):
+def _call(family, work, unit, name, *args, label=None):
     LAUNCHES["count"] += _KERNELS_PER_CALL[name]
     if PROFILE is None:
         L.call(name, *args)
@@ -42,7 +42,7 @@ def _call(family, work, unit, name, *args):
     e0.record()
     L.call(name, *args)
     e1.record()
-    PROFILE.append((family, work, unit, e0, e1))
+    PROFILE.append((family, work, unit, e0, e1, label or name))
 
 
 def device_table(ctypes_array, device):
@@ -174,6 +174,7 @@ class ConvGemm:
         self.mb = mb
         self.args = args
         self.flops_per_group = 0.0  # algorithmic FLOPs of one group (set by Conv2dPlan)
+        self.label = "conv_gemm"
         self.stats = None
 
     def set_stats(self, stats_ws, tickets, mean, rstd, eps):
@@ -182,15 +183,16 @@ class ConvGemm:
         self._stats_ptrs = (stats_ws.data_ptr(), tickets.data_ptr(), mean.data_ptr(), rstd.data_ptr())
         self.args.bn_eps = eps
 
-    def __call__(self, ng=1, bn_batch=None, stats=True):
+    def __call__(self, ng=1, bn_batch=None, stats=True, reverse=False):
         a = self.args
         a.ng, a.grid_n = ng, ng * self.mb
+        a.reverse = int(reverse)
         if self.stats is not None and stats:
             a.stats_ws, a.tickets, a.bn_mean, a.bn_rstd = self._stats_ptrs
             a.bn_batch = bn_batch
         else:
             a.stats_ws = None
-        _call("conv_gemm", self.flops_per_group * ng, "flop", "fb_conv_gemm", C.byref(a))
+        _call("conv_gemm", self.flops_per_group * ng, "flop", "fb_conv_gemm", C.byref(a), label=self.label)
 
 
 class Conv2dPlan:
@@ -264,6 +266,7 @@ class Conv2dPlan:
             g = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
                          (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0)
             g.flops_per_group = self.alg_flops
+            g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}"
             self.fwd.append(g)
         # BatchNorm statistics fused into the forward epilogue
         self.stat_rows = L.load().fb_conv_stats_rows(mtg, cout // n_tile)
@@ -313,6 +316,7 @@ class Conv2dPlan:
                 g = ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, mb, cin, dx, strides, False, n_tile_d,
                              b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups)
                 g.flops_per_group = self.alg_flops
+                g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}"
                 self.dgrads.append(g)
 
         # ---- wgrad
@@ -400,8 +404,8 @@ class Conv2dPlan:
     def forward(self, ng, wset, bn_batch=None, stats=True):
         self.fwd[wset](ng, bn_batch, stats)
 
-    def dgrad(self, ng, wset):
-        self.dgrads[wset](ng)
+    def dgrad(self, ng, wset, reverse=False):
+        self.dgrads[wset](ng, reverse=reverse)
 
     def wgrad(self, ng, gbuf, gstride):
         """weight gradient of the first ng groups -> gbuf[g*gstride + w_offset ...] (native layout) or the split-K
@@ -414,7 +418,9 @@ class Conv2dPlan:
         else:
             wa.out = self.partial.data_ptr()
             wa.out_gstride, wa.out_sstride = self.splits * self.cout * self.k_ld, self.cout * self.k_ld
-        _call("conv_wgrad", self.alg_flops * ng, "flop", "fb_conv_wgrad", C.byref(wa))
+        _call("conv_wgrad", self.alg_flops * ng, "flop", "fb_conv_wgrad", C.byref(wa),
+              label=f"wgrad {self.h}x{self.w} {self.cin}->{self.cout} k{self.k}s{self.stride} splits{self.splits}"
+                    f"{' halo' if wa.halo else ''}")
 
 
 class ReduceTable:
@@ -527,7 +533,8 @@ def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, secon
     a.ng, a.param_gstride, a.reverse = ng, param_gstride, int(reverse)
     planes = 1 + (out_lo is not None)
     per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes
-    _call("bn_fwd", per_elem * P * Cc * ng, "byte", "fb_bn_apply", C.byref(a))
+    _call("bn_fwd", per_elem * P * Cc * ng, "byte", "fb_bn_apply", C.byref(a),
+          label=f"bn_apply P{P} C{Cc} {per_elem:.0f}B/elem")
 
 
 def bn_bwd_ws_floats(P, Cc, G):
@@ -554,7 +561,7 @@ def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_o
     # distinct tensors: dA, y (+ mask) in; dy (+ dz) out -- each counted once although the two launches read twice
     per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0) + \
         (4.0 if dA2 is not None else 0.0)
-    _call("bn_bwd", per_elem * P * Cc * ng, "byte", "fb_bn_bwd", C.byref(a))
+    _call("bn_bwd", per_elem * P * Cc * ng, "byte", "fb_bn_bwd", C.byref(a), label=f"bn_bwd P{P} C{Cc} {per_elem:.0f}B/elem")
 
 
 def avgpool2_fwd(in_hi, in_lo, n, h, w, c, out_hi, out_lo):

@@ -151,7 +151,8 @@ class Trainer:
         self.world = torch.distributed.get_world_size() if self.dist else 1
         loss_fn = get_loss_fn(cfg.hyp, cfg.data.batch_size)
         self.engine = FullBatchEngine(model, self.mb, precision=cfg.impl.get("precision", "split"),
-                                      label_smoothing=loss_fn.smoothing, device=self.device)
+                                      label_smoothing=loss_fn.smoothing, device=self.device,
+                                      groups=cfg.impl.get("groups", None))
         self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **cfg.hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps

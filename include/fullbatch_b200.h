@@ -215,7 +215,8 @@ int fb_bn_stats(const float* y, int64_t P, int C, float* ws, float* mean, float*
 
 /* out = [relu]( bn(y) + [bn2(y2)] + [res] ) written as bf16 hi/lo planes (BasicBlock.forward resnets.py:214-230),
  * for ng groups of P pixels: group g uses mean/rstd[g][C] and gamma/beta + g*param_gstride (the perturbed BatchNorm
- * parameters of group g in pass 2; 0 = shared).  One streaming pass, no grid synchronisation. */
+ * parameters of group g in pass 2; 0 = shared).  One streaming pass, no grid synchronisation.  The second normalised
+ * branch and the identity residual exclude each other (a block has a downsample path or an identity shortcut). */
 typedef struct {
   const float *y, *mean, *rstd, *gamma, *beta;
   const float *y2, *mean2, *rstd2, *gamma2, *beta2; /* optional second normalised branch (downsample), NULL if none */
