@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by an OFFSET from the __shared__ array (a round trip through uintptr_t makes the compiler lose
+  // the address space: every access to the staging patch then becomes a generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -567,7 +569,9 @@ constexpr int kWgTmemCols = 512;
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by an OFFSET from the __shared__ array (a round trip through uintptr_t makes the compiler lose
+  // the address space: every access to the staging patch then becomes a generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // operand region = dY ring (2 stages of one or two 64-channel chunks) followed by the X ring, which takes the rest
   constexpr int kWgOperandBytes = kWgAStages * kWgABytes + kWgBStages * kWgBBytes;
   const int a_stage_bytes = (p.cout > 64) ? kWgABytes : kATileBytes;

@@ -155,17 +155,36 @@ __device__ __forceinline__ void bn_item_load(const fb_bn_apply_args& a, long lon
   }
 }
 
+// Shared-memory layout of the per-channel parameters: one record per channel OCTET (the 8 channels of an item), K
+// arrays of 8 floats each, padded to a record stride that keeps the 16-byte reads of 8 consecutive lanes on different
+// banks (28 / 52 floats for K = 3 / 6).
+__device__ __forceinline__ void load8_smem(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ int channel_of(long long e8, int C, int cmask) {
+  return cmask ? int(e8 & cmask) : int(e8 % C);
+}
+
 template <bool DUAL, bool RES>
 __device__ __forceinline__ void bn_item_store(const fb_bn_apply_args& a, long long off, int c, const float* sp,
                                               const BnItem& it) {
-  const int C = a.C;
-  float o[8];
+  constexpr int kRec = DUAL ? 52 : 28;
+  const float* rec = sp + (c >> 3) * kRec;
+  float mu[8], sc[8], sh[8], o[8];
+  load8_smem(rec, mu);
+  load8_smem(rec + 8, sc);
+  load8_smem(rec + 16, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = (it.y[j] - sp[c + j]) * sp[C + c + j] + sp[2 * C + c + j];
+  for (int j = 0; j < 8; ++j) o[j] = (it.y[j] - mu[j]) * sc[j] + sh[j];
   if (DUAL) {
-    const float* sp2 = sp + 3 * C;
+    load8_smem(rec + 24, mu);
+    load8_smem(rec + 32, sc);
+    load8_smem(rec + 40, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] += (it.y2[j] - sp2[c + j]) * sp2[C + c + j] + sp2[2 * C + c + j];
+    for (int j = 0; j < 8; ++j) o[j] += (it.y2[j] - mu[j]) * sc[j] + sh[j];
   }
   if (RES) {
 #pragma unroll
@@ -180,21 +199,24 @@ __device__ __forceinline__ void bn_item_store(const fb_bn_apply_args& a, long lo
 
 template <bool DUAL, bool RES>
 __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const __grid_constant__ fb_bn_apply_args a) {
-  extern __shared__ float sp[];  // [mean | rstd*gamma | beta][C] (x2 with the second branch)
+  extern __shared__ __align__(16) float sp[];  // records of [mean | rstd*gamma | beta] (x2 with the second branch)
+  constexpr int kRec = DUAL ? 52 : 28;
   griddep_wait();
   griddep_launch();
   // reverse: start with the last elements of the last group = what the producer of y (the convolution) wrote last
   const int g = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int C = a.C;
+  const int cmask = (C & (C - 1)) == 0 ? C - 1 : 0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const long long pc = (long long)g * a.param_gstride + c;
-    sp[c] = a.mean[(long long)g * C + c];
-    sp[C + c] = a.rstd[(long long)g * C + c] * a.gamma[pc];
-    sp[2 * C + c] = a.beta[pc];
+    float* rec = sp + (c >> 3) * kRec + (c & 7);
+    rec[0] = a.mean[(long long)g * C + c];
+    rec[8] = a.rstd[(long long)g * C + c] * a.gamma[pc];
+    rec[16] = a.beta[pc];
     if (DUAL) {
-      sp[3 * C + c] = a.mean2[(long long)g * C + c];
-      sp[4 * C + c] = a.rstd2[(long long)g * C + c] * a.gamma2[pc];
-      sp[5 * C + c] = a.beta2[pc];
+      rec[24] = a.mean2[(long long)g * C + c];
+      rec[32] = a.rstd2[(long long)g * C + c] * a.gamma2[pc];
+      rec[40] = a.beta2[pc];
     }
   }
   __syncthreads();
@@ -209,8 +231,8 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const __grid_constant_
     BnItem it1, it2;
     bn_item_load<DUAL, RES>(a, gbase + e1 * 8, it1);
     if (two) bn_item_load<DUAL, RES>(a, gbase + e2 * 8, it2);
-    bn_item_store<DUAL, RES>(a, gbase + e1 * 8, int((e1 * 8) % C), sp, it1);
-    if (two) bn_item_store<DUAL, RES>(a, gbase + e2 * 8, int((e2 * 8) % C), sp, it2);
+    bn_item_store<DUAL, RES>(a, gbase + e1 * 8, channel_of(e1 * 8, C, cmask), sp, it1);
+    if (two) bn_item_store<DUAL, RES>(a, gbase + e2 * 8, channel_of(e2 * 8, C, cmask), sp, it2);
   }
 }
 
@@ -348,65 +370,83 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdK k) {
   }
 }
 
-struct BnBwdCoef {
-  float mu[8], rs[8], grs[8], c1[8], c2[8];
-  __device__ __forceinline__ void load(const float* mean, const float* rstd, const float* gamma, const float* coef,
-                                       int C, int c) {
-    float ga[8];
-    load8(mean + c, mu);
-    load8(rstd + c, rs);
-    load8(gamma + c, ga);
-    load8(coef + c, c1);
-    load8(coef + C + c, c2);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) grs[j] = ga[j] * rs[j];
-  }
+// Streaming apply: per-channel coefficients (mean, rstd, gamma*rstd, mean(dz), mean(dz*xhat)) of the group in shared
+// memory, two items of 8 channels per loop round with all loads issued first (same structure as bn_apply_kernel).
+struct BnBwdItem {
+  float d[8], y[8];
 };
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdK k) {
+template <bool ADD2, bool MASK>
+__device__ __forceinline__ void bn_bwd_item_load(const fb_bn_bwd_args& a, long long off, BnBwdItem& it) {
+  load8(a.dA + off, it.d);
+  if (ADD2) {
+    float d2[8];
+    load8(a.dA2 + off, d2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) it.d[j] += d2[j];
+  }
+  if (MASK) {
+    float m[8];
+    load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) it.d[j] = m[j] > 0.f ? it.d[j] : 0.f;
+  }
+  load8(a.y + off, it.y);
+}
+
+__device__ __forceinline__ void bn_bwd_item_store(const fb_bn_bwd_args& a, long long off, int c, const float* sp,
+                                                  const BnBwdItem& it) {
+  const float* rec = sp + (c >> 3) * 44;
+  float mu[8], rs[8], grs[8], c1[8], c2[8], o[8];
+  load8_smem(rec, mu);
+  load8_smem(rec + 8, rs);
+  load8_smem(rec + 16, grs);
+  load8_smem(rec + 24, c1);
+  load8_smem(rec + 32, c2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float xhat = (it.y[j] - mu[j]) * rs[j];
+    o[j] = grs[j] * (it.d[j] - c1[j] - xhat * c2[j]);
+  }
+  store8_bf16(static_cast<bf16*>(a.dy_bf16), off, o);
+  if (a.dz_out) store8(a.dz_out + off, it.d);
+}
+
+template <bool ADD2, bool MASK>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __grid_constant__ BnBwdK k) {
+  // records per channel octet: [mean | rstd | gamma*rstd | mean(dz) | mean(dz*xhat)] x 8, stride 44 floats
+  extern __shared__ __align__(16) float sp[];
   griddep_wait();
   griddep_launch();
   const fb_bn_bwd_args& a = k.a;
   const bool backwards = !a.reverse;  // opposite direction of the reduce pass (groups included)
   const int g = backwards ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int C = a.C;
+  const int cmask = (C & (C - 1)) == 0 ? C - 1 : 0;
+  const float* coef = k.coef + (long long)g * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float rs = a.rstd[(long long)g * C + c];
+    float* rec = sp + (c >> 3) * 44 + (c & 7);
+    rec[0] = a.mean[(long long)g * C + c];
+    rec[8] = rs;
+    rec[16] = a.gamma[(long long)g * a.param_gstride + c] * rs;
+    rec[24] = coef[c];
+    rec[32] = coef[C + c];
+  }
+  __syncthreads();
   const long long total8 = a.P * C / 8;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const bool invariant = (stride * 8) % C == 0;
   const long long gbase = (long long)g * a.P * C;
-  const float* mean = a.mean + (long long)g * C;
-  const float* rstd = a.rstd + (long long)g * C;
-  const float* gamma = a.gamma + (long long)g * a.param_gstride;
-  const float* coef = k.coef + (long long)g * 2 * C;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  BnBwdCoef p;
-  if (i < total8) p.load(mean, rstd, gamma, coef, C, int(((backwards ? total8 - 1 - i : i) * 8) % C));
-  for (; i < total8; i += stride) {
-    const long long e = backwards ? total8 - 1 - i : i;
-    const long long off = gbase + e * 8;
-    if (!invariant) p.load(mean, rstd, gamma, coef, C, int((e * 8) % C));
-    float d[8], y[8], o[8];
-    load8(a.dA + off, d);
-    if (a.dA2) {
-      float d2[8];
-      load8(a.dA2 + off, d2);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] += d2[j];
-    }
-    if (a.mask_hi) {
-      float m[8];
-      load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
-    }
-    load8(a.y + off, y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (y[j] - p.mu[j]) * p.rs[j];
-      o[j] = p.grs[j] * (d[j] - p.c1[j] - xhat * p.c2[j]);
-    }
-    store8_bf16(static_cast<bf16*>(a.dy_bf16), off, o);
-    if (a.dz_out) store8(a.dz_out + off, d);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < total8;
+    const long long e1 = backwards ? total8 - 1 - i : i;
+    const long long e2 = backwards ? total8 - 1 - i2 : i2;
+    BnBwdItem it1, it2;
+    bn_bwd_item_load<ADD2, MASK>(a, gbase + e1 * 8, it1);
+    if (two) bn_bwd_item_load<ADD2, MASK>(a, gbase + e2 * 8, it2);
+    bn_bwd_item_store(a, gbase + e1 * 8, channel_of(e1 * 8, C, cmask), sp, it1);
+    if (two) bn_bwd_item_store(a, gbase + e2 * 8, channel_of(e2 * 8, C, cmask), sp, it2);
   }
 }
 
@@ -777,9 +817,13 @@ static int bwd_geometry(long long P, int C, int policy_groups, BnBwdGeom& geo) {
   return 0;
 }
 
-static int stream_grid(long long work_items) {
-  long long blocks = (work_items + 255) / 256;
-  const long long cap = (long long)kNumSMs * 16;
+// grid.x of a streaming kernel launched as (grid.x, groups): enough blocks for ~8 resident blocks per SM over all
+// groups, but every block runs at least ~8 loop rounds (the per-block prologue -- channel parameters into shared memory
+// -- is two dependent memory latencies)
+static int stream_grid(long long work_items, int groups = 1) {
+  long long blocks = (work_items + 256 * 8 - 1) / (256 * 8);
+  long long cap = ((long long)kNumSMs * 8 + groups - 1) / (groups > 0 ? groups : 1);
+  if (cap < 1) cap = 1;
   return int(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
@@ -818,9 +862,16 @@ extern "C" int fb_bn_apply(const fb_bn_apply_args* a, void* stream) {
   fb_bn_apply_args k = *a;
   if (k.ng <= 0) k.ng = 1;
   FB_REQUIRE(k.ng <= FB_MAX_GROUPS, "fb_bn_apply: at most %d groups", FB_MAX_GROUPS);
-  const size_t smem = size_t(k.y2 ? 6 : 3) * k.C * sizeof(float);
-  FB_REQUIRE(smem <= 48 * 1024, "fb_bn_apply: at most %d channels", k.y2 ? 2048 : 4096);
-  const dim3 grid(stream_grid(k.P * k.C / 16), k.ng);
+  const size_t smem = size_t(k.y2 ? 52 : 28) * (k.C / 8) * sizeof(float);
+  FB_REQUIRE(smem <= 96 * 1024, "fb_bn_apply: at most %d channels", k.y2 ? 3776 : 7008);
+  static bool configured = false;
+  if (!configured) {  // wide dual-branch layers need more than the default 48 KB of dynamic shared memory
+    FB_CUDA(cudaFuncSetAttribute(bn_apply_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    FB_CUDA(cudaFuncSetAttribute(bn_apply_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    FB_CUDA(cudaFuncSetAttribute(bn_apply_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  const dim3 grid(stream_grid(k.P * k.C / 16, k.ng), k.ng);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (k.y2) {
     FB_REQUIRE(!k.res_hi, "fb_bn_apply: a second normalised branch and an identity residual exclude each other");
@@ -856,7 +907,17 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   k.coef = k.partial + (long long)k.a.ng * k.geo.chunks * 2 * a->C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FB_CUDA(launch_pdl(bn_bwd_reduce_kernel, dim3(k.geo.chunks, k.geo.slabs, k.a.ng), dim3(256), 0, st, k));
-  FB_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(stream_grid(a->P * a->C / 8), k.a.ng), dim3(256), 0, st, k));
+  const size_t smem = size_t(44) * (a->C / 8) * sizeof(float);
+  FB_REQUIRE(smem <= 48 * 1024, "fb_bn_bwd: at most 2232 channels");
+  const dim3 grid(stream_grid(a->P * a->C / 16, k.a.ng), k.a.ng);
+  if (a->dA2 && a->mask_hi)
+    FB_CUDA(launch_pdl(bn_bwd_apply_kernel<true, true>, grid, dim3(256), smem, st, k));
+  else if (a->dA2)
+    FB_CUDA(launch_pdl(bn_bwd_apply_kernel<true, false>, grid, dim3(256), smem, st, k));
+  else if (a->mask_hi)
+    FB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true>, grid, dim3(256), smem, st, k));
+  else
+    FB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false>, grid, dim3(256), smem, st, k));
   return 0;
 }
 

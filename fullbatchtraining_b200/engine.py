@@ -278,7 +278,8 @@ class FullBatchEngine:
         self._graphs = {}
         self.l2_order = os.environ.get("FB_L2_ORDER", "1") == "1"
         # FB_WGRAD_STREAM=1: wgrad on a side stream, concurrently with the dgrad -> BatchNorm-backward chain below it
-        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("FB_WGRAD_STREAM", "0") == "1" else None
+        self.wgrad_mode = int(os.environ.get("FB_WGRAD_STREAM", "0"))
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if self.wgrad_mode else None
         self.grad_norms = None
         self.aug_params, self.aug_mean, self.aug_std = None, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
         self.norm_offset = 0
@@ -355,17 +356,23 @@ class FullBatchEngine:
         ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
                    gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
                    param_gstride=pstride, grad_gstride=self.stride, reverse=rev)
-        # wgrad only feeds the flat gradient: optionally on a side stream, concurrently with the dgrad ->
-        # BatchNorm-backward chain of the layers below (fork here, join at the end of the backward pass)
-        if self.wgrad_stream is not None:
-            main = torch.cuda.current_stream()
-            self.wgrad_stream.wait_stream(main)
-            with torch.cuda.stream(self.wgrad_stream):
-                u.plan.wgrad(ng, Gbuf, self.stride)
-        else:
+        # wgrad only feeds the flat gradient.  wgrad_mode 1 / 2: on a side stream, forked before / after the dgrad of the
+        # same layer (2: the tensor-bound wgrad then runs next to the bandwidth-bound BatchNorm backward of the layer
+        # below instead of next to its own dgrad); joined at the end of the backward pass
+        if self.wgrad_stream is not None and self.wgrad_mode == 1:
+            self._wgrad_side(u, ng, Gbuf)
+        elif self.wgrad_stream is None:
             u.plan.wgrad(ng, Gbuf, self.stride)
         if not u.stem:
             u.plan.dgrad(ng, wset, reverse=rev)
+        if self.wgrad_stream is not None and self.wgrad_mode == 2:
+            self._wgrad_side(u, ng, Gbuf)
+
+    def _wgrad_side(self, u, ng, Gbuf):
+        main = torch.cuda.current_stream()
+        self.wgrad_stream.wait_stream(main)
+        with torch.cuda.stream(self.wgrad_stream):
+            u.plan.wgrad(ng, Gbuf, self.stride)
 
     def _backward(self, ng, wset, P, pstride, Gbuf):
         self._rev = True  # the head wrote the first upstream gradient front to back
