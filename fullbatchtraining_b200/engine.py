@@ -798,9 +798,10 @@ class FullBatchEngine:
 
     def results(self, count):
         """Host read of the step scalars (one synchronisation): mean loss, correct count, grad_norms."""
-        pack = torch.cat([self.scal[:4], self.grad_norms[:count]]).tolist()
+        pack = torch.cat([self.scal[:16], self.grad_norms[:count]]).tolist()
         return dict(loss=pack[S_LOSS] / max(count, 1), correct=pack[S_CORRECT], loss_sum=pack[S_LOSS],
-                    grad_norms=torch.tensor(pack[4:], dtype=torch.float32), clipped_batches=int(pack[S_CLIPPED]))
+                    grad_norms=torch.tensor(pack[16:], dtype=torch.float32), clipped_batches=int(pack[S_CLIPPED]),
+                    scal=pack[:16])
 
     def sync_bn_counters(self):
         """num_batches_tracked += number of train-mode passes (2 per microbatch with the regulariser)."""

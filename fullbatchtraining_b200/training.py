@@ -27,6 +27,7 @@ import torch
 from .engine import FullBatchEngine
 from .modules import GradRegularizer, LabelSmoothCrossEntropyLoss
 from .optim import FlatSGD, S_GNORM, S_PNORM
+from .schedulers import build_scheduler
 
 log = logging.getLogger("fullbatch_b200")
 
@@ -41,8 +42,8 @@ def get_loss_fn(cfg_hyp, batch_size=None):
 
 def optim_interface(model, cfg_hyp, fused=False):
     """optimizers.py:10-93 for the configuration the path uses: ``Gradient Descent`` = torch.optim.SGD
-    (:25-28), scheduler cosine-4000 / cosine-decay / none (:75-87) and the linear warm-up wrapper (:89-91,
-    scheduler.py:57-66: lr = base*step/warmup up to `warmup`, the wrapped scheduler starts one step later)."""
+    (:25-28) and the reference's scheduler objects (schedulers.build_scheduler: stock torch schedulers behind the linear
+    warm-up wrapper), so ``scheduler.state_dict()`` in a checkpoint is interchangeable with the reference's."""
     if cfg_hyp.optim.name != "Gradient Descent" or cfg_hyp.optim.get("line_search", "none") != "none":
         raise ValueError(f"Optimizer {cfg_hyp.optim.name} / line search is not on the B200 path (closure optimizers "
                          "from the reference can be passed to train_with_optimizer).")
@@ -53,32 +54,15 @@ def optim_interface(model, cfg_hyp, fused=False):
         optimizer = FlatSGD(model.parameters(), **params)  # clip + SGD + param norm in one device sweep
     else:
         optimizer = torch.optim.SGD(model.parameters(), **params)
-    warmup = int(cfg_hyp.warmup or 0)
-    sched = cfg_hyp.scheduler
-
-    def after(t):
-        if sched == "cosine-4000":
-            return (1 + math.cos(math.pi * t / 4000)) / 2
-        if sched == "cosine-decay":
-            return (1 + math.cos(math.pi * t / cfg_hyp.steps)) / 2
-        if sched in ["", " ", None]:
-            return 1.0
-        raise ValueError(f"Invalid scheduler {sched} provided.")
-
-    def factor(step):
-        if warmup > 0:
-            return step / warmup if step <= warmup else after(step - warmup - 1)
-        return after(step)
-
-    scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, factor)
-    return optimizer, scheduler
+    return optimizer, build_scheduler(optimizer, cfg_hyp)
 
 
 @torch.no_grad()
 def save_checkpoint(model, optimizer, scheduler, step, file):
     """training/utils.py:43-51: the reference's 5-list [optim_state, model_state, scheduler_state, scaler_state, step]
     (scaler_state is None: no fp16 grad scaling on this path), loadable by the reference's `_load_from_checkpoint` and
-    `hubconf.py:37-40` (state_dict keys and optimizer state layout are those of the reference model / torch SGD)."""
+    `hubconf.py:37-40`: state_dict keys, the optimizer state layout (torch SGD) and the scheduler state (torch schedulers
+    / the warm-up wrapper's attribute names) are those of the reference."""
     model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}  # params are views of the flat buffer
     os.makedirs(os.path.dirname(os.path.abspath(file)), exist_ok=True)
     torch.save([optimizer.state_dict(), model_state, scheduler.state_dict(), None, step], file)
@@ -120,17 +104,22 @@ def _resident_dataset(loader, device):
     return None
 
 
+S_PNORM_PREV = 9  # scal slot: sum theta^2 at gradient-evaluation time (copied from S_PNORM before the update)
+
+
 class Trainer:
     """State of one ``train`` call; ``step()`` is one iteration of the reference's main loop (training.py:219-339)."""
 
     def __init__(self, model, trainloader, validloader, setup, cfg):
         model.train()
         self.model, self.trainloader, self.validloader, self.setup, self.cfg = model, trainloader, validloader, setup, cfg
+        hyp = cfg.hyp
+        self.stochastic = bool(hyp.train_stochastic)
         # impl.fused_optimizer (default on): FlatSGD = clip + SGD + param norm as one sweep over the flat buffers;
         # off: stock torch.optim.SGD and the torch clip of training.py:198-211
-        self.fused_opt = bool(cfg.impl.get("fused_optimizer", True)) and not cfg.hyp.train_stochastic and \
-            (cfg.hyp.grad_clip is None or float(cfg.hyp.grad_clip_norm) == 2.0)
-        self.optimizer, self.scheduler = optim_interface(model, cfg.hyp, fused=self.fused_opt)
+        self.fused_opt = bool(cfg.impl.get("fused_optimizer", True)) and not self.stochastic and \
+            (hyp.grad_clip is None or float(hyp.grad_clip_norm) == 2.0)
+        self.optimizer, self.scheduler = optim_interface(model, hyp, fused=self.fused_opt)
         self.stats = defaultdict(list)
         self.device = torch.device(setup["device"])
         if str(cfg.impl.accumulation_dtype) not in ("float", "float32") or \
@@ -139,31 +128,54 @@ class Trainer:
                              "(impl.dtype / impl.accumulation_dtype must be float)")
         if cfg.impl.mixed_precision:
             raise ValueError("impl.mixed_precision is not on the B200 path; use impl.precision = split | bf16")
-        if cfg.hyp.norm_bias.strength > 0:
-            raise ValueError("norm_bias is not on the B200 path yet")
-        if cfg.hyp.batch_clip is not None and float(cfg.hyp.grad_clip_norm) != 2.0:
+        # reference options that are not on the B200 path are refused, never silently ignored
+        if hyp.norm_bias.strength > 0:
+            raise ValueError("hyp.norm_bias is not on the B200 path")
+        if hyp.get("evaluate_ema", False):
+            raise ValueError("hyp.evaluate_ema is not on the B200 path")
+        noise = hyp.get("grad_noise", None) or {}
+        if noise.get("additive") is not None or noise.get("multiplicative") is not None:
+            raise ValueError("hyp.grad_noise is not on the B200 path")
+        if hyp.get("only_linear_layers_weight_decay", False):
+            raise ValueError("hyp.only_linear_layers_weight_decay is not on the B200 path")
+        if hyp.get("train_switch_stochastic", None) is not None or hyp.get("train_semi_stochastic", False):
+            raise ValueError("hyp.train_switch_stochastic / train_semi_stochastic are not on the B200 path")
+        if hyp.batch_clip is not None and float(hyp.grad_clip_norm) != 2.0:
             raise ValueError("batch_clip is implemented for the 2-norm only")
-        self.mb = min(cfg.data.batch_size, cfg.hyp.sub_batch)
+        # the stochastic sanity branch differentiates whole loader blocks (training.py:252-262), the full-batch
+        # branch chunks of hyp.sub_batch (training.py:155-156)
+        self.mb = cfg.data.batch_size if self.stochastic else min(cfg.data.batch_size, hyp.sub_batch)
         self.num_blocks = len(trainloader)
-        self.num_chunks = max(cfg.data.batch_size // cfg.hyp.sub_batch, 1)
+        self.num_chunks = 1 if self.stochastic else max(cfg.data.batch_size // hyp.sub_batch, 1)
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.rank = torch.distributed.get_rank() if self.dist else 0
         self.world = torch.distributed.get_world_size() if self.dist else 1
-        loss_fn = get_loss_fn(cfg.hyp, cfg.data.batch_size)
+        loss_fn = get_loss_fn(hyp, cfg.data.batch_size)
         self.engine = FullBatchEngine(model, self.mb, precision=cfg.impl.get("precision", "split"),
                                       label_smoothing=loss_fn.smoothing, device=self.device,
-                                      groups=cfg.impl.get("groups", None))
-        self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **cfg.hyp.grad_reg, mixed_precision=False,
+                                      groups=1 if self.stochastic else cfg.impl.get("groups", None))
+        self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps
-        self.acc = float(cfg.hyp.grad_reg.acc_strength)
-        self.impl = cfg.hyp.grad_reg.implementation if (self.bs != 0 or self.acc != 0) else "forward-differences"
+        self.acc = float(hyp.grad_reg.acc_strength)
+        self.impl = hyp.grad_reg.implementation if (self.bs != 0 or self.acc != 0) else "forward-differences"
+        if self.impl == "forward-differences-legacy":
+            self.acc = 0.0  # the reference's legacy path disregards pre_grads (modules.py:243-264)
         if self.fused_opt:
-            self.optimizer.bind(self.engine, cfg.hyp.grad_clip)
-        self.resident = _resident_dataset(trainloader, self.device) if cfg.impl.get("resident_dataset", True) else None
+            self.optimizer.bind(self.engine, hyp.grad_clip)
+        self.resident = _resident_dataset(trainloader, self.device) if cfg.impl.get("resident_dataset", True) and \
+            not self.stochastic else None
         # microbatches per full-batch pass (training.py:65-66,146).  A resident dataset is sharded here by contiguous
         # microbatch ranges; a streamed loader is taken as this rank's shard already (impl.setup.sharded_loader).
         local = self.num_blocks * self.num_chunks
+        if self.resident is not None:
+            n = self.resident[0].shape[0]
+            if getattr(trainloader, "batch_size", cfg.data.batch_size) != cfg.data.batch_size:
+                raise ValueError(f"the loader's batch_size {trainloader.batch_size} disagrees with "
+                                 f"cfg.data.batch_size {cfg.data.batch_size}")
+            if local * self.mb > n:  # drop_last=False with a ragged last block
+                raise ValueError(f"{local} microbatches of {self.mb} exceed the {n} samples of the dataset: the "
+                                 "full-batch path needs drop_last=True (data_preparation.py:68)")
         if self.resident is not None or self.world == 1:
             self.K = local
             self.k0, self.k1 = shard_range(self.rank, self.world, local)
@@ -180,10 +192,13 @@ class Trainer:
         self.step_count = 0
         if cfg.impl.checkpoint.name is not None:  # training.py:60-63
             self.checkpoint_file = os.path.join(cfg.original_cwd, "checkpoints", cfg.impl.checkpoint.name)
-            self.step_count = load_checkpoint(model, self.optimizer, self.scheduler, cfg.hyp.steps, device=self.device,
+            self.step_count = load_checkpoint(model, self.optimizer, self.scheduler, hyp.steps, device=self.device,
                                               file=self.checkpoint_file)
         else:
             self.checkpoint_file = None
+        # sum theta^2 for _record_stats stays on the device: initialised here (also right after a resume), refreshed by
+        # every FlatSGD step
+        self.engine.scal[S_PNORM] = self.engine.theta.double().pow(2).sum().float()
         # device-side data pipeline: raw uint8 dataset + crop/flip/normalise fused into the stem,
         # hyp.shuffle as a per-step device permutation (data_preparation.py:53-54)
         self.data_gen = torch.Generator(device=self.device)
@@ -213,36 +228,49 @@ class Trainer:
         if self.augment:
             self.engine.draw_augmentation(n, self.data_gen, self.crop_pad, self.flip_p)
 
+    def _reduce_pre(self, pre, local):
+        """training.py:139-140 across processes: every rank holds the mean raw gradient over ITS microbatches; the
+        weighted all-reduce makes it the mean over all of them (exactly the single-process pre_grads)."""
+        if self.dist:
+            self.engine.all_reduce_flat(pre, local, self.K)
+
     # training.py:121-185
     def _accumulate_full_gradient(self):
-        t0 = time.time()
-        eng, cfg, stats = self.engine, self.cfg, self.stats
-        lr = self.optimizer.param_groups[0]["lr"]
+        """Enqueues the whole full-batch gradient evaluation (no host synchronisation) and returns the mean loss as a
+        device scalar; the statistics are read by _record_stats after the optimizer step."""
+        self._t0 = time.time()
+        eng, cfg = self.engine, self.cfg
+        self._lr = self.optimizer.param_groups[0]["lr"]
+        if not self.fused_opt:  # stock optimizer: nobody refreshes sum theta^2 on the device
+            eng.scal[S_PNORM] = eng.theta.double().pow(2).sum().float()
         self._prepare_epoch()
         if self.resident is not None:
-            if self.acc != 0 and self.world > 1:
-                raise RuntimeError("acc_strength with several processes is not implemented")
-            local = eng.accumulate_resident(self.resident[0], self.resident[1], lr, self.bs, self.eps,
-                                            first=self.k0 * self.mb, count=self.k1 - self.k0, num_norms=self.K,
-                                            norm_offset=self.k0, implementation=self.impl, acc_strength=self.acc,
-                                            batch_clip=cfg.hyp.batch_clip, perm=self.perm)
+            local = self.k1 - self.k0
+            eng.accumulate_resident(self.resident[0], self.resident[1], self._lr, self.bs, self.eps,
+                                    first=self.k0 * self.mb, count=local, num_norms=self.K,
+                                    norm_offset=self.k0, implementation=self.impl, acc_strength=self.acc,
+                                    batch_clip=cfg.hyp.batch_clip, perm=self.perm,
+                                    reduce_pre=lambda pre: self._reduce_pre(pre, local))
         else:
             if self.acc != 0 or cfg.hyp.batch_clip is not None or self.impl == "central-differences":
                 raise RuntimeError("acc_strength / batch_clip / central-differences need a device-resident dataset "
                                    "(TensorDataset loader)")
-            local = eng.accumulate_stream(self.trainloader, lr, self.bs, self.eps, self.K, norm_offset=self.k0)
+            local = eng.accumulate_stream(self.trainloader, self._lr, self.bs, self.eps, self.K, norm_offset=self.k0)
         if self.dist:
             eng.all_reduce_mean(local, self.K)
         for p, g in zip(self.model.parameters(), eng.grads_list(eng.avg)):
             p.grad = g  # training.py:183 / training/utils.py:40
-        res = eng.results(self.K)  # the only host synchronisation of the step (training.py:110-115 has several)
-        # _record_stats, training.py:85-119
+        eng.scal[S_PNORM_PREV] = eng.scal[S_PNORM]  # sum theta^2 of the parameters the gradient was evaluated at
+        return eng.scal[0] / self.K
+
+    def _record_stats(self):
+        """training.py:85-119 from ONE host read of the device scalars (the reference syncs several times)."""
+        eng, cfg, stats = self.engine, self.cfg, self.stats
+        res = eng.results(self.K)
+        lr = self._lr
         for idx, entry in enumerate(res["grad_norms"].sqrt().tolist()):
             stats[f"grad_norm_train_{idx}"] += [entry]
-        if self.fused_opt and self.step_count > 0:
-            param_norm = float(eng.scal[S_PNORM])  # left on the device by the previous FlatSGD step
-        else:
-            param_norm = float(eng.theta.double().pow(2).sum())
+        param_norm = res["scal"][S_PNORM_PREV]
         full_grad_norm = float(res["grad_norms"].mean())
         full_loss = res["loss"] + 0.5 * cfg.hyp.optim.get("weight_decay", 0.0) * param_norm
         if self.bs != 0:
@@ -253,15 +281,18 @@ class Trainer:
             stats["clipped_batches"] += [res["clipped_batches"]]
         stats["train_loss"] += [res["loss"]]
         stats["train_acc"] += [res["correct"] / (self.K * self.mb)]
-        stats["train_time"] += [time.time() - t0]
+        stats["train_time"] += [time.time() - self._t0]
         stats["param_norm"] += [param_norm]
         stats["grad_norm"] += [math.sqrt(full_grad_norm)]
         stats["full_loss"] += [full_loss]
-        return torch.as_tensor(res["loss"], device=self.device)
+        if self.fused_opt and cfg.hyp.grad_clip is not None:
+            gnorm = math.sqrt(res["scal"][S_GNORM])
+            stats["preclip_gradnorm"] += [gnorm]
+            stats["clipped_step"] += [1 if gnorm > cfg.hyp.grad_clip else 0]
 
     @torch.no_grad()
     def _modify_gradient_params(self):
-        """training.py:187-215 (global clip only; next-row item f1 fuses this into the flat-buffer sweeps)."""
+        """training.py:187-215 (global clip only; the fused optimizer does it on the device inside its sweep)."""
         cfg, eng, stats = self.cfg, self.engine, self.stats
         if self.fused_opt:
             return  # FlatSGD.step clips on the device; the statistics are read after the step
@@ -276,53 +307,66 @@ class Trainer:
                 stats["clipped_step"] += [0]
 
     def _sgd_epoch(self):
-        """training.py:241-286: one optimizer step per block through the same kernels (regulariser per block)."""
+        """training.py:241-286: one optimizer step per loader block through the same kernels (raw gradient of the whole
+        block, regulariser per block).  Loss / accuracy / gradient norms accumulate on the device; one host read per
+        epoch.  Across processes the block gradients are AVERAGED: the reference sums them without dividing
+        (training.py:268-270 via training/utils.py:35), which SURVEY.md 8e lists as a defect not to reproduce."""
         eng, cfg, stats = self.engine, self.cfg, self.stats
-        acc = dict(loss=0.0, preds=0.0)
-        datapoints = 0
         t0 = time.time()
-        for inputs, labels in self.trainloader:
+        acc = torch.zeros(2, device=self.device)  # sum of block losses, sum of correct predictions
+        grad_norms = torch.zeros(max(self.num_blocks, 1), device=self.device)
+        datapoints = 0
+        for block, (inputs, labels) in enumerate(self.trainloader):
+            if inputs.shape[0] != self.mb:
+                raise RuntimeError(f"block of {inputs.shape[0]} samples, engine built for data.batch_size = {self.mb} "
+                                   "(the stochastic branch needs drop_last=True)")
             inputs = inputs.to(device=self.device, dtype=torch.float32, non_blocking=True)
             labels = labels.to(device=self.device, dtype=torch.long, non_blocking=True)
-            if inputs.shape[0] != self.mb:
-                continue
             datapoints += labels.shape[0]
 
             def closure():
                 loss, correct = eng.microbatch_gradient(inputs, labels)
-                loss, correct = float(loss), float(correct)
+                acc.add_(torch.stack([loss, correct]))
+                grad_norms[block] = eng.grad_norms[0]  # training.py:262, squared norm of the raw block gradient
                 if self.bs != 0:
-                    eng.regularize(inputs, labels, self.optimizer.param_groups[0]["lr"], self.bs, self.eps)
+                    eng.regularize(inputs, labels, self.optimizer.param_groups[0]["lr"], self.bs, self.eps, self.impl)
                 if self.dist:
-                    torch.distributed.all_reduce(eng.g)  # training.py:268-270 (SUM, no division, as the reference)
+                    eng.all_reduce_flat(eng.g, 1, self.world)
                 for p, g in zip(self.model.parameters(), eng.grads_list(eng.g)):
                     p.grad = g
-                if cfg.hyp.grad_clip is not None:
-                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), cfg.hyp.grad_clip,
-                                                   norm_type=float(cfg.hyp.grad_clip_norm))
-                acc["loss"] += loss
-                acc["preds"] += correct
-                return torch.as_tensor(loss, device=self.device)
+                if cfg.hyp.grad_clip is not None:  # training.py:271-272
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), cfg.hyp.grad_clip, norm_type=2.0)
+                return loss
 
             self.optimizer.step(closure)
-        stats["train_loss"] += [acc["loss"] / max(self.num_blocks, 1)]
-        stats["train_acc"] += [acc["preds"] / max(datapoints, 1)]
+        loss_sum, preds = acc.tolist()
+        blocks = max(self.num_blocks, 1)
+        param_norm = float(eng.theta.double().pow(2).sum())
+        full_grad_norm = float(grad_norms.mean())
+        train_loss = loss_sum / blocks
+        full_loss = train_loss + 0.5 * cfg.hyp.optim.get("weight_decay", 0.0) * param_norm
+        if self.bs != 0:
+            full_loss += self.optimizer.param_groups[0]["lr"] / 4 * self.bs * full_grad_norm
+        for idx, entry in enumerate(grad_norms.sqrt().tolist()):
+            stats[f"grad_norm_train_{idx}"] += [entry]
+        stats["train_loss"] += [train_loss]
+        stats["train_acc"] += [preds / max(datapoints, 1)]
         stats["train_time"] += [time.time() - t0]
+        stats["param_norm"] += [param_norm]
+        stats["grad_norm"] += [math.sqrt(full_grad_norm)]
+        stats["full_loss"] += [full_loss]
 
     def step(self, validate=True):
         cfg = self.cfg
         self.model.train()
-        if not cfg.hyp.train_stochastic:
+        if not self.stochastic:
             def gradient_evaluation():  # training.py:226-234
                 loss = self._accumulate_full_gradient()
                 self._modify_gradient_params()
                 return loss
 
             self.optimizer.step(gradient_evaluation)
-            if self.fused_opt and cfg.hyp.grad_clip is not None:
-                gnorm = math.sqrt(float(self.engine.scal[S_GNORM]))
-                self.stats["preclip_gradnorm"] += [gnorm]
-                self.stats["clipped_step"] += [1 if gnorm > cfg.hyp.grad_clip else 0]
+            self._record_stats()
             self.scheduler.step()
         else:
             self._sgd_epoch()
@@ -330,16 +374,21 @@ class Trainer:
         self.step_count += 1
         self.engine.sync_bn_counters()
         step = self.step_count
-        if validate and self.validloader is not None and (step % cfg.impl.validate_every_nth_step == 0
-                                                          or step == cfg.hyp.steps or cfg.dryrun or step == 1):
+        # training.py:303-304
+        if validate and self.validloader is not None and ((step - 1) % cfg.impl.validate_every_nth_step == 0
+                                                          or step >= cfg.hyp.steps or cfg.dryrun):
             evaluate(self.model, self.validloader, self.stats, self.setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun,
                      engine=self.engine if getattr(cfg.impl, "kernel_evaluate", True) else None)
         if self.rank == 0:
             log.info(status_message(self.optimizer, self.stats, step))
-            if self.checkpoint_file is not None and ((step - 1) % cfg.impl.checkpoint.save_every_nth_step == 0
-                                                     or step >= cfg.hyp.steps):  # training.py:330-335
-                save_checkpoint(self.model, self.optimizer, self.scheduler, step, self.checkpoint_file)
         return self.stats["train_loss"][-1]
+
+    def maybe_checkpoint(self):
+        """training.py:330-335 (after the divergence / full-accuracy checks of the main loop)"""
+        step, cfg = self.step_count, self.cfg
+        if self.rank == 0 and self.checkpoint_file is not None and \
+                ((step - 1) % cfg.impl.checkpoint.save_every_nth_step == 0 or step >= cfg.hyp.steps):
+            save_checkpoint(self.model, self.optimizer, self.scheduler, step, self.checkpoint_file)
 
 
 def train(model, trainloader, validloader, setup, cfg):
@@ -358,6 +407,7 @@ def train(model, trainloader, validloader, setup, cfg):
                 evaluate(model, validloader, trainer.stats, setup, cfg.impl, cfg.hyp, dryrun=cfg.dryrun,
                          engine=trainer.engine if getattr(cfg.impl, "kernel_evaluate", True) else None)
             break
+        trainer.maybe_checkpoint()
         if cfg.dryrun:
             break
     return trainer.stats

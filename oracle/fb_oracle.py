@@ -317,6 +317,69 @@ def synthetic_cifar(n, seed=1234, dtype=torch.float32):
     return x.to(dtype), y
 
 
+@torch.no_grad()
+def sgd_epochs(depth, p, buffers, X, Y, mb, steps, lr, momentum=0.9, weight_decay=5e-4, nesterov=True,
+               block_strength=0.0, eps=1e-2, smoothing=0.0, grad_clip=None, implementation="forward-differences"):
+    """The stochastic sanity branch, training.py:241-286, single process: per step one pass over the loader blocks
+    (sequential order, drop_last), per block raw gradient (:258) -> squared norm (:259) -> GradRegularizer (:260) ->
+    optional clip_grad_norm_ (:271-272) -> torch.optim.SGD step (optimizers.py:25-28; torch/optim/sgd.py: d = g + wd*theta;
+    buf = d on first use else momentum*buf + d; d = d + momentum*buf (Nesterov); theta -= lr*d); the cosine-4000
+    scheduler steps once per step (:284; no warm-up).  `p` is updated IN PLACE.  Returns per-step train_loss / train_acc
+    / mean squared raw gradient norm."""
+    import math
+
+    net = OracleResNet(depth, buffers)
+    K = X.shape[0] // mb
+    bufs = None
+    out = dict(train_loss=[], train_acc=[], grad_norm_sq=[])
+    for step in range(steps):
+        cur_lr = lr * (1 + math.cos(math.pi * step / 4000)) / 2
+        loss_sum, preds, norms = 0.0, 0.0, []
+        for k in range(K):
+            x, y = X[k * mb:(k + 1) * mb], Y[k * mb:(k + 1) * mb]
+            g, loss, correct = microbatch_gradient(net, p, x, y, smoothing)
+            norms.append(float(torch.stack([t.pow(2).sum() for t in g]).sum()))
+            if block_strength != 0:
+                g, _, _ = regularize(net, p, g, x, y, cur_lr, block_strength, eps, smoothing, implementation, None, 0.0)
+            if grad_clip is not None:  # torch.nn.utils.clip_grad_norm_: coef = clip / (norm + 1e-6), clamped to 1
+                total = torch.norm(torch.stack([torch.norm(t, 2) for t in g]), 2)
+                coef = torch.clamp(grad_clip / (total + 1e-6), max=1.0)
+                g = [t * coef for t in g]
+            d = [t + weight_decay * v for t, v in zip(g, p.values())]
+            if momentum != 0:
+                bufs = [t.clone() for t in d] if bufs is None else [b * momentum + t for b, t in zip(bufs, d)]
+                d = [t + momentum * b for t, b in zip(d, bufs)] if nesterov else bufs
+            for v, t in zip(p.values(), d):
+                v.sub_(cur_lr * t)
+            loss_sum += float(loss)
+            preds += float(correct)
+        out["train_loss"].append(loss_sum / K)
+        out["train_acc"].append(preds / (K * mb))
+        out["grad_norm_sq"].append(sum(norms) / K)
+    return out
+
+
+def structured_cifar(n, seed=4321, dtype=torch.float32):
+    """Image-like synthetic data: per class a smooth oriented pattern, plus a low-frequency random field (bilinear
+    upsampling of 4x4 noise) and a little pixel noise, standardised per channel -- spatially correlated inputs with
+    class structure, unlike the white noise of synthetic_cifar."""
+    import math
+
+    gen = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, 10, (n,), generator=gen)
+    coarse = torch.randn(n, 3, 4, 4, generator=gen)
+    field = torch.nn.functional.interpolate(coarse, size=(32, 32), mode="bilinear", align_corners=False)
+    noise = 0.1 * torch.randn(n, 3, 32, 32, generator=gen)
+    yy, xx = torch.meshgrid(torch.arange(32.0), torch.arange(32.0), indexing="ij")
+    angle = (y.float() * math.pi / 10)[:, None, None]
+    freq = (1 + (y % 3).float())[:, None, None] * 2 * math.pi / 32
+    wave = torch.sin(freq * (xx[None] * torch.cos(angle) + yy[None] * torch.sin(angle)))
+    phase = torch.tensor([0.0, 0.7, 1.9])[None, :, None, None]
+    x = field + noise + 0.8 * torch.sin(torch.asin(wave.clamp(-1, 1))[:, None] + phase)
+    x = (x - x.mean(dim=(0, 2, 3), keepdim=True)) / x.std(dim=(0, 2, 3), keepdim=True)
+    return x.to(dtype), y
+
+
 def flops_per_image(depth):
     """Algorithmic GFLOP per image for one grad-reg step (2 passes); BASELINE.md section 2."""
     return {18: 6.6580, 152: 44.6586}[depth]

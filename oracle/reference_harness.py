@@ -164,4 +164,5 @@ def run_reference_train(model, X, Y, cfg, dtype=torch.float32, record=None):
         M.GradRegularizer.__call__ = orig_call
     # with cfg.hyp.grad_clip=None, param.grad still holds the accumulated gradient (training.py:183; torch.optim.SGD
     # never writes to .grad)
-    return stats, [p.grad.detach().clone() for p in model.parameters()]
+    # (the stochastic branch zeroes the gradients after every optimizer step, training.py:280: None there)
+    return stats, [p.grad.detach().clone() if p.grad is not None else None for p in model.parameters()]

@@ -57,7 +57,7 @@ def test_gradregularizer_call_protocol():
     net = O.OracleResNet(18, b64, update_running_stats=False)
     ref, _, _ = O.forward_differences(net, p64, [g.double() for g in raw], X.double(), Y, 0.8, 0.5, 1e-2)
     err = rel(O.flat(grads), O.flat(ref))
-    assert err < 0.5, err  # FD term divides operand rounding by eps_n; fp32 itself is ~5e-2 here
+    assert err < 0.2, err  # FD term divides operand rounding by eps_n; fp32 itself is ~5e-2 here, this path 0.11
     cos = float((O.flat(grads).double() * O.flat(ref)).sum() / (O.flat(grads).double().norm() * O.flat(ref).norm()))
     assert cos > 0.98
 
@@ -108,7 +108,7 @@ def test_train_one_step_matches_oracle_and_stream_equals_resident():
     th1 = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
     d = g + 5e-4 * th0
     expect = th0 - 0.8 * 1.9 * d
-    assert rel(th1 - th0, expect - th0) < 0.3
+    assert rel(th1 - th0, expect - th0) < 0.2  # = the error of the accumulated regularised gradient (0.12)
     # host-streamed blocks give bit-identical accumulation
     model_a, model_b = fresh(), fresh()
     ta = Trainer(model_a, loader, None, setup, _cfg(mb))
@@ -138,19 +138,101 @@ def test_grad_clip_and_lr_schedule():
     assert all(math.isfinite(v) for v in trainer.stats["train_loss"])
 
 
-def test_sgd_sanity_branch_runs_through_the_same_kernels():
-    mb, n = 16, 64
+def test_sgd_sanity_branch_matches_oracle_and_reference_golden():
+    """BASELINE.json configs[4], training.py:241-286: two steps of the stochastic branch (4 blocks of 16, the
+    regulariser per block, Nesterov SGD) through `train`; parameters afterwards against the oracle in fp64 (pinned to a
+    fixture of the unmodified reference, tests/test_oracle_golden.py) within 1e-3, per-step losses within 1e-3."""
+    import json
+    import os
+
+    import numpy as np
+
+    mb, n, steps, lr = 16, 64, 2, 0.001
     X, Y = O.synthetic_cifar(n)
     loader = HostBlockLoader(X, Y, mb)
-    cfg = _cfg(mb, **{"hyp.train_stochastic": True, "hyp.grad_reg.block_strength": 0.0, "hyp.optim.lr": 0.05,
-                      "hyp.steps": 2, "hyp.grad_clip": None})
+    cfg = _cfg(mb, **{"hyp.train_stochastic": True, "hyp.optim.lr": lr, "hyp.steps": steps, "hyp.grad_clip": None})
     model = fresh()
-    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    p64 = {k: v.detach().to(DEV, torch.float64).clone() for k, v in model.named_parameters()}
+    b64 = {k: (v.detach().to(DEV).clone() if v.dtype == torch.long else v.detach().to(DEV, torch.float64).clone())
+           for k, v in model.named_buffers()}
+    th0 = O.flat(list(p64.values())).clone()
     stats = train(model, loader, None, dict(device=DEV, dtype=torch.float32), cfg)
-    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu()
-    assert len(stats["train_loss"]) == 2 and all(math.isfinite(v) for v in stats["train_loss"])
-    assert not torch.equal(before, after)
-    assert stats["train_loss"][1] < 50
+    ref = O.sgd_epochs(18, p64, b64, X.to(DEV).double(), Y.to(DEV), mb, steps, lr, block_strength=0.5, eps=1e-2)
+    # the same in fp32 (the reference's own arithmetic): its distance from fp64 is the noise floor of this trajectory
+    m32 = fresh()
+    p32 = {k: v.detach().to(DEV).clone() for k, v in m32.named_parameters()}
+    b32 = {k: v.detach().to(DEV).clone() for k, v in m32.named_buffers()}
+    ref32 = O.sgd_epochs(18, p32, b32, X.to(DEV), Y.to(DEV), mb, steps, lr, block_strength=0.5, eps=1e-2)
+    th_ref = O.flat(list(p64.values()))
+    th_32 = O.flat(list(p32.values())).double()
+    th_new = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+    moved = float((th_ref - th0).norm())
+    e_new, e32 = float((th_new - th_ref).norm()) / moved, float((th_32 - th_ref).norm()) / moved
+    l_new = max(abs(a - b) / abs(b) for a, b in zip(stats["train_loss"], ref["train_loss"]))
+    l32 = max(abs(a - b) / abs(b) for a, b in zip(ref32["train_loss"], ref["train_loss"]))
+    print(f"sgd branch: update error {e_new:.3e} (fp32 reference {e32:.3e}), loss error {l_new:.3e} (fp32 {l32:.3e}), "
+          f"theta rel {rel(th_new, th_ref):.3e}")
+    assert len(stats["train_loss"]) == steps
+    assert stats["train_acc"] == pytest.approx(ref["train_acc"], abs=1.0 / n)
+    assert rel(th_new, th_ref) < 1e-3                      # parameters after 8 optimizer steps
+    assert e_new <= 6.0 * max(e32, 2e-3) and e_new < 0.05  # the accumulated UPDATE: 6x the fp32 reference's own error
+    assert l_new <= 6.0 * max(l32, 2e-3)
+    assert [v ** 2 for v in stats["grad_norm"]] == pytest.approx(ref["grad_norm_sq"], rel=2e-2)
+    for name, buf in model.named_buffers():
+        if not name.endswith("num_batches_tracked"):
+            assert rel(buf, b64[name]) < 5e-3, name
+    # and against the fixture of the unmodified reference
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "r18_sgd_mb16_n64_f64.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    assert stats["train_loss"] == pytest.approx(meta["scalars"]["train_loss_steps"], rel=6.0 * max(l32, 2e-3))
+    fp = O.fingerprint([q.detach() for q in model.parameters()], meta["stride"])
+    assert np.linalg.norm(fp["sample"] - z["theta.sample"]) <= 1e-3 * np.linalg.norm(z["theta.sample"])
+
+
+def test_unsupported_reference_options_are_refused():
+    """options of the reference that are not on the B200 path raise instead of being silently ignored"""
+    X, Y = O.synthetic_cifar(32)
+    setup = dict(device=DEV, dtype=torch.float32)
+    for key, val in [("hyp.evaluate_ema", True), ("hyp.grad_noise.additive", 0.1), ("hyp.norm_bias.strength", 0.1),
+                     ("hyp.only_linear_layers_weight_decay", True), ("hyp.train_semi_stochastic", True),
+                     ("impl.mixed_precision", True)]:
+        with pytest.raises(ValueError):
+            Trainer(fresh(), HostBlockLoader(X, Y, 16), None, setup, _cfg(16, **{key: val}))
+    # a resident dataset whose last block is ragged (drop_last=False) cannot be walked out of bounds
+    ds = torch.utils.data.TensorDataset(*O.synthetic_cifar(40))
+    loader = torch.utils.data.DataLoader(ds, batch_size=16, sampler=torch.utils.data.SequentialSampler(ds), drop_last=False)
+    with pytest.raises(ValueError):
+        Trainer(fresh(), loader, None, setup, _cfg(16))
+    from fullbatchtraining_b200.engine import FullBatchEngine
+
+    eng = FullBatchEngine(fresh(), 16, groups=2)
+    Xd, Yd = (t.to(DEV) for t in O.synthetic_cifar(40))
+    with pytest.raises(ValueError):
+        eng.accumulate_resident(Xd, Yd, 0.8, 0.5, 1e-2, count=3)
+
+
+def test_resumed_step_records_the_same_statistics(tmp_path):
+    """param_norm / full_loss of the first step after a resume equal those of the uninterrupted run (sum theta^2 is
+    re-initialised on the device when the checkpoint is loaded)."""
+    mb, n = 16, 32
+    X, Y = O.synthetic_cifar(n)
+    setup = dict(device=DEV, dtype=torch.float32)
+
+    def run(steps, name):
+        cfg = _cfg(mb, **{"hyp.steps": steps, "hyp.grad_clip": 0.25, "impl.checkpoint.name": name,
+                          "original_cwd": str(tmp_path), "hyp.warmup": 0})
+        trainer = Trainer(fresh(), HostBlockLoader(X, Y, mb), None, setup, cfg)
+        while trainer.step_count < steps:
+            trainer.step(validate=False)
+            trainer.maybe_checkpoint()
+        return trainer.stats
+
+    full = run(3, None)
+    run(2, "r.pth")
+    resumed = run(3, "r.pth")
+    assert resumed["param_norm"][0] == pytest.approx(full["param_norm"][2], rel=1e-6) and resumed["param_norm"][0] > 0
+    assert resumed["full_loss"][0] == pytest.approx(full["full_loss"][2], rel=1e-6)
+    assert full["param_norm"][0] == pytest.approx(float(sum(p.double().pow(2).sum() for p in fresh().parameters())), rel=1e-6)
 
 
 def test_flat_sgd_matches_torch_sgd_with_clip():
@@ -208,7 +290,7 @@ def test_gradregularizer_central_differences_and_pre_grads():
     net = O.OracleResNet(18, b64, update_running_stats=False)
     ref, _, _ = O.regularize(net, p64, [g.double() for g in raw], X.double(), Y, 0.8, 0.5, 1e-2, 0.0,
                              "central-differences", [q.double() for q in pre], 0.25)
-    assert rel(O.flat(grads), O.flat(ref)) < 0.5
+    assert rel(O.flat(grads), O.flat(ref)) < 0.2
     c = float((O.flat(grads).double() * O.flat(ref)).sum() / (O.flat(grads).double().norm() * O.flat(ref).norm()))
     assert c > 0.98
 
@@ -262,6 +344,7 @@ def test_checkpoint_roundtrip_in_reference_format(tmp_path):
         trainer = Trainer(model, HostBlockLoader(X, Y, mb), None, setup, cfg)
         while trainer.step_count < steps:
             trainer.step(validate=False)
+            trainer.maybe_checkpoint()  # training.py:330-335, after the early-stop checks of the main loop
         return model, trainer
 
     m_full, _ = run(3, None)            # uninterrupted

@@ -26,9 +26,13 @@ DEV = torch.device("cuda")
 HYP = dict(lr=0.8, block_strength=0.5, eps=1e-2)
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
-# e_new <= RATIO * max(e32, FLOOR): split mode carries ~16 mantissa bits per tensor-core operand vs 24 in fp32
-RATIO_RAW, RATIO_REG = 12.0, 6.0
+# e_new <= RATIO * max(e32, FLOOR): split mode carries ~16 mantissa bits per tensor-core operand (8 for the output
+# gradient) vs 24 in fp32.  Measured on B200 (profiles/r2_parity_*.json): raw 2.0-4.6x the fp32 reference's own error,
+# regularised 1.6-2.8x, accumulated 1.7x.  The bounds below are those measurements plus ~25 % head room, and the
+# absolute caps state the accuracy actually delivered for ResNet-18 at initialisation.
+RATIO_RAW, RATIO_REG = 6.0, 3.5
 FLOOR_RAW, FLOOR_REG = 1e-3, 2e-2
+ABS_RAW_R18, ABS_REG_R18 = 2e-2, 0.2
 
 
 def rel(a, b):
@@ -40,21 +44,21 @@ def cos(a, b):
     return float((a * b).sum() / (a.norm() * b.norm()))
 
 
-def oracle_run(depth, params, buffers, X, Y, mb, dtype, keep=2):
+def oracle_run(depth, params, buffers, X, Y, mb, dtype, keep=2, **kw):
     p = {k: v.to(DEV, dtype).clone() for k, v in params.items()}
     b = {k: (v.to(DEV).clone() if v.dtype == torch.long else v.to(DEV, dtype).clone()) for k, v in buffers.items()}
-    out = O.full_batch_step(depth, p, b, X.to(DEV, dtype), Y.to(DEV), mb, keep_microbatches=keep, **HYP)
+    out = O.full_batch_step(depth, p, b, X.to(DEV, dtype), Y.to(DEV), mb, keep_microbatches=keep, **dict(HYP, **kw))
     return out, b
 
 
-def setup_case(depth, mb, n):
+def setup_case(depth, mb, n, data="randn"):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     model = construct_model(dict(name=f"ResNet{depth}", depth=depth), 3, 10)
     params = {k: v.detach().clone() for k, v in model.named_parameters()}
     buffers = {k: v.detach().clone() for k, v in model.named_buffers()}
-    X, Y = O.synthetic_cifar(n)
+    X, Y = O.synthetic_cifar(n) if data == "randn" else O.structured_cifar(n)
     return model, params, buffers, X.to(DEV), Y.to(DEV)
 
 
@@ -65,50 +69,191 @@ def dump(name, d):
     print(name, json.dumps(d))
 
 
-@pytest.mark.parametrize("depth,mb,n", [(18, 16, 32), (18, 128, 256), (152, 8, 16)],
-                         ids=["r18_mb16", "r18_mb128", "r152_mb8"])
-def test_full_batch_step_matches_oracle(depth, mb, n):
-    model, params, buffers, X, Y = setup_case(depth, mb, n)
+def compare_step(name, depth, mb, model, params, buffers, X, Y, groups=None, per_microbatch=True):
+    """One full-batch step of the engine against the oracle in fp64 (truth) and fp32 (the reference's own arithmetic);
+    returns the report that is also written to gpurun_out/parity_<name>.json."""
+    n = X.shape[0]
     ref64, buf64 = oracle_run(depth, params, buffers, X, Y, mb, torch.float64)
     ref32, _ = oracle_run(depth, params, buffers, X, Y, mb, torch.float32)
-    eng = FullBatchEngine(model, mb, precision="split")
+    eng = FullBatchEngine(model, mb, precision="split", groups=groups)
     theta0 = eng.theta.clone()
     K = eng.accumulate_resident(X, Y, HYP["lr"], HYP["block_strength"], HYP["eps"])
     res = eng.results(K)
     assert K == n // mb
     assert torch.equal(eng.theta, theta0), "parameters must be unchanged by the regulariser"
     avg64, avg32 = O.flat(ref64["avg"]), O.flat(ref32["avg"])
-    e_new, e32 = rel(eng.avg, avg64), rel(avg32, avg64)
-    rep = dict(e_new_avg=e_new, e32_avg=e32, cos_avg=cos(eng.avg, avg64), loss=res["loss"], loss64=float(ref64["loss"]),
+    rep = dict(K=K, groups=eng.G, e_new_avg=rel(eng.avg, avg64), e32_avg=rel(avg32, avg64),
+               e_new_avg_vs_fp32=rel(eng.avg, avg32), cos_avg=cos(eng.avg, avg64), cos_avg_vs_fp32=cos(eng.avg, avg32),
+               loss=res["loss"], loss64=float(ref64["loss"]), loss32=float(ref32["loss"]),
                grad_norms=res["grad_norms"].tolist(), grad_norms64=ref64["grad_norms"].tolist())
-    # per-microbatch raw / regularised gradient of microbatch 0 through the GradRegularizer protocol of the engine
-    eng.microbatch_gradient(X[:mb], Y[:mb])
-    raw = eng.g.clone()
-    eng.regularize(X[:mb], Y[:mb], HYP["lr"], HYP["block_strength"], HYP["eps"])
-    reg = eng.g.clone()
-    k64, k32 = ref64["kept"][0], ref32["kept"][0]
-    rep.update(e_new_raw=rel(raw, O.flat(k64["raw"])), e32_raw=rel(O.flat(k32["raw"]), O.flat(k64["raw"])),
-               e_new_reg=rel(reg, O.flat(k64["reg"])), e32_reg=rel(O.flat(k32["reg"]), O.flat(k64["reg"])),
-               cos_raw=cos(raw, O.flat(k64["raw"])), cos_reg=cos(reg, O.flat(k64["reg"])))
-    # scalar outputs: bounded by a multiple of the fp32 reference's own deviation from fp64 (ResNet-152 at batch 8 is so
-    # ill-conditioned at initialisation that fp32 itself is 9% / 90% off in the raw / regularised gradient)
+    if per_microbatch:
+        # raw / regularised gradient of microbatch 0 through the GradRegularizer protocol of the engine
+        eng.microbatch_gradient(X[:mb], Y[:mb])
+        raw = eng.g.clone()
+        eng.regularize(X[:mb], Y[:mb], HYP["lr"], HYP["block_strength"], HYP["eps"])
+        reg = eng.g.clone()
+        k64, k32 = ref64["kept"][0], ref32["kept"][0]
+        rep.update(e_new_raw=rel(raw, O.flat(k64["raw"])), e32_raw=rel(O.flat(k32["raw"]), O.flat(k64["raw"])),
+                   e_new_raw_vs_fp32=rel(raw, O.flat(k32["raw"])),
+                   e_new_reg=rel(reg, O.flat(k64["reg"])), e32_reg=rel(O.flat(k32["reg"]), O.flat(k64["reg"])),
+                   e_new_reg_vs_fp32=rel(reg, O.flat(k32["reg"])),
+                   cos_raw=cos(raw, O.flat(k64["raw"])), cos_reg=cos(reg, O.flat(k64["reg"])))
     l64, l32 = float(ref64["loss"]), float(ref32["loss"])
     gn64, gn32 = ref64["grad_norms"].double().cpu(), ref32["grad_norms"].double().cpu()
-    e32_loss = abs(l32 - l64) / abs(l64)
-    e32_gn = float(((gn32 - gn64).abs() / gn64).max())
-    rep.update(e32_loss=e32_loss, e32_grad_norms=e32_gn,
+    rep.update(e32_loss=abs(l32 - l64) / abs(l64), e32_grad_norms=float(((gn32 - gn64).abs() / gn64).max()),
                e_new_loss=abs(res["loss"] - l64) / abs(l64),
-               e_new_grad_norms=float(((res["grad_norms"].double().cpu() - gn64).abs() / gn64).max()))
-    dump(f"r{depth}_mb{mb}_n{n}", rep)
+               e_new_grad_norms=float(((res["grad_norms"].double() - gn64).abs() / gn64).max()),
+               correct=res["correct"], correct64=float(ref64["correct"]))
+    dump(name, rep)
+    return rep, eng, ref64, buf64
+
+
+def assert_step(rep, depth):
     # loss: forward pass with ~16-bit operands; 1e-4 for the 20 convs of ResNet-18, 1e-3 for the 155 of ResNet-152
-    assert rep["e_new_loss"] <= max(1e-4 if depth < 100 else 1e-3, RATIO_RAW * e32_loss)
-    assert rep["e_new_grad_norms"] <= max(2e-2, RATIO_RAW * e32_gn)
-    assert res["correct"] == float(ref64["correct"])
-    assert rep["e_new_raw"] <= RATIO_RAW * max(rep["e32_raw"], FLOOR_RAW)
-    assert rep["e_new_reg"] <= RATIO_REG * max(rep["e32_reg"], FLOOR_REG)
-    assert e_new <= RATIO_REG * max(e32, FLOOR_REG)
-    if e32 < 0.2:
-        assert rep["cos_avg"] > 0.98
+    assert rep["e_new_loss"] <= max(1e-4 if depth < 100 else 1e-3, RATIO_RAW * rep["e32_loss"])
+    assert rep["e_new_grad_norms"] <= max(2e-2 if depth > 100 else 2e-3, RATIO_RAW * rep["e32_grad_norms"])
+    assert rep["correct"] == rep["correct64"]
+    if "e_new_raw" in rep:
+        assert rep["e_new_raw"] <= RATIO_RAW * max(rep["e32_raw"], FLOOR_RAW)
+        assert rep["e_new_reg"] <= RATIO_REG * max(rep["e32_reg"], FLOOR_REG)
+        if depth < 100:
+            assert rep["e_new_raw"] <= ABS_RAW_R18 and rep["e_new_reg"] <= ABS_REG_R18
+            assert rep["cos_raw"] > 0.9995 and rep["cos_reg"] > 0.98
+    assert rep["e_new_avg"] <= RATIO_REG * max(rep["e32_avg"], FLOOR_REG)
+    if depth < 100:
+        assert rep["e_new_avg"] <= ABS_REG_R18
+    if rep["e32_avg"] < 0.2:  # 20 convolutions (ResNet-18) / 155 (ResNet-152) deep
+        assert rep["cos_avg"] > (0.98 if depth < 100 else 0.97)
+
+
+@pytest.mark.parametrize("depth,mb,n,groups", [(18, 16, 32, None), (18, 128, 256, None), (152, 32, 64, 2)],
+                         ids=["r18_mb16", "r18_mb128", "r152_mb32"])
+def test_full_batch_step_matches_oracle(depth, mb, n, groups):
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+    rep, _, _, _ = compare_step(f"r{depth}_mb{mb}_n{n}", depth, mb, model, params, buffers, X, Y, groups=groups)
+    assert_step(rep, depth)
+
+
+def test_resnet152_real_microbatch_in_a_conditioned_state():
+    """ResNet-152 at microbatch 32 (config 4).  At the reference's initialisation the 50 residual branches add up
+    unattenuated (zero_init_residual is off on the config path, models.py:22): squared gradient norms are ~3e6 and the
+    fp32 reference itself is 12 % / 91 % away from fp64 (raw / regularised), so nothing can be asserted there beyond the
+    ratios (test_full_batch_step_matches_oracle[r152_mb32]).  With the last BatchNorm scale of every block at 0.25 -- the
+    regime a trained network is in -- the problem is conditioned, the fp32 floor drops below 0.2 and the cosine
+    assertions are live."""
+    depth, mb, n = 152, 32, 64
+    model, _, _, X, Y = setup_case(depth, mb, n)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("bn3.weight"):
+                p.fill_(0.25)
+    params = {k: v.detach().clone() for k, v in model.named_parameters()}
+    buffers = {k: v.detach().clone() for k, v in model.named_buffers()}
+    rep, _, _, _ = compare_step("r152_mb32_n64_damped", depth, mb, model, params, buffers, X, Y, groups=2)
+    assert_step(rep, depth)
+    assert rep["e32_reg"] < 0.2 and rep["e32_avg"] < 0.2, "the state is meant to be conditioned"
+    assert rep["cos_raw"] > 0.998 and rep["cos_reg"] > 0.97 and rep["cos_avg"] > 0.97  # measured 0.9989 / 0.9765 / 0.9765
+
+
+def golden(name):
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+def check_fingerprint(z, prefix, tensors, stride, rtol):
+    import numpy as np
+
+    fp = O.fingerprint(tensors, stride)
+    assert abs(fp["total_norm"] - z[f"{prefix}.total_norm"]) <= rtol * z[f"{prefix}.total_norm"], prefix
+    assert np.linalg.norm(fp["norms"] - z[f"{prefix}.norms"]) <= rtol * np.linalg.norm(z[f"{prefix}.norms"]), prefix
+    assert np.linalg.norm(fp["sample"] - z[f"{prefix}.sample"]) <= rtol * np.linalg.norm(z[f"{prefix}.sample"]), prefix
+
+
+@pytest.mark.parametrize("name,groups", [("r18_mb128_n2000_f64", None), ("r152_mb32_n64_f64", 2)])
+def test_baseline_config_goldens_of_the_unmodified_reference(name, groups):
+    """BASELINE.json configs[0] (ResNet-18, 2,000 images -> K = 15 microbatches of 128: one launch of 8 and one of 7
+    groups) and config 4's shape (ResNet-152, microbatch 32): fixtures produced by the UNMODIFIED reference in fp64
+    (oracle/make_goldens.py).  The oracle (fp64, on this GPU) must reproduce them, and the engine is compared with
+    both: accumulated gradient, loss and the 15 per-microbatch gradient norms of `stats`."""
+    z, meta = golden(name)
+    depth, mb, n = meta["depth"], meta["mb"], meta["n"]
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+    rep, eng, ref64, buf64 = compare_step(name, depth, mb, model, params, buffers, X, Y, groups=groups,
+                                          per_microbatch=False)
+    # 1) the oracle reproduces the reference (fp64 on the GPU vs fp64 on the CPU that made the fixture)
+    check_fingerprint(z, "avg", ref64["avg"], meta["stride"], 1e-6)
+    sc = meta["scalars"]
+    assert float(ref64["loss"]) == pytest.approx(sc["train_loss"], rel=1e-9)
+    assert ref64["grad_norms"].sqrt().tolist() == pytest.approx(sc["grad_norm_train"], rel=1e-7)
+    # 2) the engine against the reference's own numbers
+    assert rep["K"] == n // mb == len(sc["grad_norm_train"])
+    assert rep["loss"] == pytest.approx(sc["train_loss"], rel=1e-4 if depth < 100 else 1e-3)
+    assert [v ** 0.5 for v in rep["grad_norms"]] == pytest.approx(sc["grad_norm_train"], rel=1e-3 if depth < 100 else 2e-2)
+    assert rep["correct"] / (rep["K"] * mb) == pytest.approx(sc["train_acc"])
+    assert_step(rep, depth)
+    # fingerprint of the engine's accumulated gradient against the fixture: per-tensor norms within the same bound
+    import numpy as np
+
+    fp = O.fingerprint(eng.grads_list(eng.avg), meta["stride"])
+    tol = RATIO_REG * max(rep["e32_avg"], FLOOR_REG)
+    assert np.linalg.norm(fp["sample"] - z["avg.sample"]) <= tol * np.linalg.norm(z["avg.sample"])
+    assert abs(fp["total_norm"] - z["avg.total_norm"]) <= tol * z["avg.total_norm"]
+
+
+def test_parity_away_from_initialisation():
+    """SURVEY.md 7 hard part 2: after three gradient-descent steps of the oracle (fp64: weights, BatchNorm parameters and
+    running statistics have moved) the fourth step's gradients are compared again."""
+    depth, mb, n = 18, 128, 256
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+    p = {k: v.to(DEV, torch.float64).clone() for k, v in params.items()}
+    b = {k: (v.to(DEV).clone() if v.dtype == torch.long else v.to(DEV, torch.float64).clone()) for k, v in buffers.items()}
+    for _ in range(3):
+        out = O.full_batch_step(depth, p, b, X.double(), Y, mb, **HYP)
+        for v, g in zip(p.values(), out["avg"]):
+            v.sub_(0.01 * g)
+    moved = rel(O.flat(list(p.values())), O.flat([v.to(DEV) for v in params.values()]))
+    assert moved > 1e-3
+    with torch.no_grad():
+        model.load_state_dict({**{k: v.float().cpu() for k, v in p.items()},
+                               **{k: (v.cpu() if v.dtype == torch.long else v.float().cpu()) for k, v in b.items()}})
+    params = {k: v.detach().clone() for k, v in model.named_parameters()}  # fp32-rounded: every path starts from these
+    buffers = {k: v.detach().clone() for k, v in model.named_buffers()}
+    rep, _, _, _ = compare_step("r18_mb128_after3steps", depth, mb, model, params, buffers, X, Y)
+    assert_step(rep, depth)
+
+
+def test_parity_on_structured_images():
+    """spatially correlated, class-structured inputs (oracle.structured_cifar) instead of white noise"""
+    depth, mb, n = 18, 128, 256
+    model, params, buffers, X, Y = setup_case(depth, mb, n, data="structured")
+    rep, _, _, _ = compare_step("r18_mb128_structured", depth, mb, model, params, buffers, X, Y)
+    assert_step(rep, depth)
+
+
+def test_config2_50k_step_against_committed_oracle_scalars():
+    """BASELINE.json configs[1] at full size (ResNet-18, 49,920 images = 390 microbatches = 48 launches of 8 groups + one
+    of 6), on bench.py's data: mean loss and mean squared gradient norm against the fp32 / fp64 ORACLE values committed in
+    tests/golden/bench_check.json (tools/make_bench_check.py), i.e. the running sums survive 390 microbatches."""
+    from fullbatchtraining_b200.data import synthetic_cifar
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_check.json")) as f:
+        exp = json.load(f)["r18_50k"]
+    mb, K = 128, exp["microbatches"]
+    torch.manual_seed(0)
+    model = construct_model(dict(name="ResNet18", depth=18), 3, 10)
+    X, Y = synthetic_cifar(K * mb, device=DEV)
+    eng = FullBatchEngine(model, mb, precision="split")
+    assert eng.accumulate_resident(X, Y, HYP["lr"], HYP["block_strength"], HYP["eps"]) == K
+    res = eng.results(K)
+    assert res["loss"] == pytest.approx(exp["loss_fp64"], rel=2e-5)
+    assert abs(res["loss"] - exp["loss_fp64"]) <= 6.0 * max(abs(exp["loss"] - exp["loss_fp64"]), 1e-6)
+    assert float(res["grad_norms"].mean()) == pytest.approx(exp["mean_grad_norm_sq_fp64"], rel=1e-3)
+    assert torch.isfinite(eng.avg).all() and 0.5 < float(eng.avg.norm()) < 50.0
+    dump("r18_50k_scalars", dict(loss=res["loss"], loss_fp32_oracle=exp["loss"], loss_fp64_oracle=exp["loss_fp64"],
+                                 mean_grad_norm_sq=float(res["grad_norms"].mean()),
+                                 mean_grad_norm_sq_fp64_oracle=exp["mean_grad_norm_sq_fp64"], avg_norm=float(eng.avg.norm())))
 
 
 def test_running_stats_and_determinism():
@@ -227,7 +372,7 @@ def test_grad_reg_variants_match_oracle(name, extra):
     assert abs(res["loss"] - float(ref64["loss"])) < 1e-4 * float(ref64["loss"])
     assert res["clipped_batches"] == ref64["clipped_batches"]
     if "acc_strength" in extra:
-        assert rel(eng.pre, O.flat(ref64["pre_grads"])) < RATIO_RAW * FLOOR_RAW * 2
+        assert rel(eng.pre, O.flat(ref64["pre_grads"])) < ABS_RAW_R18  # mean RAW gradient: 1.1-1.4e-2 at microbatch 16
     nbt = [b for k, b in model.named_buffers() if k.endswith("num_batches_tracked")][0]
     assert int(nbt) == int(buf64["stem.1.num_batches_tracked"])  # 2 or 3 passes per microbatch (+1 for the pre-pass)
 

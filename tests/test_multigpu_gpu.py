@@ -1,0 +1,102 @@
+"""Multi-GPU parity on the B200 box (self-skips below 2 GPUs; run with `gpurun --gpus 2 -- python -m pytest
+tests/test_multigpu_gpu.py -m gpu`): one process per GPU over NCCL.
+
+  * sharded accumulation + ONE weighted all-reduce of the flat buffer == the single-GPU step (training/utils.py:31-41,
+    SURVEY.md 8e), also with an `acc_strength` pre-pass whose mean raw gradient crosses the GPUs once
+    (training.py:128-142 incl. the all-reduce at :139-140);
+  * `evaluate` averages the BatchNorm buffers of the ranks first (training.py:347-357).
+"""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs at least 2 CUDA devices", allow_module_level=True)
+
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    from fullbatchtraining_b200 import construct_model
+    from fullbatchtraining_b200.config import default_cfg
+    from fullbatchtraining_b200.data import synthetic_cifar
+    from fullbatchtraining_b200.training import Trainer, evaluate
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    mb, n = 16, 16 * 7
+    X, Y = synthetic_cifar(n)
+    ds = torch.utils.data.TensorDataset(X, Y)
+    loader = torch.utils.data.DataLoader(ds, batch_size=mb, sampler=torch.utils.data.SequentialSampler(ds), drop_last=True)
+    setup = dict(device=dev, dtype=torch.float32)
+    res = {}
+    for name, extra in (("plain", {}), ("acc", {"hyp.grad_reg.acc_strength": 0.3})):
+        cfg = default_cfg({"data.batch_size": mb, "hyp.sub_batch": mb, "hyp.warmup": 0, "hyp.steps": 1,
+                           "hyp.grad_clip": None, "impl.setup.dist": True, "impl.setup.world_size": world, **extra})
+        torch.manual_seed(0)
+        model = construct_model(dict(name="ResNet18", depth=18), 3, 10)
+        tr = Trainer(model, loader, loader, setup, cfg)
+        assert tr.world == world and (tr.k0, tr.k1) == ((rank * 7) // world, ((rank + 1) * 7) // world)
+        tr._accumulate_full_gradient()
+        tr._record_stats()
+        res[name] = dict(avg=tr.engine.avg.clone().cpu(), loss=tr.stats["train_loss"][0], acc=tr.stats["train_acc"][0],
+                         norms=[tr.stats[f"grad_norm_train_{k}"][0] for k in range(7)],
+                         pre=tr.engine.pre.clone().cpu() if name == "acc" else None)
+        if name == "plain":
+            # BatchNorm buffers differ between the ranks (different microbatches); evaluate averages them first
+            before = torch.cat([b.reshape(-1).float() for b in model.buffers() if b.dtype != torch.long])
+            gathered = [torch.zeros_like(before) for _ in range(world)]
+            dist.all_gather(gathered, before)
+            tr.engine.sync_bn_counters()
+            evaluate(model, loader, tr.stats, setup, cfg.impl, cfg.hyp, engine=tr.engine)
+            after = torch.cat([b.reshape(-1).float() for b in model.buffers() if b.dtype != torch.long])
+            res["bn_differ"] = float((gathered[0] - gathered[1]).abs().max())
+            res["bn_avg_err"] = float((after - torch.stack(gathered).mean(0)).abs().max())
+            res["valid_acc"] = tr.stats["valid_acc"][0]
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_step_equals_single_gpu_step(tmp_path):
+    from fullbatchtraining_b200 import construct_model
+    from fullbatchtraining_b200.data import synthetic_cifar
+    from fullbatchtraining_b200.engine import FullBatchEngine
+
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    dev = torch.device("cuda", 0)
+    X, Y = synthetic_cifar(16 * 7)
+    X, Y = X.to(dev), Y.to(dev)
+    for name, acc in (("plain", 0.0), ("acc", 0.3)):
+        torch.manual_seed(0)
+        eng = FullBatchEngine(construct_model(dict(name="ResNet18", depth=18), 3, 10), 16, device=dev)
+        K = eng.accumulate_resident(X, Y, 0.8, 0.5, 1e-2, acc_strength=acc)
+        single = eng.results(K)
+        a, b = res[name]["avg"].double(), eng.avg.cpu().double()
+        # identical microbatches, identical per-microbatch arithmetic; only the fp32 order of the final mean differs.
+        # With acc_strength the perturbation direction contains the all-reduced mean gradient, whose last bits differ.
+        assert float((a - b).norm() / b.norm()) < (1e-6 if acc == 0 else 1e-3), name
+        assert res[name]["loss"] == pytest.approx(single["loss"], rel=1e-6)
+        assert res[name]["norms"] == pytest.approx(single["grad_norms"].sqrt().tolist(), rel=1e-6)
+        if acc:
+            p, q = res[name]["pre"].double(), eng.pre.cpu().double()
+            assert float((p - q).norm() / q.norm()) < 1e-6
+    assert res["bn_differ"] > 1e-4 and res["bn_avg_err"] < 1e-6
+    assert 0.0 <= res["valid_acc"] <= 1.0

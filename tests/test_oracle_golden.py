@@ -64,6 +64,26 @@ def test_oracle_matches_reference_golden(golden_dir, name, rtol):
     assert full == pytest.approx(sc["full_loss"], rel=max(rtol, 1e-6))
 
 
+def test_oracle_sgd_branch_matches_reference_golden(golden_dir):
+    """training.py:241-286 restated (fb_oracle.sgd_epochs) against two steps of the unmodified reference's stochastic
+    branch: parameters after 8 optimizer steps, per-step loss / accuracy / gradient norm, BatchNorm statistics."""
+    z, meta = load(golden_dir, "r18_sgd_mb16_n64_f64")
+    dt = torch.float64
+    torch.manual_seed(0)
+    p, b = O.build_resnet_state(18, dtype=dt)
+    check_fp(z, "init", list(p.values()), meta["stride"], 1e-12)
+    X, Y = O.synthetic_cifar(meta["n"], dtype=dt)
+    out = O.sgd_epochs(18, p, b, X, Y, meta["mb"], meta["extra"]["steps"], meta["hyp"]["lr"],
+                       block_strength=meta["hyp"]["block_strength"], eps=meta["hyp"]["eps"])
+    check_fp(z, "theta", list(p.values()), meta["stride"], 1e-9)
+    sc = meta["scalars"]
+    assert out["train_loss"] == pytest.approx(sc["train_loss_steps"], rel=1e-9)
+    assert out["train_acc"] == pytest.approx(sc["train_acc_steps"])
+    assert [v ** 0.5 for v in out["grad_norm_sq"]] == pytest.approx(sc["grad_norm_steps"], rel=1e-9)
+    bufs = [v for k, v in b.items() if not k.endswith("num_batches_tracked")]
+    check_fp(z, "buffers", bufs, 97, 1e-8)
+
+
 def test_microbatch_count_and_drop_last():
     # data_preparation.py:68 drop_last -> K = N // mb
     torch.manual_seed(0)
