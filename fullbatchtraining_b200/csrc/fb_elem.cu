@@ -195,6 +195,12 @@ __device__ __forceinline__ void bn_item_store(const fb_bn_apply_args& a, long lo
     for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
   }
   store8_split(static_cast<bf16*>(a.out_hi), static_cast<bf16*>(a.out_lo), off, o);
+  if (a.mask_out) {  // ReLU mask of the item as one byte (read by the backward kernels instead of the bf16 plane)
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+    a.mask_out[off >> 3] = (uint8_t)m;
+  }
 }
 
 template <bool DUAL, bool RES>
@@ -273,34 +279,63 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdK k) {
   const float* y = a.y + gbase;
   const float* dA = a.dA + gbase;
   const float* dA2 = a.dA2 ? a.dA2 + gbase : nullptr;
-  const bf16* mask = a.mask_hi ? static_cast<const bf16*>(a.mask_hi) + gbase : nullptr;
+  const bf16* mask = (a.mask_hi && !a.mask_bits) ? static_cast<const bf16*>(a.mask_hi) + gbase : nullptr;
+  const uint8_t* bits = a.mask_bits ? a.mask_bits + (gbase >> 3) : nullptr;
+  const int bit_shift = c & 4;
   const long long r0 = (long long)chunk * k.geo.rows_per_chunk;
   const long long r1 = min(P, r0 + k.geo.rows_per_chunk);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   const float4 mu = *reinterpret_cast<const float4*>(a.mean + (long long)g * C + c);
   const float4 rs = *reinterpret_cast<const float4*>(a.rstd + (long long)g * C + c);
-#pragma unroll 4
-  for (long long r = r0 + ty; r < r1; r += TY) {
-    const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
-    float4 d = *reinterpret_cast<const float4*>(dA + r * C + c);
-    if (dA2) {
-      const float4 d2 = *reinterpret_cast<const float4*>(dA2 + r * C + c);
-      d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+  // four rows per round with ALL loads issued before the arithmetic (the kernel is a pure stream: bytes in flight per
+  // thread decide its speed); rows are accumulated in the same order as a plain loop would
+  constexpr int kRows = 4;
+  for (long long r = r0 + ty; r < r1; r += (long long)kRows * TY) {
+    float4 v[kRows], d[kRows], d2[kRows];
+    uint2 mk[kRows];
+    unsigned mb[kRows];
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const long long rr = r + (long long)u * TY;
+      if (rr < r1) {
+        const long long o = rr * C + c;
+        v[u] = *reinterpret_cast<const float4*>(y + o);
+        d[u] = *reinterpret_cast<const float4*>(dA + o);
+        if (dA2) d2[u] = *reinterpret_cast<const float4*>(dA2 + o);
+        if (bits) mb[u] = bits[o >> 3];
+        if (mask) mk[u] = *reinterpret_cast<const uint2*>(mask + o);
+      }
     }
-    if (mask) {
-      const uint2 m = *reinterpret_cast<const uint2*>(mask + r * C + c);
-      const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.x));
-      const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m.y));
-      d.x = m01.x > 0.f ? d.x : 0.f;
-      d.y = m01.y > 0.f ? d.y : 0.f;
-      d.z = m23.x > 0.f ? d.z : 0.f;
-      d.w = m23.y > 0.f ? d.w : 0.f;
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const long long rr = r + (long long)u * TY;
+      if (rr < r1) {
+        float4 dd = d[u];
+        if (dA2) {
+          dd.x += d2[u].x; dd.y += d2[u].y; dd.z += d2[u].z; dd.w += d2[u].w;
+        }
+        if (bits) {
+          const unsigned m = mb[u] >> bit_shift;
+          dd.x = (m & 1u) ? dd.x : 0.f;
+          dd.y = (m & 2u) ? dd.y : 0.f;
+          dd.z = (m & 4u) ? dd.z : 0.f;
+          dd.w = (m & 8u) ? dd.w : 0.f;
+        }
+        if (mask) {
+          const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mk[u].x));
+          const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mk[u].y));
+          dd.x = m01.x > 0.f ? dd.x : 0.f;
+          dd.y = m01.y > 0.f ? dd.y : 0.f;
+          dd.z = m23.x > 0.f ? dd.z : 0.f;
+          dd.w = m23.y > 0.f ? dd.w : 0.f;
+        }
+        s1.x += dd.x; s1.y += dd.y; s1.z += dd.z; s1.w += dd.w;
+        s2.x += dd.x * (v[u].x - mu.x) * rs.x;
+        s2.y += dd.y * (v[u].y - mu.y) * rs.y;
+        s2.z += dd.z * (v[u].z - mu.z) * rs.z;
+        s2.w += dd.w * (v[u].w - mu.w) * rs.w;
+      }
     }
-    s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-    s2.x += d.x * (v.x - mu.x) * rs.x;
-    s2.y += d.y * (v.y - mu.y) * rs.y;
-    s2.z += d.z * (v.z - mu.z) * rs.z;
-    s2.w += d.w * (v.w - mu.w) * rs.w;
   }
   red[0][threadIdx.x] = s1;
   red[1][threadIdx.x] = s2;
@@ -386,10 +421,16 @@ __device__ __forceinline__ void bn_bwd_item_load(const fb_bn_bwd_args& a, long l
     for (int j = 0; j < 8; ++j) it.d[j] += d2[j];
   }
   if (MASK) {
-    float m[8];
-    load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
+    if (a.mask_bits) {
+      const unsigned m = a.mask_bits[off >> 3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) it.d[j] = m[j] > 0.f ? it.d[j] : 0.f;
+      for (int j = 0; j < 8; ++j) it.d[j] = ((m >> j) & 1u) ? it.d[j] : 0.f;
+    } else {
+      float m[8];
+      load8_bf16(static_cast<const bf16*>(a.mask_hi) + off, m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) it.d[j] = m[j] > 0.f ? it.d[j] : 0.f;
+    }
   }
   load8(a.y + off, it.y);
 }
@@ -805,7 +846,7 @@ static int bwd_geometry(long long P, int C, int policy_groups, BnBwdGeom& geo) {
   geo.slabs = c4 / geo.TX;
   const int TY = 256 / geo.TX;
   if (policy_groups < 1) policy_groups = 1;
-  long long target = (2LL * kNumSMs) / ((long long)policy_groups * geo.slabs);
+  long long target = (4LL * kNumSMs) / ((long long)policy_groups * geo.slabs);
   if (target < 1) target = 1;
   long long most = P / (TY * 4);  // >= 4 rows per thread
   if (most < 1) most = 1;
@@ -910,11 +951,12 @@ extern "C" int fb_bn_bwd(const fb_bn_bwd_args* a, void* stream) {
   const size_t smem = size_t(44) * (a->C / 8) * sizeof(float);
   FB_REQUIRE(smem <= 48 * 1024, "fb_bn_bwd: at most 2232 channels");
   const dim3 grid(stream_grid(a->P * a->C / 16, k.a.ng), k.a.ng);
-  if (a->dA2 && a->mask_hi)
+  const bool masked = a->mask_hi || a->mask_bits;
+  if (a->dA2 && masked)
     FB_CUDA(launch_pdl(bn_bwd_apply_kernel<true, true>, grid, dim3(256), smem, st, k));
   else if (a->dA2)
     FB_CUDA(launch_pdl(bn_bwd_apply_kernel<true, false>, grid, dim3(256), smem, st, k));
-  else if (a->mask_hi)
+  else if (masked)
     FB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, true>, grid, dim3(256), smem, st, k));
   else
     FB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false>, grid, dim3(256), smem, st, k));

@@ -70,6 +70,8 @@ class Act:
         self.hi = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16)
         self.lo = torch.zeros(n, h, w, c, device=device, dtype=torch.bfloat16) if split else None
         self.grad = torch.zeros(n, h, w, c, device=device, dtype=torch.float32) if grad else None
+        # ReLU mask as a bit plane (written by the BatchNorm that produces this activation, read by its backward)
+        self.mask = torch.zeros(n * h * w * c // 8, device=device, dtype=torch.uint8) if grad else None
         # second addend of the gradient (shortcut branch of the consuming block); consumers read grad + grad2, so no
         # GEMM epilogue ever has to read-modify-write
         self.grad2 = None
@@ -277,6 +279,8 @@ class FullBatchEngine:
                                     u.bn_batch, u.bn_batch.stride(0), u.cout) for u in self.units], dev)
         self._graphs = {}
         self.l2_order = os.environ.get("FB_L2_ORDER", "1") == "1"
+        # ReLU masks as bit planes (1/16 of the bytes of the bf16 plane the backward would otherwise read twice)
+        self.bit_masks = os.environ.get("FB_BIT_MASKS", "1") == "1"
         # FB_WGRAD_STREAM=1: wgrad on a side stream, concurrently with the dgrad -> BatchNorm-backward chain below it
         self.wgrad_mode = int(os.environ.get("FB_WGRAD_STREAM", "0"))
         self.wgrad_stream = torch.cuda.Stream(device=dev) if self.wgrad_mode else None
@@ -315,7 +319,8 @@ class FullBatchEngine:
         # l2_order: walk back to front = start on what the convolution wrote last (still in L2) and end where the next
         # convolution starts
         ops.bn_apply(u.y, u.mean, u.rstd, base + 4 * u.gamma_off, base + 4 * u.beta_off, u.Pg, u.cout, out.hi, out.lo,
-                     relu=relu, second=sec, res=res, ng=ng, param_gstride=pstride, reverse=self.l2_order)
+                     relu=relu, second=sec, res=res, ng=ng, param_gstride=pstride, reverse=self.l2_order,
+                     mask_out=out.mask if self.bit_masks else None)
 
     def _forward(self, ng, wset, P, pstride, Gbuf, loss_base, correct_base, pass_idx):
         """P: flat parameters (theta: pstride 0, shared; theta_p: one row per group); Gbuf: [G][stride] gradients"""
@@ -355,7 +360,8 @@ class FullBatchEngine:
         self._rev = not self._rev
         ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
                    gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
-                   param_gstride=pstride, grad_gstride=self.stride, reverse=rev)
+                   param_gstride=pstride, grad_gstride=self.stride, reverse=rev,
+                   mask_bits=act.mask if self.bit_masks else None)
         # wgrad only feeds the flat gradient.  wgrad_mode 1 / 2: on a side stream, forked before / after the dgrad of the
         # same layer (2: the tensor-bound wgrad then runs next to the bandwidth-bound BatchNorm backward of the layer
         # below instead of next to its own dgrad); joined at the end of the backward pass

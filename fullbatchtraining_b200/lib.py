@@ -68,13 +68,15 @@ class WprepEntry(C.Structure):
 class BnApplyArgs(C.Structure):
     _fields_ = [("y", vp), ("mean", vp), ("rstd", vp), ("gamma", vp), ("beta", vp), ("y2", vp), ("mean2", vp),
                 ("rstd2", vp), ("gamma2", vp), ("beta2", vp), ("res_hi", vp), ("res_lo", vp), ("relu", i32), ("P", i64),
-                ("C", i32), ("out_hi", vp), ("out_lo", vp), ("ng", i32), ("param_gstride", i64), ("reverse", i32)]
+                ("C", i32), ("out_hi", vp), ("out_lo", vp), ("ng", i32), ("param_gstride", i64), ("reverse", i32),
+                ("mask_out", vp)]
 
 
 class BnBwdArgs(C.Structure):
     _fields_ = [("dA", vp), ("dA2", vp), ("mask_hi", vp), ("y", vp), ("mean", vp), ("rstd", vp), ("gamma", vp),
                 ("P", i64), ("C", i32), ("ws", vp), ("dgamma", vp), ("dbeta", vp), ("dy_bf16", vp), ("dz_out", vp),
-                ("ng", i32), ("param_gstride", i64), ("grad_gstride", i64), ("policy_groups", i32), ("reverse", i32)]
+                ("ng", i32), ("param_gstride", i64), ("grad_gstride", i64), ("policy_groups", i32), ("reverse", i32),
+                ("mask_bits", vp)]
 
 
 class BnEmaEntry(C.Structure):

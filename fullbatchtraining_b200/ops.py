@@ -516,7 +516,7 @@ def bn_stats(y, P, Cc, ws, mean, rstd, running_mean, running_var, momentum=0.1, 
 
 
 def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, second=None, res=None, ng=1, param_gstride=0,
-             reverse=False):
+             reverse=False, mask_out=None):
     """P: pixels per group; mean / rstd: [ng][C]; gamma / beta: pointers (ints) or tensors, + g*param_gstride per group;
     second = (y2, mean2, rstd2, gamma2, beta2)"""
     def p(t):
@@ -531,8 +531,10 @@ def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, secon
     a.relu, a.P, a.C = int(relu), P, Cc
     a.out_hi, a.out_lo = out_hi.data_ptr(), L.ptr(out_lo)
     a.ng, a.param_gstride, a.reverse = ng, param_gstride, int(reverse)
+    a.mask_out = L.ptr(mask_out)
     planes = 1 + (out_lo is not None)
-    per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes
+    per_elem = 4.0 + (4.0 if second is not None else 0.0) + (2.0 * planes if res is not None else 0.0) + 2.0 * planes + \
+        (0.125 if mask_out is not None else 0.0)
     _call("bn_fwd", per_elem * P * Cc * ng, "byte", "fb_bn_apply", C.byref(a),
           label=f"bn_apply P{P} C{Cc} {per_elem:.0f}B/elem")
 
@@ -545,8 +547,9 @@ def bn_bwd_ws_floats(P, Cc, G):
 
 
 def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None, ng=1, param_gstride=0,
-           grad_gstride=0, reverse=False):
-    """gamma / dgamma / dbeta: pointers (ints) or tensors, + g*param_gstride / g*grad_gstride per group"""
+           grad_gstride=0, reverse=False, mask_bits=None):
+    """gamma / dgamma / dbeta: pointers (ints) or tensors, + g*param_gstride / g*grad_gstride per group;
+    mask_bits: the bit plane written by bn_apply (mask_out), used instead of the bf16 plane mask_hi"""
     def p(t):
         return t if isinstance(t, int) or t is None else t.data_ptr()
 
@@ -558,9 +561,10 @@ def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_o
     a.dz_out = L.ptr(dz_out)
     a.ng, a.param_gstride, a.grad_gstride = ng, param_gstride, grad_gstride
     a.policy_groups, a.reverse = POLICY_GROUPS, int(reverse)
+    a.mask_bits = L.ptr(mask_bits)
     # distinct tensors: dA, y (+ mask) in; dy (+ dz) out -- each counted once although the two launches read twice
-    per_elem = 4.0 + 4.0 + (2.0 if mask_hi is not None else 0.0) + 2.0 + (4.0 if dz_out is not None else 0.0) + \
-        (4.0 if dA2 is not None else 0.0)
+    mask_bytes = 0.125 if mask_bits is not None else (2.0 if mask_hi is not None else 0.0)
+    per_elem = 4.0 + 4.0 + mask_bytes + 2.0 + (4.0 if dz_out is not None else 0.0) + (4.0 if dA2 is not None else 0.0)
     _call("bn_bwd", per_elem * P * Cc * ng, "byte", "fb_bn_bwd", C.byref(a), label=f"bn_bwd P{P} C{Cc} {per_elem:.0f}B/elem")
 
 

@@ -228,11 +228,13 @@ typedef struct {
   int32_t ng; /* 0 -> 1 */
   int64_t param_gstride;
   int32_t reverse;
+  uint8_t* mask_out; /* optional ReLU mask as BITS for fb_bn_bwd: byte e/8, bit e%8 of element e = [out > 0] */
 } fb_bn_apply_args;
 int fb_bn_apply(const fb_bn_apply_args* args, void* stream);
 
-/* BatchNorm(+ReLU) backward for ng groups of P pixels.  dz = (dA + dA2) * [mask_hi > 0] (mask_hi NULL: no ReLU; dA2
- * NULL: no second addend).  Two launches without grid synchronisation: a column reduction whose last block per group
+/* BatchNorm(+ReLU) backward for ng groups of P pixels.  dz = (dA + dA2) * [mask > 0]; the mask is either the bit plane
+ * written by fb_bn_apply (mask_bits: 1/16 of the bytes of a bf16 plane -- the kernels are bandwidth bound) or the bf16
+ * activation plane itself (mask_hi); both NULL: no ReLU.  dA2 NULL: no second addend.  Two launches without grid synchronisation: a column reduction whose last block per group
  * finalises (fixed order), then a streaming apply.  Writes dgamma / dbeta (+ g*grad_gstride), dY as bf16 (tensor-core
  * operand) and optionally dz as fp32 (`dz_out`, the identity-branch gradient).  gamma + g*param_gstride.
  * ws: >= 16 + ng*(2*C*fb_bn_bwd_chunks + 2*C) floats, the first 64 bytes ZERO on first use (self-resetting tickets). */
@@ -251,6 +253,7 @@ typedef struct {
   int64_t param_gstride, grad_gstride;
   int32_t policy_groups; /* the reduction is cut into ~2*148/policy_groups chunks per group (0 -> ng) */
   int32_t reverse;       /* reduce back to front, apply front to back (0: the other way round) */
+  const uint8_t* mask_bits;
 } fb_bn_bwd_args;
 int fb_bn_bwd(const fb_bn_bwd_args* args, void* stream);
 int fb_bn_bwd_chunks(int64_t P, int C, int policy_groups);

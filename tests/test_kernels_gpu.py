@@ -416,9 +416,14 @@ def test_bn_apply_and_backward(variant, shape):
     out_lo = torch.empty_like(out_hi)
     relu = variant != "norelu"
     base = params.data_ptr()
+    bits = torch.zeros(ng * P * Cc // 8, device=DEV, dtype=torch.uint8)
     ops.bn_apply(y, mean, rstd, base, base + 4 * Cc, P, Cc, out_hi, out_lo, relu=relu,
                  second=(y2, mean2, rstd2, base + 8 * Cc, base + 12 * Cc) if variant == "dual" else None,
-                 res=(res_hi, res_lo) if variant == "residual" else None, ng=ng, param_gstride=pstride)
+                 res=(res_hi, res_lo) if variant == "residual" else None, ng=ng, param_gstride=pstride, mask_out=bits)
+    # the ReLU mask as a bit plane: byte e/8, bit e%8
+    exp_bits = ((out_hi.float() + out_lo.float()) > 0).view(-1, 8).to(torch.uint8)
+    exp_bits = (exp_bits << torch.arange(8, device=DEV, dtype=torch.uint8)).sum(1).to(torch.uint8)
+    assert torch.equal(bits, exp_bits)
     dA = torch.randn(ng * P, Cc, device=DEV, generator=gen)
     dA2 = torch.randn(ng * P, Cc, device=DEV, generator=gen) if variant in ("residual", "plain") else None
     gstride = 2 * Cc + 64
@@ -429,6 +434,12 @@ def test_bn_apply_and_backward(variant, shape):
     for _ in range(2):  # twice: the tickets must reset themselves
         ops.bn_bwd(dA, out_hi if relu else None, y, mean, rstd, base, P, Cc, ws, grads.data_ptr(),
                    grads.data_ptr() + 4 * Cc, dy, dz_out=dz, dA2=dA2, ng=ng, param_gstride=pstride, grad_gstride=gstride)
+    if relu:  # the bit plane instead of the bf16 plane: identical results
+        grads_b = torch.full((ng, gstride), float("nan"), device=DEV)
+        dy_b, dz_b = torch.empty_like(dy), torch.empty_like(dz)
+        ops.bn_bwd(dA, None, y, mean, rstd, base, P, Cc, ws, grads_b.data_ptr(), grads_b.data_ptr() + 4 * Cc, dy_b,
+                   dz_out=dz_b, dA2=dA2, ng=ng, param_gstride=pstride, grad_gstride=gstride, mask_bits=bits)
+        assert torch.equal(dy_b, dy) and torch.equal(dz_b, dz) and torch.equal(grads_b[:, :2 * Cc], grads[:, :2 * Cc])
     torch.cuda.synchronize()
     for g in range(ng):
         sl = slice(g * P, (g + 1) * P)
