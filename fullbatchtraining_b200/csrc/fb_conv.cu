@@ -115,6 +115,7 @@ struct alignas(64) ConvGemmKParams {
   long long group_off[4];
   int b_group_rows;  // weight rows per microbatch group (0: shared)
   int reverse;
+  int cta_pair;
   float* out;
   long long out_sn, out_sh, out_sw;
   int accumulate;
@@ -158,13 +159,16 @@ __device__ __forceinline__ void tile_origin(int tile, int tile_h, int tile_n, in
 struct SuperTile {
   int mg, tg, r, j;
 };
-__device__ __forceinline__ SuperTile decode_super(const ConvGemmKParams& p, int u, int total) {
+// u enumerates (group, tap group, row [pair], N tile); `rows` rows per (group, tap group, N tile), of which a CTA pair
+// takes two at a time (sched_rows = rows / 2, r = 2q + rank)
+__device__ __forceinline__ SuperTile decode_super(const ConvGemmKParams& p, int u, int total, int sched_rows, int pair,
+                                                  int rank) {
   if (p.reverse) u = total - 1 - u;
   SuperTile s;
   s.j = u % p.n_tiles;
   u /= p.n_tiles;
-  s.r = u % p.rows;
-  u /= p.rows;
+  s.r = (u % sched_rows) * pair + rank;
+  u /= sched_rows;
   s.tg = u % p.n_tapgroups;
   s.mg = u / p.n_tapgroups;
   return s;
@@ -255,9 +259,12 @@ __device__ __forceinline__ void finalize_bn_stats(float* epi_stage, const ConvGe
   epilogue_bar();
 }
 
-template <int N_TILE, int PA, int PB>
+template <int N_TILE, int PA, int PB, bool CTA2 = false>
 struct ConvGemmCfg {
-  static constexpr int kBBytes = N_TILE * kBlockK * 2;
+  // CTA2: a pair of CTAs (cluster of 2, cta_group::2) runs M = 256 instructions; each CTA stages its own 128 pixels of
+  // A and HALF of the rows of every B (weight) tile, so the weight traffic from L2 per CTA halves (the kernels are bound
+  // by the L2 -> SM operand bandwidth, not by the tensor pipe)
+  static constexpr int kBBytes = N_TILE * kBlockK * 2 / (CTA2 ? 2 : 1);
   static constexpr int kStageBytes = PA * kATileBytes + PB * kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -268,7 +275,9 @@ struct ConvGemmCfg {
   // stage: ONE instruction with N = 2*N_TILE computes A*[B_hi;B_lo]^T into two N_TILE-column halves that the epilogue
   // adds ("stacked" mode).  64-wide tiles: both A planes are stacked (N = 128, picks up the tiny lo*lo term);
   // 128-wide tiles: A_hi is stacked (N = 256) and A_lo multiplies B_hi only (N = 128).
-  static constexpr bool kStack = (PB == 2 && N_TILE <= 128);
+  // A CTA pair splits the N dimension of an instruction between the two CTAs' shared memories, which scrambles the
+  // column order of a stacked operand: pairs issue one instruction per operand-plane combination into natural columns.
+  static constexpr bool kStack = (PB == 2 && N_TILE <= 128 && !CTA2);
   static constexpr int kUmmaN = kStack ? 2 * N_TILE : N_TILE;
   static constexpr int kTmemCols = 2 * kUmmaN;
   // instructions per K = 16 step: stacked -> one per A plane; otherwise (a0,b0), (a0,b1) if PB == 2, (a1,b0) if PA == 2
@@ -276,9 +285,9 @@ struct ConvGemmCfg {
   static_assert(kStages >= 2, "stage does not fit twice into shared memory");
 };
 
-template <int N_TILE, int PA, int PB>
+template <int N_TILE, int PA, int PB, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
-  using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
+  using Cfg = ConvGemmCfg<N_TILE, PA, PB, CTA2>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by an OFFSET from the __shared__ array (a round trip through uintptr_t makes the compiler lose
@@ -298,6 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   // the single issuing thread, not the tensor pipe, the bottleneck)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (the leader) owns the full / accumulator-empty barriers and issues the MMAs of both CTAs
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
 #pragma unroll
@@ -312,27 +323,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();  // pair: the peer's barriers must be initialised before any use
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_wait();    // everything above overlapped the predecessor's tail
   griddep_launch();
 
-  const int total_super = p.ng * p.n_tapgroups * p.rows * p.n_tiles;
+  // Schedule: a pair works on two super-tiles that differ only in their row (r = 2q + rank): same group, tap group and
+  // N tile, hence the same weight tiles and the same number of pipeline stages, in lockstep.
+  const int sched_rows = CTA2 ? p.rows / 2 : p.rows;
+  const int total_super = p.ng * p.n_tapgroups * sched_rows * p.n_tiles;
+  const int sched_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     int s = 0;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < total_super; u += gridDim.x) {
-      const SuperTile sp = decode_super(p, u, total_super);
-      const int b_row = sp.j * N_TILE + sp.mg * p.b_group_rows;
+    for (int u = sched_first; u < total_super; u += sched_step) {
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
+      // a pair splits every weight tile: this CTA fetches rows [rank * N_TILE/2, +N_TILE/2) of it
+      const int b_row = sp.j * N_TILE + sp.mg * p.b_group_rows + (CTA2 ? (int)rank * (N_TILE / 2) : 0);
       const int tap0 = p.group_tap0[sp.tg], tap1 = tap0 + p.group_taps[sp.tg];
       for (int m = sp.r; m < p.mtg; m += p.rows) {
         int n0, h0;
@@ -343,15 +362,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&empty_bar[s], phase ^ 1, 1);
             if (elect_one()) {
               uint8_t* st = smem + s * Cfg::kStageBytes;
-              mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+              if (CTA2) {
+                // both CTAs' bytes are counted on the LEADER's full barrier (it issues the MMAs of the pair)
+                const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
 #pragma unroll
-              for (int pl = 0; pl < PA; ++pl)
-                tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
-                            h0 + tap.dh, n0);
+                for (int pl = 0; pl < PA; ++pl)
+                  tma_load_4d_pair(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], bar, cb * kBlockK, tap.dw,
+                                   h0 + tap.dh, n0);
 #pragma unroll
-              for (int pl = 0; pl < PB; ++pl)
-                tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
-                            tap.b_k0 + cb * kBlockK, b_row);
+                for (int pl = 0; pl < PB; ++pl)
+                  tma_load_2d_pair(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], bar,
+                                   tap.b_k0 + cb * kBlockK, b_row);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+#pragma unroll
+                for (int pl = 0; pl < PA; ++pl)
+                  tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
+                              h0 + tap.dh, n0);
+#pragma unroll
+                for (int pl = 0; pl < PB; ++pl)
+                  tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
+                              tap.b_k0 + cb * kBlockK, b_row);
+              }
             }
             __syncwarp();
             if (++s == STAGES) {
@@ -362,8 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1 && rank == 0) {
+    // ---------------- MMA issuer (of a pair: the leader CTA only) ----------------
     // A tcgen05.mma blocks its issuing thread until the tensor pipe has taken it, and nothing that thread executes
     // between two MMAs overlaps with them (every instruction between two MMAs adds its full latency).  The role
     // therefore runs warp-converged with an elected lane, so that the descriptors live in uniform registers and the
@@ -376,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     constexpr bool kNarrowLo = Cfg::kStack && PA == 2;
     auto ap_of = [](int c) { return (PA == 2 && c == 0) ? 1 : 0; };
     auto bp_of = [](int c) { return (!Cfg::kStack && PB == 2 && c == kC - 1) ? 1 : 0; };
-    constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, Cfg::kUmmaN, 0, 0);
-    constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+    constexpr uint32_t idesc_full = make_idesc_bf16(CTA2 ? 2 * kTileM : kTileM, Cfg::kUmmaN, 0, 0);
+    constexpr uint32_t idesc_half = make_idesc_bf16(CTA2 ? 2 * kTileM : kTileM, N_TILE, 0, 0);
     const uint32_t smem0 = smem_u32(smem);
     auto issue_stage = [&](uint32_t tmem_d, int st, int ki) {
       const uint32_t a_lo = smem_desc_lo(smem0 + st * Cfg::kStageBytes, 16);
@@ -385,18 +418,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
       for (int c = 0; c < kC; ++c) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          tc_mma_bf16_lohi(tmem_d, a_lo + ((ap_of(c) * kATileBytes + k * 32) >> 4),
-                           b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4), desc_hi, desc_hi,
-                           (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full, (ki | c | k) != 0);
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint32_t da = a_lo + ((ap_of(c) * kATileBytes + k * 32) >> 4);
+          const uint32_t db = b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4);
+          const uint32_t idesc = (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full;
+          if (CTA2) tc_mma2_bf16_lohi(tmem_d, da, db, desc_hi, desc_hi, idesc, (ki | c | k) != 0);
+          else tc_mma_bf16_lohi(tmem_d, da, db, desc_hi, desc_hi, idesc, (ki | c | k) != 0);
+        }
       }
-      tc_commit(&empty_bar[st]);
+      if (CTA2) tc_commit2(&empty_bar[st]); else tc_commit(&empty_bar[st]);  // pair: frees the stage in BOTH CTAs
     };
     int s = 0;
     uint32_t phase = 0;
     int tile_i = 0;
-    for (int u = blockIdx.x; u < total_super; u += gridDim.x) {
-      const SuperTile sp = decode_super(p, u, total_super);
+    for (int u = sched_first; u < total_super; u += sched_step) {
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
       const int k_iters = p.group_taps[sp.tg] * p.cblocks;
       for (int m = sp.r; m < p.mtg; m += p.rows, ++tile_i) {
         const int buf = tile_i & 1;
@@ -416,7 +452,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (elect_one()) {
             issue_stage(tmem_d, s, ki);
             if (pair) issue_stage(tmem_d, s1, ki + 1);
-            if (ki + 2 >= k_iters) tc_commit(&acc_full[buf]);
+            if (ki + 2 >= k_iters) {
+              if (CTA2) tc_commit2(&acc_full[buf]); else tc_commit(&acc_full[buf]);
+            }
           }
           __syncwarp();
           if (pair) {
@@ -450,8 +488,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int j = 0; j < 8; ++j) col_acc[cc][j] = 0.f;
     const bool do_stat = p.stats != nullptr;
     int tile_i = 0;
-    for (int u = blockIdx.x; u < total_super; u += gridDim.x) {
-      const SuperTile sp = decode_super(p, u, total_super);
+    for (int u = sched_first; u < total_super; u += sched_step) {
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
       const int n_tile0 = sp.j * N_TILE;
       for (int m = sp.r; m < p.mtg; m += p.rows, ++tile_i) {
         int n0, h0;
@@ -481,7 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));  // the leader waits for both CTAs
+          else mbar_arrive(&acc_empty[buf]);
+        }
       }
       if (do_stat) {
         // partial row of this super-tile, then a ticket: the last CTA of the (group, N tile) finalises its BatchNorm
@@ -503,32 +544,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
-}
-
-template <int N_TILE, int PA, int PB>
-static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<N_TILE, PA, PB>;
-  static bool configured = false;
-  if (!configured) {
-    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
-    configured = true;
+  if (CTA2) cluster_sync_all(); else __syncthreads();  // pair: no CTA may leave while its peer can still signal it
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
-  const int total_super = kp.ng * kp.n_tapgroups * kp.rows * kp.n_tiles;
-  const int grid = total_super < kNumSMs ? total_super : kNumSMs;
-  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
-  return 0;
-}
-
-template <int N_TILE>
-static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStream_t stream) {
-  if (pa == 2 && pb == 2) return launch_conv_gemm<N_TILE, 2, 2>(kp, stream);
-  if (pa == 1 && pb == 2) return launch_conv_gemm<N_TILE, 1, 2>(kp, stream);
-  if (pa == 1 && pb == 1) return launch_conv_gemm<N_TILE, 1, 1>(kp, stream);
-  set_error("fb_conv_gemm: unsupported operand planes (%d, %d)", pa, pb);
-  return FB_ERR_UNSUPPORTED;
 }
 
 // Super-tile rows per (group, N tile).  At most one row per CTA of a wave (148 / n_tiles); if the group has more M tiles
@@ -542,6 +561,73 @@ static int stats_rows(int m_tiles_per_group, int n_tiles) {
   for (int d = cap; 4 * d >= 3 * cap; --d)
     if (m_tiles_per_group % d == 0) return d;
   return cap;
+}
+
+static bool cta_pairs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FB_CTA2");  // FB_CTA2=0: single-CTA tiles everywhere
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int N_TILE, int PA, int PB>
+static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
+  if (kp.cta_pair) {
+    using Cfg = ConvGemmCfg<N_TILE, PA, PB, true>;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kNumSMs & ~1);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      FB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<N_TILE, PA, PB, true>, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    const int total = kp.ng * kp.n_tapgroups * (kp.rows / 2) * kp.n_tiles;
+    int clusters = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
+    if (clusters > total) clusters = total;
+    FB_CUDA(launch_cluster(conv_gemm_kernel<N_TILE, PA, PB, true>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes,
+                           stream, 2u, kp));
+    return 0;
+  }
+  using Cfg = ConvGemmCfg<N_TILE, PA, PB, false>;
+  static bool configured = false;
+  if (!configured) {
+    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int total_super = kp.ng * kp.n_tapgroups * kp.rows * kp.n_tiles;
+  const int grid = total_super < kNumSMs ? total_super : kNumSMs;
+  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB, false>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
+  return 0;
+}
+
+// CTA pairs need two rows of the same (group, tap group, N tile) with equally many tiles each
+static bool pair_ok(int m_tiles_per_group, int n_tiles) {
+  if (!cta_pairs_enabled() || m_tiles_per_group <= 0 || n_tiles <= 0) return false;
+  const int rows = stats_rows(m_tiles_per_group, n_tiles);
+  return rows % 2 == 0 && m_tiles_per_group % rows == 0;
+}
+
+template <int N_TILE>
+static int dispatch_conv_gemm(const ConvGemmKParams& kp, int pa, int pb, cudaStream_t stream) {
+  if (pa == 2 && pb == 2) return launch_conv_gemm<N_TILE, 2, 2>(kp, stream);
+  if (pa == 1 && pb == 2) return launch_conv_gemm<N_TILE, 1, 2>(kp, stream);
+  if (pa == 1 && pb == 1) return launch_conv_gemm<N_TILE, 1, 1>(kp, stream);
+  set_error("fb_conv_gemm: unsupported operand planes (%d, %d)", pa, pb);
+  return FB_ERR_UNSUPPORTED;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1080,6 +1166,8 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.ng = ng;
   kp.b_group_rows = a->b_group_rows;
   kp.reverse = a->reverse ? 1 : 0;
+  kp.cta_pair = a->cta_pair ? 1 : 0;
+  FB_REQUIRE(!kp.cta_pair || pair_ok(mtg, kp.n_tiles), "fb_conv_gemm: this problem cannot run as CTA pairs");
   kp.out = a->out;
   kp.out_sn = a->out_sn;
   kp.out_sh = a->out_sh;
@@ -1125,6 +1213,7 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
 }
 
 extern "C" int fb_conv_stats_rows(int m_tiles_per_group, int n_tiles) { return stats_rows(m_tiles_per_group, n_tiles); }
+extern "C" int fb_conv_pair_ok(int m_tiles_per_group, int n_tiles) { return pair_ok(m_tiles_per_group, n_tiles) ? 1 : 0; }
 
 extern "C" int fb_conv_wgrad(const fb_wgrad_args* a, void* stream) {
   FB_REQUIRE(a && a->host_dy_map && a->host_x_maps && a->out, "fb_conv_wgrad: null pointer");

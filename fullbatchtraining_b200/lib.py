@@ -38,7 +38,8 @@ class ConvGemmArgs(C.Structure):
                 ("tile_n", i32), ("grid_h", i32), ("grid_n", i32), ("n_total", i32), ("n_tile", i32), ("out", vp),
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("n_tapgroups", i32),
                 ("tapgroups", TapGroup * 4), ("mg_imgs", i32), ("ng", i32), ("b_group_rows", i32), ("reverse", i32),
-                ("stats_ws", vp), ("tickets", vp), ("bn_mean", vp), ("bn_rstd", vp), ("bn_batch", vp), ("bn_eps", f32)]
+                ("stats_ws", vp), ("tickets", vp), ("bn_mean", vp), ("bn_rstd", vp), ("bn_batch", vp), ("bn_eps", f32),
+                ("cta_pair", i32)]
 
 
 class WgradTap(C.Structure):
@@ -91,6 +92,7 @@ _SIGNATURES = {
     "fb_tmap_encode_mat2d": ([vp, vp, i32, i32, i64, i32, i32], i32),
     "fb_conv_gemm": ([C.POINTER(ConvGemmArgs), vp], i32),
     "fb_conv_stats_rows": ([i32, i32], i32),
+    "fb_conv_pair_ok": ([i32, i32], i32),
     "fb_conv_wgrad": ([C.POINTER(WgradArgs), vp], i32),
     "fb_reduce_multi": ([vp, i32, i32, vp, i64, i32, vp], i32),
     "fb_weight_prep": ([vp, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp], i32),

@@ -143,7 +143,7 @@ class ConvGemm:
     """One fb_conv_gemm problem with frozen descriptors; __call__(ng) launches it for the first ng groups."""
 
     def __init__(self, a_maps, b_maps, n_phases, a_planes, b_planes, taps, cblocks, tile, grid_h, mb, n_total, out,
-                 out_strides, accumulate, n_tile, b_group_rows=0, tapgroups=None, reverse=False):
+                 out_strides, accumulate, n_tile, b_group_rows=0, tapgroups=None, reverse=False, cta_pair=False):
         """tapgroups: optional [(tap0, n_taps, out_off_elements)] -- tap groups that run over the same pixel grid and
         write to different offsets (the four output phases of a stride-2 dgrad in one launch)."""
         self.a_maps, self.b_maps = a_maps, b_maps
@@ -169,6 +169,7 @@ class ConvGemm:
             for i, (tap0, n_taps, off) in enumerate(tapgroups):
                 args.tapgroups[i] = L.TapGroup(tap0, n_taps, off)
         args.mg_imgs = mb
+        args.cta_pair = int(cta_pair)
         args.b_group_rows = b_group_rows
         args.reverse = int(reverse)
         self.mb = mb
@@ -210,7 +211,7 @@ class Conv2dPlan:
     """
 
     def __init__(self, mb, G, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wsets, w_offset, split=True, alg_k=None,
-                 grad_cols=None, bn=None):
+                 grad_cols=None, bn=None, allow_pair=True):
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.mb, self.G, self.h, self.w, self.cin, self.cout, self.k, self.stride = mb, G, h, w, cin, cout, k, stride
@@ -258,15 +259,19 @@ class Conv2dPlan:
                 phase, dh, dw = tap_geom(kh, kw)
                 ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
         self.fwd = []
+        # CTA pairs (M = 256 tiles over two SMs): each CTA fetches half of every weight tile -> half-height B boxes
+        pair = self._use_pair(allow_pair, mtg, cout, n_tile, planes)
+        self.pair_fwd = pair
         for si, (wf_hi, wf_lo, _, _) in enumerate(wsets):
             bs = MapSet(wplanes)
             rows = cout * (G if si == 1 else 1)
             for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
-                encode_mat(bs, pl, t, taps * cin, rows, n_tile)
+                encode_mat(bs, pl, t, taps * cin, rows, n_tile // 2 if pair else n_tile)
             g = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
-                         (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0)
+                         (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0,
+                         cta_pair=pair)
             g.flops_per_group = self.alg_flops
-            g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}"
+            g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}{' pair' if pair else ''}"
             self.fwd.append(g)
         # BatchNorm statistics fused into the forward epilogue
         self.stat_rows = L.load().fb_conv_stats_rows(mtg, cout // n_tile)
@@ -308,15 +313,17 @@ class Conv2dPlan:
                                 dtaps.append((0, dh, dw, (kh * 3 + kw) * cout))
                         tapgroups.append((tap0, len(dtaps) - tap0, (ph * w + pw) * cin))
                 strides = (h * w * cin, 2 * w * cin, 2 * cin)
+            pair_d = self._use_pair(allow_pair, mtg, cin, n_tile_d, 1)
+            self.pair_dgrad = pair_d
             for si, (_, _, wd_hi, wd_lo) in enumerate(wsets):
                 ds = MapSet(wplanes)
                 rows = cin * (G if si == 1 else 1)
                 for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
-                    encode_mat(ds, pl, t, taps * cout, rows, n_tile_d)
+                    encode_mat(ds, pl, t, taps * cout, rows, n_tile_d // 2 if pair_d else n_tile_d)
                 g = ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, mb, cin, dx, strides, False, n_tile_d,
-                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups)
+                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups, cta_pair=pair_d)
                 g.flops_per_group = self.alg_flops
-                g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}"
+                g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}{' pair' if pair_d else ''}"
                 self.dgrads.append(g)
 
         # ---- wgrad
@@ -364,6 +371,19 @@ class Conv2dPlan:
         self.direct = self.splits == 1 and self.grad_cols == self.k_ld
         self.partial = None
         self.wargs = wa
+
+    @staticmethod
+    def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes):
+        """CTA pairs (fb_conv_gemm_args.cta_pair) where they pay: a pair cannot stack the hi / lo weight planes into one
+        wide instruction, so it only wins where nothing is stacked anyway (256-wide tiles) or where the stacked
+        instruction is replaced one for one (single-plane A operand = dgrad, 128-wide tiles).  Measured on B200
+        (profiles/r2_cta_pairs.txt): 4x4x512 forward 215 -> 166 us, 16x16x128 dgrad 117 -> 106 us, but 32x32x64 forward
+        258 -> 289 us.  allow_pair = "force": wherever the schedule allows (tests)."""
+        if not allow_pair or not L.load().fb_conv_pair_ok(mtg, n_total // n_tile):
+            return False
+        if allow_pair == "force" or os.environ.get("FB_PAIR_ALL") == "1":
+            return True
+        return n_tile == 256 or (a_planes == 1 and n_tile == 128)
 
     @staticmethod
     def wgrad_splits(pixel_blocks_per_group, co_tiles, slot_groups):

@@ -113,9 +113,16 @@ typedef struct {
   uint32_t* tickets;
   float *bn_mean, *bn_rstd, *bn_batch;
   float bn_eps;
+  /* CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: M = 256 tiles over two SMs, each CTA fetches half of
+   * every weight tile).  1: the B maps were encoded with boxes of n_tile / 2 rows and the launch uses pairs; only valid
+   * where fb_conv_pair_ok(...) says so (a function of ONE group's problem: results stay independent of ng).  A pair
+   * accumulates all operand-plane products in one accumulator: same products, another fp32 order than single-CTA tiles. */
+  int32_t cta_pair;
 } fb_conv_gemm_args;
 /* partial rows per (group, N tile) written to stats_ws for m_tiles_per_group x n_tiles tiles per group */
 int fb_conv_stats_rows(int m_tiles_per_group, int n_tiles);
+/* 1 if a problem with this many 128-pixel tiles per group and N tiles can run as CTA pairs (FB_CTA2=0 disables) */
+int fb_conv_pair_ok(int m_tiles_per_group, int n_tiles);
 int fb_conv_gemm(const fb_conv_gemm_args* args, void* stream);
 
 typedef struct {

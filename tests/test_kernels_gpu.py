@@ -43,7 +43,8 @@ def rel_err(a, b):
 class ConvCase:
     """A Conv2dPlan over G groups of mb images with one shared weight and G per-group weights."""
 
-    def __init__(self, mb, G, h, w, cin, cout, k, stride, use_split, seed=0, dx=True, x=None, weights=None, gy=None):
+    def __init__(self, mb, G, h, w, cin, cout, k, stride, use_split, seed=0, dx=True, x=None, weights=None, gy=None,
+                 allow_pair=True):
         g = torch.Generator(device="cuda").manual_seed(seed)
         n = G * mb
         self.mb, self.G, self.cin, self.cout, self.k, self.stride, self.h, self.w = mb, G, cin, cout, k, stride, h, w
@@ -78,7 +79,7 @@ class ConvCase:
         self.rstd = torch.zeros(G, cout, device=DEV)
         self.bn_batch = torch.zeros(G, 2, cout, device=DEV)
         self.plan = ops.Conv2dPlan(mb, G, h, w, cin, cout, k, stride, x_hi, x_lo, self.y, self.dy, self.dx, wsets, 0,
-                                   split=use_split, bn=(self.mean, self.rstd, EPS))
+                                   split=use_split, bn=(self.mean, self.rstd, EPS), allow_pair=allow_pair)
         self.use_split = use_split
         self.gstride = (cout * taps * cin + 63) // 64 * 64
         self.gbuf = torch.full((G, self.gstride), float("nan"), device=DEV)
@@ -218,6 +219,35 @@ def test_groups_are_independent_bit_for_bit(case):
     c.plan.forward(1, 1, c.bn_batch.data_ptr())
     torch.cuda.synchronize()
     assert torch.isfinite(c.y[:mb]).all() and torch.isnan(c.y[mb:]).all()
+
+
+@pytest.mark.parametrize("case", [(8, 3, 32, 32, 64, 64, 3, 1), (8, 2, 16, 16, 128, 128, 3, 1), (16, 2, 8, 8, 256, 512, 3, 2),
+                                  (16, 3, 4, 4, 512, 512, 3, 1), (8, 2, 16, 16, 64, 256, 1, 1), (4, 2, 32, 32, 64, 128, 3, 2)],
+                         ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("use_split", [True, False], ids=["split", "bf16"])
+def test_cta_pairs_match_single_cta_tiles(case, use_split):
+    """tcgen05 cta_group::2 (M = 256 tiles over two SMs, half a weight tile per CTA) against the single-CTA launch of the
+    same problem: forward with statistics and dgrad, shared and per-group weights.  Plain-bf16 operands: bit for bit.
+    Split operands: the single-CTA kernel accumulates the hi and lo weight planes in two accumulators that the epilogue
+    adds, a pair accumulates all products in one -- the same products in another fp32 order (2e-5 of the output scale)."""
+    mb, G, h, w, cin, cout, k, stride = case
+    a = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair="force")
+    b = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair=False)
+    assert a.plan.pair_fwd and not b.plan.pair_fwd, "the case is meant to exercise CTA pairs"
+    for wset in (0, 1):
+        for c in (a, b):
+            c.y.fill_(float("nan"))
+            c.dx.fill_(float("nan"))
+            c.plan.forward(G, wset, c.bn_batch.data_ptr())
+            c.plan.dgrad(G, wset)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a.y).all() and torch.isfinite(a.dx).all()
+        if use_split:
+            assert rel_err(a.y, b.y) < 2e-5 and rel_err(a.dx, b.dx) < 2e-5  # fp32 sums of up to 4,608 x 3 products
+            assert float((a.mean - b.mean).abs().max()) < 1e-6 * float(b.y.abs().max()) and rel_err(a.rstd, b.rstd) < 1e-5
+        else:
+            assert torch.equal(a.y, b.y) and torch.equal(a.dx, b.dx)
+            assert torch.equal(a.mean, b.mean) and torch.equal(a.rstd, b.rstd) and torch.equal(a.bn_batch, b.bn_batch)
 
 
 def test_weight_prep_layouts():
