@@ -112,7 +112,8 @@ class Unit:
         dx = (dx_target if dx_target is not None else x.grad) if needs_dx else None
         self.plan = ops.Conv2dPlan(eng.mb, G, h, w, x.c, cout, k, stride, x.hi, x.lo, self.y, self.dy, dx, self.w,
                                    self.w_offset, split=split, alg_k=27 if stem else None,
-                                   grad_cols=27 if stem else None, bn=(self.mean, self.rstd, BN_EPS))
+                                   grad_cols=27 if stem else None, bn=(self.mean, self.rstd, BN_EPS),
+                                   policy_groups=eng.policy_groups)
         self.out = None
 
     def bn_batch_ptr(self, pass_idx):
@@ -137,7 +138,8 @@ class FullBatchEngine:
     groups:    microbatches per launch (1..16; default ~1024 images); a pure performance knob, results do not depend on it.
     """
 
-    def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None, groups=None):
+    def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None, groups=None,
+                 policy_groups=None):
         if not isinstance(model, ResNet):
             raise RuntimeError("FullBatchEngine needs a model built by fullbatchtraining_b200.construct_model "
                                "(there is no fallback path)")
@@ -151,6 +153,9 @@ class FullBatchEngine:
         self.G = int(groups) if groups else default_groups(self.mb)
         if not 1 <= self.G <= L.FB_MAX_GROUPS:
             raise ValueError(f"groups must be in 1..{L.FB_MAX_GROUPS}")
+        # launches are tuned for `policy_groups` microbatches (default ops.POLICY_GROUPS = 8; the stochastic branch, which
+        # only ever launches one, passes 1).  Fixed per engine, independent of G: results do not depend on G.
+        self.policy_groups = int(policy_groups or ops.POLICY_GROUPS)
         self.split = precision == "split"
         self.precision = precision
         self.smoothing = float(label_smoothing)
@@ -239,7 +244,8 @@ class FullBatchEngine:
                 entries.append(u.plan.bind_partial(self.partial[o:o + pe]))
                 o += pe
         self.reduce = ops.ReduceTable(entries, dev) if entries else None
-        self.bn_ws = torch.zeros(max(ops.bn_bwd_ws_floats(u.Pg, u.cout, G) for u in self.units), device=dev)
+        self.bn_ws = torch.zeros(max(ops.bn_bwd_ws_floats(u.Pg, u.cout, G, self.policy_groups) for u in self.units),
+                                 device=dev)
         self.head_ws = torch.zeros(ops.head_ws_floats(n, cur.c), device=dev)
         self.wprep = []
         for i in range(2):
@@ -361,7 +367,7 @@ class FullBatchEngine:
         ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
                    gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
                    param_gstride=pstride, grad_gstride=self.stride, reverse=rev,
-                   mask_bits=act.mask if self.bit_masks else None)
+                   mask_bits=act.mask if self.bit_masks else None, policy_groups=self.policy_groups)
         # wgrad only feeds the flat gradient.  wgrad_mode 1 / 2: on a side stream, forked before / after the dgrad of the
         # same layer (2: the tensor-bound wgrad then runs next to the bandwidth-bound BatchNorm backward of the layer
         # below instead of next to its own dgrad); joined at the end of the backward pass

@@ -211,10 +211,12 @@ class Conv2dPlan:
     """
 
     def __init__(self, mb, G, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wsets, w_offset, split=True, alg_k=None,
-                 grad_cols=None, bn=None, allow_pair=True):
+                 grad_cols=None, bn=None, allow_pair=True, policy_groups=None):
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.mb, self.G, self.h, self.w, self.cin, self.cout, self.k, self.stride = mb, G, h, w, cin, cout, k, stride
+        # number of groups per launch the geometry is tuned for (never the ng of a launch: results must not depend on it)
+        policy = int(policy_groups or POLICY_GROUPS)
         n = G * mb
         ho, wo = h // stride, w // stride
         self.ho, self.wo = ho, wo
@@ -251,7 +253,7 @@ class Conv2dPlan:
             return ph * 2 + pw, dh, dw
 
         # ---- forward (one ConvGemm per weight set)
-        n_tile = choose_n_tile(mtg * POLICY_GROUPS, cout, planes, wplanes)
+        n_tile = choose_n_tile(mtg * policy, cout, planes, wplanes)
         self.n_tile = n_tile
         ftaps = []
         for kh in range(k):
@@ -290,7 +292,7 @@ class Conv2dPlan:
             encode_act(dys, 0, dy, n, ho, wo, cout, tile)
             self.dy_maps_d = dys
             m_tiles_d = mtg * (4 if stride == 2 else 1)  # the four output phases of a stride-2 dgrad share one launch
-            n_tile_d = choose_n_tile(m_tiles_d * POLICY_GROUPS, cin, 1, wplanes)
+            n_tile_d = choose_n_tile(m_tiles_d * policy, cin, 1, wplanes)
             if stride == 1:
                 dtaps, tapgroups = [], None
                 for kh in range(k):
@@ -358,7 +360,7 @@ class Conv2dPlan:
         wa.host_dy_map = dym.addr
         wa.planes = planes
         wa.n_taps, wa.cblocks = taps, cb_in
-        self.splits = self.wgrad_splits(mtg, co_tiles, -(-n_slots // spc))
+        self.splits = self.wgrad_splits(mtg, co_tiles, -(-n_slots // spc), policy)
         wa.slots_per_cta = spc
         wa.cout, wa.cin = cout, cin
         wa.tile_w, wa.tile_h, wa.tile_n = tile
@@ -386,9 +388,9 @@ class Conv2dPlan:
         return n_tile == 256 or (a_planes == 1 and n_tile == 128)
 
     @staticmethod
-    def wgrad_splits(pixel_blocks_per_group, co_tiles, slot_groups):
-        """split-K of ONE group's pixel blocks so that POLICY_GROUPS groups fill one wave of the 148 SMs"""
-        ctas = co_tiles * slot_groups * POLICY_GROUPS
+    def wgrad_splits(pixel_blocks_per_group, co_tiles, slot_groups, policy_groups=None):
+        """split-K of ONE group's pixel blocks so that `policy_groups` groups fill one wave of the 148 SMs"""
+        ctas = co_tiles * slot_groups * int(policy_groups or POLICY_GROUPS)
         return max(1, min(pixel_blocks_per_group, NUM_SMS // ctas))
 
     @staticmethod
@@ -559,15 +561,15 @@ def bn_apply(y, mean, rstd, gamma, beta, P, Cc, out_hi, out_lo, relu=True, secon
           label=f"bn_apply P{P} C{Cc} {per_elem:.0f}B/elem")
 
 
-def bn_bwd_ws_floats(P, Cc, G):
-    chunks = L.load().fb_bn_bwd_chunks(P, Cc, POLICY_GROUPS)
+def bn_bwd_ws_floats(P, Cc, G, policy_groups=None):
+    chunks = L.load().fb_bn_bwd_chunks(P, Cc, int(policy_groups or POLICY_GROUPS))
     if chunks <= 0:
         raise RuntimeError(f"fb_bn_bwd does not support {Cc} channels")
     return 16 + G * (2 * Cc * chunks + 2 * Cc)
 
 
 def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_out=None, dA2=None, ng=1, param_gstride=0,
-           grad_gstride=0, reverse=False, mask_bits=None):
+           grad_gstride=0, reverse=False, mask_bits=None, policy_groups=None):
     """gamma / dgamma / dbeta: pointers (ints) or tensors, + g*param_gstride / g*grad_gstride per group;
     mask_bits: the bit plane written by bn_apply (mask_out), used instead of the bf16 plane mask_hi"""
     def p(t):
@@ -580,7 +582,7 @@ def bn_bwd(dA, mask_hi, y, mean, rstd, gamma, P, Cc, ws, dgamma, dbeta, dy, dz_o
     a.dgamma, a.dbeta, a.dy_bf16 = p(dgamma), p(dbeta), dy.data_ptr()
     a.dz_out = L.ptr(dz_out)
     a.ng, a.param_gstride, a.grad_gstride = ng, param_gstride, grad_gstride
-    a.policy_groups, a.reverse = POLICY_GROUPS, int(reverse)
+    a.policy_groups, a.reverse = int(policy_groups or POLICY_GROUPS), int(reverse)
     a.mask_bits = L.ptr(mask_bits)
     # distinct tensors: dA, y (+ mask) in; dy (+ dz) out -- each counted once although the two launches read twice
     mask_bytes = 0.125 if mask_bits is not None else (2.0 if mask_hi is not None else 0.0)

@@ -153,7 +153,8 @@ class Trainer:
         loss_fn = get_loss_fn(hyp, cfg.data.batch_size)
         self.engine = FullBatchEngine(model, self.mb, precision=cfg.impl.get("precision", "split"),
                                       label_smoothing=loss_fn.smoothing, device=self.device,
-                                      groups=1 if self.stochastic else cfg.impl.get("groups", None))
+                                      groups=1 if self.stochastic else cfg.impl.get("groups", None),
+                                      policy_groups=1 if self.stochastic else None)
         self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps

