@@ -45,7 +45,9 @@ _DEFAULT = dict(
               # B200-path switches: keep the dataset in HBM when the loader wraps a TensorDataset; fused clip+SGD sweep
               resident_dataset=True, fused_optimizer=True, kernel_evaluate=True,
               # microbatches per kernel launch (None: ~1024 images per launch); results do not depend on it
-              groups=None),
+              groups=None,
+              # concurrent lanes of group launches (None: 2 if the buffers fit); results do not depend on it either
+              lanes=None),
     hyp=dict(template_name="fbgradreg", train_stochastic=False, shuffle=False, steps=3000, sub_batch=128,
              optim=dict(name="Gradient Descent", lr=0.8, momentum=0.9, weight_decay=5e-4, dampening=0.0, nesterov=True,
                         line_search="none"),

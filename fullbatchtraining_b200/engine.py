@@ -32,6 +32,7 @@ theta itself is never modified by the regulariser, so the reference's "restore f
 exact by construction.
 """
 import os
+import weakref
 
 import torch
 
@@ -86,6 +87,7 @@ class Unit:
 
     def __init__(self, eng, conv_name, bn_name, x, cout, k, stride, needs_dx=True, stem=False, dx_target=None):
         dev, split, G = eng.device, eng.split, eng.G
+        shared = eng.root.unit_by_name.get(conv_name) if eng.root is not eng else None
         self.conv_name, self.bn_name, self.x, self.stem = conv_name, bn_name, x, stem
         self.cin, self.cout, self.k, self.stride = x.c, cout, k, stride
         n, h, w = x.n, x.h, x.w
@@ -101,7 +103,10 @@ class Unit:
         bf = dict(device=dev, dtype=torch.bfloat16)
         # bf16 GEMM operands: [0] from theta (refreshed once per step), [1] of the G perturbed points (every launch)
         self.w = []
-        for rows in (1, G):
+        for si, rows in enumerate((1, G)):
+            if si == 0 and shared is not None:  # the operands of theta are the same for every lane
+                self.w.append(shared.w[0])
+                continue
             self.w.append((torch.zeros(rows * cout, taps * x.c, **bf),
                            torch.zeros(rows * cout, taps * x.c, **bf) if split else None,
                            torch.zeros(rows * x.c, taps * cout, **bf) if needs_dx else None,
@@ -115,6 +120,7 @@ class Unit:
                                    grad_cols=27 if stem else None, bn=(self.mean, self.rstd, BN_EPS),
                                    policy_groups=eng.policy_groups)
         self.out = None
+        eng.unit_by_name[conv_name] = self
 
     def bn_batch_ptr(self, pass_idx):
         return self.bn_batch.data_ptr() + pass_idx * self.bn_batch.stride(0) * 4
@@ -136,10 +142,15 @@ class FullBatchEngine:
                            2 dgrad, 2 wgrad; ~16 mantissa bits per operand): the parity mode;
                "bf16"   -- plain bf16 operands (1 MMA each): the fast mode, cannot resolve the FD perturbation.
     groups:    microbatches per launch (1..16; default ~1024 images); a pure performance knob, results do not depend on it.
+    lanes:     independent sets of activation / gradient buffers (default 2 if they fit): consecutive group launches
+               alternate between the lanes on separate streams, so the tensor-bound kernels of one launch overlap the
+               bandwidth-bound kernels of the other; the order-sensitive tail of every launch (finite-difference
+               combine, running mean, running-statistics EMA) runs on the main stream in loader order, so the result is
+               bit-identical to one lane.
     """
 
     def __init__(self, model, microbatch, precision="split", label_smoothing=0.0, device=None, groups=None,
-                 policy_groups=None):
+                 policy_groups=None, lanes=None, _parent=None):
         if not isinstance(model, ResNet):
             raise RuntimeError("FullBatchEngine needs a model built by fullbatchtraining_b200.construct_model "
                                "(there is no fallback path)")
@@ -148,7 +159,15 @@ class FullBatchEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("FullBatchEngine needs a CUDA device (B200); there is no CPU path")
         self.device = torch.device(device or "cuda")
-        self.model = model.to(self.device, torch.float32)
+        # lane 0 ("root") owns everything the lanes share; further lanes only hold a weak reference to it, so an engine
+        # is released by reference counting (its buffers are tens of GB: it must not wait for the cycle collector)
+        self._parent = weakref.ref(_parent) if _parent is not None else None
+        self._children = []
+        self.unit_by_name = {}
+        if _parent is None:
+            torch.cuda.synchronize(self.device)
+            mem0 = torch.cuda.memory_allocated(self.device)
+        self.model = model if _parent is not None else model.to(self.device, torch.float32)
         self.mb = int(microbatch)
         self.G = int(groups) if groups else default_groups(self.mb)
         if not 1 <= self.G <= L.FB_MAX_GROUPS:
@@ -163,29 +182,35 @@ class FullBatchEngine:
         dev, G = self.device, self.G
 
         # ---- flat parameter buffers, parameters() order
-        self.names, self.offsets, self.shapes = [], {}, {}
-        off = 0
-        for name, p in self.model.named_parameters():
-            self.names.append(name)
-            self.offsets[name] = off
-            self.shapes[name] = tuple(p.shape)
-            off += p.numel()
-        self.numel = off
-        self.stride = (off + 63) // 64 * 64  # elements between the flat buffers of consecutive groups
-        self.theta = torch.zeros(self.stride, device=dev)[:off]
+        if _parent is not None:  # a further lane: parameters, running mean and the boundary buffers are lane 0's
+            r = _parent
+            self.names, self.offsets, self.shapes, self.numel, self.stride = r.names, r.offsets, r.shapes, r.numel, r.stride
+            self.theta, self.avg_n, self.avg, self.g = r.theta, r.avg_n, r.avg, r.g
+            off = self.numel
+        else:
+            self.names, self.offsets, self.shapes = [], {}, {}
+            off = 0
+            for name, p in self.model.named_parameters():
+                self.names.append(name)
+                self.offsets[name] = off
+                self.shapes[name] = tuple(p.shape)
+                off += p.numel()
+            self.numel = off
+            self.stride = (off + 63) // 64 * 64  # elements between the flat buffers of consecutive groups
+            self.theta = torch.zeros(self.stride, device=dev)[:off]
+            self.avg_n = torch.zeros(self.stride, device=dev)[:off]
+            self.avg = torch.zeros(self.stride, device=dev)[:off]  # running mean in the reference's layout (param.grad)
+            self.g = torch.zeros(self.stride, device=dev)[:off]    # gradient of ONE microbatch in the reference's layout
+            with torch.no_grad():
+                for name, p in self.model.named_parameters():
+                    o = self.offsets[name]
+                    if o % 4 != 0:
+                        raise RuntimeError(f"parameter {name} is not 16-byte aligned in the flat buffer")
+                    self.theta[o:o + p.numel()].copy_(p.reshape(-1))
+                    p.data = self.theta[o:o + p.numel()].view(p.shape)
         self.theta_p = torch.zeros(G, self.stride, device=dev)
         self.g_n = torch.zeros(G, self.stride, device=dev)    # per-microbatch gradients, native layout
         self.g2_n = torch.zeros(G, self.stride, device=dev)
-        self.avg_n = torch.zeros(self.stride, device=dev)[:off]
-        self.avg = torch.zeros(self.stride, device=dev)[:off]  # running mean in the reference's layout (param.grad)
-        self.g = torch.zeros(self.stride, device=dev)[:off]    # gradient of ONE microbatch in the reference's layout
-        with torch.no_grad():
-            for name, p in self.model.named_parameters():
-                o = self.offsets[name]
-                if o % 4 != 0:
-                    raise RuntimeError(f"parameter {name} is not 16-byte aligned in the flat buffer")
-                self.theta[o:o + p.numel()].copy_(p.reshape(-1))
-                p.data = self.theta[o:o + p.numel()].view(p.shape)
         self.scal = torch.zeros(SCAL_SLOTS, device=dev)
         self.cursor = torch.zeros(1, device=dev, dtype=torch.int32)
         self.sq_ws = torch.zeros(1024 * G, device=dev, dtype=torch.float64)
@@ -295,6 +320,27 @@ class FullBatchEngine:
         self.norm_offset = 0
         self.bn_passes = 0  # number of train-mode forward passes since the last sync of num_batches_tracked
         self.h2d_bytes = 0
+        self.stream = torch.cuda.Stream(device=dev)       # this lane's compute stream
+        self.commit_done = torch.cuda.Event()             # its previous launch has been combined: g / g2 are free again
+        if _parent is None:
+            # further lanes, if their buffers fit next to lane 0's (FB_LANES / lanes= overrides; 1 = no concurrency)
+            want = int(lanes or os.environ.get("FB_LANES", "2"))
+            torch.cuda.synchronize(dev)
+            footprint = torch.cuda.memory_allocated(dev) - mem0
+            for _ in range(1, max(want, 1)):
+                free = torch.cuda.mem_get_info(dev)[0]
+                if footprint * 1.15 > free * 0.8:
+                    break
+                self._children.append(FullBatchEngine(model, microbatch, precision, label_smoothing, device, self.G,
+                                                      policy_groups, _parent=self))
+
+    @property
+    def root(self):
+        return self if self._parent is None else self._parent()
+
+    @property
+    def lanes(self):
+        return [self] + self._children
 
     # ------------------------------------------------------------------------------------------------------------
     def _view(self, flat, name):
@@ -476,20 +522,27 @@ class FullBatchEngine:
         return logits
 
     # ------------------------------------------------------------------------------------------------------------
-    def _group_ops(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate, write_g,
-                   mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
-        """One group launch of ng microbatches.
+    @staticmethod
+    def _num_passes(block_strength, mode, impl, acc):
+        """train-mode forward passes of one group launch: pass 1 (unless the raw gradient is given) + the FD passes"""
+        regularise = (block_strength != 0 or acc != 0) and mode != "raw"
+        return (0 if mode == "reg" else 1) + ((2 if impl == "central" else 1) if regularise else 0)
+
+    def _compute_ops(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, mode="full",
+                     impl="forward", acc=0.0, target="avg"):
+        """The lane-local part of one group launch of ng microbatches: im2col, pass 1, gradient norms / eps_n, the
+        finite-difference pass(es).  Touches only this lane's buffers (and disjoint entries of grad_norms), so launches
+        of different lanes may run concurrently.
         mode "full": whole per-microbatch recipe; "raw": pass 1 only (training.py:76-83 + :162);
         "reg": regulariser only, self.g_n[0] already holds the raw gradient of the microbatch (modules.py:211-241).
-        impl "forward" | "central" (modules.py:211-241 / :266-300); acc: acc_strength with self.pre_n as pre_grads;
-        batch_clip: per-microbatch L2 clip before the running mean (training.py:166-168); target "avg" | "pre"
-        (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into self.pre_n)."""
-        dst = self.avg_n if target == "avg" else self.pre_n
+        impl "forward" | "central" (modules.py:211-241 / :266-300); acc: acc_strength with root.pre_n as pre_grads;
+        target "avg" | "pre" (the acc_strength pre-pass of training.py:128-142 accumulates raw gradients into pre_n)."""
+        root = self.root
         mb, st, n = self.mb, self.stride, self.numel
         cur = self.cursor if use_cursor else None
         if x_src.dtype == torch.uint8:  # raw HWC dataset: crop / flip / normalise fused into the im2col
-            ops.stem_im2col_u8aug(x_src, labels_src, perm, cur, first, mb, ng * mb, self.aug_params, self.aug_mean,
-                                  self.aug_std, self.patches.hi, self.patches.lo, self.labels_mb)
+            ops.stem_im2col_u8aug(x_src, labels_src, perm, cur, first, mb, ng * mb, root.aug_params, root.aug_mean,
+                                  root.aug_std, self.patches.hi, self.patches.lo, self.labels_mb)
         else:
             ops.stem_im2col(x_src, labels_src, perm, cur, first, mb, ng * mb, self.patches.hi, self.patches.lo,
                             self.labels_mb)
@@ -501,15 +554,13 @@ class FullBatchEngine:
             passes += 1
         norms = None
         if target == "avg":
-            norms = self.grad_norms[self.norm_offset:] if self.norm_offset else self.grad_norms
+            norms = root.grad_norms[root.norm_offset:] if root.norm_offset else root.grad_norms
         simple = acc == 0
         # |g_k|^2 -> grad_norms[k] (training.py:162) and, without acc_strength, eps_k = eps / (bs * |g_k|) (modules.py:223)
         ops.flat_sqnorm(g, n, self.sq_ws, self.scal, S_N2G, ng=ng, gstride=st, norms_out=norms, cursor=self.cursor,
                         eps_mode=1 if simple else 0, bs=block_strength, eps=eps, eps_base=S_EPSG)
-        regularise = (block_strength != 0 or acc != 0) and mode != "raw"
-        fused_mean = dst if (accumulate and batch_clip is None) else None
-        if regularise:
-            pre = self.pre_n if acc != 0 else None
+        if (block_strength != 0 or acc != 0) and mode != "raw":
+            pre = root.pre_n if acc != 0 else None
             if not simple:  # |bs*g + acc*pre|^2 -> eps_k (modules.py:217-223)
                 ops.flat_sqnorm(g, n, self.sq_ws, self.scal, S_VSQG, ng=ng, gstride=st, y=pre, a=block_strength, b=acc,
                                 eps_mode=2, eps=eps, eps_base=S_EPSG)
@@ -522,6 +573,22 @@ class FullBatchEngine:
                 self._forward(ng, 1, self.theta_p, st, gbuf, S_LOSS2G, S_CORR2G, passes)
                 self._backward(ng, 1, self.theta_p, st, gbuf)
                 passes += 1
+        return passes
+
+    def _commit_ops(self, ng, block_strength, accumulate, write_g, mode="full", impl="forward", acc=0.0, batch_clip=None,
+                    target="avg", cursor_step=None):
+        """The order-sensitive tail of a group launch: finite-difference combine + running mean of the ng microbatches in
+        loader order (modules.py:232-240, training.py:45-47,166-168), the running-statistics EMA of every BatchNorm
+        (pass 1 of microbatch k, pass 2 of k, pass 1 of k+1, ...) and the loss / accuracy sums.  Runs on the main stream,
+        launch after launch, whichever lane computed the gradients."""
+        root = self.root
+        dst = root.avg_n if target == "avg" else root.pre_n
+        st, n = self.stride, self.numel
+        g, g2 = self.g_n, self.g2_n
+        passes = self._num_passes(block_strength, mode, impl, acc)
+        regularise = (block_strength != 0 or acc != 0) and mode != "raw"
+        fused_mean = dst if (accumulate and batch_clip is None) else None
+        if regularise:
             ops.fd_combine(g, g2, None if impl == "forward" else self._g3(), st, fused_mean, n, ng, self.scal, S_EPSG,
                            S_CF, self.cursor, write_g or batch_clip is not None)
             if accumulate and batch_clip is not None:
@@ -529,10 +596,16 @@ class FullBatchEngine:
                 ops.mean_accumulate(g, st, dst, n, ng, self.cursor, self.scal, S_REGSQG, batch_clip, S_CLIPPED)
         elif accumulate:
             ops.mean_accumulate(g, st, dst, n, ng, self.cursor, self.scal, S_N2G, batch_clip or 0.0, S_CLIPPED)
-        # running statistics: EMA over (microbatch, pass) in the reference's order
         self.ema(passes, ng, BN_MOMENTUM)
         if mode != "reg":
-            ops.group_finish(self.cursor, ng, self.scal, S_LOSS, S_CORRECT, S_LOSSG, S_CORRG)
+            ops.group_finish(self.cursor, ng, self.scal, S_LOSS, S_CORRECT, S_LOSSG, S_CORRG, cursor_step=cursor_step)
+
+    def _group_ops(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate, write_g,
+                   mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
+        """One whole group launch on the current stream (single-microbatch protocols)."""
+        passes = self._compute_ops(x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, mode, impl, acc,
+                                   target)
+        self._commit_ops(ng, block_strength, accumulate, write_g, mode, impl, acc, batch_clip, target)
         return passes
 
     def _g3(self):
@@ -541,14 +614,43 @@ class FullBatchEngine:
         return self.g3_n
 
     def _pre(self):
-        if not hasattr(self, "pre_n"):
-            self.pre_n = torch.zeros(self.stride, device=self.device)[:self.numel]
-            self.pre = torch.zeros(self.stride, device=self.device)[:self.numel]
-        return self.pre_n
+        root = self.root
+        if not hasattr(root, "pre_n"):
+            root.pre_n = torch.zeros(self.stride, device=self.device)[:self.numel]
+            root.pre = torch.zeros(self.stride, device=self.device)[:self.numel]
+        return root.pre_n
+
+    def _graph_key(self, x_src, labels_src, perm, *rest):
+        root = self.root
+        return (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), *rest,
+                root.grad_norms.data_ptr(), root.norm_offset,
+                None if root.aug_params is None else root.aug_params.data_ptr(), tuple(root.aug_mean), tuple(root.aug_std))
+
+    def _capture(self, parts, mode):
+        """Warm-up run of the callables in `parts` (sets kernel attributes, loads modules) with the state restored
+        afterwards, then ONE CUDA graph per part."""
+        torch.cuda.synchronize()  # other lanes may still be writing shared entries
+        state = self._save_state(mode)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for fn in parts:
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore_state(state)
+        graphs = []
+        for fn in parts:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            graphs.append(graph)
+        return graphs
 
     def _program(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate=True,
                  write_g=False, use_graph=True, mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
-        """Returns a callable running one group launch of ng microbatches; captured into a CUDA graph on first use."""
+        """Returns a callable running one whole group launch of ng microbatches on the current stream; captured into a
+        CUDA graph on first use."""
         if acc != 0 or target == "pre":
             self._pre()
         if impl == "central":
@@ -557,40 +659,50 @@ class FullBatchEngine:
                 batch_clip, target)
         if not use_graph:
             return lambda: self._group_ops(*args)
-        key = (x_src.data_ptr(), labels_src.data_ptr(), None if perm is None else perm.data_ptr(), first, use_cursor, ng,
-               float(block_strength), float(eps), accumulate, write_g, mode, impl, float(acc), batch_clip, target,
-               self.grad_norms.data_ptr(), self.norm_offset,
-               None if self.aug_params is None else self.aug_params.data_ptr(), tuple(self.aug_mean), tuple(self.aug_std))
+        key = self._graph_key(x_src, labels_src, perm, "whole", first, use_cursor, ng, float(block_strength), float(eps),
+                              accumulate, write_g, mode, impl, float(acc), batch_clip, target)
         if key not in self._graphs:
-            state = self._save_state(mode)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):  # warm-up launch (sets kernel attributes, loads modules) outside capture
-                self._group_ops(*args)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            self._restore_state(state)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._group_ops(*args)
-            self._graphs[key] = (graph, (x_src, labels_src, perm))
-        return self._graphs[key][0].replay
+            graphs = self._capture([lambda: self._group_ops(*args)], mode)
+            self._graphs[key] = (graphs, (x_src, labels_src, perm))
+        return self._graphs[key][0][0].replay
+
+    def _lane_programs(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, cursor_step,
+                       use_graph=True, mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
+        """(compute, commit) callables of one group launch on THIS lane: `compute` for the lane's stream, `commit` for the
+        main stream; each captured into its own CUDA graph on first use."""
+        if acc != 0 or target == "pre":
+            self._pre()
+        if impl == "central":
+            self._g3()
+        cargs = (x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, mode, impl, acc, target)
+        margs = (ng, block_strength, True, False, mode, impl, acc, batch_clip, target, cursor_step)
+        if not use_graph:
+            return (lambda: self._compute_ops(*cargs)), (lambda: self._commit_ops(*margs))
+        key = self._graph_key(x_src, labels_src, perm, "lane", first, use_cursor, ng, float(block_strength), float(eps),
+                              cursor_step, mode, impl, float(acc), batch_clip, target)
+        if key not in self._graphs:
+            graphs = self._capture([lambda: self._compute_ops(*cargs), lambda: self._commit_ops(*margs)], mode)
+            self._graphs[key] = (graphs, (x_src, labels_src, perm))
+        compute, commit = self._graphs[key][0]
+        return compute.replay, commit.replay
 
     def _save_state(self, mode):
+        root = self.root
         bufs = [b.clone() for b in self.model.buffers()]
-        return dict(avg=self.avg_n.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
-                    norms=self.grad_norms.clone(), g=self.g_n[0].clone() if mode == "reg" else None,
-                    pre=self.pre_n.clone() if hasattr(self, "pre_n") else None)
+        return dict(avg=root.avg_n.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
+                    norms=root.grad_norms.clone(), g=self.g_n[0].clone() if mode == "reg" else None,
+                    pre=root.pre_n.clone() if hasattr(root, "pre_n") else None)
 
     def _restore_state(self, st):
-        self.avg_n.copy_(st["avg"])
+        root = self.root
+        root.avg_n.copy_(st["avg"])
         self.scal.copy_(st["scal"])
         self.cursor.copy_(st["cursor"])
-        self.grad_norms.copy_(st["norms"])
+        root.grad_norms.copy_(st["norms"])
         if st["g"] is not None:
             self.g_n[0].copy_(st["g"])
         if st["pre"] is not None:
-            self.pre_n.copy_(st["pre"])
+            root.pre_n.copy_(st["pre"])
         for b, s in zip(self.model.buffers(), st["bufs"]):
             b.copy_(s)
 
@@ -605,7 +717,8 @@ class FullBatchEngine:
         int8 [num_samples, 4] buffer (dx, dy, flip, 0) indexed by position in the epoch order.  None disables."""
         if self.aug_params is None or self.aug_params.shape[0] < num_samples:
             self.aug_params = torch.zeros(num_samples, 4, device=self.device, dtype=torch.int8)
-            self._graphs.clear()
+            for lane in self.lanes:
+                lane._graphs.clear()
         n = self.aug_params.shape[0]
         off = torch.randint(0, 2 * crop_padding + 1, (n, 2), device=self.device, generator=generator)
         flips = (torch.rand(n, device=self.device, generator=generator) < flip)
@@ -615,28 +728,79 @@ class FullBatchEngine:
 
     def set_lr(self, lr):
         """correction factor lr/4 of modules.py:214, kept on the device so captured graphs stay valid"""
-        self.scal[S_CF] = lr / 4
+        for lane in self.lanes:
+            lane.scal[S_CF] = lr / 4
 
     def begin_step(self, num_microbatches):
         if self.grad_norms is None or self.grad_norms.numel() < num_microbatches + self.G:
             self.grad_norms = torch.zeros(max(num_microbatches, 16) + self.G, device=self.device)
-            self._graphs.clear()
+            for lane in self.lanes:
+                lane._graphs.clear()
         self.grad_norms.zero_()
         self.avg_n.zero_()
-        self.scal[S_LOSS:S_CORRECT + 1] = 0
-        self.scal[S_CLIPPED] = 0
-        self.cursor.zero_()
+        self._reset_sums()
         self.wprep[0](self.theta)  # theta is constant during the step: pass-1 operands once, not per launch
 
+    def _reset_sums(self):
+        for lane in self.lanes:
+            lane.scal[S_LOSS:S_CORRECT + 1] = 0
+            lane.scal[S_CLIPPED] = 0
+            lane.cursor.zero_()
+
+    def _begin_lanes(self):
+        """Lane l starts at microbatch l*G and advances by lanes*G per launch: its cursor always is the index (in loader
+        order) of the first microbatch of its current launch."""
+        for l, lane in enumerate(self.lanes):
+            lane.cursor.fill_(l * self.G)
+        self._fork = torch.cuda.Event()
+        self._fork.record(torch.cuda.current_stream())
+
+    def _launch(self, j, ng, make, wait=None, after=None):
+        """Group launch number j of a pass: compute on lane j % lanes (its own stream, once its previous launch has been
+        combined), commit on the current (main) stream -- commits therefore run in launch order."""
+        lanes = self.lanes
+        lane = lanes[j % len(lanes)]
+        main = torch.cuda.current_stream()
+        compute, commit = make(lane, ng, len(lanes) * self.G)
+        if len(lanes) == 1:  # no concurrency: everything in stream order
+            if wait is not None:
+                main.wait_event(wait)
+            compute()
+            if after is not None:
+                after.record(main)
+            commit()
+            return
+        with torch.cuda.stream(lane.stream):
+            lane.stream.wait_event(self._fork)
+            lane.stream.wait_event(lane.commit_done)
+            if wait is not None:
+                lane.stream.wait_event(wait)
+            compute()
+            if after is not None:
+                after.record(lane.stream)
+            done = torch.cuda.Event()
+            done.record(lane.stream)
+        main.wait_event(done)
+        commit()
+        lane.commit_done.record(main)
+
+    def _fold_lanes(self):
+        """loss / accuracy / clip counters of the other lanes into lane 0's (device side, main stream)"""
+        for lane in self.lanes[1:]:
+            for slot in (S_LOSS, S_CORRECT, S_CLIPPED):  # (not S_CF: every lane carries its own copy of lr/4)
+                self.scal[slot] += lane.scal[slot]
+                lane.scal[slot] = 0
+
     def _run_groups(self, count, make):
-        """count microbatches as full launches of G groups plus one shorter launch"""
+        """count microbatches as full launches of G groups plus one shorter launch, alternating between the lanes;
+        make(lane, ng, cursor_step) -> (compute, commit)"""
+        self._begin_lanes()
         full, rem = divmod(count, self.G)
-        if full:
-            run = make(self.G)
-            for _ in range(full):
-                run()
+        for j in range(full):
+            self._launch(j, self.G, make)
         if rem:
-            make(rem)()
+            self._launch(full, rem, make)
+        self._fold_lanes()
 
     def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
                             num_norms=None, norm_offset=0, implementation="forward-differences", acc_strength=0.0,
@@ -663,18 +827,17 @@ class FullBatchEngine:
         if acc_strength != 0:
             # training.py:128-142: extra sweep for the mean raw gradient (pre_grads)
             self._pre().zero_()
-            self._run_groups(count, lambda ng: self._program(X, Y, perm, first, True, ng, 0.0, eps, use_graph=use_graph,
-                                                             mode="raw", impl=impl, batch_clip=batch_clip, target="pre"))
+            self._run_groups(count, lambda lane, ng, step: lane._lane_programs(
+                X, Y, perm, first, True, ng, 0.0, eps, step, use_graph=use_graph, mode="raw", impl=impl,
+                batch_clip=batch_clip, target="pre"))
             if reduce_pre is not None:
                 reduce_pre(self.pre_n)
             self.from_native(self.pre_n, self.pre)
             self.bn_passes += count
-            self.scal[S_LOSS:S_CORRECT + 1] = 0
-            self.scal[S_CLIPPED] = 0
-            self.cursor.zero_()
-        self._run_groups(count, lambda ng: self._program(X, Y, perm, first, True, ng, block_strength, eps,
-                                                         use_graph=use_graph, impl=impl, acc=acc_strength,
-                                                         batch_clip=batch_clip))
+            self._reset_sums()
+        self._run_groups(count, lambda lane, ng, step: lane._lane_programs(
+            X, Y, perm, first, True, ng, block_strength, eps, step, use_graph=use_graph, impl=impl, acc=acc_strength,
+            batch_clip=batch_clip))
         self.from_native(self.avg_n, self.avg)
         regularised = block_strength != 0 or acc_strength != 0
         self.bn_passes += count * ((3 if impl == "central" else 2) if regularised else 1)
@@ -683,42 +846,45 @@ class FullBatchEngine:
     def _stages(self):
         if not hasattr(self, "_x_stage"):
             n = self.G * self.mb
-            self._x_stage = [torch.zeros(n, 3, 32, 32, device=self.device) for _ in range(2)]
-            self._y_stage = [torch.zeros(n, device=self.device, dtype=torch.int64) for _ in range(2)]
-            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            k = len(self.lanes) + 1  # one staging buffer per lane in flight + one being filled
+            self._x_stage = [torch.zeros(n, 3, 32, 32, device=self.device) for _ in range(k)]
+            self._y_stage = [torch.zeros(n, device=self.device, dtype=torch.int64) for _ in range(k)]
+            self._stage_free = [torch.cuda.Event() for _ in range(k)]
             self._copy_stream = torch.cuda.Stream()
         return self._x_stage, self._y_stage
 
     def accumulate_stream(self, loader, lr, block_strength, eps, num_microbatches, use_graph=True, norm_offset=0):
         """Full-batch accumulation over blocks (inputs [B,3,32,32], labels [B]) coming from a host-side iterable (the
         reference's DataLoader protocol, training.py:148-152): every block is split into microbatches
-        (torch.chunk, training.py:155-156), copied host->device on a copy stream into one of two staging buffers of G
-        microbatches and consumed by a captured graph, so the copies of launch j+1 overlap the compute of launch j."""
+        (torch.chunk, training.py:155-156), copied host->device on a copy stream into one of the staging buffers of G
+        microbatches and consumed by the captured graphs of a lane, so the copies of the next launches overlap the
+        compute of the current ones."""
         xs, ys = self._stages()
         self.begin_step(num_microbatches)
         self.norm_offset = int(norm_offset)
         self.set_lr(lr)
-        main = torch.cuda.current_stream()
-        mb = self.mb
-        state = dict(k=0, slot=0, stage=0, h2d=0)
+        self._begin_lanes()
+        mb, n_stage = self.mb, len(xs)
+        state = dict(k=0, slot=0, launch=0, h2d=0)
 
         def flush():
-            i, ng = state["stage"], state["slot"]
+            j, ng = state["launch"], state["slot"]
             if ng == 0:
                 return
+            i = j % n_stage
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
-            main.wait_event(ready)
-            self._program(xs[i], ys[i], None, 0, False, ng, block_strength, eps, use_graph=use_graph)()
-            self._stage_free[i].record(main)
-            state["stage"], state["slot"] = i ^ 1, 0
+            self._launch(j, ng, lambda lane, g, step: lane._lane_programs(xs[i], ys[i], None, 0, False, g, block_strength,
+                                                                          eps, step, use_graph=use_graph),
+                         wait=ready, after=self._stage_free[i])
+            state["launch"], state["slot"] = j + 1, 0
 
         for inputs, labels in loader:
             chunks = max(labels.shape[0] // mb, 1)
             for xc, yc in zip(torch.chunk(inputs, chunks, dim=0), torch.chunk(labels, chunks, dim=0)):
                 if xc.shape[0] != mb:
                     raise RuntimeError(f"microbatch of {xc.shape[0]} samples, engine built for {mb} (drop_last?)")
-                i, j = state["stage"], state["slot"]
+                i, j = state["launch"] % n_stage, state["slot"]
                 with torch.cuda.stream(self._copy_stream):
                     if j == 0:
                         self._copy_stream.wait_event(self._stage_free[i])
@@ -730,6 +896,7 @@ class FullBatchEngine:
                 if state["slot"] == self.G:
                     flush()
         flush()
+        self._fold_lanes()
         self.from_native(self.avg_n, self.avg)
         self.bn_passes += state["k"] * (2 if block_strength != 0 else 1)
         self.h2d_bytes = state["h2d"]

@@ -639,8 +639,9 @@ def mean_accumulate(grad, gstride, avg, n, ng, cursor, scal=None, norm_base=0, c
           L.ptr(cursor), L.ptr(scal), norm_base, clip, clipped_slot)
 
 
-def group_finish(cursor, ng, scal, loss_slot, correct_slot, loss_base, correct_base):
-    _call("misc", 8.0 * ng + 16.0, "byte", "fb_group_finish", cursor.data_ptr(), ng, scal.data_ptr(), loss_slot,
+def group_finish(cursor, ng, scal, loss_slot, correct_slot, loss_base, correct_base, cursor_step=None):
+    _call("misc", 8.0 * ng + 16.0, "byte", "fb_group_finish", cursor.data_ptr(), ng,
+          ng if cursor_step is None else cursor_step, scal.data_ptr(), loss_slot,
           correct_slot, loss_base, correct_base)
 
 

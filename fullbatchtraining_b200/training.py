@@ -154,7 +154,8 @@ class Trainer:
         self.engine = FullBatchEngine(model, self.mb, precision=cfg.impl.get("precision", "split"),
                                       label_smoothing=loss_fn.smoothing, device=self.device,
                                       groups=1 if self.stochastic else cfg.impl.get("groups", None),
-                                      policy_groups=1 if self.stochastic else None)
+                                      policy_groups=1 if self.stochastic else None,
+                                      lanes=1 if self.stochastic else cfg.impl.get("lanes", None))
         self.gradreg = GradRegularizer(model, self.optimizer, loss_fn, **hyp.grad_reg, mixed_precision=False,
                                        engine=self.engine)
         self.bs, self.eps = self.gradreg.block_strength, self.gradreg.eps

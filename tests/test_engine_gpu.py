@@ -297,6 +297,40 @@ def test_result_does_not_depend_on_the_group_count():
             assert torch.equal(a, b)
 
 
+def test_result_does_not_depend_on_the_lane_count():
+    """Two lanes (alternating group launches on two streams, commits in loader order) == one lane, bit for bit; also for
+    the acc_strength pre-pass and through the host-streamed path."""
+    from fullbatchtraining_b200.data import HostBlockLoader
+
+    depth, mb, n = 18, 16, 112
+    for extra in (dict(), dict(acc_strength=0.3, batch_clip=5.0)):
+        outs = []
+        for lanes in (1, 2):
+            model, params, buffers, X, Y = setup_case(depth, mb, n)
+            eng = FullBatchEngine(model, mb, precision="split", groups=2, lanes=lanes)
+            assert len(eng.lanes) == lanes
+            K = eng.accumulate_resident(X, Y, 0.8, 0.5, 1e-2, **extra)
+            res = eng.results(K)
+            outs.append((eng.avg.clone(), res["grad_norms"].clone(), torch.tensor([res["loss_sum"], res["correct"],
+                                                                                   float(res["clipped_batches"])]),
+                         torch.cat([b.reshape(-1).float() for b in model.buffers()])))
+            assert K == 7
+        for i, (a, b) in enumerate(zip(*outs)):
+            if i == 2:  # loss / accuracy / clip counters: summed per lane, then over the lanes (another fp32 order)
+                assert torch.allclose(a, b, rtol=1e-6)
+            else:       # accumulated gradient, gradient norms, BatchNorm running statistics: bit for bit
+                assert torch.equal(a, b)
+    # streamed from the host: three staging buffers, two lanes
+    model, params, buffers, X, Y = setup_case(depth, mb, n)
+    eng = FullBatchEngine(model, mb, precision="split", groups=2, lanes=2)
+    K = eng.accumulate_stream(HostBlockLoader(X.cpu(), Y.cpu(), mb), 0.8, 0.5, 1e-2, n // mb)
+    model1, _, _, _, _ = setup_case(depth, mb, n)
+    eng1 = FullBatchEngine(model1, mb, precision="split", groups=2, lanes=1)
+    eng1.accumulate_resident(X, Y, 0.8, 0.5, 1e-2)
+    assert K == 7 and torch.equal(eng.avg, eng1.avg)
+    assert eng.results(K)["loss_sum"] == pytest.approx(eng1.results(K)["loss_sum"], rel=1e-6)
+
+
 def test_graph_replay_equals_eager():
     depth, mb, n = 18, 16, 48
     model, params, buffers, X, Y = setup_case(depth, mb, n)
