@@ -57,7 +57,7 @@ def test_wgrad_policies():
 def test_default_groups(monkeypatch):
     monkeypatch.delenv("FB_GROUPS", raising=False)
     assert engine.default_groups(128) == 8
-    assert engine.default_groups(32) == 16
+    assert engine.default_groups(32) == 8
     assert engine.default_groups(2048) == 1
     monkeypatch.setenv("FB_GROUPS", "3")
     assert engine.default_groups(128) == 3
