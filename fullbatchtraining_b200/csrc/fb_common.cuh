@@ -278,6 +278,22 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast within a cluster: the box lands at the same offset in the shared memory of every CTA in `mask`, and each of
+// their barriers (same offset) receives the bytes
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once all MMAs this CTA issued so far have completed
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
                                                  int c2, int c3) {
   asm volatile(

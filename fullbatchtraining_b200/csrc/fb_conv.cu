@@ -116,6 +116,8 @@ struct alignas(64) ConvGemmKParams {
   int b_group_rows;  // weight rows per microbatch group (0: shared)
   int reverse;
   int cta_pair;
+  int dbg;   // FB_CONV_DBG (timing experiments only, results are wrong): 1 no A loads, 2 no B loads, 4 no stores, 8 no epilogue
+  int halo;  // 1: the taps come in triples (dh = -1, 0, 1 at one dw) that share ONE haloed A box of tile_h + 2 rows
   float* out;
   long long out_sn, out_sh, out_sw;
   int accumulate;
@@ -285,20 +287,41 @@ struct ConvGemmCfg {
   static_assert(kStages >= 2, "stage does not fit twice into shared memory");
 };
 
-template <int N_TILE, int PA, int PB, bool CTA2>
+// MODE 3: independent CTAs, 3x3 / stride 1 over tiles of whole image rows: the three taps of a filter COLUMN read row-
+// shifted windows of one haloed A box (tile_h + 2 rows, fetched once per (dw, channel block) instead of three times: the
+// kernels sit at the L2 throughput cap, and A is 1/2 .. 2/3 of their operand bytes).  The operand area is an A ring of
+// two haloed boxes and a B ring of per-tap weight tiles; the A box of a triple rides on the full barrier of its first
+// B tile, so the MMA role waits for B slots only.
+// MODE 0: independent CTAs.  MODE 1: CTA pairs (cta_group::2, see ConvGemmCfg).  MODE 2: clusters of two CTAs that work
+// on two rows of the same (group, tap group, N tile) in lockstep and SHARE the weight tiles: each CTA fetches half of
+// every B tile and multicasts it into both shared memories (half the weight bytes from L2 per CTA); everything else,
+// including the instruction sequence and hence every accumulator bit, is as in MODE 0.
+template <int N_TILE, int PA, int PB, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmKParams p) {
+  constexpr bool CTA2 = MODE == 1;
+  constexpr bool MCAST = MODE == 2;
+  constexpr bool CLUSTER = MODE == 1 || MODE == 2;
+  constexpr bool HALO = MODE == 3;
   using Cfg = ConvGemmCfg<N_TILE, PA, PB, CTA2>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGES = HALO ? 8 : Cfg::kStages;  // HALO: upper bound of the B ring (the barrier arrays)
+  constexpr int kOperandBytes = HALO ? kSmemBudget : Cfg::kStages * Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by an OFFSET from the __shared__ array (a round trip through uintptr_t makes the compiler lose
   // the address space: every access to the staging patch then becomes a generic LD.E / ST.E instead of LDS / STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + kEpiStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + kOperandBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOperandBytes + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_empty = acc_empty + 2;        // [2] (HALO: the haloed A boxes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+  // HALO geometry: bytes of one haloed box of one plane, byte shift of one image row, B ring slots that fit
+  const int halo_bytes = HALO ? (p.tile_h + 2) * p.tile_w * 128 : 0;
+  const int halo_row_bytes = p.tile_w * 128;
+  int nb = HALO ? (kSmemBudget - 2 * PA * halo_bytes) / (PB * Cfg::kBBytes) : STAGES;
+  nb = nb > STAGES ? STAGES : nb;
+  uint8_t* b_ring = smem + 2 * PA * halo_bytes;
   volatile uint32_t* last_flag = tmem_slot + 1;  // "this CTA took the last ticket of its (group, N tile)"
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, and the producer / MMA roles below run
@@ -308,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   // CTA pair: rank 0 (the leader) owns the full / accumulator-empty barriers and issues the MMAs of both CTAs
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const uint32_t rank = CLUSTER ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 32) {  // descriptor fetch overlaps the barrier / TMEM set-up
 #pragma unroll
@@ -319,9 +342,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MCAST ? 2 : 1);  // multicast: a stage is free when BOTH CTAs' MMAs have read it
     }
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_empty[b], 1);
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
     }
@@ -331,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (CTA2) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();  // pair: the peer's barriers must be initialised before any use
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();  // the peer's barriers must be initialised before any use
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_wait();    // everything above overlapped the predecessor's tail
@@ -339,19 +363,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   // Schedule: a pair works on two super-tiles that differ only in their row (r = 2q + rank): same group, tap group and
   // N tile, hence the same weight tiles and the same number of pipeline stages, in lockstep.
-  const int sched_rows = CTA2 ? p.rows / 2 : p.rows;
+  const int sched_rows = CLUSTER ? p.rows / 2 : p.rows;
   const int total_super = p.ng * p.n_tapgroups * sched_rows * p.n_tiles;
-  const int sched_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int sched_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int sched_first = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_step = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  if (warp == 0) {
+  if (HALO && warp == 0) {
+    // ---------------- TMA producer, haloed A boxes ----------------
+    int s = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int u = sched_first; u < total_super; u += sched_step) {
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, 1, 0);
+      const int b_row = sp.j * N_TILE + sp.mg * p.b_group_rows;
+      const int tap0 = p.group_tap0[sp.tg], tap1 = tap0 + p.group_taps[sp.tg];
+      for (int m = sp.r; m < p.mtg; m += p.rows) {
+        int n0, h0;
+        tile_origin(sp.mg * p.mtg + m, p.tile_h, p.tile_n, p.grid_h, n0, h0);
+        for (int t = tap0; t < tap1; t += 3) {
+          const fb_tap tap = p.taps[t];  // dh = -1 of the triple
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&a_empty[as], aphase ^ 1, 5);
+#pragma unroll 1
+            for (int j = 0; j < 3; ++j) {
+              const int b_k0 = p.taps[t + j].b_k0;
+              mbar_wait(&empty_bar[s], phase ^ 1, 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 2) ? 0 : PB * Cfg::kBBytes) +
+                                                        ((j == 0 && !(p.dbg & 1)) ? PA * halo_bytes : 0));
+                if (j == 0 && !(p.dbg & 1)) {
+#pragma unroll
+                  for (int pl = 0; pl < PA; ++pl)
+                    tma_load_4d(smem + (as * PA + pl) * halo_bytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s],
+                                cb * kBlockK, tap.dw, h0 - 1, n0);
+                }
+#pragma unroll
+                for (int pl = 0; pl < ((p.dbg & 2) ? 0 : PB); ++pl)
+                  tma_load_2d(b_ring + (s * PB + pl) * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s], b_k0 + cb * kBlockK,
+                              b_row);
+              }
+              __syncwarp();
+              if (++s == nb) {
+                s = 0;
+                phase ^= 1;
+              }
+            }
+            as ^= 1;
+            aphase ^= (as == 0) ? 1u : 0u;
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ---------------- TMA producer ----------------
     int s = 0;
     uint32_t phase = 0;
     for (int u = sched_first; u < total_super; u += sched_step) {
-      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CLUSTER ? 2 : 1, (int)rank);
       // a pair splits every weight tile: this CTA fetches rows [rank * N_TILE/2, +N_TILE/2) of it
-      const int b_row = sp.j * N_TILE + sp.mg * p.b_group_rows + (CTA2 ? (int)rank * (N_TILE / 2) : 0);
+      const int b_row = sp.j * N_TILE + sp.mg * p.b_group_rows + (CLUSTER ? (int)rank * (N_TILE / 2) : 0);
       const int tap0 = p.group_tap0[sp.tg], tap1 = tap0 + p.group_taps[sp.tg];
       for (int m = sp.r; m < p.mtg; m += p.rows) {
         int n0, h0;
@@ -374,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int pl = 0; pl < PB; ++pl)
                   tma_load_2d_pair(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], bar,
                                    tap.b_k0 + cb * kBlockK, b_row);
-              } else {
+              } else if (MCAST) {
+                // own A tile + the full B tile: this CTA's half and the peer's land on the barrier of this stage
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
 #pragma unroll
                 for (int pl = 0; pl < PA; ++pl)
@@ -382,6 +452,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                               h0 + tap.dh, n0);
 #pragma unroll
                 for (int pl = 0; pl < PB; ++pl)
+                  tma_load_2d_mcast(st + PA * kATileBytes + pl * Cfg::kBBytes + rank * (Cfg::kBBytes / 2), &p.b_maps[pl],
+                                    &full_bar[s], tap.b_k0 + cb * kBlockK, b_row, (uint16_t)3);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 1) ? 0 : PA * kATileBytes) + ((p.dbg & 2) ? 0 : PB * Cfg::kBBytes));
+#pragma unroll
+                for (int pl = 0; pl < ((p.dbg & 1) ? 0 : PA); ++pl)
+                  tma_load_4d(st + pl * kATileBytes, &p.a_maps[tap.phase * PA + pl], &full_bar[s], cb * kBlockK, tap.dw,
+                              h0 + tap.dh, n0);
+#pragma unroll
+                for (int pl = 0; pl < ((p.dbg & 2) ? 0 : PB); ++pl)
                   tma_load_2d(st + PA * kATileBytes + pl * Cfg::kBBytes, &p.b_maps[pl], &full_bar[s],
                               tap.b_k0 + cb * kBlockK, b_row);
               }
@@ -395,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1 && rank == 0) {
+  } else if (warp == 1 && (rank == 0 || !CTA2)) {
     // ---------------- MMA issuer (of a pair: the leader CTA only) ----------------
     // A tcgen05.mma blocks its issuing thread until the tensor pipe has taken it, and nothing that thread executes
     // between two MMAs overlaps with them (every instruction between two MMAs adds its full latency).  The role
@@ -426,18 +506,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           else tc_mma_bf16_lohi(tmem_d, da, db, desc_hi, desc_hi, idesc, (ki | c | k) != 0);
         }
       }
-      if (CTA2) tc_commit2(&empty_bar[st]); else tc_commit(&empty_bar[st]);  // pair: frees the stage in BOTH CTAs
+      if (CTA2) tc_commit2(&empty_bar[st]);  // pair: frees the stage in BOTH CTAs
+      else if (MCAST) tc_commit_mcast(&empty_bar[st], (uint16_t)3);
+      else tc_commit(&empty_bar[st]);
+    };
+    // HALO: B slot st against the window of A box `as` shifted by j rows; the box is released after its third tap
+    const uint32_t b_ring0 = smem_u32(b_ring);
+    auto issue_halo = [&](uint32_t tmem_d, int st, int ki, int as, int j) {
+      const uint32_t a_lo = smem_desc_lo(smem0 + as * PA * halo_bytes + j * halo_row_bytes, 16);
+      const uint32_t b_lo = smem_desc_lo(b_ring0 + st * PB * Cfg::kBBytes, 16);
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint32_t da = a_lo + ((ap_of(c) * halo_bytes + k * 32) >> 4);
+          const uint32_t db = b_lo + ((bp_of(c) * Cfg::kBBytes + k * 32) >> 4);
+          const uint32_t idesc = (kNarrowLo && c == 0 && ki != 0) ? idesc_half : idesc_full;
+          tc_mma_bf16_lohi(tmem_d, da, db, desc_hi, desc_hi, idesc, (ki | c | k) != 0);
+        }
+      }
+      tc_commit(&empty_bar[st]);
+      if (j == 2) tc_commit(&a_empty[as]);
     };
     int s = 0;
     uint32_t phase = 0;
     int tile_i = 0;
+    int as = 0, aj = 0;  // HALO: current A box and tap of its triple
     for (int u = sched_first; u < total_super; u += sched_step) {
-      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CLUSTER ? 2 : 1, (int)rank);
       const int k_iters = p.group_taps[sp.tg] * p.cblocks;
       for (int m = sp.r; m < p.mtg; m += p.rows, ++tile_i) {
         const int buf = tile_i & 1;
         const uint32_t tmem_d = tmem_base + buf * Cfg::kUmmaN;
         mbar_wait(&acc_empty[buf], ((tile_i >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator
+        if (HALO) {
+          // rounds of two B slots while the ring has room for two more in flight, else of one
+          const int per_round = nb >= 4 ? 2 : 1;
+          for (int ki = 0; ki < k_iters; ki += per_round) {
+            const bool two = per_round == 2 && ki + 1 < k_iters;
+            int s1 = s + 1;
+            uint32_t phase1 = phase;
+            if (s1 == nb) {
+              s1 = 0;
+              phase1 ^= 1;
+            }
+            mbar_wait(&full_bar[s], phase, 2);
+            if (two) mbar_wait(&full_bar[s1], phase1, 2);
+            tc_fence_after();
+            const int as1 = aj == 2 ? (as ^ 1) : as, aj1 = aj == 2 ? 0 : aj + 1;
+            if (elect_one()) {
+              issue_halo(tmem_d, s, ki, as, aj);
+              if (two) issue_halo(tmem_d, s1, ki + 1, as1, aj1);
+              if (ki + per_round >= k_iters) tc_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+            if (two) {
+              as = aj1 == 2 ? (as1 ^ 1) : as1;
+              aj = aj1 == 2 ? 0 : aj1 + 1;
+              s = s1 + 1;
+              phase = phase1;
+              if (s == nb) {
+                s = 0;
+                phase ^= 1;
+              }
+            } else {
+              as = as1;
+              aj = aj1;
+              s = s1;
+              phase = phase1;
+            }
+          }
+          continue;
+        }
         for (int ki = 0; ki < k_iters; ki += 2) {
           const bool pair = ki + 1 < k_iters;
           int s1 = s + 1;
@@ -489,19 +629,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool do_stat = p.stats != nullptr;
     int tile_i = 0;
     for (int u = sched_first; u < total_super; u += sched_step) {
-      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CTA2 ? 2 : 1, (int)rank);
+      const SuperTile sp = decode_super(p, u, total_super, sched_rows, CLUSTER ? 2 : 1, (int)rank);
       const int n_tile0 = sp.j * N_TILE;
       for (int m = sp.r; m < p.mtg; m += p.rows, ++tile_i) {
         int n0, h0;
         tile_origin(sp.mg * p.mtg + m, p.tile_h, p.tile_n, p.grid_h, n0, h0);
-        const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h;
+        const bool valid = (n0 + n) < p.grid_n && (h0 + h) < p.grid_h && !(p.dbg & 4);
         const long long row_off = p.group_off[sp.tg] + (long long)(n0 + n) * p.out_sn +
                                   (long long)(h0 + h) * p.out_sh + (long long)w * p.out_sw + n_tile0;
         const int buf = tile_i & 1;
         mbar_wait(&acc_full[buf], (tile_i >> 1) & 1, 3);
         tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < N_TILE / 32; ++cc) {  // unrolled: col_acc must stay in registers
+        for (int cc = 0; cc < ((p.dbg & 8) ? 0 : N_TILE / 32); ++cc) {  // unrolled: col_acc must stay in registers
           const int c = 2 * cc + eg;
           uint32_t v[16];
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kUmmaN + c * 16;
@@ -544,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   }
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();  // pair: no CTA may leave while its peer can still signal it
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();  // no CTA may leave while its peer can still signal it
   if (warp == 1) {
     if (CTA2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -571,46 +711,75 @@ static bool cta_pairs_enabled() {
   return on;
 }
 
+template <int N_TILE, int PA, int PB, int MODE>
+static int launch_conv_gemm_cluster(const ConvGemmKParams& kp, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<N_TILE, PA, PB, MODE == 1>;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs & ~1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    FB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<N_TILE, PA, PB, MODE>, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  const int total = kp.ng * kp.n_tapgroups * (kp.rows / 2) * kp.n_tiles;
+  int clusters = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
+  if (clusters > total) clusters = total;
+  FB_CUDA(launch_cluster(conv_gemm_kernel<N_TILE, PA, PB, MODE>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes,
+                         stream, 2u, kp));
+  return 0;
+}
+
+constexpr int kHaloSmemBytes = kSmemBudget + kEpiStageBytes + 1024 + 256;
+
+template <int N_TILE, int PA, int PB>
+static int launch_conv_gemm_halo(const ConvGemmKParams& kp, cudaStream_t stream) {
+  if constexpr (N_TILE <= 128) {
+    static bool configured = false;
+    if (!configured) {
+      FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kHaloSmemBytes));
+      configured = true;
+    }
+    const int halo_bytes = (kp.tile_h + 2) * kp.tile_w * 128;
+    const int nb = (kSmemBudget - 2 * PA * halo_bytes) / (PB * ConvGemmCfg<N_TILE, PA, PB, false>::kBBytes);
+    FB_REQUIRE(nb >= 2, "fb_conv_gemm: the haloed boxes leave no room for two weight tiles");
+    const int total_super = kp.ng * kp.n_tapgroups * kp.rows * kp.n_tiles;
+    const int grid = total_super < kNumSMs ? total_super : kNumSMs;
+    FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB, 3>, dim3(grid), dim3(kThreads), kHaloSmemBytes, stream, kp));
+    return 0;
+  } else {
+    set_error("fb_conv_gemm: haloed A boxes need n_tile <= 128");
+    return FB_ERR_UNSUPPORTED;
+  }
+}
+
 template <int N_TILE, int PA, int PB>
 static int launch_conv_gemm(const ConvGemmKParams& kp, cudaStream_t stream) {
-  if (kp.cta_pair) {
-    using Cfg = ConvGemmCfg<N_TILE, PA, PB, true>;
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(kNumSMs & ~1);
-      cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int n = 0;
-      FB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<N_TILE, PA, PB, true>, &cfg));
-      max_clusters = n > 0 ? n : 1;
-    }
-    const int total = kp.ng * kp.n_tapgroups * (kp.rows / 2) * kp.n_tiles;
-    int clusters = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
-    if (clusters > total) clusters = total;
-    FB_CUDA(launch_cluster(conv_gemm_kernel<N_TILE, PA, PB, true>, dim3(2 * clusters), dim3(kThreads), Cfg::kSmemBytes,
-                           stream, 2u, kp));
-    return 0;
-  }
+  if (kp.halo) return launch_conv_gemm_halo<N_TILE, PA, PB>(kp, stream);
+  if (kp.cta_pair == 2) return launch_conv_gemm_cluster<N_TILE, PA, PB, 2>(kp, stream);
+  if (kp.cta_pair) return launch_conv_gemm_cluster<N_TILE, PA, PB, 1>(kp, stream);
   using Cfg = ConvGemmCfg<N_TILE, PA, PB, false>;
   static bool configured = false;
   if (!configured) {
-    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, PA, PB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes));
     configured = true;
   }
   const int total_super = kp.ng * kp.n_tapgroups * kp.rows * kp.n_tiles;
   const int grid = total_super < kNumSMs ? total_super : kNumSMs;
-  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB, false>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
+  FB_CUDA(launch_pdl(conv_gemm_kernel<N_TILE, PA, PB, 0>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, kp));
   return 0;
 }
 
@@ -1166,8 +1335,25 @@ extern "C" int fb_conv_gemm(const fb_conv_gemm_args* a, void* stream) {
   kp.ng = ng;
   kp.b_group_rows = a->b_group_rows;
   kp.reverse = a->reverse ? 1 : 0;
-  kp.cta_pair = a->cta_pair ? 1 : 0;
+  kp.cta_pair = a->cta_pair == 2 ? 2 : (a->cta_pair ? 1 : 0);
   FB_REQUIRE(!kp.cta_pair || pair_ok(mtg, kp.n_tiles), "fb_conv_gemm: this problem cannot run as CTA pairs");
+  kp.halo = a->halo ? 1 : 0;
+  {
+    static const int dbg = [] {
+      const char* e = getenv("FB_CONV_DBG");
+      return e ? atoi(e) : 0;
+    }();
+    kp.dbg = dbg;
+  }
+  if (kp.halo) {
+    FB_REQUIRE(!kp.cta_pair && a->tile_n == 1 && a->n_taps % 3 == 0 && a->n_tapgroups <= 1,
+               "fb_conv_gemm: haloed A boxes need single-image tiles, taps in triples and independent CTAs");
+    for (int t = 0; t < a->n_taps; t += 3)
+      for (int j = 0; j < 3; ++j)
+        FB_REQUIRE(a->taps[t + j].dh == j - 1 && a->taps[t + j].dw == a->taps[t].dw &&
+                       a->taps[t + j].phase == a->taps[t].phase,
+                   "fb_conv_gemm: tap triple %d is not (dh = -1, 0, 1) at one dw", t / 3);
+  }
   kp.out = a->out;
   kp.out_sn = a->out_sn;
   kp.out_sh = a->out_sh;

@@ -39,7 +39,7 @@ class ConvGemmArgs(C.Structure):
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("n_tapgroups", i32),
                 ("tapgroups", TapGroup * 4), ("mg_imgs", i32), ("ng", i32), ("b_group_rows", i32), ("reverse", i32),
                 ("stats_ws", vp), ("tickets", vp), ("bn_mean", vp), ("bn_rstd", vp), ("bn_batch", vp), ("bn_eps", f32),
-                ("cta_pair", i32)]
+                ("cta_pair", i32), ("halo", i32)]
 
 
 class WgradTap(C.Structure):

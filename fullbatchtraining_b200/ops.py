@@ -143,7 +143,8 @@ class ConvGemm:
     """One fb_conv_gemm problem with frozen descriptors; __call__(ng) launches it for the first ng groups."""
 
     def __init__(self, a_maps, b_maps, n_phases, a_planes, b_planes, taps, cblocks, tile, grid_h, mb, n_total, out,
-                 out_strides, accumulate, n_tile, b_group_rows=0, tapgroups=None, reverse=False, cta_pair=False):
+                 out_strides, accumulate, n_tile, b_group_rows=0, tapgroups=None, reverse=False, cta_pair=False,
+                 halo=False):
         """tapgroups: optional [(tap0, n_taps, out_off_elements)] -- tap groups that run over the same pixel grid and
         write to different offsets (the four output phases of a stride-2 dgrad in one launch)."""
         self.a_maps, self.b_maps = a_maps, b_maps
@@ -170,6 +171,7 @@ class ConvGemm:
                 args.tapgroups[i] = L.TapGroup(tap0, n_taps, off)
         args.mg_imgs = mb
         args.cta_pair = int(cta_pair)
+        args.halo = int(halo)
         args.b_group_rows = b_group_rows
         args.reverse = int(reverse)
         self.mb = mb
@@ -260,20 +262,30 @@ class Conv2dPlan:
             for kw in range(k):
                 phase, dh, dw = tap_geom(kh, kw)
                 ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
+        # haloed A boxes: the three taps of a filter column share one box of tile_h + 2 rows (taps dw-major)
+        halo = self._use_halo(allow_pair, k, stride, tile, n_tile, planes)
+        self.halo_fwd = halo
+        if halo:
+            ftaps = [(0, kh - 1, kw - 1, (kh * k + kw) * cin) for kw in range(k) for kh in range(k)]
+            xs_f = MapSet(planes)
+            for pl, t in enumerate((x_hi, x_lo)[:planes]):
+                encode_act(xs_f, pl, t, n, h, w, cin, (tile[0], tile[1] + 2, tile[2]))
+        else:
+            xs_f = xs
         self.fwd = []
         # CTA pairs (M = 256 tiles over two SMs): each CTA fetches half of every weight tile -> half-height B boxes
-        pair = self._use_pair(allow_pair, mtg, cout, n_tile, planes)
+        pair = 0 if halo else self._use_pair(allow_pair, mtg, cout, n_tile, planes)
         self.pair_fwd = pair
         for si, (wf_hi, wf_lo, _, _) in enumerate(wsets):
             bs = MapSet(wplanes)
             rows = cout * (G if si == 1 else 1)
             for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
                 encode_mat(bs, pl, t, taps * cin, rows, n_tile // 2 if pair else n_tile)
-            g = ConvGemm(xs, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
+            g = ConvGemm(xs_f, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
                          (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0,
-                         cta_pair=pair)
+                         cta_pair=pair, halo=halo)
             g.flops_per_group = self.alg_flops
-            g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}{' pair' if pair else ''}"
+            g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}{('', ' pair', ' mcast')[pair]}{' halo' if halo else ''}"
             self.fwd.append(g)
         # BatchNorm statistics fused into the forward epilogue
         self.stat_rows = L.load().fb_conv_stats_rows(mtg, cout // n_tile)
@@ -315,17 +327,25 @@ class Conv2dPlan:
                                 dtaps.append((0, dh, dw, (kh * 3 + kw) * cout))
                         tapgroups.append((tap0, len(dtaps) - tap0, (ph * w + pw) * cin))
                 strides = (h * w * cin, 2 * w * cin, 2 * cin)
-            pair_d = self._use_pair(allow_pair, mtg, cin, n_tile_d, 1)
+            halo_d = self._use_halo(allow_pair, k, stride, tile, n_tile_d, 1)
+            self.halo_dgrad = halo_d
+            if halo_d:
+                dtaps = [(0, 1 - kh, 1 - kw, (kh * k + kw) * cout) for kw in (2, 1, 0) for kh in (2, 1, 0)]
+                dys_d = MapSet(1)
+                encode_act(dys_d, 0, dy, n, ho, wo, cout, (tile[0], tile[1] + 2, tile[2]))
+            else:
+                dys_d = dys
+            pair_d = 0 if halo_d else self._use_pair(allow_pair, mtg, cin, n_tile_d, 1)
             self.pair_dgrad = pair_d
             for si, (_, _, wd_hi, wd_lo) in enumerate(wsets):
                 ds = MapSet(wplanes)
                 rows = cin * (G if si == 1 else 1)
                 for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
                     encode_mat(ds, pl, t, taps * cout, rows, n_tile_d // 2 if pair_d else n_tile_d)
-                g = ConvGemm(dys, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, mb, cin, dx, strides, False, n_tile_d,
-                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups, cta_pair=pair_d)
+                g = ConvGemm(dys_d, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, mb, cin, dx, strides, False, n_tile_d,
+                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups, cta_pair=pair_d, halo=halo_d)
                 g.flops_per_group = self.alg_flops
-                g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}{' pair' if pair_d else ''}"
+                g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}{('', ' pair', ' mcast')[pair_d]}{' halo' if halo_d else ''}"
                 self.dgrads.append(g)
 
         # ---- wgrad
@@ -375,17 +395,41 @@ class Conv2dPlan:
         self.wargs = wa
 
     @staticmethod
-    def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes):
-        """CTA pairs (fb_conv_gemm_args.cta_pair) where they pay: a pair cannot stack the hi / lo weight planes into one
-        wide instruction, so it only wins where nothing is stacked anyway (256-wide tiles) or where the stacked
-        instruction is replaced one for one (single-plane A operand = dgrad, 128-wide tiles).  Measured on B200
-        (profiles/r2_cta_pairs.txt): 4x4x512 forward 215 -> 166 us, 16x16x128 dgrad 117 -> 106 us, but 32x32x64 forward
-        258 -> 289 us.  allow_pair = "force": wherever the schedule allows (tests)."""
-        if not allow_pair or not L.load().fb_conv_pair_ok(mtg, n_total // n_tile):
+    def _use_halo(allow_pair, k, stride, tile, n_tile, a_planes):
+        """Haloed A boxes (fb_conv_gemm_args.halo) for 3x3 / stride-1 convolutions whose 128-pixel tiles are whole rows
+        of one image (32x32: 4 rows, 16x16: 8 rows) and whose N tile leaves room for the two boxes (<= 128).
+        Policy from the B200 measurements in profiles/r2_conv_limits.txt: the conv GEMMs run within 5-20 % of the
+        time they take with ALL operand loads switched off (the tcgen05 instruction stream is the bound, not L2), so
+        fewer operand bytes only pay on the 64-wide split forward (32x32x64: 257 -> 243 us); 128-wide tiles have room
+        for three weight slots only next to the boxes and lose (204 -> 233 us).
+        allow_pair = "halo" / "nohalo" force it on / off (tests); FB_HALO=0 disables, FB_HALO=all widens."""
+        ok = k == 3 and stride == 1 and tile[2] == 1 and n_tile <= 128
+        if not ok or allow_pair == "nohalo" or allow_pair == "force" or allow_pair == "mcast" or not allow_pair:
             return False
-        if allow_pair == "force" or os.environ.get("FB_PAIR_ALL") == "1":
+        env = os.environ.get("FB_HALO", "1")
+        if allow_pair == "halo" or env == "all":
             return True
-        return n_tile == 256 or (a_planes == 1 and n_tile == 128)
+        return env != "0" and a_planes == 2 and n_tile == 64
+
+    @staticmethod
+    def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes):
+        """Cluster mode of a conv GEMM (fb_conv_gemm_args.cta_pair): 0 = independent CTAs, 1 = CTA pairs (cta_group::2),
+        2 = clusters of two CTAs that share every weight tile by TMA multicast (bit-identical to 0).
+        A pair cannot stack the hi / lo weight planes into one wide instruction, so it only wins where nothing is
+        stacked anyway (256-wide tiles) or where the stacked instruction is replaced one for one (single-plane A
+        operand = dgrad, 128-wide tiles).  Measured on B200 (profiles/r2_cta_pairs.txt): 4x4x512 forward 215 -> 166 us,
+        16x16x128 dgrad 117 -> 106 us, but 32x32x64 forward 258 -> 289 us.  The multicast mode halves the weight bytes a
+        CTA pulls from L2, which turned out not to be the bound (FB_MCAST=1 enables it where the schedule allows).  allow_pair = "force" / "mcast": that mode wherever
+        the schedule allows (tests)."""
+        if not allow_pair or not L.load().fb_conv_pair_ok(mtg, n_total // n_tile):
+            return 0
+        if allow_pair == "mcast":
+            return 2
+        if allow_pair == "force" or os.environ.get("FB_PAIR_ALL") == "1":
+            return 1
+        if n_tile == 256 or (a_planes == 1 and n_tile == 128):
+            return 1
+        return 2 if os.environ.get("FB_MCAST", "0") == "1" else 0  # measured within +-2 % of independent CTAs: off
 
     @staticmethod
     def wgrad_splits(pixel_blocks_per_group, co_tiles, slot_groups, policy_groups=None):

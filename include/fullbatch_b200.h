@@ -116,8 +116,14 @@ typedef struct {
   /* CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: M = 256 tiles over two SMs, each CTA fetches half of
    * every weight tile).  1: the B maps were encoded with boxes of n_tile / 2 rows and the launch uses pairs; only valid
    * where fb_conv_pair_ok(...) says so (a function of ONE group's problem: results stay independent of ng).  A pair
-   * accumulates all operand-plane products in one accumulator: same products, another fp32 order than single-CTA tiles. */
+   * accumulates all operand-plane products in one accumulator: same products, another fp32 order than single-CTA tiles.
+   * 2: clusters of two independent CTAs that fetch half of every weight tile each and multicast it to both (same maps
+   * and conditions as 1; bit-identical to 0). */
   int32_t cta_pair;
+  /* 1: haloed A boxes for 3x3 / stride-1 problems whose tiles are whole rows of one image (tile_n == 1).  The A maps
+   * were encoded with boxes of tile_h + 2 rows, the taps come in triples (dh = -1, 0, 1 at one dw): one box fetch per
+   * (dw, channel block) serves three taps (the K order becomes dw-major; still a function of one group's problem). */
+  int32_t halo;
 } fb_conv_gemm_args;
 /* partial rows per (group, N tile) written to stats_ws for m_tiles_per_group x n_tiles tiles per group */
 int fb_conv_stats_rows(int m_tiles_per_group, int n_tiles);

@@ -250,6 +250,58 @@ def test_cta_pairs_match_single_cta_tiles(case, use_split):
             assert torch.equal(a.mean, b.mean) and torch.equal(a.rstd, b.rstd) and torch.equal(a.bn_batch, b.bn_batch)
 
 
+@pytest.mark.parametrize("case", [(8, 3, 32, 32, 64, 64, 3, 1), (8, 2, 16, 16, 128, 128, 3, 1), (16, 2, 8, 8, 256, 512, 3, 2),
+                                  (16, 3, 4, 4, 512, 512, 3, 1), (8, 2, 16, 16, 64, 256, 1, 1), (4, 2, 32, 32, 64, 128, 3, 2)],
+                         ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("use_split", [True, False], ids=["split", "bf16"])
+def test_weight_multicast_is_bit_identical_to_independent_ctas(case, use_split):
+    """Clusters of two CTAs sharing every weight tile by TMA multicast (cta_pair = 2) issue exactly the instructions of
+    two independent CTAs: outputs, fused BatchNorm statistics and dgrad are bit for bit those of the plain launch."""
+    mb, G, h, w, cin, cout, k, stride = case
+    a = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair="mcast")
+    b = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair=False)
+    assert a.plan.pair_fwd == 2 and not b.plan.pair_fwd, "the case is meant to exercise the multicast mode"
+    for wset in (0, 1):
+        for c in (a, b):
+            c.y.fill_(float("nan"))
+            c.dx.fill_(float("nan"))
+            c.plan.forward(G, wset, c.bn_batch.data_ptr())
+            c.plan.dgrad(G, wset)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a.y).all() and torch.isfinite(a.dx).all()
+        assert torch.equal(a.y, b.y) and torch.equal(a.dx, b.dx)
+        assert torch.equal(a.mean, b.mean) and torch.equal(a.rstd, b.rstd) and torch.equal(a.bn_batch, b.bn_batch)
+
+
+@pytest.mark.parametrize("case", [(8, 3, 32, 32, 64, 64, 3, 1), (8, 2, 16, 16, 128, 128, 3, 1), (4, 2, 32, 32, 128, 64, 3, 1),
+                                  (8, 1, 16, 16, 64, 128, 3, 1), (3, 2, 32, 32, 64, 64, 3, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("use_split", [True, False], ids=["split", "bf16"])
+def test_haloed_boxes_match_per_tap_boxes(case, use_split):
+    """3x3 / stride-1 forward and dgrad with ONE haloed A box per filter column (fb_conv_gemm_args.halo) against the
+    launch that fetches a box per tap: the same products summed column-major instead of row-major over the taps (fp32
+    order: 2e-5 of the output scale), fused BatchNorm statistics included; per-group weights; image borders."""
+    mb, G, h, w, cin, cout, k, stride = case
+    a = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair="halo")
+    b = ConvCase(mb, G, h, w, cin, cout, k, stride, use_split, allow_pair="nohalo")
+    assert a.plan.halo_fwd and a.plan.halo_dgrad and not b.plan.halo_fwd and not b.plan.halo_dgrad
+    for wset in (0, 1):
+        for c in (a, b):
+            c.y.fill_(float("nan"))
+            c.dx.fill_(float("nan"))
+            c.plan.forward(G, wset, c.bn_batch.data_ptr())
+            c.plan.dgrad(G, wset)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a.y).all() and torch.isfinite(a.dx).all()
+        assert rel_err(a.y, b.y) < 2e-5 and rel_err(a.dx, b.dx) < 2e-5
+        assert float((a.mean - b.mean).abs().max()) < 1e-6 * float(b.y.abs().max()) and rel_err(a.rstd, b.rstd) < 1e-5
+    # twice the same launch: bit-identical
+    y0 = a.y.clone()
+    a.plan.forward(G, 1, a.bn_batch.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(y0, a.y)
+
+
 def test_weight_prep_layouts():
     g = torch.Generator(device="cuda").manual_seed(3)
     cout, cin = 128, 64
