@@ -254,17 +254,17 @@ __global__ void __launch_bounds__(256) mean_accumulate_kernel(float* __restrict_
   }
 }
 
-__global__ void group_finish_kernel(int* cursor, int ng, int cursor_step, float* scal, int loss_slot, int correct_slot,
-                                    int loss_base, int correct_base) {
+__global__ void group_finish_kernel(int* cursor, int ng, int cursor_step, const float* scal, float* totals, int loss_slot,
+                                    int correct_slot, int loss_base, int correct_base) {
   griddep_wait();
   griddep_launch();
-  float loss = scal[loss_slot], correct = scal[correct_slot];
+  float loss = totals[loss_slot], correct = totals[correct_slot];
   for (int g = 0; g < ng; ++g) {  // training.py:172-173, loader order
     loss += scal[loss_base + g];
     correct += scal[correct_base + g];
   }
-  scal[loss_slot] = loss;
-  scal[correct_slot] = correct;
+  totals[loss_slot] = loss;
+  totals[correct_slot] = correct;
   *cursor += cursor_step;
 }
 
@@ -391,11 +391,12 @@ extern "C" int fb_mean_accumulate(float* grad, int64_t gstride, float* avg, int6
   return 0;
 }
 
-extern "C" int fb_group_finish(int32_t* cursor, int ng, int cursor_step, float* scal, int loss_slot, int correct_slot,
-                               int loss_base, int correct_base, void* stream) {
-  FB_REQUIRE(cursor && scal && ng >= 1 && ng <= FB_MAX_GROUPS && cursor_step >= 0, "fb_group_finish: bad arguments");
+extern "C" int fb_group_finish(int32_t* cursor, int ng, int cursor_step, const float* scal, float* totals, int loss_slot,
+                               int correct_slot, int loss_base, int correct_base, void* stream) {
+  FB_REQUIRE(cursor && scal && totals && ng >= 1 && ng <= FB_MAX_GROUPS && cursor_step >= 0,
+             "fb_group_finish: bad arguments");
   FB_CUDA(launch_pdl(group_finish_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), (int*)cursor, ng,
-                     cursor_step, scal, loss_slot, correct_slot, loss_base, correct_base));
+                     cursor_step, scal, totals, loss_slot, correct_slot, loss_base, correct_base));
   return 0;
 }
 

@@ -599,7 +599,10 @@ class FullBatchEngine:
             ops.mean_accumulate(g, st, dst, n, ng, self.cursor, self.scal, S_N2G, batch_clip or 0.0, S_CLIPPED)
         self.ema(passes, ng, BN_MOMENTUM)
         if mode != "reg":
-            ops.group_finish(self.cursor, ng, self.scal, S_LOSS, S_CORRECT, S_LOSSG, S_CORRG, cursor_step=cursor_step)
+            # the sums live in lane 0's scalars: commits run in loader order on the main stream, so the loss is added up
+            # microbatch by microbatch whatever the group and lane counts are
+            ops.group_finish(self.cursor, ng, self.scal, S_LOSS, S_CORRECT, S_LOSSG, S_CORRG, cursor_step=cursor_step,
+                             totals=self.root.scal)
 
     def _group_ops(self, x_src, labels_src, perm, first, use_cursor, ng, block_strength, eps, accumulate, write_g,
                    mode="full", impl="forward", acc=0.0, batch_clip=None, target="avg"):
@@ -690,13 +693,14 @@ class FullBatchEngine:
     def _save_state(self, mode):
         root = self.root
         bufs = [b.clone() for b in self.model.buffers()]
-        return dict(avg=root.avg_n.clone(), scal=self.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
+        return dict(avg=root.avg_n.clone(), scal=self.scal.clone(), totals=root.scal.clone(), cursor=self.cursor.clone(), bufs=bufs,
                     norms=root.grad_norms.clone(), g=self.g_n[0].clone() if mode == "reg" else None,
                     pre=root.pre_n.clone() if hasattr(root, "pre_n") else None)
 
     def _restore_state(self, st):
         root = self.root
         root.avg_n.copy_(st["avg"])
+        root.scal.copy_(st["totals"])  # the loss / accuracy sums of every lane's commits live in lane 0's scalars
         self.scal.copy_(st["scal"])
         self.cursor.copy_(st["cursor"])
         root.grad_norms.copy_(st["norms"])
@@ -786,11 +790,11 @@ class FullBatchEngine:
         lane.commit_done.record(main)
 
     def _fold_lanes(self):
-        """loss / accuracy / clip counters of the other lanes into lane 0's (device side, main stream)"""
+        """clip counters of the other lanes into lane 0's (device side, main stream; whole numbers: any order is exact).
+        The loss / accuracy sums are accumulated in lane 0's scalars by every lane's commit (fb_group_finish totals)."""
         for lane in self.lanes[1:]:
-            for slot in (S_LOSS, S_CORRECT, S_CLIPPED):  # (not S_CF: every lane carries its own copy of lr/4)
-                self.scal[slot] += lane.scal[slot]
-                lane.scal[slot] = 0
+            self.scal[S_CLIPPED] += lane.scal[S_CLIPPED]
+            lane.scal[S_CLIPPED] = 0
 
     def _run_groups(self, count, make):
         """count microbatches as full launches of G groups plus one shorter launch, alternating between the lanes;

@@ -112,7 +112,7 @@ _SIGNATURES = {
     "fb_perturb_ranges": ([vp, vp, i64, vp, vp, i32, i64, f32, f32, f32, vp, i32, vp, i64, i32, vp], i32),
     "fb_fd_combine": ([vp, vp, vp, i64, vp, i64, i32, vp, i32, i32, vp, i32, vp], i32),
     "fb_mean_accumulate": ([vp, i64, vp, i64, i32, vp, vp, i32, f32, i32, vp], i32),
-    "fb_group_finish": ([vp, i32, i32, vp, i32, i32, i32, i32, vp], i32),
+    "fb_group_finish": ([vp, i32, i32, vp, vp, i32, i32, i32, i32, vp], i32),
     "fb_flat_scale": ([vp, i64, f32, vp], i32),
     "fb_flat_relayout": ([vp, vp, i64, vp, i32, i32, i32, vp], i32),
     "fb_sgd_step": ([vp, vp, vp, i64, vp, i32, f32, f32, f32, f32, f32, i32, i32, i32, vp, i32, vp], i32),

@@ -398,18 +398,15 @@ class Conv2dPlan:
     def _use_halo(allow_pair, k, stride, tile, n_tile, a_planes):
         """Haloed A boxes (fb_conv_gemm_args.halo) for 3x3 / stride-1 convolutions whose 128-pixel tiles are whole rows
         of one image (32x32: 4 rows, 16x16: 8 rows) and whose N tile leaves room for the two boxes (<= 128).
-        Policy from the B200 measurements in profiles/r2_conv_limits.txt: the conv GEMMs run within 5-20 % of the
-        time they take with ALL operand loads switched off (the tcgen05 instruction stream is the bound, not L2), so
-        fewer operand bytes only pay on the 64-wide split forward (32x32x64: 257 -> 243 us); 128-wide tiles have room
-        for three weight slots only next to the boxes and lose (204 -> 233 us).
-        allow_pair = "halo" / "nohalo" force it on / off (tests); FB_HALO=0 disables, FB_HALO=all widens."""
+        B200 measurements (profiles/r2_conv_limits.txt): the conv GEMMs run within 5-20 % of the time they take with
+        ALL operand loads switched off (the tcgen05 instruction stream is the bound, not L2), so fetching a third to a
+        half fewer operand bytes is worth only ~1 % of the step (39.0k -> 39.45k images/s in a 50k-image run, mostly
+        the 64-wide split forward: 257 -> 243 us).  allow_pair = "halo" / "nohalo" force it on / off (tests);
+        FB_HALO=0 disables."""
         ok = k == 3 and stride == 1 and tile[2] == 1 and n_tile <= 128
         if not ok or allow_pair == "nohalo" or allow_pair == "force" or allow_pair == "mcast" or not allow_pair:
             return False
-        env = os.environ.get("FB_HALO", "1")
-        if allow_pair == "halo" or env == "all":
-            return True
-        return env != "0" and a_planes == 2 and n_tile == 64
+        return allow_pair == "halo" or os.environ.get("FB_HALO", "1") != "0"
 
     @staticmethod
     def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes):
@@ -683,10 +680,11 @@ def mean_accumulate(grad, gstride, avg, n, ng, cursor, scal=None, norm_base=0, c
           L.ptr(cursor), L.ptr(scal), norm_base, clip, clipped_slot)
 
 
-def group_finish(cursor, ng, scal, loss_slot, correct_slot, loss_base, correct_base, cursor_step=None):
+def group_finish(cursor, ng, scal, loss_slot, correct_slot, loss_base, correct_base, cursor_step=None, totals=None):
+    """totals: the scalar block that holds the loss / accuracy sums (shared by all lanes; default: scal itself)"""
     _call("misc", 8.0 * ng + 16.0, "byte", "fb_group_finish", cursor.data_ptr(), ng,
-          ng if cursor_step is None else cursor_step, scal.data_ptr(), loss_slot,
-          correct_slot, loss_base, correct_base)
+          ng if cursor_step is None else cursor_step, scal.data_ptr(), (scal if totals is None else totals).data_ptr(),
+          loss_slot, correct_slot, loss_base, correct_base)
 
 
 def flat_scale(x, n, alpha):

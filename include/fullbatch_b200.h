@@ -330,10 +330,12 @@ int fb_fd_combine(float* grad, const float* g_plus, const float* g_minus, int64_
 int fb_mean_accumulate(float* grad, int64_t gstride, float* avg, int64_t n, int ng, const int32_t* cursor, float* scal,
                        int norm_base, float clip, int clipped_slot, void* stream);
 /* End of a group launch: *cursor += cursor_step (the number of microbatches until this lane's next launch: ng for one
- * lane, lanes * G when launches alternate between lanes); scal[loss_slot] += scal[loss_base + g], scal[correct_slot] +=
- * scal[correct_base + g] for g in order (training.py:172-173) */
-int fb_group_finish(int32_t* cursor, int ng, int cursor_step, float* scal, int loss_slot, int correct_slot, int loss_base,
-                    int correct_base, void* stream);
+ * lane, lanes * G when launches alternate between lanes); totals[loss_slot] += scal[loss_base + g],
+ * totals[correct_slot] += scal[correct_base + g] for g in order (training.py:172-173).  `totals` is shared by all lanes
+ * (may be `scal` itself): called in loader order, the loss is summed microbatch by microbatch whatever ng and the lane
+ * count are. */
+int fb_group_finish(int32_t* cursor, int ng, int cursor_step, const float* scal, float* totals, int loss_slot,
+                    int correct_slot, int loss_base, int correct_base, void* stream);
 /* x *= alpha over n elements (rank-weighting before the all-reduce, training/utils.py:31-41) */
 int fb_flat_scale(float* x, int64_t n, float alpha, void* stream);
 

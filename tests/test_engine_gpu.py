@@ -69,13 +69,13 @@ def dump(name, d):
     print(name, json.dumps(d))
 
 
-def compare_step(name, depth, mb, model, params, buffers, X, Y, groups=None, per_microbatch=True):
+def compare_step(name, depth, mb, model, params, buffers, X, Y, groups=None, per_microbatch=True, precision="split"):
     """One full-batch step of the engine against the oracle in fp64 (truth) and fp32 (the reference's own arithmetic);
     returns the report that is also written to gpurun_out/parity_<name>.json."""
     n = X.shape[0]
     ref64, buf64 = oracle_run(depth, params, buffers, X, Y, mb, torch.float64)
     ref32, _ = oracle_run(depth, params, buffers, X, Y, mb, torch.float32)
-    eng = FullBatchEngine(model, mb, precision="split", groups=groups)
+    eng = FullBatchEngine(model, mb, precision=precision, groups=groups)
     theta0 = eng.theta.clone()
     K = eng.accumulate_resident(X, Y, HYP["lr"], HYP["block_strength"], HYP["eps"])
     res = eng.results(K)
@@ -132,6 +132,26 @@ def test_full_batch_step_matches_oracle(depth, mb, n, groups):
     model, params, buffers, X, Y = setup_case(depth, mb, n)
     rep, _, _, _ = compare_step(f"r{depth}_mb{mb}_n{n}", depth, mb, model, params, buffers, X, Y, groups=groups)
     assert_step(rep, depth)
+
+
+def test_numerics_ablation_plain_bf16_against_split_operands():
+    """The numerics decision of DESIGN.md section 4 as a measurement: the same step with single bf16 operands (one product
+    per MAC, `precision="bf16"`) and with hi/lo split operands (3 / 2 / 2 products), each against the fp64 oracle, next
+    to the fp32 oracle's own error.  Plain bf16 fails the parity bars of this file by an order of magnitude on the
+    finite-difference term; the split operands pass them.  Written to gpurun_out/parity_ablation_r18_mb128_n256.json."""
+    out = {}
+    for precision in ("bf16", "split"):
+        model, params, buffers, X, Y = setup_case(18, 128, 256)
+        rep, eng, _, _ = compare_step(f"ablation_{precision}", 18, 128, model, params, buffers, X, Y, precision=precision)
+        out[precision] = {k: rep[k] for k in ("e_new_raw", "e_new_reg", "e_new_avg", "cos_raw", "cos_reg", "cos_avg",
+                                              "e_new_loss", "e_new_grad_norms")}
+        out["fp32_oracle"] = {k: rep[k] for k in ("e32_raw", "e32_reg", "e32_avg", "e32_loss", "e32_grad_norms")}
+        del eng
+    dump("ablation_r18_mb128_n256", out)
+    s, b = out["split"], out["bf16"]
+    assert s["e_new_raw"] * 20 < b["e_new_raw"] and s["e_new_reg"] * 5 < b["e_new_reg"]
+    # plain bf16 would not pass assert_step
+    assert b["e_new_raw"] > RATIO_RAW * max(out["fp32_oracle"]["e32_raw"], FLOOR_RAW)
 
 
 def test_resnet152_real_microbatch_in_a_conditioned_state():
@@ -315,11 +335,8 @@ def test_result_does_not_depend_on_the_lane_count():
                                                                                    float(res["clipped_batches"])]),
                          torch.cat([b.reshape(-1).float() for b in model.buffers()])))
             assert K == 7
-        for i, (a, b) in enumerate(zip(*outs)):
-            if i == 2:  # loss / accuracy / clip counters: summed per lane, then over the lanes (another fp32 order)
-                assert torch.allclose(a, b, rtol=1e-6)
-            else:       # accumulated gradient, gradient norms, BatchNorm running statistics: bit for bit
-                assert torch.equal(a, b)
+        for a, b in zip(*outs):  # gradient, gradient norms, loss / accuracy / clip counters, running statistics
+            assert torch.equal(a, b)
     # streamed from the host: three staging buffers, two lanes
     model, params, buffers, X, Y = setup_case(depth, mb, n)
     eng = FullBatchEngine(model, mb, precision="split", groups=2, lanes=2)
@@ -328,7 +345,7 @@ def test_result_does_not_depend_on_the_lane_count():
     eng1 = FullBatchEngine(model1, mb, precision="split", groups=2, lanes=1)
     eng1.accumulate_resident(X, Y, 0.8, 0.5, 1e-2)
     assert K == 7 and torch.equal(eng.avg, eng1.avg)
-    assert eng.results(K)["loss_sum"] == pytest.approx(eng1.results(K)["loss_sum"], rel=1e-6)
+    assert eng.results(K)["loss_sum"] == eng1.results(K)["loss_sum"]
 
 
 def test_graph_replay_equals_eager():

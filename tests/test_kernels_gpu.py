@@ -719,6 +719,10 @@ def test_flat_fd_kernels():
     scal[80:80 + G] = torch.tensor([3.0, 4.0, 5.0], device=DEV)
     ops.group_finish(cursor, G, scal, 0, 1, 64, 80)
     assert int(cursor) == 2 + G and float(scal[0]) == 1.5 + 0.875 and float(scal[1]) == 22.0
+    # sums kept in another scalar block (shared by the lanes), cursor advanced by the lanes' stride
+    totals = torch.zeros(8, device=DEV)
+    ops.group_finish(cursor, G, scal, 0, 1, 64, 80, cursor_step=2 * G, totals=totals)
+    assert int(cursor) == 2 + 3 * G and float(totals[0]) == 0.875 and float(totals[1]) == 12.0 and float(scal[0]) == 2.375
     x = grad[0, :n].clone()
     ops.flat_scale(x, n, 0.25)
     assert torch.equal(x, grad[0, :n] * 0.25)
