@@ -325,7 +325,8 @@ class FullBatchEngine:
         self.commit_done = torch.cuda.Event()             # its previous launch has been combined: g / g2 are free again
         if _parent is None:
             # further lanes, if their buffers fit next to lane 0's (FB_LANES / lanes= overrides; 1 = no concurrency)
-            want = int(lanes or os.environ.get("FB_LANES", "2"))
+            # default: 2; 3 where a launch is small (< 1,024 images: ResNet-152 at microbatch 32 gains another 3.5 %)
+            want = int(lanes or os.environ.get("FB_LANES", "2" if self.G * self.mb >= 1024 else "3"))
             torch.cuda.synchronize(dev)
             footprint = torch.cuda.memory_allocated(dev) - mem0
             for _ in range(1, max(want, 1)):
