@@ -119,7 +119,7 @@ class Unit:
         self.plan = ops.Conv2dPlan(eng.mb, G, h, w, x.c, cout, k, stride, x.hi, x.lo, self.y, self.dy, dx, self.w,
                                    self.w_offset, split=split, alg_k=27 if stem else None,
                                    grad_cols=27 if stem else None, bn=(self.mean, self.rstd, BN_EPS),
-                                   policy_groups=eng.policy_groups)
+                                   policy_groups=eng.policy_groups, fwd_hi_only=eng.precision == "split_w")
         self.out = None
         eng.unit_by_name[conv_name] = self
 
@@ -155,7 +155,7 @@ class FullBatchEngine:
         if not isinstance(model, ResNet):
             raise RuntimeError("FullBatchEngine needs a model built by fullbatchtraining_b200.construct_model "
                                "(there is no fallback path)")
-        if precision not in ("split", "bf16"):
+        if precision not in ("split", "bf16", "split_w"):
             raise ValueError(f"unknown precision {precision!r}")
         if not torch.cuda.is_available():
             raise RuntimeError("FullBatchEngine needs a CUDA device (B200); there is no CPU path")
@@ -176,7 +176,7 @@ class FullBatchEngine:
         # launches are tuned for `policy_groups` microbatches (default ops.POLICY_GROUPS = 8; the stochastic branch, which
         # only ever launches one, passes 1).  Fixed per engine, independent of G: results do not depend on G.
         self.policy_groups = int(policy_groups or ops.POLICY_GROUPS)
-        self.split = precision == "split"
+        self.split = precision in ("split", "split_w")  # "split_w": numerics ablation, forward reads x_hi only
         self.precision = precision
         self.smoothing = float(label_smoothing)
         self.classes = model.fc.out_features

@@ -213,7 +213,9 @@ class Conv2dPlan:
     """
 
     def __init__(self, mb, G, h, w, cin, cout, k, stride, x_hi, x_lo, y, dy, dx, wsets, w_offset, split=True, alg_k=None,
-                 grad_cols=None, bn=None, allow_pair=True, policy_groups=None):
+                 grad_cols=None, bn=None, allow_pair=True, policy_groups=None, fwd_hi_only=False):
+        """fwd_hi_only: the forward GEMM reads only the hi plane of the activations (2 products per MAC instead of 3:
+        drops x_lo * w_hi; numerics ablation, engine precision "split_w")."""
         assert k in (1, 3) and stride in (1, 2) and cin % 64 == 0 and cout % 64 == 0
         assert not (k == 1 and stride == 2)
         self.mb, self.G, self.h, self.w, self.cin, self.cout, self.k, self.stride = mb, G, h, w, cin, cout, k, stride
@@ -255,7 +257,14 @@ class Conv2dPlan:
             return ph * 2 + pw, dh, dw
 
         # ---- forward (one ConvGemm per weight set)
-        n_tile = choose_n_tile(mtg * policy, cout, planes, wplanes)
+        fplanes = 1 if fwd_hi_only else planes  # operand planes of the forward A operand
+        xs_fwd = xs
+        if fplanes != planes:
+            xs_fwd = MapSet(nph)
+            for p in range(nph):
+                encode_act(xs_fwd, p, x_hi, n, h, w, cin, tile, phase=(p // 2, p % 2) if stride == 2 else None)
+            self.x_maps_fwd = xs_fwd
+        n_tile = choose_n_tile(mtg * policy, cout, fplanes, wplanes)
         self.n_tile = n_tile
         ftaps = []
         for kh in range(k):
@@ -263,25 +272,25 @@ class Conv2dPlan:
                 phase, dh, dw = tap_geom(kh, kw)
                 ftaps.append((phase, dh, dw, (kh * k + kw) * cin))
         # haloed A boxes: the three taps of a filter column share one box of tile_h + 2 rows (taps dw-major)
-        halo = self._use_halo(allow_pair, k, stride, tile, n_tile, planes)
+        halo = self._use_halo(allow_pair, k, stride, tile, n_tile, fplanes)
         self.halo_fwd = halo
         if halo:
             ftaps = [(0, kh - 1, kw - 1, (kh * k + kw) * cin) for kw in range(k) for kh in range(k)]
-            xs_f = MapSet(planes)
-            for pl, t in enumerate((x_hi, x_lo)[:planes]):
+            xs_f = MapSet(fplanes)
+            for pl, t in enumerate((x_hi, x_lo)[:fplanes]):
                 encode_act(xs_f, pl, t, n, h, w, cin, (tile[0], tile[1] + 2, tile[2]))
         else:
-            xs_f = xs
+            xs_f = xs_fwd
         self.fwd = []
         # CTA pairs (M = 256 tiles over two SMs): each CTA fetches half of every weight tile -> half-height B boxes
-        pair = 0 if halo else self._use_pair(allow_pair, mtg, cout, n_tile, planes)
+        pair = 0 if halo else self._use_pair(allow_pair, mtg, cout, n_tile, fplanes)
         self.pair_fwd = pair
         for si, (wf_hi, wf_lo, _, _) in enumerate(wsets):
             bs = MapSet(wplanes)
             rows = cout * (G if si == 1 else 1)
             for pl, t in enumerate((wf_hi, wf_lo)[:wplanes]):
                 encode_mat(bs, pl, t, taps * cin, rows, n_tile // 2 if pair else n_tile)
-            g = ConvGemm(xs_f, bs, nph, planes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
+            g = ConvGemm(xs_f, bs, nph, fplanes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
                          (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0,
                          cta_pair=pair, halo=halo)
             g.flops_per_group = self.alg_flops

@@ -142,7 +142,7 @@ def test_numerics_ablation_plain_bf16_against_split_operands():
     to the fp32 oracle's own error.  Plain bf16 fails the parity bars of this file by an order of magnitude on the
     finite-difference term; the split operands pass them.  Written to gpurun_out/parity_ablation_r18_mb128_n256.json."""
     out = {}
-    for precision in ("bf16", "split"):
+    for precision in ("bf16", "split_w", "split"):  # split_w: forward without the x_lo * w_hi product (2 per MAC)
         model, params, buffers, X, Y = setup_case(18, 128, 256)
         rep, eng, _, _ = compare_step(f"ablation_{precision}", 18, 128, model, params, buffers, X, Y, precision=precision)
         out[precision] = {k: rep[k] for k in ("e_new_raw", "e_new_reg", "e_new_avg", "cos_raw", "cos_reg", "cos_avg",
