@@ -64,6 +64,17 @@ def default_groups(microbatch):
     return max(1, min(8, L.FB_MAX_GROUPS, 1024 // max(int(microbatch), 1)))
 
 
+def launch_sizes(count, groups):
+    """Microbatches per group launch for a pass over `count` microbatches: as few launches as `groups` allows, sizes
+    equal up to one (49 -> 7 x 7 rather than 6 x 8 + 1: a launch of one group costs about as much as one of three).
+    Results do not depend on the sizes (every reduction order is a function of ONE group's problem)."""
+    if count <= 0:
+        return []
+    n = -(-count // groups)
+    q, r = divmod(count, n)
+    return [q + 1] * r + [q] * (n - r)
+
+
 class Act:
     """An activation tensor [n,h,w,c]: bf16 hi/lo planes (+ fp32 gradient buffer when it needs one)."""
 
@@ -753,24 +764,27 @@ class FullBatchEngine:
             lane.scal[S_CLIPPED] = 0
             lane.cursor.zero_()
 
+    def launch_sizes(self, count):
+        return launch_sizes(count, self.G)
+
     def _begin_lanes(self):
-        """Lane l starts at microbatch l*G and advances by lanes*G per launch: its cursor always is the index (in loader
-        order) of the first microbatch of its current launch."""
-        for l, lane in enumerate(self.lanes):
-            lane.cursor.fill_(l * self.G)
+        """A lane's cursor is the index (in loader order) of the first microbatch of its current launch; _launch sets it
+        on the lane's stream once the lane's previous launch has been committed."""
         self._fork = torch.cuda.Event()
         self._fork.record(torch.cuda.current_stream())
 
-    def _launch(self, j, ng, make, wait=None, after=None):
-        """Group launch number j of a pass: compute on lane j % lanes (its own stream, once its previous launch has been
-        combined), commit on the current (main) stream -- commits therefore run in launch order."""
+    def _launch(self, j, ng, make, start, wait=None, after=None):
+        """Group launch number j of a pass, microbatches start .. start + ng - 1: compute on lane j % lanes (its own
+        stream, once its previous launch has been combined), commit on the current (main) stream -- commits therefore
+        run in launch order."""
         lanes = self.lanes
         lane = lanes[j % len(lanes)]
         main = torch.cuda.current_stream()
-        compute, commit = make(lane, ng, len(lanes) * self.G)
+        compute, commit = make(lane, ng, 0)
         if len(lanes) == 1:  # no concurrency: everything in stream order
             if wait is not None:
                 main.wait_event(wait)
+            lane.cursor.fill_(start)
             compute()
             if after is not None:
                 after.record(main)
@@ -781,6 +795,7 @@ class FullBatchEngine:
             lane.stream.wait_event(lane.commit_done)
             if wait is not None:
                 lane.stream.wait_event(wait)
+            lane.cursor.fill_(start)
             compute()
             if after is not None:
                 after.record(lane.stream)
@@ -798,14 +813,13 @@ class FullBatchEngine:
             lane.scal[S_CLIPPED] = 0
 
     def _run_groups(self, count, make):
-        """count microbatches as full launches of G groups plus one shorter launch, alternating between the lanes;
+        """count microbatches as launches of launch_sizes(count) groups, alternating between the lanes;
         make(lane, ng, cursor_step) -> (compute, commit)"""
         self._begin_lanes()
-        full, rem = divmod(count, self.G)
-        for j in range(full):
-            self._launch(j, self.G, make)
-        if rem:
-            self._launch(full, rem, make)
+        start = 0
+        for j, ng in enumerate(self.launch_sizes(count)):
+            self._launch(j, ng, make, start)
+            start += ng
         self._fold_lanes()
 
     def accumulate_resident(self, X, Y, lr, block_strength, eps, first=0, count=None, perm=None, use_graph=True,
@@ -871,7 +885,8 @@ class FullBatchEngine:
         self.set_lr(lr)
         self._begin_lanes()
         mb, n_stage = self.mb, len(xs)
-        state = dict(k=0, slot=0, launch=0, h2d=0)
+        state = dict(k=0, slot=0, launch=0, h2d=0, start=0)
+        sizes = self.launch_sizes(num_microbatches)
 
         def flush():
             j, ng = state["launch"], state["slot"]
@@ -882,8 +897,8 @@ class FullBatchEngine:
             ready.record(self._copy_stream)
             self._launch(j, ng, lambda lane, g, step: lane._lane_programs(xs[i], ys[i], None, 0, False, g, block_strength,
                                                                           eps, step, use_graph=use_graph),
-                         wait=ready, after=self._stage_free[i])
-            state["launch"], state["slot"] = j + 1, 0
+                         state["start"], wait=ready, after=self._stage_free[i])
+            state["launch"], state["slot"], state["start"] = j + 1, 0, state["start"] + ng
 
         for inputs, labels in loader:
             chunks = max(labels.shape[0] // mb, 1)
@@ -899,7 +914,7 @@ class FullBatchEngine:
                 state["h2d"] += xc.numel() * xc.element_size() + yc.numel() * yc.element_size()
                 state["k"] += 1
                 state["slot"] = j + 1
-                if state["slot"] == self.G:
+                if state["slot"] == (sizes[state["launch"]] if state["launch"] < len(sizes) else self.G):
                     flush()
         flush()
         self._fold_lanes()

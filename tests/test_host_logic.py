@@ -54,6 +54,21 @@ def test_wgrad_policies():
     assert "ng" not in inspect.signature(ops.choose_n_tile).parameters
 
 
+def test_launch_sizes_are_balanced():
+    # as few launches as G allows, sizes equal up to one, loader order preserved by the caller
+    assert engine.launch_sizes(390, 8) == [8] * 47 + [7] * 2
+    assert engine.launch_sizes(49, 8) == [7] * 7
+    assert engine.launch_sizes(48, 8) == [8] * 6
+    assert engine.launch_sizes(15, 8) == [8, 7]
+    assert engine.launch_sizes(3, 8) == [3]
+    assert engine.launch_sizes(0, 8) == []
+    for count in range(1, 200):
+        for G in (1, 2, 5, 8, 16):
+            sizes = engine.launch_sizes(count, G)
+            assert sum(sizes) == count and max(sizes) <= G and max(sizes) - min(sizes) <= 1
+            assert len(sizes) == -(-count // G)
+
+
 def test_default_groups(monkeypatch):
     monkeypatch.delenv("FB_GROUPS", raising=False)
     assert engine.default_groups(128) == 8
