@@ -215,7 +215,9 @@ def load_traffic(args, family):
         return None, None
     with open(path) as f:
         t = json.load(f)
-    entry = t.get(f"{args.workload}:{args.precision}", {}).get(family)
+    # r18_2k / r18_500k replay the very same group launch (8 microbatches of 128) as r18_50k
+    workload = "r18_50k" if args.workload in ("r18_2k", "r18_500k") else args.workload
+    entry = t.get(f"{workload}:{args.precision}", {}).get(family)
     return (entry["dram_bytes_per_launch"], t.get("source")) if entry else (None, None)
 
 
@@ -395,6 +397,8 @@ def run_ours(args):
     step_tflops = value * gflop / 1e3
     if sgd:
         del trainer0
+    engine_info = dict(microbatches_per_launch=eng.G, lanes=len(eng.lanes),
+                       device_memory_gib=round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1))
     del eng, model
     torch.cuda.empty_cache()
 
@@ -440,7 +444,8 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit="images/s",
                     n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
                     scaling="strong", vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "bf16x2 (hi+lo)",
-                    data="synthetic", config=workload_config(args), clocks=clocks,
+                    data="synthetic", config=dict(workload_config(args), **engine_info),
+                    clocks=clocks,
                     e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, api="fullbatchtraining_b200.training.Trainer.step"),
                     gpu_launches=launches_per_group * group_launches * args.steps, roofline=roofline,
