@@ -39,7 +39,7 @@ class ConvGemmArgs(C.Structure):
                 ("out_sn", i64), ("out_sh", i64), ("out_sw", i64), ("accumulate", i32), ("n_tapgroups", i32),
                 ("tapgroups", TapGroup * 4), ("mg_imgs", i32), ("ng", i32), ("b_group_rows", i32), ("reverse", i32),
                 ("stats_ws", vp), ("tickets", vp), ("bn_mean", vp), ("bn_rstd", vp), ("bn_batch", vp), ("bn_eps", f32),
-                ("cta_pair", i32), ("halo", i32)]
+                ("cta_pair", i32), ("halo", i32), ("policy_groups", i32), ("sched_k_iters", i32)]
 
 
 class WgradTap(C.Structure):
@@ -91,8 +91,8 @@ _SIGNATURES = {
     "fb_tmap_encode_act4d": ([vp, vp, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32, i32], i32),
     "fb_tmap_encode_mat2d": ([vp, vp, i32, i32, i64, i32, i32], i32),
     "fb_conv_gemm": ([C.POINTER(ConvGemmArgs), vp], i32),
-    "fb_conv_stats_rows": ([i32, i32], i32),
-    "fb_conv_pair_ok": ([i32, i32], i32),
+    "fb_conv_stats_rows": ([i32, i32, i32, i32], i32),
+    "fb_conv_pair_ok": ([i32, i32, i32, i32], i32),
     "fb_conv_wgrad": ([C.POINTER(WgradArgs), vp], i32),
     "fb_reduce_multi": ([vp, i32, i32, vp, i64, i32, vp], i32),
     "fb_weight_prep": ([vp, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp], i32),

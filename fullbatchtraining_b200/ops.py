@@ -144,7 +144,7 @@ class ConvGemm:
 
     def __init__(self, a_maps, b_maps, n_phases, a_planes, b_planes, taps, cblocks, tile, grid_h, mb, n_total, out,
                  out_strides, accumulate, n_tile, b_group_rows=0, tapgroups=None, reverse=False, cta_pair=False,
-                 halo=False):
+                 halo=False, policy_groups=1, sched_k_iters=0):
         """tapgroups: optional [(tap0, n_taps, out_off_elements)] -- tap groups that run over the same pixel grid and
         write to different offsets (the four output phases of a stride-2 dgrad in one launch)."""
         self.a_maps, self.b_maps = a_maps, b_maps
@@ -172,6 +172,8 @@ class ConvGemm:
         args.mg_imgs = mb
         args.cta_pair = int(cta_pair)
         args.halo = int(halo)
+        args.policy_groups = int(policy_groups)
+        args.sched_k_iters = int(sched_k_iters)
         args.b_group_rows = b_group_rows
         args.reverse = int(reverse)
         self.mb = mb
@@ -283,7 +285,8 @@ class Conv2dPlan:
             xs_f = xs_fwd
         self.fwd = []
         # CTA pairs (M = 256 tiles over two SMs): each CTA fetches half of every weight tile -> half-height B boxes
-        pair = 0 if halo else self._use_pair(allow_pair, mtg, cout, n_tile, fplanes)
+        k_iters = taps * cb_in if bn is not None else 0  # tile schedule of launches that collect statistics
+        pair = 0 if halo else self._use_pair(allow_pair, mtg, cout, n_tile, fplanes, policy, k_iters)
         self.pair_fwd = pair
         for si, (wf_hi, wf_lo, _, _) in enumerate(wsets):
             bs = MapSet(wplanes)
@@ -292,12 +295,12 @@ class Conv2dPlan:
                 encode_mat(bs, pl, t, taps * cin, rows, n_tile // 2 if pair else n_tile)
             g = ConvGemm(xs_f, bs, nph, fplanes, wplanes, ftaps, cb_in, tile, ho, mb, cout, y,
                          (ho * wo * cout, wo * cout, cout), False, n_tile, b_group_rows=cout if si == 1 else 0,
-                         cta_pair=pair, halo=halo)
+                         cta_pair=pair, halo=halo, policy_groups=policy, sched_k_iters=k_iters)
             g.flops_per_group = self.alg_flops
             g.label = f"fwd{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile}{('', ' pair', ' mcast')[pair]}{' halo' if halo else ''}"
             self.fwd.append(g)
         # BatchNorm statistics fused into the forward epilogue
-        self.stat_rows = L.load().fb_conv_stats_rows(mtg, cout // n_tile)
+        self.stat_rows = L.load().fb_conv_stats_rows(mtg, cout // n_tile, policy, k_iters)
         if bn is not None:
             mean, rstd, eps = bn
             dev = y.device
@@ -344,7 +347,7 @@ class Conv2dPlan:
                 encode_act(dys_d, 0, dy, n, ho, wo, cout, (tile[0], tile[1] + 2, tile[2]))
             else:
                 dys_d = dys
-            pair_d = 0 if halo_d else self._use_pair(allow_pair, mtg, cin, n_tile_d, 1)
+            pair_d = 0 if halo_d else self._use_pair(allow_pair, mtg, cin, n_tile_d, 1, policy, 0)
             self.pair_dgrad = pair_d
             for si, (_, _, wd_hi, wd_lo) in enumerate(wsets):
                 ds = MapSet(wplanes)
@@ -352,7 +355,8 @@ class Conv2dPlan:
                 for pl, t in enumerate((wd_hi, wd_lo)[:wplanes]):
                     encode_mat(ds, pl, t, taps * cout, rows, n_tile_d // 2 if pair_d else n_tile_d)
                 g = ConvGemm(dys_d, ds, 1, 1, wplanes, dtaps, cb_out, tile, ho, mb, cin, dx, strides, False, n_tile_d,
-                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups, cta_pair=pair_d, halo=halo_d)
+                             b_group_rows=cin if si == 1 else 0, tapgroups=tapgroups, cta_pair=pair_d, halo=halo_d,
+                             policy_groups=policy)
                 g.flops_per_group = self.alg_flops
                 g.label = f"dgrad{si} {h}x{w} {cin}->{cout} k{k}s{stride} nt{n_tile_d}{('', ' pair', ' mcast')[pair_d]}{' halo' if halo_d else ''}"
                 self.dgrads.append(g)
@@ -418,7 +422,7 @@ class Conv2dPlan:
         return allow_pair == "halo" or os.environ.get("FB_HALO", "1") != "0"
 
     @staticmethod
-    def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes):
+    def _use_pair(allow_pair, mtg, n_total, n_tile, a_planes, policy_groups, sched_k_iters):
         """Cluster mode of a conv GEMM (fb_conv_gemm_args.cta_pair): 0 = independent CTAs, 1 = CTA pairs (cta_group::2),
         2 = clusters of two CTAs that share every weight tile by TMA multicast (bit-identical to 0).
         A pair cannot stack the hi / lo weight planes into one wide instruction, so it only wins where nothing is
@@ -427,7 +431,7 @@ class Conv2dPlan:
         16x16x128 dgrad 117 -> 106 us, but 32x32x64 forward 258 -> 289 us.  The multicast mode halves the weight bytes a
         CTA pulls from L2, which turned out not to be the bound (FB_MCAST=1 enables it where the schedule allows).  allow_pair = "force" / "mcast": that mode wherever
         the schedule allows (tests)."""
-        if not allow_pair or not L.load().fb_conv_pair_ok(mtg, n_total // n_tile):
+        if not allow_pair or not L.load().fb_conv_pair_ok(mtg, n_total // n_tile, policy_groups, sched_k_iters):
             return 0
         if allow_pair == "mcast":
             return 2

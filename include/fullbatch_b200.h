@@ -124,11 +124,17 @@ typedef struct {
    * were encoded with boxes of tile_h + 2 rows, the taps come in triples (dh = -1, 0, 1 at one dw): one box fetch per
    * (dw, channel block) serves three taps (the K order becomes dw-major; still a function of one group's problem). */
   int32_t halo;
+  /* Tile schedule = partial-statistics rows per group (fb_conv_stats_rows; a function of ONE group's problem and of
+   * these two constants of the caller, never of ng).  policy_groups: groups per launch the schedule is tuned for
+   * (<= 0: 1).  sched_k_iters: K iterations (taps x channel blocks) of one tile for launches that collect statistics
+   * -- fewer, longer super-tiles amortise the statistics flush; 0: one row per CTA of a wave (dgrad). */
+  int32_t policy_groups;
+  int32_t sched_k_iters;
 } fb_conv_gemm_args;
 /* partial rows per (group, N tile) written to stats_ws for m_tiles_per_group x n_tiles tiles per group */
-int fb_conv_stats_rows(int m_tiles_per_group, int n_tiles);
+int fb_conv_stats_rows(int m_tiles_per_group, int n_tiles, int policy_groups, int sched_k_iters);
 /* 1 if a problem with this many 128-pixel tiles per group and N tiles can run as CTA pairs (FB_CTA2=0 disables) */
-int fb_conv_pair_ok(int m_tiles_per_group, int n_tiles);
+int fb_conv_pair_ok(int m_tiles_per_group, int n_tiles, int policy_groups, int sched_k_iters);
 int fb_conv_gemm(const fb_conv_gemm_args* args, void* stream);
 
 typedef struct {
