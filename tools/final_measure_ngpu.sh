@@ -3,8 +3,8 @@ N=$1
 mkdir -p gpurun_out/f
 if [ "$N" = "2" ]; then timeout 900 python -m pytest tests/test_multigpu_gpu.py -x -q -m gpu > gpurun_out/f/pytest_multigpu.txt 2>&1; tail -3 gpurun_out/f/pytest_multigpu.txt; fi
 for wl in r18_50k r18_500k; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --workload $wl --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/f/r2_bench_${N}gpu_${wl}_v5.json 2> gpurun_out/f/bench_${N}gpu_${wl}.err
-  python - gpurun_out/f/r2_bench_${N}gpu_${wl}_v5.json <<'PY'
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --workload $wl --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/f/r2_bench_${N}gpu_${wl}_v6.json 2> gpurun_out/f/bench_${N}gpu_${wl}.err
+  python - gpurun_out/f/r2_bench_${N}gpu_${wl}_v6.json <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
