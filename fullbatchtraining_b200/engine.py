@@ -324,6 +324,8 @@ class FullBatchEngine:
         self.l2_order = os.environ.get("FB_L2_ORDER", "1") == "1"
         # ReLU masks as bit planes (1/16 of the bytes of the bf16 plane the backward would otherwise read twice)
         self.bit_masks = os.environ.get("FB_BIT_MASKS", "1") == "1"
+        # projection-shortcut blocks: the main branch's last BatchNorm backward leaves dz in out.grad for the shortcut's
+        self.dz_hand_over = os.environ.get("FB_DZ_HAND_OVER", "1") == "1"
         # FB_WGRAD_STREAM=1: wgrad on a side stream, concurrently with the dgrad -> BatchNorm-backward chain below it
         self.wgrad_mode = int(os.environ.get("FB_WGRAD_STREAM", "0"))
         self.wgrad_stream = torch.cuda.Stream(device=dev) if self.wgrad_mode else None
@@ -415,18 +417,26 @@ class FullBatchEngine:
                          self.smoothing, self.head_ws, self.scal, loss_base, correct_base, gb + fw, gb + fb, a.grad,
                          ng=ng, param_gstride=pstride, grad_gstride=self.stride)
 
-    def _unit_backward(self, u, ng, wset, P, pstride, Gbuf, act, dz_out=None):
-        """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad."""
+    def _unit_backward(self, u, ng, wset, P, pstride, Gbuf, act, dz_out=None, premasked=False):
+        """BN(+ReLU) backward of `u` from the gradient of activation `act` (= grad + grad2), then wgrad and dgrad.
+        premasked: act.grad already holds dz = mask * (grad + grad2) (left there by the BatchNorm backward of the other
+        branch that ends in `act`)."""
         pb, gb = P.data_ptr(), Gbuf.data_ptr()
         # l2_order: the reduce pass starts where the producer of the upstream gradient ended, the apply pass walks the
         # other way, the dgrad starts where the apply ended -- the direction alternates from layer to layer so that each
         # kernel begins on the ~100 MB its predecessor left in L2
         rev = self._rev and self.l2_order
         self._rev = not self._rev
-        ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
-                   gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
-                   param_gstride=pstride, grad_gstride=self.stride, reverse=rev,
-                   mask_bits=act.mask if self.bit_masks else None, policy_groups=self.policy_groups)
+        if premasked:
+            ops.bn_bwd(act.grad, None, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
+                       gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=None, dA2=None, ng=ng,
+                       param_gstride=pstride, grad_gstride=self.stride, reverse=rev, mask_bits=None,
+                       policy_groups=self.policy_groups)
+        else:
+            ops.bn_bwd(act.grad, act.hi, u.y, u.mean, u.rstd, pb + 4 * u.gamma_off, u.Pg, u.cout, self.bn_ws,
+                       gb + 4 * u.gamma_off, gb + 4 * u.beta_off, u.dy, dz_out=dz_out, dA2=act.grad2, ng=ng,
+                       param_gstride=pstride, grad_gstride=self.stride, reverse=rev,
+                       mask_bits=act.mask if self.bit_masks else None, policy_groups=self.policy_groups)
         # wgrad only feeds the flat gradient.  wgrad_mode 1 / 2: on a side stream, forked before / after the dgrad of the
         # same layer (2: the tensor-bound wgrad then runs next to the bandwidth-bound BatchNorm backward of the layer
         # below instead of next to its own dgrad); joined at the end of the backward pass
@@ -439,6 +449,13 @@ class FullBatchEngine:
         if self.wgrad_stream is not None and self.wgrad_mode == 2:
             self._wgrad_side(u, ng, Gbuf)
 
+    def _shortcut_backward(self, blk, ng, wset, P, pstride, Gbuf, premasked):
+        """Projection shortcut: its input gradient goes to the block input's second gradient buffer (grad2)."""
+        self._unit_backward(blk.ds, ng, wset, P, pstride, Gbuf, blk.out, premasked=premasked)
+        if blk.pooled is not None:
+            x = blk.x
+            ops.avgpool2_bwd(blk.pooled.grad, ng * self.mb, x.h, x.w, x.c, x.grad2, accumulate=False)
+
     def _wgrad_side(self, u, ng, Gbuf):
         main = torch.cuda.current_stream()
         self.wgrad_stream.wait_stream(main)
@@ -450,20 +467,20 @@ class FullBatchEngine:
         for blk in reversed(self.blocks):
             out = blk.out
             last = len(blk.units) - 1
-            if blk.ds is not None:
-                # shortcut branch: its input gradient goes to the block input's second gradient buffer (grad2)
-                d = blk.ds
-                self._unit_backward(d, ng, wset, P, pstride, Gbuf, out)
-                if blk.pooled is not None:
-                    x = blk.x
-                    ops.avgpool2_bwd(blk.pooled.grad, ng * self.mb, x.h, x.w, x.c, x.grad2, accumulate=False)
-                dz_out = None
-            else:
-                dz_out = blk.x.grad2  # identity shortcut: dz of the last BN is the shortcut gradient
+            # dz = mask * (grad + grad2) of the block output is what both branches that end in it start from.  Identity
+            # shortcut: the last BatchNorm's backward writes it to the block input's grad2.  Projection shortcut: it
+            # writes it over out.grad in place (element-wise, by the thread that read the element), and the shortcut's
+            # BatchNorm backward then reads ONE premasked tensor instead of two addends and the mask, twice
+            hand_over = blk.ds is not None and self.dz_hand_over
+            dz_out = blk.x.grad2 if blk.ds is None else (out.grad if hand_over else None)
+            if blk.ds is not None and not hand_over:
+                self._shortcut_backward(blk, ng, wset, P, pstride, Gbuf, premasked=False)
             for i in range(last, -1, -1):
                 u = blk.units[i]
                 if i == last:
                     self._unit_backward(u, ng, wset, P, pstride, Gbuf, out, dz_out=dz_out)
+                    if hand_over:
+                        self._shortcut_backward(blk, ng, wset, P, pstride, Gbuf, premasked=True)
                 else:
                     self._unit_backward(u, ng, wset, P, pstride, Gbuf, u.out)
         self._unit_backward(self.stem, ng, wset, P, pstride, Gbuf, self.a0)
