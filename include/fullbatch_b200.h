@@ -253,9 +253,13 @@ int fb_bn_apply(const fb_bn_apply_args* args, void* stream);
 
 /* BatchNorm(+ReLU) backward for ng groups of P pixels.  dz = (dA + dA2) * [mask > 0]; the mask is either the bit plane
  * written by fb_bn_apply (mask_bits: 1/16 of the bytes of a bf16 plane -- the kernels are bandwidth bound) or the bf16
- * activation plane itself (mask_hi); both NULL: no ReLU.  dA2 NULL: no second addend.  Two launches without grid synchronisation: a column reduction whose last block per group
- * finalises (fixed order), then a streaming apply.  Writes dgamma / dbeta (+ g*grad_gstride), dY as bf16 (tensor-core
- * operand) and optionally dz as fp32 (`dz_out`, the identity-branch gradient).  gamma + g*param_gstride.
+ * activation plane itself (mask_hi); both NULL: no ReLU (dA is taken as dz).  dA2 NULL: no second addend.  Two launches
+ * without grid synchronisation: a column reduction whose last block per group finalises (fixed order), then a streaming
+ * apply.  Writes dgamma / dbeta (+ g*grad_gstride), dY as bf16 (tensor-core operand) and optionally dz as fp32
+ * (`dz_out`: the gradient of the shortcut branch that ends in the same activation).  dz_out may alias dA (in place:
+ * every element is read and written by one thread).  With two addends dz_out is stored by the REDUCE launch and read
+ * back by the apply launch instead of dA, dA2 and the mask (one fp32 read per element less; same bits).
+ * gamma + g*param_gstride.
  * ws: >= 16 + ng*(2*C*fb_bn_bwd_chunks + 2*C) floats, the first 64 bytes ZERO on first use (self-resetting tickets). */
 typedef struct {
   const float* dA;
