@@ -522,6 +522,16 @@ def test_bn_apply_and_backward(variant, shape):
         ops.bn_bwd(dA, None, y, mean, rstd, base, P, Cc, ws, grads_b.data_ptr(), grads_b.data_ptr() + 4 * Cc, dy_b,
                    dz_out=dz_b, dA2=dA2, ng=ng, param_gstride=pstride, grad_gstride=gstride, mask_bits=bits)
         assert torch.equal(dy_b, dy) and torch.equal(dz_b, dz) and torch.equal(grads_b[:, :2 * Cc], grads[:, :2 * Cc])
+    # dz written over dA in place (projection-shortcut blocks), then consumed premasked by a second BatchNorm backward
+    # without addend or mask: the same dY / dgamma / dbeta bits as the masked two-addend call
+    dA_ip, grads_ip, dy_ip = dA.clone(), torch.full((ng, gstride), float("nan"), device=DEV), torch.empty_like(dy)
+    ops.bn_bwd(dA_ip, out_hi if relu else None, y, mean, rstd, base, P, Cc, ws, grads_ip.data_ptr(),
+               grads_ip.data_ptr() + 4 * Cc, dy_ip, dz_out=dA_ip, dA2=dA2, ng=ng, param_gstride=pstride, grad_gstride=gstride)
+    assert torch.equal(dA_ip, dz) and torch.equal(dy_ip, dy) and torch.equal(grads_ip[:, :2 * Cc], grads[:, :2 * Cc])
+    grads_pm, dy_pm = torch.full((ng, gstride), float("nan"), device=DEV), torch.empty_like(dy)
+    ops.bn_bwd(dA_ip, None, y, mean, rstd, base, P, Cc, ws, grads_pm.data_ptr(), grads_pm.data_ptr() + 4 * Cc, dy_pm,
+               ng=ng, param_gstride=pstride, grad_gstride=gstride)
+    assert torch.equal(dy_pm, dy) and torch.equal(grads_pm[:, :2 * Cc], grads[:, :2 * Cc])
     torch.cuda.synchronize()
     for g in range(ng):
         sl = slice(g * P, (g + 1) * P)
